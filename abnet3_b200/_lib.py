@@ -1,0 +1,74 @@
+"""ctypes binding of the C ABI (include/abnet3_b200.h).
+
+The shared library is the product: there is NO Python / torch fallback for any
+of these entry points.  A missing library raises at import of this module's
+``lib()``; a non-sm_100 device makes every call fail with ABN_ENOSYS.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libabnet3_b200.so")
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+_L = _c.c_int64
+_F = _c.c_float
+
+# name -> (restype, argtypes); mirrors include/abnet3_b200.h declaration order
+SIGNATURES = {
+    "abn_version": (_I, []),
+    "abn_last_error": (_c.c_char_p, []),
+    "abn_device_info": (_I, [_P, _P, _P, _P]),
+    "abn_cosine_distance": (_I, [_P, _L, _I, _P, _I, _I, _P, _P, _P, _P]),
+    "abn_dtw_from_dist": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "abn_align_pairs": (_I, [_P, _L, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "abn_diff_pairs": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "abn_compact_paths": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "abn_gather_batch": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
+    "abn_pair_loss": (_I, [_P, _P, _P, _L, _I, _I, _F, _F, _P, _P, _P, _P]),
+    "abn_linear_forward": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P, _P]),
+    "abn_linear_backward": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "abn_optimizer_step": (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _F, _L, _P]),
+}
+
+_lib = None
+
+
+class AbnError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("abnet3_b200 error %d: %s" % (code, text))
+        self.code = code
+
+
+def lib():
+    """Load libabnet3_b200.so (built by ``python -m abnet3_b200.build``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(
+                "%s is missing: build it with `python -m abnet3_b200.build` "
+                "(nvcc, sm_100a).  There is no fallback path." % SO_PATH)
+        handle = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise AbnError(rc, lib().abn_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

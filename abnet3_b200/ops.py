@@ -1,0 +1,218 @@
+"""Typed wrappers over the C ABI: torch tensors in, torch tensors out.
+
+torch is used here for device memory, streams and prefix sums only; all the
+arithmetic of the hot path happens inside libabnet3_b200.so.  Every function
+requires CUDA tensors and raises if the library or an sm_100 device is missing.
+"""
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+MAX_TOKEN_FRAMES = 96            # ABN_MAX_TOKEN_FRAMES
+ACT = {None: 0, "none": 0, "sigmoid": 1, "tanh": 2, "relu": 3}
+LOSS_KIND = {"coscos2": 0, "cosmargin": 1}
+OPT_KIND = {"sgd": 0, "adadelta": 1, "adam": 2}
+
+AlignResult = namedtuple(
+    "AlignResult", "idx1 idx2 path_off path_len cost valid")
+
+
+def _req(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError("%s must be a CUDA tensor (no CPU path exists)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _excl_cumsum(counts):
+    """[n] -> int64 [n+1] exclusive prefix sums (device)."""
+    off = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=counts.device)
+    torch.cumsum(counts.to(torch.int64), 0, out=off[1:])
+    return off
+
+
+def align_pairs(feat, pair_tok, max_frames=None):
+    """Fused cosine distance + DTW + traceback for every pair
+    (abnet3/utils.py:147-153 per pair).  Returns an AlignResult whose idx1/idx2
+    hold GLOBAL feature rows in per-pair slots of capacity n1+n2-1 starting at
+    path_off[p]; valid[p] == 0 means the reference would have dropped the pair.
+    """
+    _req(feat, torch.float32, "feat")
+    _req(pair_tok, torch.int32, "pair_tok")
+    P = pair_tok.shape[0]
+    dev = feat.device
+    if max_frames is None:
+        max_frames = int(pair_tok[:, [1, 3]].max().item()) if P else 1
+    cap = (pair_tok[:, 1] + pair_tok[:, 3] - 1).clamp_min(0)
+    path_off = _excl_cumsum(cap)
+    total = int(path_off[-1].item()) if P else 0
+    idx1 = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    idx2 = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    path_len = torch.zeros(P, dtype=torch.int32, device=dev)
+    cost = torch.full((P,), float("nan"), dtype=torch.float64, device=dev)
+    valid = torch.zeros(P, dtype=torch.uint8, device=dev)
+    check(_lib.lib().abn_align_pairs(
+        ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1),
+        ptr(path_off), ptr(idx1), ptr(idx2), ptr(path_len), ptr(cost), ptr(valid),
+        stream_ptr()))
+    return AlignResult(idx1, idx2, path_off, path_len, cost, valid)
+
+
+def cosine_distance(feat, pair_tok, max_frames=None):
+    """Batched abnet3/utils.py:40-60.  Returns (dist float32 flat, dist_off, valid)."""
+    _req(feat, torch.float32, "feat")
+    _req(pair_tok, torch.int32, "pair_tok")
+    P = pair_tok.shape[0]
+    dev = feat.device
+    if max_frames is None:
+        max_frames = int(pair_tok[:, [1, 3]].max().item()) if P else 1
+    cells = (pair_tok[:, 1].to(torch.int64) * pair_tok[:, 3].to(torch.int64)).clamp_min(0)
+    dist_off = _excl_cumsum(cells)
+    total = int(dist_off[-1].item()) if P else 0
+    dist = torch.full((max(total, 1),), float("nan"), dtype=torch.float32, device=dev)
+    valid = torch.zeros(P, dtype=torch.uint8, device=dev)
+    check(_lib.lib().abn_cosine_distance(
+        ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1),
+        ptr(dist_off), ptr(dist), ptr(valid), stream_ptr()))
+    return dist, dist_off, valid
+
+
+def dtw_from_dist(dist, dist_off, shape, max_frames=None):
+    """Batched DTW on given float64 matrices (the call at abnet3/utils.py:149-151).
+    Returns (path1, path2, path_off, path_len, cost, valid) with LOCAL indices."""
+    _req(dist, torch.float64, "dist")
+    _req(dist_off, torch.int64, "dist_off")
+    _req(shape, torch.int32, "shape")
+    P = shape.shape[0]
+    dev = dist.device
+    if max_frames is None:
+        max_frames = int(shape.max().item()) if P else 1
+    cap = (shape[:, 0] + shape[:, 1] - 1).clamp_min(0)
+    path_off = _excl_cumsum(cap)
+    total = int(path_off[-1].item()) if P else 0
+    p1 = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    p2 = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    path_len = torch.zeros(P, dtype=torch.int32, device=dev)
+    cost = torch.full((P,), float("nan"), dtype=torch.float64, device=dev)
+    valid = torch.zeros(P, dtype=torch.uint8, device=dev)
+    check(_lib.lib().abn_dtw_from_dist(
+        ptr(dist), ptr(dist_off), ptr(shape), P, max(max_frames, 1), ptr(path_off),
+        ptr(p1), ptr(p2), ptr(path_len), ptr(cost), ptr(valid), stream_ptr()))
+    return p1, p2, path_off, path_len, cost, valid
+
+
+def diff_pairs(pair_tok, stretch=False):
+    """Frame-index pairs of 'diff' pairs (abnet3/dataloader.py:208-231).
+    Returns (idx1, idx2, out_off): rows of pair p at out_off[p]..out_off[p+1]."""
+    _req(pair_tok, torch.int32, "pair_tok")
+    P = pair_tok.shape[0]
+    n1, n2 = pair_tok[:, 1], pair_tok[:, 3]
+    rows = torch.maximum(n1, n2) if stretch else torch.minimum(n1, n2)
+    rows = torch.where((n1 > 0) & (n2 > 0), rows, torch.zeros_like(rows))
+    out_off = _excl_cumsum(rows)
+    total = int(out_off[-1].item()) if P else 0
+    idx1 = torch.empty(max(total, 1), dtype=torch.int32, device=pair_tok.device)
+    idx2 = torch.empty(max(total, 1), dtype=torch.int32, device=pair_tok.device)
+    check(_lib.lib().abn_diff_pairs(ptr(pair_tok), P, int(bool(stretch)), ptr(out_off),
+                                    ptr(idx1), ptr(idx2), stream_ptr()))
+    return idx1[:total], idx2[:total], out_off
+
+
+def compact_paths(res):
+    """Dense (idx1, idx2, dst_off) table from an AlignResult
+    (what FramesDataLoader.load_all_frames accumulates, dataloader.py:642-653)."""
+    P = res.path_len.numel()
+    dst_off = _excl_cumsum(res.path_len)
+    total = int(dst_off[-1].item()) if P else 0
+    d1 = torch.empty(max(total, 1), dtype=torch.int32, device=res.idx1.device)
+    d2 = torch.empty(max(total, 1), dtype=torch.int32, device=res.idx1.device)
+    check(_lib.lib().abn_compact_paths(ptr(res.idx1), ptr(res.idx2), ptr(res.path_off),
+                                       ptr(dst_off), ptr(res.path_len), P, ptr(d1), ptr(d2),
+                                       stream_ptr()))
+    return d1[:total], d2[:total], dst_off
+
+
+def gather_batch(feat, idx1, idx2, y=None, sel=None, n=None, out=None):
+    """X1 = feat[idx1[sel]], X2 = feat[idx2[sel]], y_out = float(y[sel])."""
+    _req(feat, torch.float32, "feat")
+    _req(idx1, torch.int32, "idx1")
+    _req(idx2, torch.int32, "idx2")
+    if sel is not None:
+        _req(sel, torch.int64, "sel")
+        n = sel.numel() if n is None else n
+    elif n is None:
+        n = idx1.numel()
+    if y is not None:
+        _req(y, torch.int8, "y")
+    dim = feat.shape[1]
+    if out is None:
+        x1 = torch.empty((n, dim), dtype=torch.float32, device=feat.device)
+        x2 = torch.empty((n, dim), dtype=torch.float32, device=feat.device)
+        yo = torch.empty(n, dtype=torch.float32, device=feat.device)
+    else:
+        x1, x2, yo = out
+    check(_lib.lib().abn_gather_batch(ptr(feat), dim, ptr(idx1), ptr(idx2), ptr(y), ptr(sel),
+                                      n, ptr(x1), ptr(x2), ptr(yo), stream_ptr()))
+    return x1, x2, yo
+
+
+def pair_loss(e1, e2, y, kind="coscos2", margin=0.5, scale=1.0, loss_out=None,
+              need_grad=True):
+    """Fused loss value + gradients (abnet3/loss.py:46-67, :85-105).
+    Returns (loss[1], de1, de2); ``loss_out`` is accumulated into when given."""
+    _req(e1, torch.float32, "e1")
+    _req(e2, torch.float32, "e2")
+    _req(y, torch.float32, "y")
+    n, dim = e1.shape
+    loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32,
+                                                            device=e1.device)
+    de1 = torch.empty_like(e1) if need_grad else None
+    de2 = torch.empty_like(e2) if need_grad else None
+    check(_lib.lib().abn_pair_loss(ptr(e1), ptr(e2), ptr(y), n, dim, LOSS_KIND[kind],
+                                   float(margin), float(scale), ptr(loss), ptr(de1), ptr(de2),
+                                   stream_ptr()))
+    return loss, de1, de2
+
+
+def linear_forward(x, W, b, act, precision=0, out=None):
+    _req(x, torch.float32, "x")
+    _req(W, torch.float32, "W")
+    m, n_in = x.shape
+    n_out = W.shape[0]
+    y = out if out is not None else torch.empty((m, n_out), dtype=torch.float32, device=x.device)
+    check(_lib.lib().abn_linear_forward(ptr(x), ptr(W), ptr(b), m, n_in, n_out, ACT[act],
+                                        precision, ptr(y), stream_ptr()))
+    return y
+
+
+def linear_backward(x, W, y, dy, act, precision=0, need_dx=True, dW=None, db=None,
+                    accumulate=False):
+    """dy is overwritten with dz = dy * act'(y).  Returns (dx, dW, db)."""
+    _req(dy, torch.float32, "dy")
+    m, n_in = x.shape
+    n_out = W.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    if dW is None:
+        dW = torch.empty_like(W)
+        db = torch.empty(n_out, dtype=torch.float32, device=x.device)
+        accumulate = False
+    check(_lib.lib().abn_linear_backward(ptr(x), ptr(W), ptr(y), ptr(dy), m, n_in, n_out,
+                                         ACT[act], precision, int(accumulate), ptr(dx), ptr(dW),
+                                         ptr(db), stream_ptr()))
+    return dx, dW, db
+
+
+def optimizer_step(param, grad, state0, state1, kind, lr, momentum=0.0, grad_scale=1.0,
+                   step=1):
+    _req(param, torch.float32, "param")
+    _req(grad, torch.float32, "grad")
+    check(_lib.lib().abn_optimizer_step(ptr(param), ptr(grad), ptr(state0), ptr(state1),
+                                        param.numel(), OPT_KIND[kind], float(lr),
+                                        float(momentum), float(grad_scale), int(step),
+                                        stream_ptr()))

@@ -1,0 +1,295 @@
+"""Host-side mirror of the alignment primitives of /root/reference/abnet3/utils.py.
+
+Same names, argument meaning and error behaviour as the reference for the hot
+path -- ``cosine_distance`` (:40-60), ``DTW`` (the external call at :149-151),
+``get_dtw_alignment`` (:147-153), ``Features_Accessor`` (:118-145),
+``read_dataset`` / ``group_pairs`` / ``read_pairs`` (:156-208),
+``read_spkid_file`` (:23-31) -- with the arithmetic done by the sm_100a kernels
+behind the C ABI (abnet3_b200/_lib.py).  There is no CPU fallback: without the
+library or an sm_100 GPU these functions raise.
+
+New, batched surface (what the dataloaders use): ``FeatureTable`` (the whole
+corpus as one device-resident [n_rows, dim] table plus per-file row ranges),
+``BatchAligner`` (pre-allocated, device-resident alignment of a pair list) and
+``align_pairs_host`` (host buffers in, host paths out).
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+__all__ = ["cosine_distance", "DTW", "get_dtw_alignment", "Features_Accessor",
+           "FeatureTable", "BatchAligner", "align_pairs_host", "read_dataset",
+           "group_pairs", "read_pairs", "read_spkid_file", "read_spk_list"]
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("abnet3_b200 needs an sm_100 GPU: there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ----------------------------------------------------------- per-pair API ---
+def cosine_distance(x, y):
+    """abnet3/utils.py:40-60.  float32 (or float64, computed in float32 after
+    the reference's own dtype assert) [n1, D], [n2, D] -> float64 [n1, n2];
+    raises AssertionError where the reference's ``assert np.all(d >= 0)`` fails."""
+    assert (x.dtype == np.float64 and y.dtype == np.float64) or (
+        x.dtype == np.float32 and y.dtype == np.float32)
+    n1, n2 = x.shape[0], y.shape[0]
+    dev = _device()
+    feat = torch.from_numpy(np.ascontiguousarray(
+        np.concatenate([x, y]).astype(np.float32))).to(dev)
+    tok = torch.tensor([[0, n1, n1, n2]], dtype=torch.int32, device=dev)
+    dist, _, valid = ops.cosine_distance(feat, tok, max_frames=max(n1, n2))
+    d = dist[:n1 * n2].cpu().numpy().astype(np.float64).reshape(n1, n2)
+    assert bool(valid.item()) and np.all(d >= 0)
+    return d
+
+
+def DTW(x, y, return_alignment=False, dist_function=None, dist_array=None):
+    """The external ``dtw.DTW`` as the reference calls it (abnet3/utils.py:149-151):
+    returns ``(cost, None, (path_len, path1, path2))`` when ``return_alignment``
+    else ``cost``.  ``dist_array`` float64 [n1, n2] (computed with
+    ``cosine_distance`` when omitted)."""
+    if dist_array is None:
+        dist_array = cosine_distance(x, y) if dist_function is None else dist_function(x, y)
+    d = np.ascontiguousarray(dist_array, dtype=np.float64)
+    n1, n2 = d.shape
+    dev = _device()
+    p1, p2, _, plen, cost, valid = ops.dtw_from_dist(
+        torch.from_numpy(d.ravel()).to(dev),
+        torch.tensor([0, n1 * n2], dtype=torch.int64, device=dev),
+        torch.tensor([[n1, n2]], dtype=torch.int32, device=dev), max_frames=max(n1, n2))
+    if not bool(valid.item()):
+        raise ValueError("invalid distance matrix (NaN or negative entry)")
+    L = int(plen.item())
+    c = float(cost.item())
+    if not return_alignment:
+        return c
+    return c, None, (L, p1[:L].cpu().numpy().astype(np.intp), p2[:L].cpu().numpy().astype(np.intp))
+
+
+def get_dtw_alignment(feat1, feat2):
+    """abnet3/utils.py:147-153 for ONE pair (fused kernel).  Raises
+    AssertionError when the reference would (NaN distance)."""
+    n1, n2 = feat1.shape[0], feat2.shape[0]
+    dev = _device()
+    feat = torch.from_numpy(np.ascontiguousarray(
+        np.concatenate([feat1, feat2]).astype(np.float32))).to(dev)
+    tok = torch.tensor([[0, n1, n1, n2]], dtype=torch.int32, device=dev)
+    res = ops.align_pairs(feat, tok, max_frames=max(n1, n2))
+    assert bool(res.valid.item()), "cosine distance holds a NaN (utils.py:59)"
+    L = int(res.path_len.item())
+    path1 = res.idx1[:L].cpu().numpy().astype(np.intp)
+    path2 = (res.idx2[:L].cpu().numpy() - n1).astype(np.intp)
+    assert len(path1) == len(path2)
+    return path1, path2
+
+
+# ------------------------------------------------------------ batched API ---
+class BatchAligner(object):
+    """Device-resident batched ``get_dtw_alignment`` over a pair list.
+
+    Buffers are allocated once and reused, so ``align`` enqueues exactly one
+    kernel (plus a tiny prefix sum when the pair list changes) and never
+    synchronises.  The returned AlignResult aliases the internal buffers and
+    is valid until the next ``align``."""
+
+    def __init__(self, feat, max_pairs=0, max_frames=ops.MAX_TOKEN_FRAMES):
+        self.feat = feat
+        self.max_frames = int(max_frames)
+        self._cap_pairs = 0
+        self._cap_rows = 0
+        self._off_key = None
+        if max_pairs:
+            self._reserve(max_pairs, max_pairs * (2 * self.max_frames - 1))
+
+    def _reserve(self, n_pairs, n_rows):
+        dev = self.feat.device
+        if n_rows > self._cap_rows:
+            self.idx1 = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            self.idx2 = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            self._cap_rows = n_rows
+        if n_pairs > self._cap_pairs:
+            self.path_len = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+            self.cost = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+            self.valid = torch.empty(n_pairs, dtype=torch.uint8, device=dev)
+            self._cap_pairs = n_pairs
+
+    def _offsets(self, pair_tok):
+        key = (pair_tok.data_ptr(), pair_tok._version, pair_tok.shape[0])
+        if key != self._off_key:
+            cap = (pair_tok[:, 1] + pair_tok[:, 3] - 1).clamp_min(0)
+            self._off = ops._excl_cumsum(cap)
+            self._off_total = int(self._off[-1].item())
+            self._off_key = key
+        return self._off, self._off_total
+
+    def align(self, pair_tok):
+        from . import _lib
+        P = pair_tok.shape[0]
+        off, total = self._offsets(pair_tok)
+        self._reserve(P, max(total, 1))
+        _lib.check(_lib.lib().abn_align_pairs(
+            _lib.ptr(self.feat), self.feat.shape[0], self.feat.shape[1], _lib.ptr(pair_tok), P,
+            self.max_frames, _lib.ptr(off), _lib.ptr(self.idx1), _lib.ptr(self.idx2),
+            _lib.ptr(self.path_len), _lib.ptr(self.cost), _lib.ptr(self.valid),
+            _lib.stream_ptr()))
+        return ops.AlignResult(self.idx1, self.idx2, off, self.path_len[:P], self.cost[:P],
+                               self.valid[:P])
+
+
+_pinned = {}
+
+
+def _pinned_buf(name, numel, dtype):
+    buf = _pinned.get(name)
+    if buf is None or buf.numel() < numel or buf.dtype != dtype:
+        buf = torch.empty(max(numel, 1), dtype=dtype, pin_memory=True)
+        _pinned[name] = buf
+    return buf[:numel]
+
+
+def align_pairs_host(feat_host, pair_tok_host, max_frames=None):
+    """Host buffers in, host results out -- the call a user of the reference's
+    dataloader would make for a whole pair list.
+
+    ``feat_host`` [n_rows, dim] float32 and ``pair_tok_host`` [P, 4] int32 are
+    (ideally pinned) CPU tensors.  Copies both to the GPU, aligns every pair,
+    compacts the paths and copies them back.  Returns CPU tensors
+    ``(idx1, idx2, pair_off, path_len, cost, valid)``: pair p's aligned global
+    rows are ``idx1[pair_off[p]:pair_off[p+1]]`` / ``idx2[...]``."""
+    dev = _device()
+    feat = feat_host.to(dev, non_blocking=True)
+    tok = pair_tok_host.to(dev, non_blocking=True)
+    if max_frames is None:
+        max_frames = int(pair_tok_host[:, [1, 3]].max().item()) if tok.shape[0] else 1
+    res = ops.align_pairs(feat, tok, max_frames=max_frames)
+    d1, d2, doff = ops.compact_paths(res)
+    P = tok.shape[0]
+    out = (_pinned_buf("idx1", d1.numel(), torch.int32), _pinned_buf("idx2", d2.numel(), torch.int32),
+           _pinned_buf("off", P + 1, torch.int64), _pinned_buf("len", P, torch.int32),
+           _pinned_buf("cost", P, torch.float64), _pinned_buf("valid", P, torch.uint8))
+    for dst, src in zip(out, (d1, d2, doff, res.path_len, res.cost, res.valid)):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
+# ------------------------------------------------- features / pair parsing ---
+class FeatureTable(object):
+    """The whole corpus as ONE [n_rows, dim] float32 table (what
+    ``read_feats`` loads into RAM, abnet3/utils.py:211-217), device resident,
+    with per-file row ranges and frame times for token slicing."""
+
+    def __init__(self, features, times=None, device=None):
+        """``features``: {file: ndarray [n, dim]}; ``times``: {file: ndarray [n]}
+        (frame centres in seconds; default 0.0025 + 0.01 k, features.py:195)."""
+        self.files = list(features.keys())
+        self.row0, self.nrows, self.times = {}, {}, {}
+        rows = 0
+        for f in self.files:
+            a = features[f]
+            self.row0[f], self.nrows[f] = rows, a.shape[0]
+            self.times[f] = (np.asarray(times[f], dtype=np.float64) if times is not None
+                             else 0.0025 + 0.01 * np.arange(a.shape[0]))
+            rows += a.shape[0]
+        host = np.ascontiguousarray(
+            np.concatenate([np.asarray(features[f]) for f in self.files]).astype(np.float32))
+        self.dim = host.shape[1]
+        self.host = host
+        self.device = device if device is not None else _device()
+        self.feat = torch.from_numpy(host).to(self.device)
+
+    def _key(self, f):
+        if f in self.row0:
+            return f
+        alt = f.encode("UTF-8") if isinstance(f, str) else f.decode("UTF-8")
+        return alt                     # utils.py:135-137: bytes or str file keys
+
+    def token_by_time(self, f, on, off):
+        """(row_start, n_frames) of the frames with on <= t <= off
+        (abnet3/utils.py:128-131, inclusive on both ends)."""
+        f = self._key(f)
+        t = self.times[f]
+        lo = int(np.searchsorted(t, on, side="left"))
+        hi = int(np.searchsorted(t, off, side="right"))
+        return self.row0[f] + lo, max(hi - lo, 0)
+
+    def token_by_frames(self, f, frame_on, frame_off):
+        """abnet3/utils.py:141-145: ``features[f][frame_on:frame_off]`` with
+        Python slice clamping."""
+        f = self._key(f)
+        n = self.nrows[f]
+        lo, hi, _ = slice(frame_on, frame_off).indices(n)
+        return self.row0[f] + lo, max(hi - lo, 0)
+
+
+class Features_Accessor(object):
+    """abnet3/utils.py:118-145 on top of a FeatureTable: ``get`` /
+    ``get_between_frames`` return host float32 rows like the reference."""
+
+    def __init__(self, times, features):
+        first = features[list(features.keys())[0]]
+        if first.dtype != np.float32:            # utils.py:122-125, :228-235
+            features = {k: v.astype(np.float32) for k, v in features.items()}
+            print('Casted features to correct type np.float32')
+        self.times = times
+        self.features = features
+        self.table = FeatureTable(features, times)
+
+    def get(self, f, on, off):
+        s, n = self.table.token_by_time(f, on, off)
+        return self.table.host[s:s + n]
+
+    def get_between_frames(self, f, frame_on, frame_off):
+        s, n = self.table.token_by_frames(f, frame_on, frame_off)
+        return self.table.host[s:s + n]
+
+
+def read_spkid_file(spkid_file):
+    """abnet3/utils.py:23-31"""
+    spk = {}
+    with open(spkid_file, 'r') as fh:
+        for line in fh.readlines():
+            fid, spkid = line.strip().split(" ")
+            assert not (fid in spk)
+            spk[fid] = spkid
+    return spk
+
+
+def read_spk_list(spk_file):
+    """abnet3/utils.py:34-37"""
+    with open(spk_file, 'r') as fh:
+        return [line.strip() for line in fh.readlines()]
+
+
+def read_dataset(dataset_file):
+    """abnet3/utils.py:156-173: [(f1, s1, e1, f2, s2, e2, pair_type), ...]"""
+    pairs = []
+    with open(dataset_file, 'r') as fh:
+        for line in fh.readlines():
+            tokens = line.strip().split(" ")
+            assert len(tokens) == 7
+            f1, s1, e1, f2, s2, e2, pair_type = tokens
+            s1, e1, s2, e2 = float(s1), float(e1), float(s2), float(e2)
+            assert pair_type in ['same', 'diff'], \
+                'Unsupported pair type {0}'.format(pair_type)
+            pairs.append((f1, s1, e1, f2, s2, e2, pair_type))
+    return pairs
+
+
+def group_pairs(pairs):
+    """abnet3/utils.py:176-193"""
+    grouped_pairs = {'same': [], 'diff': []}
+    for f1, s1, e1, f2, s2, e2, pair_type in pairs:
+        assert pair_type in grouped_pairs, \
+            'Unsupported pair type {0}'.format(pair_type)
+        grouped_pairs[pair_type].append((f1, s1, e1, f2, s2, e2))
+    return grouped_pairs
+
+
+def read_pairs(pair_file):
+    """abnet3/utils.py:196-208"""
+    return group_pairs(read_dataset(pair_file))

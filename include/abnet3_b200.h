@@ -1,0 +1,206 @@
+/*
+ * abnet3_b200.h -- C ABI of the B200-native ABnet3 hot path.
+ *
+ * One shared library (abnet3_b200/libabnet3_b200.so), plain C signatures:
+ * device pointers, sizes and a CUDA stream; no torch / C++ types.  Every
+ * entry point ENQUEUES work on the caller's stream and returns immediately
+ * (0 = ABN_OK, otherwise an errno-style code; abn_last_error() gives the
+ * text).  Nothing allocates behind the caller's back: outputs and workspaces
+ * are caller-owned device buffers.  Re-entrant per stream; one host thread
+ * per GPU (one process per GPU under torchrun).
+ *
+ * The reference (bootphon/abnet3) has no FFI: its boundary for this path is
+ * the Python surface cited at each entry point below (paths relative to
+ * /root/reference).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Token / pair encoding used throughout
+ * -------------------------------------
+ *   feat      [n_rows, dim] float32, row-major: every feature file of the
+ *             corpus concatenated (abnet3/utils.py:211-217 loads them all,
+ *             :122-125 forces float32).  dim % 4 == 0, 16-byte aligned base.
+ *   pair_tok  [n_pairs, 4] int32: (row_start_1, n_frames_1, row_start_2,
+ *             n_frames_2) -- the two tokens of a pair as row ranges of feat,
+ *             i.e. what Features_Accessor.get / get_between_frames slice
+ *             (abnet3/utils.py:128-145).
+ */
+#ifndef ABNET3_B200_H
+#define ABNET3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABN_OK       0
+#define ABN_EIO      5   /* CUDA runtime / launch error                  */
+#define ABN_ENOMEM  12   /* workspace too small                          */
+#define ABN_EINVAL  22   /* bad argument                                 */
+#define ABN_ERANGE  34   /* size outside what the kernels support        */
+#define ABN_ENOSYS  38   /* device is not sm_100 (no fallback by design) */
+
+/* longest token (frames) abn_align_pairs / abn_cosine_distance / abn_dtw_from_dist
+ * accept; `max_frames` arguments are an upper bound on every n1, n2 of the call
+ * (it sizes shared memory; a pair exceeding it comes back with valid = 0) */
+#define ABN_MAX_TOKEN_FRAMES 96
+
+typedef void *abn_stream_t; /* a cudaStream_t */
+
+#if defined(__GNUC__)
+#define ABN_API __attribute__((visibility("default")))
+#else
+#define ABN_API
+#endif
+
+/* library version (major*10000 + minor*100 + patch) and last error text of
+ * the calling thread */
+ABN_API int abn_version(void);
+ABN_API const char *abn_last_error(void);
+
+/* Device facts for launch sizing / bench reporting.  Any pointer may be NULL. */
+ABN_API int abn_device_info(int *sm_count, int *cc_major, int *cc_minor,
+                    size_t *smem_optin_bytes);
+
+/* ------------------------------------------------------------------------
+ * (1) Batched cosine frame distance.
+ * Replaces abnet3/utils.py:40-60 `cosine_distance(x, y)`, one call per pair.
+ *   dist_off [n_pairs+1] int64: pair p's n1*n2 matrix (row-major, ld = n2)
+ *            starts at dist[dist_off[p]].
+ *   dist     float32.  The reference computes in float32 and widens to
+ *            float64 at the end (utils.py:49-53), so float32 storage holds
+ *            exactly the values the reference returns.
+ *   valid    [n_pairs] uint8, 0 when the matrix holds a NaN / negative entry
+ *            (the reference's `assert np.all(d >= 0)`, utils.py:59).
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_cosine_distance(const float *feat, int64_t n_rows, int dim,
+                        const int32_t *pair_tok, int n_pairs, int max_frames,
+                        const int64_t *dist_off, float *dist, uint8_t *valid,
+                        abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (2) Batched DTW + traceback on GIVEN float64 distance matrices.
+ * Replaces the external call at abnet3/utils.py:149-151
+ *   `DTW(feat1, feat2, return_alignment=True, dist_array=distance_array)`.
+ *   shape    [n_pairs, 2] int32 (n1, n2); dist/dist_off as above but float64.
+ *   path_off [n_pairs+1] int64 with path_off[p+1]-path_off[p] >= n1+n2-1.
+ *   path1/2  LOCAL frame indices, forward order, at path_off[p] .. +path_len.
+ *   cost     C[n1-1, n2-1]; valid as above.
+ * Tie rule: diagonal, then i-1, then j-1 (oracle/dtw_oracle.c).
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_dtw_from_dist(const double *dist, const int64_t *dist_off,
+                      const int32_t *shape, int n_pairs, int max_frames,
+                      const int64_t *path_off, int32_t *path1, int32_t *path2,
+                      int32_t *path_len, double *cost, uint8_t *valid,
+                      abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (1)+(2) fused: align every 'same' pair of a pair list.
+ * Replaces abnet3/utils.py:147-153 `get_dtw_alignment` as called per pair by
+ * abnet3/dataloader.py:183-206 and :642-653.  Distances and accumulated costs
+ * never leave the SM.
+ *   idx1/idx2 GLOBAL row ids into feat (row_start + local path index), i.e.
+ *             the rows `feat1[path1, :]`, `feat2[path2, :]` gather
+ *             (dataloader.py:204-205), at path_off[p] .. +path_len[p].
+ *   valid[p] == 0 reproduces "exception -> pair dropped"
+ *             (dataloader.py:188-191); then path_len[p] = 0.
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_align_pairs(const float *feat, int64_t n_rows, int dim,
+                    const int32_t *pair_tok, int n_pairs, int max_frames,
+                    const int64_t *path_off, int32_t *idx1, int32_t *idx2,
+                    int32_t *path_len, double *cost, uint8_t *valid,
+                    abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Frame-index pairs of 'diff' pairs (no DTW).
+ * Replaces abnet3/dataloader.py:208-231 (and :655-666):
+ *   stretch == 0: both tokens truncated to min(n1,n2) leading frames;
+ *   stretch != 0: `align_different_words` -- the longer token in X1, the
+ *                 shorter one stretched by rint(linspace(0, min-1, max)) in X2.
+ *   out_off [n_pairs+1] int64: where pair p's rows go; rows written =
+ *           min(n1,n2) (stretch == 0) or max(n1,n2).
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_diff_pairs(const int32_t *pair_tok, int n_pairs, int stretch,
+                   const int64_t *out_off, int32_t *idx1, int32_t *idx2,
+                   abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Compact the per-pair path slots written by abn_align_pairs into a dense
+ * frame-pair table (what FramesDataLoader.load_all_frames builds,
+ * dataloader.py:642-653): for every pair with path_len > 0, copy its
+ * path_len entries from (src_off[p]) to (dst_off[p]).
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_compact_paths(const int32_t *src1, const int32_t *src2,
+                      const int64_t *src_off, const int64_t *dst_off,
+                      const int32_t *path_len, int n_pairs, int32_t *dst1,
+                      int32_t *dst2, abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Batch generation: gather feature rows for a batch of frame pairs.
+ * Replaces the row gathers of abnet3/dataloader.py:204-205, :250-255 and
+ * FramesDataLoader.load_batch (:673-684).
+ *   sel   [n] int64 or NULL: positions in idx1/idx2/y_in (the permutation /
+ *         batch slice); NULL = 0..n-1.
+ *   x1,x2 [n, dim] float32 out; y_out [n] float32 out (NULL to skip);
+ *   y_in  [*] int8 labels (+1 / -1) or NULL.
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_gather_batch(const float *feat, int dim, const int32_t *idx1,
+                     const int32_t *idx2, const int8_t *y_in,
+                     const int64_t *sel, int64_t n, float *x1, float *x2,
+                     float *y_out, abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (4) Fused pair loss + gradient.
+ * Replaces abnet3/loss.py:46-67 (coscos2) and :85-105 (cosmargin) together
+ * with the autograd backward the trainer runs (abnet3/trainer.py:237-240).
+ *   kind   0 = coscos2, 1 = cosmargin(margin)
+ *   y      [n] float32 labels (+1 same, -1 diff, anything else: raw cosine)
+ *   scale  multiplies loss and gradients (1/n for avg=True, the multitask
+ *          weight, ...)
+ *   loss   [1] float32, ACCUMULATED into (caller zeroes it)
+ *   de1/2  [n, dim] float32 gradients w.r.t. e1 / e2 (NULL: forward only)
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_pair_loss(const float *e1, const float *e2, const float *y, int64_t n,
+                  int dim, int kind, float margin, float scale, float *loss,
+                  float *de1, float *de2, abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (3) Embedder MLP layers.
+ * Replace one `Linear -> Dropout(p=0) -> activation` block of
+ * abnet3/model.py:133-170 (forward) and its autograd backward.
+ *   act: 0 none, 1 sigmoid, 2 tanh, 3 relu
+ *   W [n_out, n_in] row-major float32 (nn.Linear layout), b [n_out].
+ *   precision: 0 = fp32 SIMT (parity path), 1 = bf16 tcgen05 tensor cores
+ * Forward:   y[m, n_out] = act(x[m, n_in] @ W^T + b)
+ * Backward:  dz = dy * act'(y);  dx = dz @ W (NULL to skip);
+ *            dW += dz^T @ x;  db += colsum(dz)   (accumulate == 0: overwrite)
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_linear_forward(const float *x, const float *W, const float *b,
+                       int64_t m, int n_in, int n_out, int act, int precision,
+                       float *y, abn_stream_t stream);
+ABN_API int abn_linear_backward(const float *x, const float *W, const float *y,
+                        float *dy /* overwritten with dz */, int64_t m,
+                        int n_in, int n_out, int act, int precision,
+                        int accumulate, float *dx, float *dW, float *db,
+                        abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Fused optimizer step over one flat parameter bucket.
+ * Replaces `optimizer.step()` of abnet3/trainer.py:240 for the optimizers the
+ * trainer offers (:68-87) that the configs use: kind 0 = SGD with momentum
+ * (torch.optim.SGD, dampening 0), 1 = Adadelta (rho 0.9, eps 1e-6),
+ * 2 = Adam (betas 0.9/0.999, eps 1e-8).
+ *   grad_scale multiplies the gradient first (1/world_size after a
+ *   sum-allreduce).  state0/state1: momentum buffer | (square_avg, acc_delta)
+ *   | (exp_avg, exp_avg_sq); step = 1-based step count (Adam bias correction).
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_optimizer_step(float *param, const float *grad, float *state0,
+                       float *state1, int64_t n, int kind, float lr,
+                       float momentum, float grad_scale, int64_t step,
+                       abn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABNET3_B200_H */

@@ -1,0 +1,252 @@
+"""GPU parity: kernels (1) cosine distance and (2) DTW + traceback through the
+C ABI against the CPU oracle on identical seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from abnet3_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _flat_dist(mats):
+    off = np.zeros(len(mats) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([m.size for m in mats])
+    flat = np.concatenate([m.ravel() for m in mats]) if mats else np.zeros(0)
+    shape = np.array([m.shape for m in mats], dtype=np.int32).reshape(-1, 2)
+    return flat.astype(np.float64), off, shape
+
+
+def _run_dtw(mats):
+    flat, off, shape = _flat_dist(mats)
+    p1, p2, poff, plen, cost, valid = ops.dtw_from_dist(
+        torch.from_numpy(flat).to(DEV), torch.from_numpy(off).to(DEV),
+        torch.from_numpy(shape).to(DEV))
+    torch.cuda.synchronize()
+    return (p1.cpu().numpy(), p2.cpu().numpy(), poff.cpu().numpy(), plen.cpu().numpy(),
+            cost.cpu().numpy(), valid.cpu().numpy())
+
+
+def test_dtw_bit_exact_on_golden_matrices(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dtw.npz"))
+    mats = [g["d%d" % k] for k in range(int(g["n_cases"]))]
+    mats += [g["tie_d%d" % k] for k in range(int(g["n_tie_cases"]))]
+    p1, p2, poff, plen, cost, valid = _run_dtw(mats)
+    names = ["%d" % k for k in range(int(g["n_cases"]))] + \
+            ["tie_%d" % k for k in range(int(g["n_tie_cases"]))]
+    for i, nm in enumerate(names):
+        pre = "tie_" if nm.startswith("tie_") else ""
+        k = nm.replace("tie_", "")
+        assert valid[i] == 1
+        assert cost[i] == float(g["%scost%s" % (pre, k)])       # bit-exact float64
+        s = slice(poff[i], poff[i] + plen[i])
+        np.testing.assert_array_equal(p1[s], g["%sp1_%s" % (pre, k)])
+        np.testing.assert_array_equal(p2[s], g["%sp2_%s" % (pre, k)])
+
+
+def test_dtw_bit_exact_on_random_float64_matrices():
+    # genuine float64 D (sums round): the wavefront must still match the
+    # sequential recurrence bit for bit, and exact ties follow the oracle's rule
+    rng = np.random.default_rng(11)
+    mats = []
+    for _ in range(300):
+        n1, n2 = rng.integers(1, 97, 2)
+        mats.append(rng.random((n1, n2)))
+    for n1, n2 in [(1, 1), (1, 96), (96, 1), (96, 96), (33, 64), (64, 33), (32, 32), (65, 2)]:
+        mats.append(rng.random((n1, n2)))
+    # coarse grids: many exact ties
+    for _ in range(100):
+        n1, n2 = rng.integers(2, 60, 2)
+        mats.append(rng.integers(0, 3, (n1, n2)).astype(np.float64) * 0.25)
+    p1, p2, poff, plen, cost, valid = _run_dtw(mats)
+    n_ties = 0
+    for i, d in enumerate(mats):
+        c, q1, q2, ties = oracle.dtw(d, return_ties=True)
+        n_ties += ties
+        assert valid[i] == 1 and cost[i] == c
+        s = slice(poff[i], poff[i] + plen[i])
+        np.testing.assert_array_equal(p1[s], q1)
+        np.testing.assert_array_equal(p2[s], q2)
+    assert n_ties > 100          # the tie rule really was exercised
+
+
+def test_dtw_invalid_matrices_are_flagged():
+    a = np.full((5, 7), 0.5)
+    b = a.copy(); b[2, 3] = np.nan
+    c = a.copy(); c[0, 0] = -1.0
+    _, _, _, plen, cost, valid = _run_dtw([a, b, c])
+    assert list(valid) == [1, 0, 0] and plen[1] == 0 and plen[2] == 0
+    assert np.isnan(cost[1]) and np.isnan(cost[2])
+
+
+def _gpu_distance(feat, pairs):
+    dist, off, valid = ops.cosine_distance(torch.from_numpy(feat).to(DEV),
+                                           torch.from_numpy(pairs).to(DEV))
+    torch.cuda.synchronize()
+    return dist.cpu().numpy(), off.cpu().numpy(), valid.cpu().numpy()
+
+
+def test_cosine_distance_against_reference_golden(golden_dir):
+    # golden = the LIVE reference's cosine_distance (float32 arithmetic).  A GPU
+    # cannot reproduce BLAS sgemm's summation order, so parity is "float32
+    # rounding noise": |d_gpu - d_ref| <= 2e-6 absolute (d in [0, 1]).
+    g = np.load(os.path.join(golden_dir, "cosine.npz"))
+    for k in range(int(g["n_cases"])):
+        x, y, ref = g["x%d" % k], g["y%d" % k], g["d%d" % k]
+        n1, n2 = x.shape[0], y.shape[0]
+        if max(n1, n2) > ops.MAX_TOKEN_FRAMES:
+            continue
+        feat = np.concatenate([x, y]).astype(np.float32)
+        pairs = np.array([[0, n1, n1, n2]], dtype=np.int32)
+        dist, off, valid = _gpu_distance(feat, pairs)
+        d = dist[:n1 * n2].reshape(n1, n2)
+        assert valid[0] == 1
+        # zero-norm rules (utils.py:55-58) are exact
+        np.testing.assert_array_equal(d[(ref == 1.0) | (ref == 0.0)],
+                                      ref[(ref == 1.0) | (ref == 0.0)])
+        np.testing.assert_allclose(d, ref, rtol=0, atol=2e-6)
+
+
+def test_cosine_distance_identical_frames_follow_nan_rule(golden_dir):
+    # cos > 1 by rounding -> arccos NaN -> the reference asserts and the pair is
+    # dropped (utils.py:59, dataloader.py:190-191).  Which identical frames
+    # round above 1 depends on the summation order, so only the RULE is
+    # checked: valid == 0 iff the GPU matrix holds a NaN.
+    g = np.load(os.path.join(golden_dir, "cosine.npz"))
+    x = g["x_identical"]
+    n = x.shape[0]
+    feat = np.concatenate([x, x]).astype(np.float32)
+    dist, off, valid = _gpu_distance(feat, np.array([[0, n, n, n]], dtype=np.int32))
+    d = dist[:n * n]
+    assert bool(valid[0]) == (not np.isnan(d).any())
+    off_diag = d.reshape(n, n)[~np.eye(n, dtype=bool)]
+    assert not np.isnan(off_diag).any()
+
+
+@pytest.fixture(scope="module")
+def small_corpus():
+    c = synth.make_corpus(600, cluster_size=8, tokens_per_file=150, seed=3)
+    pairs = synth.make_same_pairs(c, 400, seed=4)
+    return c, pairs
+
+
+def test_align_pairs_end_to_end_vs_oracle(small_corpus):
+    """get_dtw_alignment (utils.py:147-153) batched.  Bar (BASELINE north_star):
+    costs within 1e-6 relative; paths bit-exact except where float32 rounding of
+    the distance flips a near-tie -- every differing path is re-scored under the
+    ORACLE's distance matrix and must be optimal to 1e-6 relative."""
+    c, pairs = small_corpus
+    feat = c.feat.numpy()
+    res = ops.align_pairs(c.feat.to(DEV), pairs.to(DEV))
+    torch.cuda.synchronize()
+    idx1, idx2 = res.idx1.cpu().numpy(), res.idx2.cpu().numpy()
+    off, plen = res.path_off.cpu().numpy(), res.path_len.cpu().numpy()
+    cost, valid = res.cost.cpu().numpy(), res.valid.cpu().numpy()
+    recs = oracle.align_pairs(feat, pairs.numpy())
+    mismatched = 0
+    for p, (r, tk) in enumerate(zip(recs, pairs.numpy().tolist())):
+        assert bool(valid[p]) == r["valid"]
+        s1, n1, s2, n2 = tk
+        g1 = idx1[off[p]:off[p] + plen[p]] - s1
+        g2 = idx2[off[p]:off[p] + plen[p]] - s2
+        assert abs(cost[p] - r["cost"]) <= 1e-6 * r["cost"]
+        if len(g1) == len(r["path1"]) and (g1 == r["path1"]).all() and (g2 == r["path2"]).all():
+            continue
+        mismatched += 1
+        rescored = oracle.path_cost(r["dist"], g1, g2)
+        assert abs(rescored - r["cost"]) <= 1e-6 * r["cost"]
+    assert mismatched <= max(2, len(recs) // 50)
+
+
+def test_align_pairs_is_bit_exact_given_its_own_distances(small_corpus):
+    """Isolates the DTW stage of the FUSED kernel: feed the GPU's own float32
+    distance matrices to the oracle DTW -> paths and costs must be identical."""
+    c, pairs = small_corpus
+    feat_d, pairs_d = c.feat.to(DEV), pairs.to(DEV)
+    res = ops.align_pairs(feat_d, pairs_d)
+    dist, doff, dvalid = ops.cosine_distance(feat_d, pairs_d)
+    torch.cuda.synchronize()
+    idx1, idx2 = res.idx1.cpu().numpy(), res.idx2.cpu().numpy()
+    off, plen = res.path_off.cpu().numpy(), res.path_len.cpu().numpy()
+    cost = res.cost.cpu().numpy()
+    dist, doff = dist.cpu().numpy(), doff.cpu().numpy()
+    for p, (s1, n1, s2, n2) in enumerate(pairs.numpy().tolist()):
+        d = dist[doff[p]:doff[p + 1]].reshape(n1, n2).astype(np.float64)
+        cst, q1, q2 = oracle.dtw(d)
+        assert cost[p] == cst
+        np.testing.assert_array_equal(idx1[off[p]:off[p] + plen[p]] - s1, q1)
+        np.testing.assert_array_equal(idx2[off[p]:off[p] + plen[p]] - s2, q2)
+
+
+def test_align_pairs_edge_shapes():
+    rng = np.random.default_rng(2)
+    feat = rng.standard_normal((400, 280)).astype(np.float32)
+    feat[7] = 0.0                                       # zero-norm frame
+    pairs = np.array([[0, 1, 1, 1], [0, 1, 10, 96], [10, 96, 0, 1], [100, 96, 200, 96],
+                      [0, 20, 30, 20], [5, 0, 30, 20], [390, 20, 0, 20], [40, 17, 90, 33]],
+                     dtype=np.int32)
+    res = ops.align_pairs(torch.from_numpy(feat).to(DEV), torch.from_numpy(pairs).to(DEV))
+    torch.cuda.synchronize()
+    valid = res.valid.cpu().numpy()
+    plen = res.path_len.cpu().numpy()
+    assert valid[5] == 0 and plen[5] == 0               # empty token (s > e, dataloader.py:184)
+    assert valid[6] == 0                                # token runs past the table
+    recs = oracle.align_pairs(feat, pairs[[0, 1, 2, 3, 4, 7]])
+    idx1, idx2, off = res.idx1.cpu().numpy(), res.idx2.cpu().numpy(), res.path_off.cpu().numpy()
+    for p, r in zip([0, 1, 2, 3, 4, 7], recs):
+        assert valid[p] == 1 and r["valid"]
+        s1, n1, s2, n2 = pairs[p]
+        g1 = idx1[off[p]:off[p] + plen[p]] - s1
+        g2 = idx2[off[p]:off[p] + plen[p]] - s2
+        assert g1[0] == 0 and g2[0] == 0 and g1[-1] == n1 - 1 and g2[-1] == n2 - 1
+        rescored = oracle.path_cost(r["dist"], g1, g2)
+        assert abs(rescored - r["cost"]) <= 1e-6 * max(r["cost"], 1e-30)
+
+
+def test_token_longer_than_limit_is_refused():
+    feat = torch.zeros((300, 280), device=DEV)
+    pairs = torch.tensor([[0, 120, 130, 50]], dtype=torch.int32, device=DEV)
+    with pytest.raises(Exception):
+        ops.align_pairs(feat, pairs)
+
+
+def test_diff_pairs_match_reference_row_selection():
+    pairs = np.array([[100, 20, 500, 35], [100, 35, 500, 20], [10, 30, 700, 30],
+                      [0, 1, 50, 9], [0, 0, 50, 9]], dtype=np.int32)
+    for stretch in (False, True):
+        i1, i2, off = ops.diff_pairs(torch.from_numpy(pairs).to(DEV), stretch=stretch)
+        torch.cuda.synchronize()
+        i1, i2, off = i1.cpu().numpy(), i2.cpu().numpy(), off.cpu().numpy()
+        for p, (s1, n1, s2, n2) in enumerate(pairs.tolist()):
+            if n1 <= 0 or n2 <= 0:
+                assert off[p + 1] == off[p]
+                continue
+            (srcA, srcB), a, b, _ = oracle.diff_pair_indices(n1, n2, stretch)
+            sa = s1 if srcA == 1 else s2
+            sb = s1 if srcB == 1 else s2
+            np.testing.assert_array_equal(i1[off[p]:off[p + 1]], sa + a)
+            np.testing.assert_array_equal(i2[off[p]:off[p + 1]], sb + b)
+
+
+def test_compact_and_gather(small_corpus):
+    c, pairs = small_corpus
+    feat_d = c.feat.to(DEV)
+    res = ops.align_pairs(feat_d, pairs.to(DEV))
+    d1, d2, doff = ops.compact_paths(res)
+    torch.cuda.synchronize()
+    plen, off = res.path_len.cpu().numpy(), res.path_off.cpu().numpy()
+    ref1 = np.concatenate([res.idx1.cpu().numpy()[off[p]:off[p] + plen[p]] for p in range(len(plen))])
+    np.testing.assert_array_equal(d1.cpu().numpy(), ref1)
+    n = d1.numel()
+    y = torch.ones(n, dtype=torch.int8, device=DEV)
+    y[::3] = -1
+    sel = torch.randperm(n, device=DEV)[:1000]
+    x1, x2, yo = ops.gather_batch(feat_d, d1, d2, y, sel)
+    torch.cuda.synchronize()
+    assert torch.equal(x1, feat_d[d1[sel].long()]) and torch.equal(x2, feat_d[d2[sel].long()])
+    assert torch.equal(yo, y[sel].float())
