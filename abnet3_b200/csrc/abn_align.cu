@@ -1,6 +1,6 @@
 // abn_align.cu -- kernels (1) cosine frame distance and (2) DTW wavefront +
-// traceback, fused: one CTA aligns one token pair; the distance matrix, the
-// accumulated costs and the traceback directions never leave the SM.
+// traceback, fused: one CTA aligns one token pair at a time; the distance
+// matrix, the accumulated costs and the traceback directions never leave the SM.
 //
 // Reference behaviour reproduced (paths relative to /root/reference):
 //   cosine_distance     abnet3/utils.py:40-60   (float32 arithmetic, zero-norm
@@ -10,12 +10,21 @@
 //   get_dtw_alignment   abnet3/utils.py:147-153, batched over the pair list
 //                       like abnet3/dataloader.py:183-206 / :642-653
 //
-// Data flow per CTA (128 threads):
+// Design
+// ------
+// Token pairs are ragged (20-80 frames in the canonical corpus), and the
+// distance stage is a small dense contraction per pair, so pairs are first
+// bucketed on the device into SIZE CLASSES (ceil(n1/16), ceil(n2/16)); every
+// class has its own kernel instantiation with a right-sized register tile and
+// shared-memory footprint (more resident CTAs for short tokens, no wasted
+// FMAs on padding beyond 16 frames, a few KB of code per kernel).  Inside a
+// class kernel (128 threads, persistent over the class's pair list):
 //   HBM --cp.async 16 B--> smem K-chunks of both tokens (double buffered)
-//       --LDS.128--> register-tiled fp32 FMA (fixed k order => run-to-run and
-//       GPU-count invariant) --> norms, divide, acosf --> D in smem (aliases
-//       the staging buffers) --> warp 0: anti-diagonal wavefront in fp64 with
-//       warp shuffles, 1 byte direction per cell in smem --> lane 0 traceback
+//       --LDS.128--> register-tiled fp32 FMA, accumulated per 40-wide chunk
+//       in a fixed order (run-to-run and GPU-count invariant) --> norms,
+//       divide, acosf --> D in smem (aliases the staging buffers)
+//       --> warp 0: branch-free anti-diagonal wavefront in fp64 with warp
+//       shuffles, 1 byte direction per cell in smem --> lane 0 traceback
 //       --> all threads write global frame-index pairs.
 #include "abn_common.cuh"
 
@@ -24,53 +33,74 @@ namespace abn {
 constexpr int AL_THREADS = 128;
 constexpr int KC = 40;           // floats of K staged per chunk (one fbank frame of the 7-stack)
 constexpr int KCP = KC + 4;      // smem row stride: 11 x 16 B, odd => LDS.128 conflict-free
-constexpr int KCP4 = KCP / 4;
-constexpr int NM_LIMIT = 96;     // longest token of the single-tile kernel
-constexpr float PI_F = 3.14159274101257324f;   // float32(np.pi)
+constexpr int NM_LIMIT = ABN_MAX_TOKEN_FRAMES;   // 96 = 6 x 16
+constexpr int NCLS_SIDE = NM_LIMIT / 16;         // 6
+constexpr int NCLS = NCLS_SIDE * NCLS_SIDE;      // 36 (+1 pseudo class: invalid shape)
+constexpr float PI_F = 3.14159274101257324f;     // float32(np.pi)
 
-struct AlignLayout {
-    int nm, ldd;
-    unsigned stage_bytes, dirs_off, norms_off, path_off, misc_off, total;
+// workspace layout (bytes): counts[37] | class_off[38] | cursor[37] | order[n_pairs]
+constexpr size_t WS_COUNTS = 0, WS_OFF = 256, WS_CURSOR = 512, WS_ORDER = 1024;
+
+struct AlignArgs {
+    const float *feat; int64_t n_rows; int dim;
+    const int32_t *pair_tok; int n_pairs;
+    const int64_t *path_off; int32_t *idx1; int32_t *idx2; int32_t *path_len;
+    double *cost; uint8_t *valid;
+    const int64_t *dist_off; float *dist_out;      // distance-only mode when dist_out != null
+    const int32_t *order; const int32_t *class_off;
 };
 
-__host__ __device__ inline AlignLayout align_layout(int nm, int dist_elem_bytes) {
-    AlignLayout L;
-    L.nm = nm;
-    L.ldd = nm + 2;  // (ldd - 1) odd: the wavefront's lane stride is bank-conflict free
-    L.stage_bytes = 2u * nm * KCP * 4u;
-    unsigned dbytes = (unsigned)nm * L.ldd * dist_elem_bytes;
-    L.dirs_off = (dbytes + 15u) & ~15u;
-    unsigned alias_end = L.dirs_off + (unsigned)nm * nm;
-    unsigned region = 2u * L.stage_bytes;
-    if (alias_end > region) region = alias_end;
-    L.norms_off = (region + 15u) & ~15u;
-    L.path_off = L.norms_off + 2u * nm * 4u;
-    L.misc_off = L.path_off + 2u * nm * 2u;
-    L.total = L.misc_off + 32u;
-    return L;
+__host__ __device__ constexpr unsigned a16(unsigned x) { return (x + 15u) & ~15u; }
+
+template <int RA, int NCG>
+struct ClassLayout {
+    static constexpr int ROWS_A = 16 * RA, ROWS_B = 16 * NCG;
+    static constexpr int LDD = ROWS_B + 2;   // (LDD-1) odd: the wavefront's lane stride
+    static constexpr unsigned STAGE_BYTES = (ROWS_A + ROWS_B) * KCP * 4u;
+    static constexpr unsigned DIRS_OFF = a16(ROWS_A * LDD * 4u);
+    static constexpr unsigned ALIAS_END = DIRS_OFF + ROWS_A * ROWS_B;
+    static constexpr unsigned REGION = 2u * STAGE_BYTES > ALIAS_END ? 2u * STAGE_BYTES : ALIAS_END;
+    static constexpr unsigned NORMS_OFF = a16(REGION);
+    static constexpr unsigned PATH_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
+    static constexpr unsigned MISC_OFF = a16(PATH_OFF + 2u * (ROWS_A + ROWS_B));
+    static constexpr unsigned TOTAL = MISC_OFF + 32u;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // ---------------------------------------------------------------- staging --
-__device__ __forceinline__ void stage_chunk(float *buf, const float *g1, const float *g2,
-                                            int n1, int n2, int nm, int dim, int k0, int kc4,
+// thread -> (16-byte piece = tid & 15, row = tid >> 4): a warp copies two rows
+// of 160 contiguous bytes each per instruction
+__device__ __forceinline__ void stage_chunk(unsigned buf_addr, const float *g1, const float *g2,
+                                            int n1, int n2, int rows_a, int dim, int k0, int kc4,
                                             int tid) {
     const int piece = tid & 15, r0 = tid >> 4;
     if (piece < kc4) {
         const float *s1 = g1 + k0 + piece * 4;
-        float *d1 = buf + piece * 4;
+        const unsigned d1 = buf_addr + piece * 16;
         for (int r = r0; r < n1; r += AL_THREADS / 16)
-            cp_async16(d1 + r * KCP, s1 + (size_t)r * dim);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d1 + r * (KCP * 4)),
+                         "l"(s1 + (size_t)r * dim) : "memory");
         const float *s2 = g2 + k0 + piece * 4;
-        float *d2 = buf + nm * KCP + piece * 4;
+        const unsigned d2 = buf_addr + rows_a * (KCP * 4) + piece * 16;
         for (int r = r0; r < n2; r += AL_THREADS / 16)
-            cp_async16(d2 + r * KCP, s2 + (size_t)r * dim);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d2 + r * (KCP * 4)),
+                         "l"(s2 + (size_t)r * dim) : "memory");
     }
 }
 
-__device__ __forceinline__ float row_sumsq(const float *row, int kc4, float acc) {
-    const float4 *p = reinterpret_cast<const float4 *>(row);
+__device__ __forceinline__ float row_sumsq(unsigned row_addr, int kc4) {
+    float acc = 0.f;
     for (int k4 = 0; k4 < kc4; ++k4) {
-        float4 v = p[k4];
+        const float4 v = lds128(row_addr + k4 * 16);
         acc = fmaf(v.x, v.x, acc);
         acc = fmaf(v.y, v.y, acc);
         acc = fmaf(v.z, v.z, acc);
@@ -83,42 +113,43 @@ __device__ __forceinline__ float row_sumsq(const float *row, int kc4, float acc)
 // Thread grid 16 (rows) x 8 (cols): thread (ti, tj) owns rows ti + 16 r and
 // columns tj + 8 c.  Inside a warp that is 8 consecutive rows x 4 consecutive
 // columns, so every LDS.128 is one conflict-free wavefront with broadcast.
-template <int RA, int NCG>   // NCG = 16-column groups
-__device__ __forceinline__ void pair_distance(unsigned char *smem, const AlignLayout &L,
-                                              const float *g1, const float *g2, int n1, int n2,
-                                              int dim, float *dist_smem, float *dist_gmem,
-                                              int &bad) {
+// Every dot product is the sum over the K chunks of a sequential fp32 FMA
+// chain over the chunk: fixed order, and ~3x tighter than one long chain.
+template <int RA, int NCG>
+__device__ __forceinline__ void pair_distance(unsigned char *smem, const float *g1,
+                                              const float *g2, int n1, int n2, int dim,
+                                              float *dist_gmem, int &bad) {
+    using L = ClassLayout<RA, NCG>;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int ti = (warp >> 1) * 8 + (lane >> 2);
     const int tj = (warp & 1) * 4 + (lane & 3);
-    const int nm = L.nm;
-    float *stage[2] = {reinterpret_cast<float *>(smem),
-                       reinterpret_cast<float *>(smem + L.stage_bytes)};
-    float *norms = reinterpret_cast<float *>(smem + L.norms_off);
+    const unsigned sbase = smem_u32(smem);
+    float *norms = reinterpret_cast<float *>(smem + L::NORMS_OFF);
+    float *Ds = reinterpret_cast<float *>(smem);
 
-    float acc[RA][2 * NCG];
+    float tot[RA][2 * NCG];
 #pragma unroll
     for (int r = 0; r < RA; ++r)
 #pragma unroll
-        for (int c = 0; c < 2 * NCG; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < 2 * NCG; ++c) tot[r][c] = 0.f;
 
     // row-norm ownership: combined row index q in [0, n1 + n2)
     const int q0 = tid, q1 = tid + AL_THREADS;
     const int nq = n1 + n2;
-    const int row0 = q0 < n1 ? q0 : nm + (q0 - n1);
-    const int row1 = q1 < n1 ? q1 : nm + (q1 - n1);
+    const int row0 = q0 < n1 ? q0 : L::ROWS_A + (q0 - n1);
+    const int row1 = q1 < n1 ? q1 : L::ROWS_A + (q1 - n1);
     float ss0 = 0.f, ss1 = 0.f;
 
     const int nchunks = (dim + KC - 1) / KC;
-    stage_chunk(stage[0], g1, g2, n1, n2, nm, dim, 0, min(KC, dim) / 4, tid);
+    stage_chunk(sbase, g1, g2, n1, n2, L::ROWS_A, dim, 0, min(KC, dim) / 4, tid);
     cp_async_commit();
     for (int ch = 0; ch < nchunks; ++ch) {
         const int k0 = ch * KC;
         const int kc4 = min(KC, dim - k0) / 4;
         if (ch + 1 < nchunks) {
             const int k1 = k0 + KC;
-            stage_chunk(stage[(ch + 1) & 1], g1, g2, n1, n2, nm, dim, k1,
+            stage_chunk(sbase + ((ch + 1) & 1) * L::STAGE_BYTES, g1, g2, n1, n2, L::ROWS_A, dim, k1,
                         min(KC, dim - k1) / 4, tid);
             cp_async_commit();
             cp_async_wait<1>();
@@ -126,22 +157,28 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const AlignLa
             cp_async_wait<0>();
         }
         __syncthreads();
-        const float *buf = stage[ch & 1];
-        if (q0 < nq) ss0 = row_sumsq(buf + row0 * KCP, kc4, ss0);
-        if (q1 < nq) ss1 = row_sumsq(buf + row1 * KCP, kc4, ss1);
+        const unsigned buf = sbase + (ch & 1) * L::STAGE_BYTES;
+        if (q0 < nq) ss0 += row_sumsq(buf + row0 * (KCP * 4), kc4);
+        if (q1 < nq) ss1 += row_sumsq(buf + row1 * (KCP * 4), kc4);
 
-        const float4 *A4 = reinterpret_cast<const float4 *>(buf) + ti * KCP4;
-        const float4 *B4 = reinterpret_cast<const float4 *>(buf) + (nm + tj) * KCP4;
+        float acc[RA][2 * NCG];
+#pragma unroll
+        for (int r = 0; r < RA; ++r)
+#pragma unroll
+            for (int c = 0; c < 2 * NCG; ++c) acc[r][c] = 0.f;
+        const unsigned a_addr = buf + ti * (KCP * 4);
+        const unsigned b_addr = buf + (L::ROWS_A + tj) * (KCP * 4);
 #pragma unroll 2
         for (int k4 = 0; k4 < kc4; ++k4) {
             float4 a[RA];
 #pragma unroll
-            for (int r = 0; r < RA; ++r) a[r] = A4[(16 * r) * KCP4 + k4];
+            for (int r = 0; r < RA; ++r) a[r] = lds128(a_addr + (16 * r) * (KCP * 4) + k4 * 16);
 #pragma unroll
             for (int cg = 0; cg < NCG; ++cg) {
                 float4 b[2];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) b[c] = B4[(8 * (2 * cg + c)) * KCP4 + k4];
+                for (int c = 0; c < 2; ++c)
+                    b[c] = lds128(b_addr + (8 * (2 * cg + c)) * (KCP * 4) + k4 * 16);
 #pragma unroll
                 for (int r = 0; r < RA; ++r)
 #pragma unroll
@@ -155,7 +192,11 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const AlignLa
                     }
             }
         }
-        __syncthreads();   // everyone done with stage[ch & 1] before it is refilled
+#pragma unroll
+        for (int r = 0; r < RA; ++r)
+#pragma unroll
+            for (int c = 0; c < 2 * NCG; ++c) tot[r][c] += acc[r][c];
+        __syncthreads();   // everyone done with this stage before it is refilled
     }
     if (q0 < nq) norms[row0] = sqrtf(ss0);
     if (q1 < nq) norms[row1] = sqrtf(ss1);
@@ -171,39 +212,19 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const AlignLa
         for (int c = 0; c < 2 * NCG; ++c) {
             const int j = tj + 8 * c;
             if (j >= n2) continue;
-            const float yn = norms[nm + j];
+            const float yn = norms[L::ROWS_A + j];
             float d;
             if (xn == 0.f || yn == 0.f) {
                 d = (xn == 0.f && yn == 0.f) ? 0.f : 1.f;
             } else {
-                const float cs = __fdiv_rn(acc[r][c], __fmul_rn(xn, yn));
+                const float cs = __fdiv_rn(tot[r][c], __fmul_rn(xn, yn));
                 d = __fdiv_rn(acosf(cs), PI_F);
             }
             if (!(d >= 0.f)) bad = 1;
             if (dist_gmem) dist_gmem[(size_t)i * n2 + j] = d;
-            else dist_smem[i * L.ldd + j] = d;
+            else Ds[i * L::LDD + j] = d;
         }
     }
-}
-
-__device__ __forceinline__ void dispatch_distance(unsigned char *smem, const AlignLayout &L,
-                                                  const float *g1, const float *g2, int n1,
-                                                  int n2, int dim, float *dist_smem,
-                                                  float *dist_gmem, int &bad) {
-    const int ra = (n1 + 15) >> 4;     // 1..6
-    const int ncg = (n2 + 15) >> 4;    // 1..6
-#define ABN_CASE(RA_, NCG_)                                                                \
-    case (RA_) * 8 + (NCG_):                                                               \
-        pair_distance<RA_, NCG_>(smem, L, g1, g2, n1, n2, dim, dist_smem, dist_gmem, bad); \
-        break;
-#define ABN_ROW(RA_) ABN_CASE(RA_, 1) ABN_CASE(RA_, 2) ABN_CASE(RA_, 3) \
-                     ABN_CASE(RA_, 4) ABN_CASE(RA_, 5) ABN_CASE(RA_, 6)
-    switch (ra * 8 + ncg) {
-        ABN_ROW(1) ABN_ROW(2) ABN_ROW(3) ABN_ROW(4) ABN_ROW(5) ABN_ROW(6)
-        default: break;
-    }
-#undef ABN_ROW
-#undef ABN_CASE
 }
 
 // ------------------------------------------------------------ DTW (kernel 2)
@@ -212,7 +233,8 @@ __device__ __forceinline__ void dispatch_distance(unsigned char *smem, const Ali
 // neighbour is a register; across lanes it is one fp64 shuffle per step.
 // C[i,j] = D[i,j] + min(C[i-1,j-1], C[i-1,j], C[i,j-1]) with the oracle's tie
 // order (diag, up, left): one add per cell, so results are bit-identical to
-// the sequential recurrence for any float64 D.
+// the sequential recurrence for any float64 D.  The body is branch-free:
+// out-of-range cells compute on a clamped address and are not committed.
 template <typename DT, int G>
 __device__ __forceinline__ double dtw_wavefront(const DT *D, int ldd, uint8_t *dirs, int ldr,
                                                 int n1, int n2, int lane) {
@@ -225,28 +247,27 @@ __device__ __forceinline__ double dtw_wavefront(const DT *D, int ldd, uint8_t *d
     const int T = n1 + n2 - 1;
     for (int t = 0; t < T; ++t) {
         double up0 = __shfl_up_sync(0xffffffffu, cur[G - 1], 1);
-        if (lane == 0) up0 = INF;
+        up0 = lane == 0 ? INF : up0;
         const double dg0 = nbprev;
         nbprev = up0;
         double nw[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int i = i0 + g, j = t - i;
+            const bool ok = (i < n1) & ((unsigned)j < (unsigned)n2);
+            const int cell = ok ? i * ldd + j : 0;
+            const double d = (double)D[cell];
             const double up = g == 0 ? up0 : cur[g - 1];
             const double dg = g == 0 ? dg0 : prev[g - 1];
             const double lf = cur[g];
-            nw[g] = lf;
-            if (i < n1 && j >= 0 && j < n2) {
-                const double d = (double)D[i * ldd + j];
-                uint8_t dir;
-                double m;
-                if (dg <= up && dg <= lf) { dir = DIR_DIAG; m = dg; }
-                else if (up <= lf)        { dir = DIR_UP;   m = up; }
-                else                      { dir = DIR_LEFT; m = lf; }
-                if ((i | j) == 0) m = 0.0;
-                nw[g] = d + m;
-                dirs[i * ldr + j] = dir;
-            }
+            const bool up_le = up <= lf;
+            const double m1 = up_le ? up : lf;
+            const bool use_dg = dg <= m1;          // dg <= up && dg <= lf
+            double m = use_dg ? dg : m1;
+            const uint8_t dir = use_dg ? DIR_DIAG : (up_le ? DIR_UP : DIR_LEFT);
+            m = (i | j) == 0 ? 0.0 : m;
+            nw[g] = ok ? d + m : lf;
+            if (ok) dirs[i * ldr + j] = dir;
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) { prev[g] = cur[g]; cur[g] = nw[g]; }
@@ -254,26 +275,16 @@ __device__ __forceinline__ double dtw_wavefront(const DT *D, int ldd, uint8_t *d
     // C[n1-1, n2-1] lives in lane (n1-1)/G, slot (n1-1)%G
     double c = 0.0;
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-        if ((n1 - 1) % G == g) c = cur[g];
+    for (int g = 0; g < G; ++g) c = ((n1 - 1) % G == g) ? cur[g] : c;
     return __shfl_sync(0xffffffffu, c, (n1 - 1) / G);
-}
-
-template <typename DT>
-__device__ __forceinline__ double dtw_dispatch(const DT *D, int ldd, uint8_t *dirs, int ldr,
-                                               int n1, int n2, int lane) {
-    const int g = (n1 + 31) >> 5;
-    if (g == 1) return dtw_wavefront<DT, 1>(D, ldd, dirs, ldr, n1, n2, lane);
-    if (g == 2) return dtw_wavefront<DT, 2>(D, ldd, dirs, ldr, n1, n2, lane);
-    return dtw_wavefront<DT, 3>(D, ldd, dirs, ldr, n1, n2, lane);
 }
 
 // lane 0: follow the stored directions from (n1-1, n2-1) back to (0, 0)
 __device__ __forceinline__ int traceback(const uint8_t *dirs, int ldr, int n1, int n2,
                                          uint8_t *pb_i, uint8_t *pb_j) {
-    int i = n1 - 1, j = n2 - 1, L = 0;
-    pb_i[0] = (uint8_t)i; pb_j[0] = (uint8_t)j; L = 1;
-    while (i > 0 || j > 0) {
+    int i = n1 - 1, j = n2 - 1, L = 1;
+    pb_i[0] = (uint8_t)i; pb_j[0] = (uint8_t)j;
+    while ((i | j) != 0) {
         const uint8_t d = dirs[i * ldr + j];
         i -= (d != DIR_LEFT);
         j -= (d != DIR_UP);
@@ -282,67 +293,128 @@ __device__ __forceinline__ int traceback(const uint8_t *dirs, int ldr, int n1, i
     return L;
 }
 
-// --------------------------------------------------------------- kernels ---
-__global__ void __launch_bounds__(AL_THREADS, 3)
-align_pairs_kernel(const float *__restrict__ feat, int64_t n_rows, int dim,
-                   const int32_t *__restrict__ pair_tok, int n_pairs,
-                   const int64_t *__restrict__ path_off, int32_t *__restrict__ idx1,
-                   int32_t *__restrict__ idx2, int32_t *__restrict__ path_len,
-                   double *__restrict__ cost, uint8_t *__restrict__ valid, int nm,
-                   const int64_t *__restrict__ dist_off, float *__restrict__ dist_out) {
-    // dist_out != nullptr: distance-only mode (abn_cosine_distance) -- D goes to
-    // global memory and the DTW stage is skipped.
+// ------------------------------------------------------------ class kernel --
+template <int RA, int NCG>
+__global__ void __launch_bounds__(AL_THREADS)
+align_class_kernel(const AlignArgs a) {
+    using L = ClassLayout<RA, NCG>;
+    constexpr int CLS = (RA - 1) * NCLS_SIDE + (NCG - 1);
+    constexpr int G = (RA + 1) / 2;            // DTW rows per lane: ceil(16 RA / 32)
     extern __shared__ __align__(16) unsigned char smem[];
-    const AlignLayout L = align_layout(nm, 4);
-    const int p = blockIdx.x;
-    if (p >= n_pairs) return;
-    const int4 tk = reinterpret_cast<const int4 *>(pair_tok)[p];
-    const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
     const int tid = threadIdx.x;
-    const bool shape_ok = n1 > 0 && n2 > 0 && n1 <= nm && n2 <= nm && s1 >= 0 && s2 >= 0 &&
-                          (int64_t)s1 + n1 <= n_rows && (int64_t)s2 + n2 <= n_rows;
-    if (!shape_ok) {   // dataloader.py:184 / :188-191: the pair is skipped
-        if (tid == 0) {
-            valid[p] = 0;
-            if (!dist_out) { path_len[p] = 0; cost[p] = nan(""); }
-        }
-        return;
-    }
+    const int beg = a.class_off[CLS], end = a.class_off[CLS + 1];
     float *Ds = reinterpret_cast<float *>(smem);
-    uint8_t *dirs = smem + L.dirs_off;
-    uint8_t *pb_i = smem + L.path_off;
-    uint8_t *pb_j = pb_i + 2 * nm;
-    int *misc = reinterpret_cast<int *>(smem + L.misc_off);
+    uint8_t *dirs = smem + L::DIRS_OFF;
+    uint8_t *pb_i = smem + L::PATH_OFF;
+    uint8_t *pb_j = pb_i + (L::ROWS_A + L::ROWS_B);
+    int *misc = reinterpret_cast<int *>(smem + L::MISC_OFF);
 
-    int bad = 0;
-    dispatch_distance(smem, L, feat + (size_t)s1 * dim, feat + (size_t)s2 * dim, n1, n2, dim, Ds,
-                      dist_out ? dist_out + dist_off[p] : nullptr, bad);
-    bad = __syncthreads_or(bad);
-    if (dist_out) {
-        if (tid == 0) valid[p] = bad ? 0 : 1;
-        return;
+    for (int it = beg + blockIdx.x; it < end; it += gridDim.x) {
+        const int p = a.order[it];
+        const int4 tk = reinterpret_cast<const int4 *>(a.pair_tok)[p];
+        const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
+        int bad = 0;
+        pair_distance<RA, NCG>(smem, a.feat + (size_t)s1 * a.dim, a.feat + (size_t)s2 * a.dim, n1,
+                               n2, a.dim, a.dist_out ? a.dist_out + a.dist_off[p] : nullptr, bad);
+        bad = __syncthreads_or(bad);
+        if (a.dist_out) {
+            if (tid == 0) a.valid[p] = bad ? 0 : 1;
+            continue;
+        }
+        if (bad) {     // utils.py:59 assert fails -> dataloader.py:190-191 drops the pair
+            if (tid == 0) { a.path_len[p] = 0; a.cost[p] = nan(""); a.valid[p] = 0; }
+            continue;
+        }
+        if (tid < 32) {
+            const double c = dtw_wavefront<float, G>(Ds, L::LDD, dirs, L::ROWS_B, n1, n2, tid);
+            __syncwarp();
+            if (tid == 0) {
+                const int len = traceback(dirs, L::ROWS_B, n1, n2, pb_i, pb_j);
+                misc[0] = len;
+                a.path_len[p] = len;
+                a.cost[p] = c;
+                a.valid[p] = 1;
+            }
+        }
+        __syncthreads();
+        const int len = misc[0];
+        const int64_t off = a.path_off[p];
+        for (int k = tid; k < len; k += AL_THREADS) {
+            a.idx1[off + k] = s1 + (int)pb_i[len - 1 - k];
+            a.idx2[off + k] = s2 + (int)pb_j[len - 1 - k];
+        }
+        __syncthreads();   // smem is reused by the next pair
     }
-    if (bad) {         // utils.py:59 assert fails -> dataloader.py:190-191 drops the pair
-        if (tid == 0) { path_len[p] = 0; cost[p] = nan(""); valid[p] = 0; }
-        return;
-    }
-    if (tid < 32) {
-        const double c = dtw_dispatch<float>(Ds, L.ldd, dirs, nm, n1, n2, tid);
-        __syncwarp();
-        if (tid == 0) {
-            const int len = traceback(dirs, nm, n1, n2, pb_i, pb_j);
-            misc[0] = len;
-            path_len[p] = len;
-            cost[p] = c;
-            valid[p] = 1;
+}
+
+// ------------------------------------------------------- size-class bucketing
+__device__ __forceinline__ int pair_class(const int4 tk, int64_t n_rows) {
+    const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
+    const bool ok = n1 > 0 && n2 > 0 && n1 <= NM_LIMIT && n2 <= NM_LIMIT && s1 >= 0 && s2 >= 0 &&
+                    (int64_t)s1 + n1 <= n_rows && (int64_t)s2 + n2 <= n_rows;
+    return ok ? ((n1 + 15) / 16 - 1) * NCLS_SIDE + ((n2 + 15) / 16 - 1) : NCLS;
+}
+
+constexpr int BK_THREADS = 256, BK_ITEMS = 4;
+
+__global__ void __launch_bounds__(BK_THREADS)
+class_count_kernel(const AlignArgs a, int *__restrict__ counts) {
+    __shared__ int hist[NCLS + 1];
+    if (threadIdx.x <= NCLS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * BK_THREADS * BK_ITEMS;
+#pragma unroll
+    for (int u = 0; u < BK_ITEMS; ++u) {
+        const int p = base + u * BK_THREADS + threadIdx.x;
+        if (p < a.n_pairs) {
+            const int c = pair_class(reinterpret_cast<const int4 *>(a.pair_tok)[p], a.n_rows);
+            atomicAdd(&hist[c], 1);
+            if (c == NCLS) {   // dataloader.py:184 / :188-191: the pair is skipped
+                a.valid[p] = 0;
+                if (!a.dist_out) { a.path_len[p] = 0; a.cost[p] = nan(""); }
+            }
         }
     }
     __syncthreads();
-    const int len = misc[0];
-    const int64_t off = path_off[p];
-    for (int k = tid; k < len; k += AL_THREADS) {
-        idx1[off + k] = s1 + (int)pb_i[len - 1 - k];
-        idx2[off + k] = s2 + (int)pb_j[len - 1 - k];
+    if (threadIdx.x <= NCLS && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], hist[threadIdx.x]);
+}
+
+__global__ void class_scan_kernel(const int *__restrict__ counts, int *__restrict__ class_off) {
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int c = 0; c <= NCLS; ++c) { class_off[c] = s; s += counts[c]; }
+        class_off[NCLS + 1] = s;
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+class_scatter_kernel(const AlignArgs a, const int *__restrict__ class_off,
+                     int *__restrict__ cursor, int32_t *__restrict__ order) {
+    __shared__ int hist[NCLS + 1];
+    __shared__ int gbase[NCLS + 1];
+    if (threadIdx.x <= NCLS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * BK_THREADS * BK_ITEMS;
+    int cls[BK_ITEMS], rank[BK_ITEMS];
+#pragma unroll
+    for (int u = 0; u < BK_ITEMS; ++u) {
+        const int p = base + u * BK_THREADS + threadIdx.x;
+        cls[u] = -1;
+        rank[u] = 0;
+        if (p < a.n_pairs) {
+            cls[u] = pair_class(reinterpret_cast<const int4 *>(a.pair_tok)[p], a.n_rows);
+            rank[u] = atomicAdd(&hist[cls[u]], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x <= NCLS && hist[threadIdx.x])
+        gbase[threadIdx.x] =
+            class_off[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], hist[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < BK_ITEMS; ++u) {
+        const int p = base + u * BK_THREADS + threadIdx.x;
+        if (cls[u] >= 0) order[gbase[cls[u]] + rank[u]] = p;
     }
 }
 
@@ -393,7 +465,11 @@ dtw_from_dist_kernel(const double *__restrict__ dist, const int64_t *__restrict_
         return;
     }
     if (tid < 32) {
-        const double c = dtw_dispatch<double>(Ds, L.ldd, dirs, nm, n1, n2, tid);
+        const int g = (n1 + 31) >> 5;
+        double c;
+        if (g == 1)      c = dtw_wavefront<double, 1>(Ds, L.ldd, dirs, nm, n1, n2, tid);
+        else if (g == 2) c = dtw_wavefront<double, 2>(Ds, L.ldd, dirs, nm, n1, n2, tid);
+        else             c = dtw_wavefront<double, 3>(Ds, L.ldd, dirs, nm, n1, n2, tid);
         __syncwarp();
         if (tid == 0) {
             const int len = traceback(dirs, nm, n1, n2, pb_i, pb_j);
@@ -435,7 +511,7 @@ __global__ void diff_pairs_kernel(const int32_t *__restrict__ pair_tok, int n_pa
         const int smax = n1 >= n2 ? s1 : s2, smin = n1 <= n2 ? s1 : s2;
         const int lmax = max(n1, n2), lmin = min(n1, n2);
         // numpy.linspace(0, lmin-1, lmax): step = (lmin-1)/(lmax-1) in float64,
-        // y[k] = k*step (+0), last element forced to stop; rint = half-to-even
+        // y[k] = k*step, last element forced to stop; rint = half-to-even
         const double step = lmax > 1 ? (double)(lmin - 1) / (double)(lmax - 1) : 0.0;
         for (int k = lane; k < lmax; k += 32) {
             double v = (double)k * step;
@@ -486,60 +562,140 @@ __global__ void gather_batch_kernel(const float *__restrict__ feat, int dim,
     if (side == 0 && lane == 0 && y_out) y_out[k] = y_in ? (float)y_in[pos] : 1.f;
 }
 
+// ----------------------------------------------------------- host dispatch --
+struct ClassLaunch {
+    void (*kernel)(const AlignArgs);
+    unsigned smem;
+    int grid;      // resident CTAs on the whole device (persistent launch)
+};
+
+template <int RA, int NCG>
+static int prepare_class(ClassLaunch &cl, int sm_count) {
+    using L = ClassLayout<RA, NCG>;
+    cl.kernel = align_class_kernel<RA, NCG>;
+    cl.smem = L::TOTAL;
+    if (cudaFuncSetAttribute(align_class_kernel<RA, NCG>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)L::TOTAL) != cudaSuccess)
+        return set_error(ABN_EIO, "cudaFuncSetAttribute(smem=%u) failed for class %d,%d", L::TOTAL,
+                         RA, NCG);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_class_kernel<RA, NCG>,
+                                                      AL_THREADS, L::TOTAL) != cudaSuccess ||
+        per_sm < 1)
+        return set_error(ABN_EIO, "occupancy query failed for class %d,%d", RA, NCG);
+    cl.grid = per_sm * sm_count;
+    return ABN_OK;
+}
+
+template <int RA>
+static int prepare_row(ClassLaunch *tab, int sm_count) {
+    int rc = ABN_OK;
+    if (!rc) rc = prepare_class<RA, 1>(tab[(RA - 1) * NCLS_SIDE + 0], sm_count);
+    if (!rc) rc = prepare_class<RA, 2>(tab[(RA - 1) * NCLS_SIDE + 1], sm_count);
+    if (!rc) rc = prepare_class<RA, 3>(tab[(RA - 1) * NCLS_SIDE + 2], sm_count);
+    if (!rc) rc = prepare_class<RA, 4>(tab[(RA - 1) * NCLS_SIDE + 3], sm_count);
+    if (!rc) rc = prepare_class<RA, 5>(tab[(RA - 1) * NCLS_SIDE + 4], sm_count);
+    if (!rc) rc = prepare_class<RA, 6>(tab[(RA - 1) * NCLS_SIDE + 5], sm_count);
+    return rc;
+}
+
+static int class_table(const ClassLaunch **out) {
+    static ClassLaunch tab[NCLS];
+    static int state = 0;        // 0 = not built, 1 = ok  (one device per process)
+    if (state == 0) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int rc = ABN_OK;
+        if (!rc) rc = prepare_row<1>(tab, sms);
+        if (!rc) rc = prepare_row<2>(tab, sms);
+        if (!rc) rc = prepare_row<3>(tab, sms);
+        if (!rc) rc = prepare_row<4>(tab, sms);
+        if (!rc) rc = prepare_row<5>(tab, sms);
+        if (!rc) rc = prepare_row<6>(tab, sms);
+        if (rc) return rc;
+        state = 1;
+    }
+    *out = tab;
+    return ABN_OK;
+}
+
+static int run_align(AlignArgs a, int max_frames, void *workspace, size_t workspace_bytes,
+                     cudaStream_t st, const char *who) {
+    if (max_frames <= 0) return set_error(ABN_EINVAL, "%s: max_frames must be positive", who);
+    if (max_frames > NM_LIMIT)
+        return set_error(ABN_ERANGE, "%s: token of %d frames exceeds %d", who, max_frames, NM_LIMIT);
+    const size_t need = WS_ORDER + sizeof(int32_t) * (size_t)a.n_pairs;
+    if (!workspace || workspace_bytes < need)
+        return set_error(ABN_ENOMEM, "%s: workspace of %zu bytes needed, %zu given", who, need,
+                         workspace_bytes);
+    const ClassLaunch *tab = nullptr;
+    if (int rc = class_table(&tab)) return rc;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    int *counts = reinterpret_cast<int *>(ws + WS_COUNTS);
+    int *class_off = reinterpret_cast<int *>(ws + WS_OFF);
+    int *cursor = reinterpret_cast<int *>(ws + WS_CURSOR);
+    int32_t *order = reinterpret_cast<int32_t *>(ws + WS_ORDER);
+    a.order = order;
+    a.class_off = class_off;
+    cudaMemsetAsync(ws, 0, WS_ORDER, st);
+    const int per_block = BK_THREADS * BK_ITEMS;
+    const int blocks = (a.n_pairs + per_block - 1) / per_block;
+    class_count_kernel<<<blocks, BK_THREADS, 0, st>>>(a, counts);
+    class_scan_kernel<<<1, 32, 0, st>>>(counts, class_off);
+    class_scatter_kernel<<<blocks, BK_THREADS, 0, st>>>(a, class_off, cursor, order);
+    const int side = (max_frames + 15) / 16;
+    // large classes first: their pairs take longest, the small ones fill the tail
+    for (int ra = side; ra >= 1; --ra)
+        for (int ncg = side; ncg >= 1; --ncg) {
+            const ClassLaunch &cl = tab[(ra - 1) * NCLS_SIDE + (ncg - 1)];
+            const int grid = cl.grid < a.n_pairs ? cl.grid : a.n_pairs;
+            cl.kernel<<<grid, AL_THREADS, cl.smem, st>>>(a);
+        }
+    return check_launch(who);
+}
+
 }  // namespace abn
 
 // ------------------------------------------------------------------ C ABI --
 using namespace abn;
 
-static int pick_nm(const char *who, int max_frames, int *nm) {
-    if (max_frames <= 0) return set_error(ABN_EINVAL, "%s: max_frames must be positive", who);
-    if (max_frames > NM_LIMIT)
-        return set_error(ABN_ERANGE, "%s: token of %d frames exceeds %d", who, max_frames,
-                         NM_LIMIT);
-    *nm = ((max_frames < 16 ? 16 : max_frames) + 15) & ~15;
-    return ABN_OK;
+extern "C" size_t abn_align_workspace_bytes(int n_pairs) {
+    return WS_ORDER + sizeof(int32_t) * (size_t)(n_pairs > 0 ? n_pairs : 0);
 }
 
 extern "C" int abn_align_pairs(const float *feat, int64_t n_rows, int dim,
                                const int32_t *pair_tok, int n_pairs, int max_frames,
                                const int64_t *path_off, int32_t *idx1, int32_t *idx2,
-                               int32_t *path_len, double *cost, uint8_t *valid,
-                               abn_stream_t stream) {
+                               int32_t *path_len, double *cost, uint8_t *valid, void *workspace,
+                               size_t workspace_bytes, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (n_pairs == 0) return ABN_OK;
     if (!feat || !pair_tok || !path_off || !idx1 || !idx2 || !path_len || !cost || !valid ||
         n_pairs < 0 || dim <= 0 || (dim & 3))
         return set_error(ABN_EINVAL, "abn_align_pairs: bad argument (dim must be a multiple of 4)");
-    cudaStream_t st = (cudaStream_t)stream;
-    int nm = 0;
-    if (int rc = pick_nm("abn_align_pairs", max_frames, &nm)) return rc;
-    const AlignLayout L = align_layout(nm, 4);
-    cudaFuncSetAttribute(align_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)L.total);
-    align_pairs_kernel<<<n_pairs, AL_THREADS, L.total, st>>>(
-        feat, n_rows, dim, pair_tok, n_pairs, path_off, idx1, idx2, path_len, cost, valid, nm,
-        nullptr, nullptr);
-    return check_launch("abn_align_pairs");
+    AlignArgs a{};
+    a.feat = feat; a.n_rows = n_rows; a.dim = dim; a.pair_tok = pair_tok; a.n_pairs = n_pairs;
+    a.path_off = path_off; a.idx1 = idx1; a.idx2 = idx2; a.path_len = path_len; a.cost = cost;
+    a.valid = valid; a.dist_off = nullptr; a.dist_out = nullptr;
+    return run_align(a, max_frames, workspace, workspace_bytes, (cudaStream_t)stream,
+                     "abn_align_pairs");
 }
 
 extern "C" int abn_cosine_distance(const float *feat, int64_t n_rows, int dim,
                                    const int32_t *pair_tok, int n_pairs, int max_frames,
                                    const int64_t *dist_off, float *dist, uint8_t *valid,
-                                   abn_stream_t stream) {
+                                   void *workspace, size_t workspace_bytes, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (n_pairs == 0) return ABN_OK;
     if (!feat || !pair_tok || !dist_off || !dist || !valid || n_pairs < 0 || dim <= 0 || (dim & 3))
         return set_error(ABN_EINVAL, "abn_cosine_distance: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    int nm = 0;
-    if (int rc = pick_nm("abn_cosine_distance", max_frames, &nm)) return rc;
-    const AlignLayout L = align_layout(nm, 4);
-    cudaFuncSetAttribute(align_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)L.total);
-    align_pairs_kernel<<<n_pairs, AL_THREADS, L.total, st>>>(
-        feat, n_rows, dim, pair_tok, n_pairs, nullptr, nullptr, nullptr, nullptr, nullptr, valid,
-        nm, dist_off, dist);
-    return check_launch("abn_cosine_distance");
+    AlignArgs a{};
+    a.feat = feat; a.n_rows = n_rows; a.dim = dim; a.pair_tok = pair_tok; a.n_pairs = n_pairs;
+    a.valid = valid; a.dist_off = dist_off; a.dist_out = dist;
+    return run_align(a, max_frames, workspace, workspace_bytes, (cudaStream_t)stream,
+                     "abn_cosine_distance");
 }
 
 extern "C" int abn_dtw_from_dist(const double *dist, const int64_t *dist_off, const int32_t *shape,
@@ -551,13 +707,16 @@ extern "C" int abn_dtw_from_dist(const double *dist, const int64_t *dist_off, co
     if (!dist || !dist_off || !shape || !path_off || !path1 || !path2 || !path_len || !cost ||
         !valid || n_pairs < 0)
         return set_error(ABN_EINVAL, "abn_dtw_from_dist: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    int nm = 0;
-    if (int rc = pick_nm("abn_dtw_from_dist", max_frames, &nm)) return rc;
+    if (max_frames <= 0)
+        return set_error(ABN_EINVAL, "abn_dtw_from_dist: max_frames must be positive");
+    if (max_frames > NM_LIMIT)
+        return set_error(ABN_ERANGE, "abn_dtw_from_dist: matrix side %d exceeds %d", max_frames,
+                         NM_LIMIT);
+    const int nm = ((max_frames < 16 ? 16 : max_frames) + 15) & ~15;
     const DtwLayout L = dtw_layout(nm);
     cudaFuncSetAttribute(dtw_from_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)L.total);
-    dtw_from_dist_kernel<<<n_pairs, AL_THREADS, L.total, st>>>(
+    dtw_from_dist_kernel<<<n_pairs, AL_THREADS, L.total, (cudaStream_t)stream>>>(
         dist, dist_off, shape, n_pairs, path_off, path1, path2, path_len, cost, valid, nm);
     return check_launch("abn_dtw_from_dist");
 }

@@ -37,6 +37,11 @@ def _excl_cumsum(counts):
     return off
 
 
+def _workspace(n_pairs, device):
+    nbytes = _lib.lib().abn_align_workspace_bytes(n_pairs)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
 def align_pairs(feat, pair_tok, max_frames=None):
     """Fused cosine distance + DTW + traceback for every pair
     (abnet3/utils.py:147-153 per pair).  Returns an AlignResult whose idx1/idx2
@@ -57,10 +62,11 @@ def align_pairs(feat, pair_tok, max_frames=None):
     path_len = torch.zeros(P, dtype=torch.int32, device=dev)
     cost = torch.full((P,), float("nan"), dtype=torch.float64, device=dev)
     valid = torch.zeros(P, dtype=torch.uint8, device=dev)
+    ws, ws_bytes = _workspace(P, dev)
     check(_lib.lib().abn_align_pairs(
         ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1),
         ptr(path_off), ptr(idx1), ptr(idx2), ptr(path_len), ptr(cost), ptr(valid),
-        stream_ptr()))
+        ptr(ws), ws_bytes, stream_ptr()))
     return AlignResult(idx1, idx2, path_off, path_len, cost, valid)
 
 
@@ -77,9 +83,10 @@ def cosine_distance(feat, pair_tok, max_frames=None):
     total = int(dist_off[-1].item()) if P else 0
     dist = torch.full((max(total, 1),), float("nan"), dtype=torch.float32, device=dev)
     valid = torch.zeros(P, dtype=torch.uint8, device=dev)
+    ws, ws_bytes = _workspace(P, dev)
     check(_lib.lib().abn_cosine_distance(
         ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1),
-        ptr(dist_off), ptr(dist), ptr(valid), stream_ptr()))
+        ptr(dist_off), ptr(dist), ptr(valid), ptr(ws), ws_bytes, stream_ptr()))
     return dist, dist_off, valid
 
 

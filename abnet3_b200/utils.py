@@ -115,6 +115,7 @@ class BatchAligner(object):
             self.path_len = torch.empty(n_pairs, dtype=torch.int32, device=dev)
             self.cost = torch.empty(n_pairs, dtype=torch.float64, device=dev)
             self.valid = torch.empty(n_pairs, dtype=torch.uint8, device=dev)
+            self._ws, self._ws_bytes = ops._workspace(n_pairs, dev)
             self._cap_pairs = n_pairs
 
     def _offsets(self, pair_tok):
@@ -135,7 +136,7 @@ class BatchAligner(object):
             _lib.ptr(self.feat), self.feat.shape[0], self.feat.shape[1], _lib.ptr(pair_tok), P,
             self.max_frames, _lib.ptr(off), _lib.ptr(self.idx1), _lib.ptr(self.idx2),
             _lib.ptr(self.path_len), _lib.ptr(self.cost), _lib.ptr(self.valid),
-            _lib.stream_ptr()))
+            _lib.ptr(self._ws), self._ws_bytes, _lib.stream_ptr()))
         return ops.AlignResult(self.idx1, self.idx2, off, self.path_len[:P], self.cost[:P],
                                self.valid[:P])
 

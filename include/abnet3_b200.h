@@ -63,6 +63,11 @@ ABN_API const char *abn_last_error(void);
 ABN_API int abn_device_info(int *sm_count, int *cc_major, int *cc_minor,
                     size_t *smem_optin_bytes);
 
+/* Device workspace abn_align_pairs / abn_cosine_distance need for a call over
+ * n_pairs pairs (they bucket the pairs into token-length classes on the device
+ * and keep the per-class pair order there). */
+ABN_API size_t abn_align_workspace_bytes(int n_pairs);
+
 /* ------------------------------------------------------------------------
  * (1) Batched cosine frame distance.
  * Replaces abnet3/utils.py:40-60 `cosine_distance(x, y)`, one call per pair.
@@ -77,6 +82,7 @@ ABN_API int abn_device_info(int *sm_count, int *cc_major, int *cc_minor,
 ABN_API int abn_cosine_distance(const float *feat, int64_t n_rows, int dim,
                         const int32_t *pair_tok, int n_pairs, int max_frames,
                         const int64_t *dist_off, float *dist, uint8_t *valid,
+                        void *workspace, size_t workspace_bytes,
                         abn_stream_t stream);
 
 /* ------------------------------------------------------------------------
@@ -110,6 +116,7 @@ ABN_API int abn_align_pairs(const float *feat, int64_t n_rows, int dim,
                     const int32_t *pair_tok, int n_pairs, int max_frames,
                     const int64_t *path_off, int32_t *idx1, int32_t *idx2,
                     int32_t *path_len, double *cost, uint8_t *valid,
+                    void *workspace, size_t workspace_bytes,
                     abn_stream_t stream);
 
 /* ------------------------------------------------------------------------
