@@ -100,7 +100,7 @@ pair_loss_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
 //   BK: B stored [N][K] (k contiguous)   else [K][N]
 constexpr int GM = 128, GN = 64, GK = 16, GT = 256;
 
-enum { EPI_BIAS_ACT = 0, EPI_STORE = 1, EPI_ACCUM = 2 };
+enum { EPI_BIAS_ACT = 0, EPI_STORE = 1, EPI_ACCUM = 2, EPI_ADD = 3 };
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
     switch (act) {
@@ -220,6 +220,7 @@ sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__
             float *dst = C + (size_t)gm * ldc + gn;
             if (epi == EPI_BIAS_ACT) *dst = act_fwd(v + (bias ? bias[gn] : 0.f), act);
             else if (epi == EPI_STORE) *dst = v;
+            else if (epi == EPI_ADD) *dst += v;
             else atomicAdd(dst, v);
         }
     }
@@ -322,6 +323,8 @@ int launch_act_backward(const float *y, float *dy, int64_t m, int n_out, int act
 int simt_linear_backward(const float *x, const float *W, const float *y, float *dy, int64_t m,
                          int n_in, int n_out, int act, int accumulate, float *dx, float *dW,
                          float *db, cudaStream_t st) {
+    const int acc_dx = accumulate & 2;
+    accumulate &= 1;
     if (!accumulate) {
         if (db) cudaMemsetAsync(db, 0, sizeof(float) * n_out, st);
         if (dW) cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)n_out * n_in, st);
@@ -330,7 +333,8 @@ int simt_linear_backward(const float *x, const float *W, const float *y, float *
     if (dx) {   // dx[m, n_in] = dz[m, n_out] @ W[n_out, n_in]
         dim3 grid((n_in + GN - 1) / GN, (unsigned)((m + GM - 1) / GM), 1);
         sgemm_kernel<true, false><<<grid, GT, 0, st>>>(dy, W, dx, (int)m, n_in, n_out, n_out, n_in,
-                                                       n_in, EPI_STORE, nullptr, 0, n_out);
+                                                       n_in, acc_dx ? EPI_ADD : EPI_STORE, nullptr,
+                                                       0, n_out);
         if (int rc = check_launch("abn_linear_backward(dgrad)")) return rc;
     }
     if (dW) {   // dW[n_out, n_in] += dz^T[n_out, m] @ x[m, n_in], split over m

@@ -170,7 +170,7 @@ def gather_batch(feat, idx1, idx2, y=None, sel=None, n=None, out=None):
 
 
 def pair_loss(e1, e2, y, kind="coscos2", margin=0.5, scale=1.0, loss_out=None,
-              need_grad=True):
+              need_grad=True, grads=None):
     """Fused loss value + gradients (abnet3/loss.py:46-67, :85-105).
     Returns (loss[1], de1, de2); ``loss_out`` is accumulated into when given."""
     _req(e1, torch.float32, "e1")
@@ -179,8 +179,11 @@ def pair_loss(e1, e2, y, kind="coscos2", margin=0.5, scale=1.0, loss_out=None,
     n, dim = e1.shape
     loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32,
                                                             device=e1.device)
-    de1 = torch.empty_like(e1) if need_grad else None
-    de2 = torch.empty_like(e2) if need_grad else None
+    if grads is not None:
+        de1, de2 = grads
+    else:
+        de1 = torch.empty_like(e1) if need_grad else None
+        de2 = torch.empty_like(e2) if need_grad else None
     check(_lib.lib().abn_pair_loss(ptr(e1), ptr(e2), ptr(y), n, dim, LOSS_KIND[kind],
                                    float(margin), float(scale), ptr(loss), ptr(de1), ptr(de2),
                                    stream_ptr()))
@@ -199,18 +202,22 @@ def linear_forward(x, W, b, act, precision=0, out=None):
 
 
 def linear_backward(x, W, y, dy, act, precision=0, need_dx=True, dW=None, db=None,
-                    accumulate=False):
+                    accumulate=False, dx=None, accumulate_dx=False):
     """dy is overwritten with dz = dy * act'(y).  Returns (dx, dW, db)."""
     _req(dy, torch.float32, "dy")
     m, n_in = x.shape
     n_out = W.shape[0]
-    dx = torch.empty_like(x) if need_dx else None
+    if dx is None:
+        dx = torch.empty_like(x) if need_dx else None
+        accumulate_dx = False
     if dW is None:
         dW = torch.empty_like(W)
         db = torch.empty(n_out, dtype=torch.float32, device=x.device)
         accumulate = False
     check(_lib.lib().abn_linear_backward(ptr(x), ptr(W), ptr(y), ptr(dy), m, n_in, n_out,
-                                         ACT[act], precision, int(accumulate), ptr(dx), ptr(dW),
+                                         ACT[act], precision,
+                                         int(bool(accumulate)) | (2 if accumulate_dx else 0),
+                                         ptr(dx), ptr(dW),
                                          ptr(db), stream_ptr()))
     return dx, dW, db
 

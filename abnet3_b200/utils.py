@@ -20,7 +20,7 @@ from . import ops
 
 __all__ = ["cosine_distance", "DTW", "get_dtw_alignment", "Features_Accessor",
            "FeatureTable", "BatchAligner", "align_pairs_host", "read_dataset",
-           "group_pairs", "read_pairs", "read_spkid_file", "read_spk_list"]
+           "group_pairs", "read_pairs", "read_spkid_file", "read_spk_list", "read_feats"]
 
 
 def _device():
@@ -218,6 +218,20 @@ class FeatureTable(object):
         hi = int(np.searchsorted(t, off, side="right"))
         return self.row0[f] + lo, max(hi - lo, 0)
 
+    def tokens_by_time(self, files, on, off):
+        """Vectorised ``token_by_time`` over arrays: -> int32 [n, 2] (row_start, n)."""
+        files = np.asarray([self._key(f) for f in files], dtype=object)
+        on, off = np.asarray(on, dtype=np.float64), np.asarray(off, dtype=np.float64)
+        out = np.zeros((len(files), 2), dtype=np.int32)
+        for f in set(files.tolist()):
+            m = np.nonzero(files == f)[0]
+            t = self.times[f]
+            lo = np.searchsorted(t, on[m], side="left")
+            hi = np.searchsorted(t, off[m], side="right")
+            out[m, 0] = self.row0[f] + lo
+            out[m, 1] = np.maximum(hi - lo, 0)
+        return out
+
     def token_by_frames(self, f, frame_on, frame_off):
         """abnet3/utils.py:141-145: ``features[f][frame_on:frame_off]`` with
         Python slice clamping."""
@@ -247,6 +261,40 @@ class Features_Accessor(object):
     def get_between_frames(self, f, frame_on, frame_off):
         s, n = self.table.token_by_frames(f, frame_on, frame_off)
         return self.table.host[s:s + n]
+
+
+def read_feats(features_file, align_features_file=None):
+    """abnet3/utils.py:211-226: load the WHOLE feature file and return
+    ``(features_accessor, align_features, feat_dim)``.
+
+    The reference reads the h5features container with the `h5features` package,
+    which is not installed in this image; on-disk formats are a
+    "next" row of SURVEY.md 8f.  Accepted here: a ``.npz`` archive with one
+    ``<file>`` array [n, dim] per file and optional ``times/<file>`` arrays, an
+    in-memory ``{file: array}`` dict, or -- when `h5features` is importable --
+    the reference's own format."""
+    if isinstance(features_file, Features_Accessor):
+        return features_file, None, features_file.table.dim
+    if isinstance(features_file, dict):
+        feats, times = features_file, None
+    elif str(features_file).endswith(".npz"):
+        z = np.load(features_file)
+        feats = {k: z[k] for k in z.files if not k.startswith("times/")}
+        times = {k: z["times/" + k] for k in feats} if any(
+            k.startswith("times/") for k in z.files) else None
+    else:
+        try:
+            import h5features
+        except ImportError:
+            raise ImportError("reading %r needs the `h5features` package (not installed); "
+                              "pass a .npz archive or a {file: array} dict" % (features_file,))
+        with h5features.Reader(features_file, 'features') as fh:
+            data = fh.read()
+        times, feats = data.dict_labels(), data.dict_features()
+    if times is None:
+        times = {k: 0.0025 + 0.01 * np.arange(v.shape[0]) for k, v in feats.items()}
+    acc = Features_Accessor(times, feats)
+    return acc, None, acc.table.dim
 
 
 def read_spkid_file(spkid_file):

@@ -181,7 +181,9 @@ ABN_API int abn_pair_loss(const float *e1, const float *e2, const float *y, int6
  *   precision: 0 = fp32 SIMT (parity path), 1 = bf16 tcgen05 tensor cores
  * Forward:   y[m, n_out] = act(x[m, n_in] @ W^T + b)
  * Backward:  dz = dy * act'(y);  dx = dz @ W (NULL to skip);
- *            dW += dz^T @ x;  db += colsum(dz)   (accumulate == 0: overwrite)
+ *            dW += dz^T @ x;  db += colsum(dz)
+ *   accumulate: bit 0 set = add into dW / db (else overwrite them);
+ *               bit 1 set = add into dx (two heads feeding one trunk)
  * ---------------------------------------------------------------------- */
 ABN_API int abn_linear_forward(const float *x, const float *W, const float *b,
                        int64_t m, int n_in, int n_out, int act, int precision,

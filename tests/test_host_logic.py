@@ -1,0 +1,147 @@
+"""CPU: host-side logic of the reference surface (pair parsing, token slicing,
+splits, sharding, step agreement over gloo) -- no kernel is called."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from abnet3_b200 import utils as U
+from abnet3_b200 import dataloader as DL
+from abnet3_b200 import trainer as TR
+from oracle.align import FeaturesAccessor, diff_pair_indices
+
+
+def test_read_dataset_group_pairs(tmp_path):
+    p = tmp_path / "dataset"
+    p.write_text("f1 0.10 0.55 f2 1.00 1.42 same\nf1 0.10 0.55 f3 2.00 2.30 diff\n")
+    pairs = U.read_dataset(str(p))
+    assert pairs == [("f1", 0.10, 0.55, "f2", 1.00, 1.42, "same"),
+                     ("f1", 0.10, 0.55, "f3", 2.00, 2.30, "diff")]
+    g = U.group_pairs(pairs)
+    assert g["same"] == [("f1", 0.10, 0.55, "f2", 1.00, 1.42)] and len(g["diff"]) == 1
+    (tmp_path / "bad").write_text("f1 0 1 f2 0 1 other\n")
+    with pytest.raises(AssertionError):
+        U.read_dataset(str(tmp_path / "bad"))
+
+
+def test_spkid_file(tmp_path):
+    p = tmp_path / "spk"
+    p.write_text("f1 A\nf2 A\nf3 B\n")
+    spk = U.read_spkid_file(str(p))
+    assert spk == {"f1": "A", "f2": "A", "f3": "B"}
+
+
+class _HostTable(U.FeatureTable):
+    """FeatureTable without the device copy (CPU test only)."""
+
+    def __init__(self, features, times=None):
+        super().__init__(features, times, device=torch.device("cpu"))
+
+
+def test_token_slicing_matches_reference_accessor():
+    rng = np.random.default_rng(0)
+    feats = {"a": rng.standard_normal((500, 8)).astype(np.float32),
+             "b": rng.standard_normal((300, 8)).astype(np.float32)}
+    times = {k: 0.0025 + 0.01 * np.arange(v.shape[0]) for k, v in feats.items()}
+    table = _HostTable(feats, times)
+    acc = FeaturesAccessor(times, feats)
+    for f, on, off in [("a", 0.0, 0.5), ("a", 1.0025, 1.5025), ("b", 2.9, 9.0), ("b", 0.5, 0.4),
+                       ("a", 0.0125, 0.0125), ("b", 1.234, 1.777)]:
+        s, n = table.token_by_time(f, on, off)
+        ref = acc.get(f, on, off)
+        assert n == ref.shape[0]
+        np.testing.assert_array_equal(table.host[s:s + n], ref)
+    vec = table.tokens_by_time(["a", "b", "a"], [0.0, 0.5, 1.0025], [0.5, 0.4, 1.5025])
+    assert vec[:, 1].tolist() == [table.token_by_time("a", 0.0, 0.5)[1], 0,
+                                  table.token_by_time("a", 1.0025, 1.5025)[1]]
+    for f, a, b in [("a", 10, 60), ("b", 290, 400), ("a", 50, 40), ("b", -5, 7)]:
+        s, n = table.token_by_frames(f, a, b)
+        np.testing.assert_array_equal(table.host[s:s + n], acc.get_between_frames(f, a, b))
+
+
+def test_diff_rows_match_reference_selection():
+    for n1, n2 in [(20, 35), (35, 20), (30, 30), (1, 9), (9, 1)]:
+        for stretch in (False, True):
+            (srcA, srcB), a, b, nlab = diff_pair_indices(n1, n2, stretch)
+            r1, r2, nl = DL._diff_rows((100, n1, 500, n2), stretch)
+            sa = 100 if srcA == 1 else 500
+            sb = 100 if srcB == 1 else 500
+            np.testing.assert_array_equal(r1, sa + a)
+            np.testing.assert_array_equal(r2, sb + b)
+            assert nl == nlab == min(n1, n2)
+
+
+def test_pairs_loader_split_on_reference_fixture(golden_dir):
+    # the reference's own pair file (test/data/dataloader/pairs_knn.txt)
+    loader = DL.PairsDataLoader(os.path.join(golden_dir, "pairs_knn.txt"), None,
+                                os.path.join(golden_dir, "id_to_file.txt"),
+                                ratio_split_train_test=0.7, train_iterations=2,
+                                test_iterations=2)
+    loader.load_pairs()
+    allp = loader.pairs["train"] + loader.pairs["test"]
+    assert all(len(p) == 6 for p in allp)
+    for p in allp:
+        assert p[0] in ["file%d" % i for i in range(5)] and p[3] in ["file%d" % i for i in range(5)]
+    # split_each_file (dataloader.py:484-508): thresholds at 70 % of each file's last frame
+    last = {}
+    for line in open(os.path.join(golden_dir, "pairs_knn.txt")):
+        f1, f2, b1, e1, b2, e2, _ = line.split(" ")
+        last["file" + f1] = max(last.get("file" + f1, 0), int(e1))
+        last["file" + f2] = max(last.get("file" + f2, 0), int(e2))
+    for f1, s1, e1, f2, s2, e2 in loader.pairs["train"]:
+        assert s1 < 0.7 * last[f1] and s2 <= 0.7 * last[f2]
+    for f1, s1, e1, f2, s2, e2 in loader.pairs["test"]:
+        assert s1 > 0.7 * last[f1] and s2 > 0.7 * last[f2]
+    files_split = DL.PairsDataLoader(os.path.join(golden_dir, "pairs_knn.txt"), None, None,
+                                     split_method=DL.PairsDataLoader.SPLIT_FILES)
+    files_split.load_pairs()
+    dev_files = {p[0] for p in files_split.pairs["test"]} | {p[3] for p in files_split.pairs["test"]}
+    trn_files = {p[0] for p in files_split.pairs["train"]} | {p[3] for p in files_split.pairs["train"]}
+    assert not (dev_files & trn_files)
+
+
+def test_shard_pairs_partitions_the_list():
+    pairs = list(range(103))
+    shards = [TR.shard_pairs(pairs, r, 4) for r in range(4)]
+    assert sorted(sum(shards, [])) == pairs
+    assert max(map(len, shards)) - min(map(len, shards)) <= 1
+
+
+def _gloo_worker(rank, world, port, n_batches, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # each rank owns a shard with a different number of batches: everybody must
+    # stop after the SHORTEST shard, and a flat "gradient" all-reduce sums up
+    steps = 0
+    it = iter(range(n_batches[rank]))
+    bucket_sum = 0.0
+    while True:
+        b = next(it, None)
+        if not TR.all_ranks_have_batch(b is not None, "cpu", world):
+            break
+        g = torch.full((8,), float(rank + 1))
+        dist.all_reduce(g)
+        bucket_sum += float(g[0])
+        steps += 1
+    out.put((rank, steps, bucket_sum))
+    dist.destroy_process_group()
+
+
+def test_step_agreement_and_gradient_allreduce_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, n_batches = 2, [5, 3]
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n_batches, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [3, 3]                   # shortest shard decides
+    assert [r[2] for r in res] == [9.0, 9.0]               # (1 + 2) summed over 3 steps
