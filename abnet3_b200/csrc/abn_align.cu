@@ -33,12 +33,16 @@ namespace abn {
 constexpr int AL_THREADS = 128;
 constexpr int KC = 40;           // floats of K staged per chunk (one fbank frame of the 7-stack)
 constexpr int KCP = KC + 4;      // smem row stride: 11 x 16 B, odd => LDS.128 conflict-free
-constexpr int NM_LIMIT = ABN_MAX_TOKEN_FRAMES;   // 96 = 6 x 16
-constexpr int NCLS_SIDE = NM_LIMIT / 16;         // 6
-constexpr int NCLS = NCLS_SIDE * NCLS_SIDE;      // 36 (+1 pseudo class: invalid shape)
+constexpr int NM_SHORT = 96;                     // longest token of the fused class kernels (6 x 16)
+constexpr int NM_LIMIT = ABN_MAX_TOKEN_FRAMES;   // longest token overall (tiled kernel)
+constexpr int NCLS_SIDE = NM_SHORT / 16;         // 6
+constexpr int NCLS = NCLS_SIDE * NCLS_SIDE;      // 36 size classes
+constexpr int CLS_LONG = NCLS;                   // pseudo class: a token longer than NM_SHORT
+constexpr int CLS_INVALID = NCLS + 1;            // pseudo class: invalid shape
+constexpr int NBINS = NCLS + 2;
 constexpr float PI_F = 3.14159274101257324f;     // float32(np.pi)
 
-// workspace layout (bytes): counts[37] | class_off[38] | cursor[37] | order[n_pairs]
+// workspace layout (bytes): counts[38] | class_off[39] | cursor[38] | order[n_pairs]
 constexpr size_t WS_COUNTS = 0, WS_OFF = 256, WS_CURSOR = 512, WS_ORDER = 1024;
 
 struct AlignArgs {
@@ -118,7 +122,7 @@ __device__ __forceinline__ float row_sumsq(unsigned row_addr, int kc4) {
 template <int RA, int NCG>
 __device__ __forceinline__ void pair_distance(unsigned char *smem, const float *g1,
                                               const float *g2, int n1, int n2, int dim,
-                                              float *dist_gmem, int &bad) {
+                                              float *dist_gmem, int ld_gmem, int &bad) {
     using L = ClassLayout<RA, NCG>;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -221,7 +225,7 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const float *
                 d = __fdiv_rn(acosf(cs), PI_F);
             }
             if (!(d >= 0.f)) bad = 1;
-            if (dist_gmem) dist_gmem[(size_t)i * n2 + j] = d;
+            if (dist_gmem) dist_gmem[(size_t)i * ld_gmem + j] = d;
             else Ds[i * L::LDD + j] = d;
         }
     }
@@ -315,7 +319,8 @@ align_class_kernel(const AlignArgs a) {
         const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
         int bad = 0;
         pair_distance<RA, NCG>(smem, a.feat + (size_t)s1 * a.dim, a.feat + (size_t)s2 * a.dim, n1,
-                               n2, a.dim, a.dist_out ? a.dist_out + a.dist_off[p] : nullptr, bad);
+                               n2, a.dim, a.dist_out ? a.dist_out + a.dist_off[p] : nullptr, n2,
+                               bad);
         bad = __syncthreads_or(bad);
         if (a.dist_out) {
             if (tid == 0) a.valid[p] = bad ? 0 : 1;
@@ -352,15 +357,17 @@ __device__ __forceinline__ int pair_class(const int4 tk, int64_t n_rows) {
     const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
     const bool ok = n1 > 0 && n2 > 0 && n1 <= NM_LIMIT && n2 <= NM_LIMIT && s1 >= 0 && s2 >= 0 &&
                     (int64_t)s1 + n1 <= n_rows && (int64_t)s2 + n2 <= n_rows;
-    return ok ? ((n1 + 15) / 16 - 1) * NCLS_SIDE + ((n2 + 15) / 16 - 1) : NCLS;
+    if (!ok) return CLS_INVALID;
+    if (n1 > NM_SHORT || n2 > NM_SHORT) return CLS_LONG;
+    return ((n1 + 15) / 16 - 1) * NCLS_SIDE + ((n2 + 15) / 16 - 1);
 }
 
 constexpr int BK_THREADS = 256, BK_ITEMS = 4;
 
 __global__ void __launch_bounds__(BK_THREADS)
 class_count_kernel(const AlignArgs a, int *__restrict__ counts) {
-    __shared__ int hist[NCLS + 1];
-    if (threadIdx.x <= NCLS) hist[threadIdx.x] = 0;
+    __shared__ int hist[NBINS];
+    if (threadIdx.x < NBINS) hist[threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * BK_THREADS * BK_ITEMS;
 #pragma unroll
@@ -369,30 +376,30 @@ class_count_kernel(const AlignArgs a, int *__restrict__ counts) {
         if (p < a.n_pairs) {
             const int c = pair_class(reinterpret_cast<const int4 *>(a.pair_tok)[p], a.n_rows);
             atomicAdd(&hist[c], 1);
-            if (c == NCLS) {   // dataloader.py:184 / :188-191: the pair is skipped
+            if (c == CLS_INVALID) {   // dataloader.py:184 / :188-191: the pair is skipped
                 a.valid[p] = 0;
                 if (!a.dist_out) { a.path_len[p] = 0; a.cost[p] = nan(""); }
             }
         }
     }
     __syncthreads();
-    if (threadIdx.x <= NCLS && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], hist[threadIdx.x]);
+    if (threadIdx.x < NBINS && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], hist[threadIdx.x]);
 }
 
 __global__ void class_scan_kernel(const int *__restrict__ counts, int *__restrict__ class_off) {
     if (threadIdx.x == 0) {
         int s = 0;
-        for (int c = 0; c <= NCLS; ++c) { class_off[c] = s; s += counts[c]; }
-        class_off[NCLS + 1] = s;
+        for (int c = 0; c < NBINS; ++c) { class_off[c] = s; s += counts[c]; }
+        class_off[NBINS] = s;
     }
 }
 
 __global__ void __launch_bounds__(BK_THREADS)
 class_scatter_kernel(const AlignArgs a, const int *__restrict__ class_off,
                      int *__restrict__ cursor, int32_t *__restrict__ order) {
-    __shared__ int hist[NCLS + 1];
-    __shared__ int gbase[NCLS + 1];
-    if (threadIdx.x <= NCLS) hist[threadIdx.x] = 0;
+    __shared__ int hist[NBINS];
+    __shared__ int gbase[NBINS];
+    if (threadIdx.x < NBINS) hist[threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * BK_THREADS * BK_ITEMS;
     int cls[BK_ITEMS], rank[BK_ITEMS];
@@ -407,7 +414,7 @@ class_scatter_kernel(const AlignArgs a, const int *__restrict__ class_off,
         }
     }
     __syncthreads();
-    if (threadIdx.x <= NCLS && hist[threadIdx.x])
+    if (threadIdx.x < NBINS && hist[threadIdx.x])
         gbase[threadIdx.x] =
             class_off[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], hist[threadIdx.x]);
     __syncthreads();
@@ -415,6 +422,184 @@ class_scatter_kernel(const AlignArgs a, const int *__restrict__ class_off,
     for (int u = 0; u < BK_ITEMS; ++u) {
         const int p = base + u * BK_THREADS + threadIdx.x;
         if (cls[u] >= 0) order[gbase[cls[u]] + rank[u]] = p;
+    }
+}
+
+
+// ------------------------------------------------- long tokens (> 96 frames)
+// One CTA walks the n1 x n2 matrix in 96 x 96 tiles, band by band: the tile's
+// distances are computed into smem exactly like a (6,6) class pair, then warp 0
+// sweeps the tile with the accumulated costs of the row above (`top`) and of
+// the column to the left (`left`) as boundary conditions, so the recurrence is
+// the same cell-by-cell sequence of float64 operations as the un-tiled sweep.
+// Directions are packed 2 bits per cell for the whole matrix in smem.
+constexpr int LT = NM_SHORT;     // tile side
+
+struct LongLayout {
+    int ldp;                     // bytes per row of the packed direction matrix
+    unsigned top0_off, top1_off, left_off, dirs_off, path_off, misc_off, total;
+};
+__host__ __device__ inline LongLayout long_layout(int nmax) {
+    using L = ClassLayout<NCLS_SIDE, NCLS_SIDE>;
+    LongLayout o;
+    o.ldp = (nmax + 3) / 4;
+    o.top0_off = a16(L::PATH_OFF);                       // the class layout's path / misc area is unused
+    o.top1_off = o.top0_off + 8u * (nmax + 1);
+    o.left_off = o.top1_off + 8u * (nmax + 1);
+    o.dirs_off = a16(o.left_off + 8u * LT);
+    o.path_off = a16(o.dirs_off + (unsigned)nmax * o.ldp);
+    o.misc_off = a16(o.path_off + 4u * 2u * nmax);       // two uint16 arrays of 2 nmax entries
+    o.total = o.misc_off + 32u;
+    return o;
+}
+
+// top[1 + j] = C[i0 - 1][j] (top[0] unused pad so that top[j0] is the corner of column j0)
+template <int G>
+__device__ __forceinline__ double tile_wavefront(const float *D, int ldd, int h, int w, int i0g,
+                                                 int j0g, const double *top, double *top_next,
+                                                 double *left, uint8_t *dirs, int ldp, int lane) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double cur[G], prev[G];
+    unsigned bits[G];
+    const int r0 = lane * G;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        cur[g] = prev[g] = (r0 + g < h) ? left[r0 + g] : INF;
+        bits[g] = 0;
+    }
+    // value "two steps ago" of the row above this lane's first row: its left boundary
+    double nbprev = lane == 0 ? top[j0g] : ((r0 - 1 < h) ? left[r0 - 1] : INF);
+    const int T = h + w - 1;
+    for (int t = 0; t < T; ++t) {
+        double up0 = __shfl_up_sync(0xffffffffu, cur[G - 1], 1);
+        if (lane == 0) up0 = top[1 + j0g + min(t, w - 1)];
+        const double dg0 = nbprev;
+        nbprev = up0;
+        double nw[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int r = r0 + g, j = t - r;
+            const bool ok = (r < h) & ((unsigned)j < (unsigned)w);
+            const int cell = ok ? r * ldd + j : 0;
+            const double d = (double)D[cell];
+            const double up = g == 0 ? up0 : cur[g - 1];
+            const double dg = g == 0 ? dg0 : prev[g - 1];
+            const double lf = cur[g];
+            const bool up_le = up <= lf;
+            const double m1 = up_le ? up : lf;
+            const bool use_dg = dg <= m1;
+            double m = use_dg ? dg : m1;
+            const unsigned dir = use_dg ? DIR_DIAG : (up_le ? DIR_UP : DIR_LEFT);
+            m = ((i0g + r) | (j0g + j)) == 0 ? 0.0 : m;
+            const double v = d + m;
+            nw[g] = ok ? v : lf;
+            if (ok) {
+                bits[g] |= dir << (2 * (j & 3));
+                if ((j & 3) == 3 || j == w - 1) {
+                    dirs[(i0g + r) * ldp + ((j0g + j) >> 2)] = (uint8_t)bits[g];
+                    bits[g] = 0;
+                }
+                if (r == h - 1) top_next[1 + j0g + j] = v;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) { prev[g] = cur[g]; cur[g] = nw[g]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        if (r0 + g < h) left[r0 + g] = cur[g];          // right column -> next tile's left
+    double c = 0.0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) c = ((h - 1) % G == g) ? cur[g] : c;
+    return __shfl_sync(0xffffffffu, c, (h - 1) / G);
+}
+
+__global__ void __launch_bounds__(AL_THREADS)
+align_long_kernel(const AlignArgs a, int nmax) {
+    using L = ClassLayout<NCLS_SIDE, NCLS_SIDE>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const LongLayout LL = long_layout(nmax);
+    const int tid = threadIdx.x;
+    const int beg = a.class_off[CLS_LONG], end = a.class_off[CLS_LONG + 1];
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    float *Ds = reinterpret_cast<float *>(smem);
+    double *topbuf[2] = {reinterpret_cast<double *>(smem + LL.top0_off),
+                         reinterpret_cast<double *>(smem + LL.top1_off)};
+    double *left = reinterpret_cast<double *>(smem + LL.left_off);
+    uint8_t *dirs = smem + LL.dirs_off;
+    uint16_t *pb_i = reinterpret_cast<uint16_t *>(smem + LL.path_off);
+    uint16_t *pb_j = pb_i + 2 * nmax;
+    int *misc = reinterpret_cast<int *>(smem + LL.misc_off);
+
+    for (int it = beg + blockIdx.x; it < end; it += gridDim.x) {
+        const int p = a.order[it];
+        const int4 tk = reinterpret_cast<const int4 *>(a.pair_tok)[p];
+        const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
+        if (n1 > nmax || n2 > nmax) {      // max_frames promised by the caller was too small
+            if (tid == 0) {
+                a.valid[p] = 0;
+                if (!a.dist_out) { a.path_len[p] = 0; a.cost[p] = nan(""); }
+            }
+            continue;
+        }
+        for (int j = tid; j <= n2; j += AL_THREADS) topbuf[0][j] = INF;
+        int any_bad = 0;
+        double cost = 0.0;
+        int band = 0;
+        for (int i0 = 0; i0 < n1 && !any_bad; i0 += LT, ++band) {
+            const int h = min(LT, n1 - i0);
+            const double *top = topbuf[band & 1];
+            double *top_next = topbuf[(band + 1) & 1];
+            for (int r = tid; r < LT; r += AL_THREADS) left[r] = INF;
+            if (tid == 0) top_next[0] = INF;
+            for (int j0 = 0; j0 < n2; j0 += LT) {
+                const int w = min(LT, n2 - j0);
+                int bad = 0;
+                pair_distance<NCLS_SIDE, NCLS_SIDE>(
+                    smem, a.feat + (size_t)(s1 + i0) * a.dim, a.feat + (size_t)(s2 + j0) * a.dim, h,
+                    w, a.dim,
+                    a.dist_out ? a.dist_out + a.dist_off[p] + (size_t)i0 * n2 + j0 : nullptr, n2,
+                    bad);
+                bad = __syncthreads_or(bad);
+                if (bad) { any_bad = 1; break; }
+                if (!a.dist_out && tid < 32)
+                    cost = tile_wavefront<3>(Ds, L::LDD, h, w, i0, j0, top, top_next, left, dirs,
+                                             LL.ldp, tid);
+                __syncthreads();
+            }
+        }
+        if (a.dist_out) {
+            if (tid == 0) a.valid[p] = any_bad ? 0 : 1;
+            continue;
+        }
+        if (any_bad) {
+            if (tid == 0) { a.path_len[p] = 0; a.cost[p] = nan(""); a.valid[p] = 0; }
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) {
+            int i = n1 - 1, j = n2 - 1, len = 1;
+            pb_i[0] = (uint16_t)i; pb_j[0] = (uint16_t)j;
+            while ((i | j) != 0) {
+                const unsigned d = (dirs[i * LL.ldp + (j >> 2)] >> (2 * (j & 3))) & 3u;
+                i -= (d != DIR_LEFT);
+                j -= (d != DIR_UP);
+                pb_i[len] = (uint16_t)i; pb_j[len] = (uint16_t)j; ++len;
+            }
+            misc[0] = len;
+            a.path_len[p] = len;
+            a.cost[p] = cost;
+            a.valid[p] = 1;
+        }
+        __syncthreads();
+        const int len = misc[0];
+        const int64_t off = a.path_off[p];
+        for (int k = tid; k < len; k += AL_THREADS) {
+            a.idx1[off + k] = s1 + (int)pb_i[len - 1 - k];
+            a.idx2[off + k] = s2 + (int)pb_j[len - 1 - k];
+        }
+        __syncthreads();
     }
 }
 
@@ -645,7 +830,23 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
     class_count_kernel<<<blocks, BK_THREADS, 0, st>>>(a, counts);
     class_scan_kernel<<<1, 32, 0, st>>>(counts, class_off);
     class_scatter_kernel<<<blocks, BK_THREADS, 0, st>>>(a, class_off, cursor, order);
-    const int side = (max_frames + 15) / 16;
+    if (max_frames > NM_SHORT) {
+        static int long_grid = 0;
+        const int nmax = max_frames;
+        const LongLayout LL = long_layout(nmax);
+        if (cudaFuncSetAttribute(align_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)LL.total) != cudaSuccess)
+            return set_error(ABN_EIO, "%s: cannot reserve %u bytes of shared memory", who, LL.total);
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_long_kernel, AL_THREADS,
+                                                      LL.total);
+        long_grid = (per_sm > 0 ? per_sm : 1) * sms;
+        const int grid = long_grid < a.n_pairs ? long_grid : a.n_pairs;
+        align_long_kernel<<<grid, AL_THREADS, LL.total, st>>>(a, nmax);
+    }
+    const int side = ((max_frames < NM_SHORT ? max_frames : NM_SHORT) + 15) / 16;
     // large classes first: their pairs take longest, the small ones fill the tail
     for (int ra = side; ra >= 1; --ra)
         for (int ncg = side; ncg >= 1; --ncg) {
@@ -709,9 +910,9 @@ extern "C" int abn_dtw_from_dist(const double *dist, const int64_t *dist_off, co
         return set_error(ABN_EINVAL, "abn_dtw_from_dist: bad argument");
     if (max_frames <= 0)
         return set_error(ABN_EINVAL, "abn_dtw_from_dist: max_frames must be positive");
-    if (max_frames > NM_LIMIT)
+    if (max_frames > NM_SHORT)
         return set_error(ABN_ERANGE, "abn_dtw_from_dist: matrix side %d exceeds %d", max_frames,
-                         NM_LIMIT);
+                         NM_SHORT);
     const int nm = ((max_frames < 16 ? 16 : max_frames) + 15) & ~15;
     const DtwLayout L = dtw_layout(nm);
     cudaFuncSetAttribute(dtw_from_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -11,7 +11,8 @@ import torch
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
-MAX_TOKEN_FRAMES = 96            # ABN_MAX_TOKEN_FRAMES
+MAX_TOKEN_FRAMES = 512           # ABN_MAX_TOKEN_FRAMES (abn_align_pairs / abn_cosine_distance)
+MAX_DTW_FROM_DIST = 96           # abn_dtw_from_dist test hook (single tile)
 ACT = {None: 0, "none": 0, "sigmoid": 1, "tanh": 2, "relu": 3}
 LOSS_KIND = {"coscos2": 0, "cosmargin": 1}
 OPT_KIND = {"sgd": 0, "adadelta": 1, "adam": 2}

@@ -6,9 +6,9 @@ seeded synthetic corpus with the SHAPE of the reference's input:
 * 40-dim "filterbank" frames, AR(1)-smoothed along time so that neighbouring
   frames are correlated and DTW paths are not trivial;
 * word *types* (clusters): every token of a type is a randomly time-warped
-  (+-30 %), noisy (SNR ~ 10 dB) rendition of the type's prototype, 20-80
-  frames long, so 'same' pairs align meaningfully and no two frames are
-  bit-identical;
+  (local rate +-30 %), noisy (SNR ~ 10 dB) rendition of the type's prototype,
+  its length drawn uniformly from 20-80 frames, so 'same' pairs align
+  meaningfully and no two frames are bit-identical;
 * tokens laid out back to back in files, per-file mean/variance normalisation,
   then the 7-frame stack with zero padding at file edges exactly as
   /root/reference/abnet3/features.py:135-159 (`stack_fbanks`), giving
@@ -69,13 +69,13 @@ def make_corpus(n_tokens, cluster_size=16, len_range=(20, 80), n_fbank=40, stack
     tok_cluster = tok_cluster[torch.randperm(n_clusters * cluster_size, generator=g,
                                              device=dev)][:n_tokens]
     base = proto_len[tok_cluster].to(f32)
-    scale = 1.0 + warp * (2.0 * torch.rand(n_tokens, generator=g, device=dev) - 1.0)
-    tok_len = torch.clamp(torch.round(base * scale), lo, hi).to(torch.int64)
+    # token lengths ~ U{lo..hi} (BASELINE.json: "20-80 frames"), independent of the type
+    tok_len = torch.randint(lo, hi + 1, (n_tokens,), generator=g, device=dev)
 
     # random monotone warp: positive increments, normalised to [0, proto_len-1]
     pos_idx = torch.arange(hi, device=dev).unsqueeze(0)                     # [1, hi]
     live = pos_idx < tok_len.unsqueeze(1)                                   # [N, hi]
-    inc = 0.5 + torch.rand(n_tokens, hi, generator=g, device=dev)
+    inc = 1.0 + warp * (2.0 * torch.rand(n_tokens, hi, generator=g, device=dev) - 1.0)
     cum = torch.cumsum(inc * live, 1)
     first = cum[:, :1]
     last = torch.gather(cum, 1, (tok_len - 1).unsqueeze(1))

@@ -43,8 +43,9 @@ extern "C" {
 
 /* longest token (frames) abn_align_pairs / abn_cosine_distance / abn_dtw_from_dist
  * accept; `max_frames` arguments are an upper bound on every n1, n2 of the call
- * (it sizes shared memory; a pair exceeding it comes back with valid = 0) */
-#define ABN_MAX_TOKEN_FRAMES 96
+ * (it sizes shared memory; a pair exceeding it comes back with valid = 0).
+ * Tokens up to 96 frames take the fused single-tile kernels; longer ones a tiled one. */
+#define ABN_MAX_TOKEN_FRAMES 512
 
 typedef void *abn_stream_t; /* a cudaStream_t */
 
@@ -94,6 +95,7 @@ ABN_API int abn_cosine_distance(const float *feat, int64_t n_rows, int dim,
  *   path1/2  LOCAL frame indices, forward order, at path_off[p] .. +path_len.
  *   cost     C[n1-1, n2-1]; valid as above.
  * Tie rule: diagonal, then i-1, then j-1 (oracle/dtw_oracle.c).
+ * Test hook for the bit-exact mode: matrices up to 96 x 96.
  * ---------------------------------------------------------------------- */
 ABN_API int abn_dtw_from_dist(const double *dist, const int64_t *dist_off,
                       const int32_t *shape, int n_pairs, int max_frames,

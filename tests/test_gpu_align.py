@@ -209,10 +209,51 @@ def test_align_pairs_edge_shapes():
 
 
 def test_token_longer_than_limit_is_refused():
-    feat = torch.zeros((300, 280), device=DEV)
-    pairs = torch.tensor([[0, 120, 130, 50]], dtype=torch.int32, device=DEV)
+    feat = torch.zeros((1300, 280), device=DEV)
+    pairs = torch.tensor([[0, 600, 650, 50]], dtype=torch.int32, device=DEV)
     with pytest.raises(Exception):
         ops.align_pairs(feat, pairs)
+
+
+def test_long_tokens_tiled_path_vs_oracle():
+    """Tokens above 96 frames (config C5 sweeps 50-400; the reference's own pair file
+    holds 98-frame tokens) take the tiled kernel: 96 x 96 distance tiles, DTW carried
+    across tiles through boundary rows / columns.  Same bar as the fused path, plus:
+    bit-exact against the oracle DTW run on the GPU's own distances."""
+    from oracle.make_golden import smooth_tokens
+    rng = np.random.default_rng(21)
+    shapes = [(98, 56), (97, 97), (200, 130), (96, 193), (400, 400), (101, 30), (50, 50)]
+    feats, pairs, row = [], [], 0
+    for n1, n2 in shapes:
+        x = smooth_tokens(rng, n1, 280)
+        warp = np.minimum((np.arange(n2) * n1) // n2, n1 - 1)
+        y = (0.75 * x[warp] + 0.5 * smooth_tokens(rng, n2, 280)).astype(np.float32)
+        feats += [x, y]
+        pairs.append([row, n1, row + n1, n2])
+        row += n1 + n2
+    feat = np.concatenate(feats)
+    pairs = np.array(pairs, dtype=np.int32)
+    fd, pd = torch.from_numpy(feat).to(DEV), torch.from_numpy(pairs).to(DEV)
+    res = ops.align_pairs(fd, pd)
+    dist, doff, dvalid = ops.cosine_distance(fd, pd)
+    torch.cuda.synchronize()
+    idx1, idx2 = res.idx1.cpu().numpy(), res.idx2.cpu().numpy()
+    off, plen = res.path_off.cpu().numpy(), res.path_len.cpu().numpy()
+    cost, valid = res.cost.cpu().numpy(), res.valid.cpu().numpy()
+    dist, doff = dist.cpu().numpy(), doff.cpu().numpy()
+    recs = oracle.align_pairs(feat, pairs)
+    for p, (r, (s1, n1, s2, n2)) in enumerate(zip(recs, pairs.tolist())):
+        assert valid[p] == 1 and r["valid"] and dvalid[p].item() == 1
+        g1 = idx1[off[p]:off[p] + plen[p]] - s1
+        g2 = idx2[off[p]:off[p] + plen[p]] - s2
+        d_gpu = dist[doff[p]:doff[p + 1]].reshape(n1, n2).astype(np.float64)
+        np.testing.assert_allclose(d_gpu, r["dist"], rtol=0, atol=2e-6)
+        c, q1, q2 = oracle.dtw(d_gpu)                    # DTW stage alone: bit-exact
+        assert cost[p] == c
+        np.testing.assert_array_equal(g1, q1)
+        np.testing.assert_array_equal(g2, q2)
+        assert abs(cost[p] - r["cost"]) <= 1e-6 * r["cost"]     # end to end vs the oracle
+        assert abs(oracle.path_cost(r["dist"], g1, g2) - r["cost"]) <= 1e-6 * r["cost"]
 
 
 def test_diff_pairs_match_reference_row_selection():
