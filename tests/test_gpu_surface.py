@@ -148,7 +148,8 @@ def test_fused_train_step_matches_autograd_and_torch_optim(opt, lr):
             # O(lr) steps of either sign, so compare in units of the step size
             diff = (v.cpu() - ref[k].detach()).abs()
             assert float(diff.max()) <= 2 * 3 * lr
-            assert float((diff > 1e-4 * lr + 1e-4 * ref[k].detach().abs()).float().mean()) < 2e-3
+            assert float(diff.mean()) <= 0.01 * lr
+            assert float((diff > 0.1 * lr).float().mean()) < 1e-3
         else:
             _close(v, ref[k].detach(), rtol=2e-4, atol=2e-6)
 
