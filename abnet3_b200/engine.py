@@ -109,6 +109,28 @@ class SiameseTrainStep(object):
         self.world = dist.get_world_size(process_group) if dist.is_available() and \
             dist.is_initialized() else 1
         self._rows = -1
+        self.wgrad_split_k = 8
+        if self.precision == 1:
+            self._alloc_bf16_weights()
+
+    # ---- bf16 tensor-core path: operand copies of the weights -----------------
+    def _all_layers(self):
+        return self.trunk + [l for h in self.heads for l in h]
+
+    def _alloc_bf16_weights(self):
+        dev = self.bucket.param.device
+        self.wb, self.wtb = {}, {}
+        for W, _, _ in self._all_layers():
+            n_out, n_in = W.shape
+            self.wb[id(W)] = torch.zeros((n_out, ops.pad8(n_in)), dtype=torch.bfloat16, device=dev)
+            self.wtb[id(W)] = torch.zeros((n_in, ops.pad8(n_out)), dtype=torch.bfloat16, device=dev)
+        self.refresh_bf16_weights()
+
+    def refresh_bf16_weights(self):
+        """bf16 W and W^T operand copies of the fp32 master weights (after every
+        optimizer step, or after load_state_dict)."""
+        for W, _, _ in self._all_layers():
+            ops.cast_bf16(W.data, self.wb[id(W)], self.wtb[id(W)])
 
     # buffers for a given number of rows (2B): activations and their gradients
     def _reserve(self, rows):
@@ -123,11 +145,81 @@ class SiameseTrainStep(object):
         self.dacts = [buf(W.shape[0]) for W, _, _ in self.trunk]
         self.head_acts = [[buf(W.shape[0]) for W, _, _ in h] for h in self.heads]
         self.head_dacts = [[buf(W.shape[0]) for W, _, _ in h] for h in self.heads]
+        if self.precision == 1:
+            ldm = ops.pad8(rows)
+
+            def b16(r, c):
+                return torch.zeros((r, c), dtype=torch.bfloat16, device=dev)
+
+            d_in = self.trunk[0][0].shape[1]
+            self.xb, self.xbT = b16(rows, ops.pad8(d_in)), b16(d_in, ldm)
+            mk = lambda layers: [(b16(rows, ops.pad8(W.shape[0])), b16(W.shape[0], ldm))
+                                 for W, _, _ in layers]
+            self.actb = mk(self.trunk)              # (a bf16, a^T bf16) per trunk layer
+            self.dzb = mk(self.trunk)               # (dz bf16, dz^T bf16)
+            self.head_actb = [mk(h) for h in self.heads]
+            self.head_dzb = [mk(h) for h in self.heads]
         self._rows = rows
+
+    def _forward_bf16(self, x):
+        rows = x.shape[0]
+        ops.cast_bf16(x, self.xb, self.xbT)
+        hb = self.xb
+        for l, (W, b, act) in enumerate(self.trunk):
+            n_out, n_in = W.shape
+            ops.gemm_bf16_tn(hb, self.wb[id(W)], rows, n_out, n_in, ops.EPI_BIAS_ACT, b.data, act,
+                             out_f32=self.acts[l], out_bf16=self.actb[l][0],
+                             outT_bf16=self.actb[l][1])
+            hb = self.actb[l][0]
+        outs = []
+        for hi, head in enumerate(self.heads):
+            gb = hb
+            for l, (W, b, act) in enumerate(head):
+                n_out, n_in = W.shape
+                ops.gemm_bf16_tn(gb, self.wb[id(W)], rows, n_out, n_in, ops.EPI_BIAS_ACT, b.data,
+                                 act, out_f32=self.head_acts[hi][l],
+                                 out_bf16=self.head_actb[hi][l][0],
+                                 outT_bf16=self.head_actb[hi][l][1])
+                gb = self.head_actb[hi][l][0]
+            outs.append(self.head_acts[hi][-1])
+        return outs if self.heads else self.acts[-1]
+
+    def _layer_backward_bf16(self, rows, W, b, act, y, dy, dzb, in_bT, dx, dx_accumulate):
+        """One layer: dz (bf16 + transposed), db, dgrad into dx (fp32), wgrad into W.grad."""
+        n_out, n_in = W.shape
+        b.grad.zero_()
+        W.grad.zero_()
+        ops.act_backward_bf16(y, dy, act, dz=dzb[0], dzT=dzb[1], db=b.grad)
+        if dx is not None:
+            ops.gemm_bf16_tn(dzb[0], self.wtb[id(W)], rows, n_in, n_out,
+                             ops.EPI_ATOMIC if dx_accumulate else ops.EPI_STORE, out_f32=dx)
+        ops.gemm_bf16_tn(dzb[1], in_bT, n_out, n_in, rows, ops.EPI_ATOMIC, out_f32=W.grad,
+                         split_k=self.wgrad_split_k)
+
+    def _backward_bf16(self, x):
+        rows = x.shape[0]
+        if self.heads:
+            first = True
+            for hi, head in enumerate(self.heads):
+                for l in reversed(range(len(head))):
+                    W, b, act = head[l]
+                    in_bT = self.head_actb[hi][l - 1][1] if l > 0 else self.actb[-1][1]
+                    dx = self.head_dacts[hi][l - 1] if l > 0 else self.dacts[-1]
+                    self._layer_backward_bf16(rows, W, b, act, self.head_acts[hi][l],
+                                              self.head_dacts[hi][l], self.head_dzb[hi][l], in_bT,
+                                              dx, l == 0 and not first)
+                first = False
+        for l in reversed(range(len(self.trunk))):
+            W, b, act = self.trunk[l]
+            in_bT = self.actb[l - 1][1] if l > 0 else self.xbT
+            self._layer_backward_bf16(rows, W, b, act, self.acts[l], self.dacts[l], self.dzb[l],
+                                      in_bT, self.dacts[l - 1] if l > 0 else None, False)
 
     def forward(self, x):
         """x [rows, input_dim] -> embeddings (last trunk act, or the two heads)."""
         self._reserve(x.shape[0])
+        if self.precision == 1:
+            return self._forward_bf16(x)
         h = x
         for l, (W, b, act) in enumerate(self.trunk):
             h = ops.linear_forward(h, W.data, b.data, act, self.precision, out=self.acts[l])
@@ -159,6 +251,8 @@ class SiameseTrainStep(object):
                           grads=(de[:n], de[n:]))
 
     def backward(self, x):
+        if self.precision == 1:
+            return self._backward_bf16(x)
         trunk = self.trunk
         if self.heads:
             first = True
@@ -196,4 +290,6 @@ class SiameseTrainStep(object):
         self.step_count += 1
         ops.optimizer_step(self.bucket.trained_param, grad, self.state0, self.state1, self.kind,
                            self.lr, self.momentum, scale, self.step_count)
+        if self.precision == 1:
+            self.refresh_bf16_weights()
         return self.loss_buf

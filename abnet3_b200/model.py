@@ -38,7 +38,20 @@ class _LinearActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act, precision):
         x = x.contiguous()
-        y = ops.linear_forward(x, weight, bias, act, precision)
+        if precision == 1:
+            # tensor-core forward (tcgen05): bf16 operand copies made on the fly; the
+            # training engine keeps them resident instead (abnet3_b200.engine)
+            m, n_in = x.shape
+            n_out = weight.shape[0]
+            xb = torch.empty((m, ops.pad8(n_in)), dtype=torch.bfloat16, device=x.device)
+            wb = torch.empty((n_out, ops.pad8(n_in)), dtype=torch.bfloat16, device=x.device)
+            ops.cast_bf16(x, xb)
+            ops.cast_bf16(weight.detach(), wb)
+            y = torch.empty((m, n_out), dtype=torch.float32, device=x.device)
+            ops.gemm_bf16_tn(xb, wb, m, n_out, n_in, ops.EPI_BIAS_ACT, bias.detach(), act,
+                             out_f32=y)
+        else:
+            y = ops.linear_forward(x, weight, bias, act, 0)
         ctx.save_for_backward(x, weight, y)
         ctx.act, ctx.precision = act, precision
         return y
@@ -47,7 +60,9 @@ class _LinearActFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight, y = ctx.saved_tensors
         dz = dy.contiguous().clone()          # overwritten with dy * act'(y)
-        dx, dW, db = ops.linear_backward(x, weight, y, dz, ctx.act, ctx.precision,
+        # autograd backward always takes the fp32 kernels (the fused engine has the
+        # tensor-core backward)
+        dx, dW, db = ops.linear_backward(x, weight, y, dz, ctx.act, 0,
                                          need_dx=ctx.needs_input_grad[0])
         return dx, dW, db, None, None
 
