@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="pairs in the CPU baseline sample (0 = 1024 x cores)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the C3 training-step leg")
+    ap.add_argument("--train-steps", type=int, default=40)
+    ap.add_argument("--train-batch", type=int, default=8192, help="frame pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -214,6 +217,111 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------- train leg ---
+MLP_FLOP_PER_FRAME_PAIR = 7.72e6     # 280-500-500-500-100, fwd + dgrad + wgrad, 2 rows
+
+
+def bench_train(args, corpus, pairs, res, world, rank, dev):
+    """Config C3: batches of `train_batch` frame pairs (aligned same pairs + 1:1
+    diff pairs) through gather -> MLP fwd -> coscos2 -> bwd -> [all-reduce] ->
+    Adadelta, the canonical buckeye.yaml setup (abnet3/trainer.py:226-256)."""
+    import torch
+    import torch.distributed as dist
+    from abnet3_b200 import ops, synth
+    from abnet3_b200.engine import SiameseTrainStep
+    from abnet3_b200.model import SiameseNetwork
+
+    # frame-pair table: same pairs from the alignment above + as many diff pairs
+    n_sub = min(pairs.shape[0], 200_000)
+    sub = ops.AlignResult(res.idx1, res.idx2, res.path_off[:n_sub + 1].contiguous(),
+                          res.path_len[:n_sub].contiguous(), res.cost[:n_sub], res.valid[:n_sub])
+    s1, s2, _ = ops.compact_paths(sub)
+    dpairs = synth.make_diff_pairs(corpus, n_sub, seed=100 + rank)
+    d1, d2, _ = ops.diff_pairs(dpairs, stretch=False)
+    idx1 = torch.cat([s1, d1]).contiguous()
+    idx2 = torch.cat([s2, d2]).contiguous()
+    y = torch.cat([torch.ones(s1.numel(), dtype=torch.int8, device=dev),
+                   -torch.ones(d1.numel(), dtype=torch.int8, device=dev)]).contiguous()
+    n_fp = idx1.numel()
+    B = args.train_batch
+    perm = torch.randperm(n_fp, device=dev)
+    feat = corpus.feat
+    buf = torch.empty((2 * B, feat.shape[1]), dtype=torch.float32, device=dev)
+    yb = torch.empty(B, dtype=torch.float32, device=dev)
+    out = {}
+    stream = torch.cuda.current_stream()
+    for prec in ("bf16", "fp32"):
+        torch.manual_seed(0)
+        net = SiameseNetwork(input_dim=feat.shape[1], num_hidden_layers=2, hidden_dim=500,
+                             output_dim=100, p_dropout=0.0, activation_layer="sigmoid",
+                             precision=prec).to(dev)
+        step = SiameseTrainStep(net, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
+        steps = args.train_steps if prec == "bf16" else max(5, args.train_steps // 4)
+
+        def one(i):
+            lo = (i * B) % max(n_fp - B, 1)
+            ops.gather_batch(feat, idx1, idx2, y, perm[lo:lo + B], B, out=(buf[:B], buf[B:], yb))
+            return step.step(buf, B, yb)
+
+        for i in range(5):
+            one(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        beg.record(stream)
+        for i in range(steps):
+            loss = one(5 + i)
+        end.record(stream)
+        torch.cuda.synchronize()
+        ms = beg.elapsed_time(end)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        rate = world * B * steps / (ms * 1e-3)
+        out[prec] = {"frame_pairs_per_s": rate, "ms_per_step": ms / steps, "steps": steps,
+                     "loss": float(loss.item()),
+                     "mlp_tflops": rate * MLP_FLOP_PER_FRAME_PAIR / 1e12 / world}
+        if prec == "bf16":
+            # e2e: the batch's index pairs and labels come from pinned host memory and the
+            # loss is read back every step (the reference's `.data[0]`, trainer.py:242)
+            h1 = idx1[perm[:B * 8]].cpu().pin_memory()
+            h2 = idx2[perm[:B * 8]].cpu().pin_memory()
+            hy = y[perm[:B * 8]].cpu().pin_memory()
+            e_steps = 8
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(e_steps):
+                sl = slice(i * B, (i + 1) * B)
+                a = h1[sl].to(dev, non_blocking=True)
+                b = h2[sl].to(dev, non_blocking=True)
+                c = hy[sl].to(dev, non_blocking=True)
+                ops.gather_batch(feat, a, b, c, None, B, out=(buf[:B], buf[B:], yb))
+                lv = float(step.step(buf, B, yb).item())
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            out["e2e"] = {"value": world * B * e_steps / float(tt.item()),
+                          "unit": "frame pairs/s", "h2d_bytes_per_step": B * 9,
+                          "d2h_bytes_per_step": 4, "steps": e_steps, "last_loss": lv}
+    peak = 1378.8
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak = float(json.load(fh)["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    return {"metric": "trained_frame_pairs_per_sec", "unit": "frame pairs/s",
+            "config": "C3: SiameseNetwork 280-500-500-500-100 sigmoid, coscos2(avg=False), Adadelta, "
+                      "%d frame pairs per GPU per step (aligned same + 1:1 diff)" % B,
+            "value": out["bf16"]["frame_pairs_per_s"], "precision": "bf16 tcgen05 (fp32 accumulate)",
+            "ms_per_step": out["bf16"]["ms_per_step"],
+            "tensor_util": out["bf16"]["mlp_tflops"] / peak, "tensor_peak_tflops": peak,
+            "fp32_simt": out["fp32"], "bf16": out["bf16"], "e2e": out.get("e2e"),
+            "frame_pairs_in_table": int(n_fp)}
+
+
 # -------------------------------------------------------------------- ours ---
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -312,11 +420,16 @@ def run_ours(args, rank, world, local_rank):
                "call": "abnet3_b200.utils.align_pairs_host(feat_host, pair_tok_host)"}
         del host_feat
 
+    # ---- C3 leg: siamese training steps on the aligned frame pairs ---------
+    train = None
+    if not args.no_train:
+        train = bench_train(args, corpus, pairs, res, world, rank, dev)
+
     # ---- CPU baseline (rank 0, N == 1 only) --------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_s = args.cpu_sample or 1024 * cores
+        n_s = args.cpu_sample or 8192 * cores
         n_s = min(n_s, P)
         sp = pairs[:n_s].cpu().numpy()
         # the sample's tokens live in the first rows it touches; copy the whole table once
@@ -350,6 +463,7 @@ def run_ours(args, rank, world, local_rank):
                          "traffic": (traffic_pp * P if traffic_pp else None),
                          "fp32_tflops": flops / (kern_ms * 1e-3) / 1e12},
             "e2e": e2e,
+            "train": train,
             "cpu_baseline": cpu,
             "gpu_launches": args.steps,
             "clocks": clocks,
