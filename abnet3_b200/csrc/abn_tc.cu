@@ -15,7 +15,7 @@
 // row-per-thread epilogue writes the transpose coalesced for free).
 //
 // CTA = 192 threads, one 128 x BN output tile:
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d, 128B swizzle, 3-stage mbarrier ring
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //               (M=128, N=BN, K=16) x4 per 64-wide K block, tcgen05.commit frees the stage
 //   warps 2-5   epilogue: tcgen05.ld 32x32b (one TMEM lane = one output row per thread),
@@ -31,7 +31,7 @@ namespace abn {
 
 constexpr int TC_BM = 128;        // UMMA_M
 constexpr int TC_BK = 64;         // bf16 elements per K block = one 128-byte swizzle row
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 3;        // 96 KB of operand stages: two CTAs per SM
 constexpr int TC_THREADS = 192;
 constexpr int UMMA_K = 16;
 
@@ -140,7 +140,7 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 
 // ---------------------------------------------------------------- kernel ---
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int M, int N, int K, int k_blocks_per_split, const TcEpilogue ep) {
     constexpr unsigned A_BYTES = TC_BM * TC_BK * 2;       // 16 KB

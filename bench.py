@@ -258,10 +258,12 @@ def bench_train(args, corpus, pairs, res, world, rank, dev):
         step = SiameseTrainStep(net, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
         steps = args.train_steps if prec == "bf16" else max(5, args.train_steps // 4)
 
+        sx, sy = step.input_buffers(B)
+
         def one(i):
             lo = (i * B) % max(n_fp - B, 1)
-            ops.gather_batch(feat, idx1, idx2, y, perm[lo:lo + B], B, out=(buf[:B], buf[B:], yb))
-            return step.step(buf, B, yb)
+            ops.gather_batch(feat, idx1, idx2, y, perm[lo:lo + B], B, out=(sx[:B], sx[B:], sy))
+            return step.step(sx, B, sy, graph=True)
 
         for i in range(5):
             one(i)
@@ -297,8 +299,8 @@ def bench_train(args, corpus, pairs, res, world, rank, dev):
                 a = h1[sl].to(dev, non_blocking=True)
                 b = h2[sl].to(dev, non_blocking=True)
                 c = hy[sl].to(dev, non_blocking=True)
-                ops.gather_batch(feat, a, b, c, None, B, out=(buf[:B], buf[B:], yb))
-                lv = float(step.step(buf, B, yb).item())
+                ops.gather_batch(feat, a, b, c, None, B, out=(sx[:B], sx[B:], sy))
+                lv = float(step.step(sx, B, sy, graph=True).item())
             dt = time.perf_counter() - t0
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             if world > 1:

@@ -154,6 +154,26 @@ def test_fused_train_step_matches_autograd_and_torch_optim(opt, lr):
             _close(v, ref[k].detach(), rtol=2e-4, atol=2e-6)
 
 
+def test_graphed_step_equals_eager_step():
+    """CUDA-graph replay of the step must give the eager step's parameters."""
+    torch.manual_seed(3)
+    cfg = dict(input_dim=280, num_hidden_layers=2, hidden_dim=500, output_dim=100, p_dropout=0.0,
+               activation_layer="sigmoid")
+    a, b = SiameseNetwork(**cfg).to(DEV), SiameseNetwork(**cfg).to(DEV)
+    b.load_state_dict(a.state_dict())
+    sa = SiameseTrainStep(a, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
+    sb = SiameseTrainStep(b, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
+    n = 1024
+    for it in range(5):
+        x = torch.randn(2 * n, 280, device=DEV)
+        y = torch.where(torch.rand(n, device=DEV) < 0.5, 1.0, -1.0)
+        la = sa.step(x, n, y).clone()
+        lb = sb.step(x, n, y, graph=True).clone()
+        _close(lb, la, rtol=1e-5)
+    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
+        _close(w, v, rtol=1e-4, atol=1e-6)      # split-K wgrad uses fp32 atomics: order noise only
+
+
 def test_fused_multitask_step_matches_autograd():
     torch.manual_seed(1)
     net = SiameseMultitaskNetwork(input_dim=280, num_hidden_layers_shared=2,
