@@ -20,15 +20,15 @@ constexpr float COS_EPS = 1e-6f;
 
 __global__ void __launch_bounds__(LOSS_WARPS * 32)
 pair_loss_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
-                 const float *__restrict__ y, int64_t n, int dim, int kind, float margin,
-                 float scale, float *__restrict__ loss, float *__restrict__ de1,
+                 const float *__restrict__ y, int64_t n, int dim, int64_t ld, int kind,
+                 float margin, float scale, float *__restrict__ loss, float *__restrict__ de1,
                  float *__restrict__ de2) {
     __shared__ float wsum[LOSS_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float local = 0.f;
     for (int64_t row = (int64_t)blockIdx.x * LOSS_WARPS + warp; row < n;
          row += (int64_t)gridDim.x * LOSS_WARPS) {
-        const float *a = e1 + row * dim, *b = e2 + row * dim;
+        const float *a = e1 + row * ld, *b = e2 + row * ld;
         float av[4], bv[4];
         float dot = 0.f, na = 0.f, nb = 0.f;
 #pragma unroll
@@ -66,7 +66,7 @@ pair_loss_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
             const float g = dldc * scale;
             const float ka = ra > COS_EPS ? c / (an * an) : 0.f;
             const float kb = rb > COS_EPS ? c / (bn * bn) : 0.f;
-            float *ga = de1 + row * dim, *gb = de2 + row * dim;
+            float *ga = de1 + row * ld, *gb = de2 + row * ld;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int k = lane + 32 * u;
@@ -288,17 +288,18 @@ __global__ void optimizer_kernel(float *__restrict__ p, const float *__restrict_
 using namespace abn;
 
 extern "C" int abn_pair_loss(const float *e1, const float *e2, const float *y, int64_t n, int dim,
-                             int kind, float margin, float scale, float *loss, float *de1,
-                             float *de2, abn_stream_t stream) {
+                             int64_t ld, int kind, float margin, float scale, float *loss,
+                             float *de1, float *de2, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (n == 0) return ABN_OK;
-    if (!e1 || !e2 || !y || !loss || n < 0 || dim <= 0 || (kind != 0 && kind != 1) ||
+    if (ld == 0) ld = dim;
+    if (!e1 || !e2 || !y || !loss || n < 0 || dim <= 0 || ld < dim || (kind != 0 && kind != 1) ||
         ((de1 == nullptr) != (de2 == nullptr)))
         return set_error(ABN_EINVAL, "abn_pair_loss: bad argument");
     int64_t blocks = (n + LOSS_WARPS - 1) / LOSS_WARPS;
     if (blocks > 148 * 8) blocks = 148 * 8;
     pair_loss_kernel<<<(unsigned)blocks, LOSS_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        e1, e2, y, n, dim, kind, margin, scale, loss, de1, de2);
+        e1, e2, y, n, dim, ld, kind, margin, scale, loss, de1, de2);
     return check_launch("abn_pair_loss");
 }
 

@@ -19,7 +19,9 @@
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //               (M=128, N=BN, K=16) x4 per 64-wide K block, tcgen05.commit frees the stage
 //   warps 2-5   epilogue: tcgen05.ld 32x32b (one TMEM lane = one output row per thread),
-//               bias + activation, fp32 / bf16 / transposed-bf16 stores or fp32 atomics
+//               bias + activation (forward) or  x act'(y_below) (dgrad), staged through smem so
+//               that the fp32 / bf16 / transposed-bf16 stores, the fp32 atomics (split-K wgrad)
+//               and the bias-gradient column sums are all coalesced
 // K and N tails are handled by TMA out-of-bounds zero fill; no operand padding
 // beyond a leading dimension that is a multiple of 8 elements (16-byte rows).
 #include <cuda.h>
@@ -35,7 +37,7 @@ constexpr int TC_STAGES = 3;        // 96 KB of operand stages: two CTAs per SM
 constexpr int TC_THREADS = 192;
 constexpr int UMMA_K = 16;
 
-enum { TC_EPI_BIAS_ACT = 0, TC_EPI_STORE = 1, TC_EPI_ATOMIC = 2 };
+enum { TC_EPI_BIAS_ACT = 0, TC_EPI_STORE = 1, TC_EPI_ATOMIC = 2, TC_EPI_DGRAD_ACT = 3 };
 
 struct TcEpilogue {
     int mode, act;
@@ -43,6 +45,8 @@ struct TcEpilogue {
     float *out_f32; long long ld_f32;
     __nv_bfloat16 *out_bf16; long long ld_bf16;
     __nv_bfloat16 *outT_bf16; long long ld_T;
+    const __nv_bfloat16 *yprev; long long ld_yprev;   // DGRAD_ACT: forward output of the layer below
+    float *db;                                        // column sums of the written values (+=)
 };
 
 // ------------------------------------------------------------------- PTX ---
@@ -211,81 +215,83 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tc_commit(tfull);                       // accumulator complete
             }
         } else {
-            // epilogue warps 2..5: TMEM lane group = warp % 4
+            // epilogue warps 2..5 (128 threads).  Phase 1: TMEM lane group = warp % 4, one
+            // output row per thread -> bias/activation -> fp32 tile in smem (the operand stages
+            // are dead once the accumulator is complete).  Phase 2: row pass, lanes along
+            // columns => every global access is a contiguous 64-128 B segment.  Phase 3: column
+            // pass, lanes along rows => the transposed bf16 copy and the bias-gradient column
+            // sums are coalesced too.  CS_LD is odd: all three phases are bank-conflict free.
+            constexpr int CS_LD = BN + 1;
+            float *Cs = reinterpret_cast<float *>(smem_raw + (base - smem_u32_of(smem_raw)));
             const int lg = warp & 3;
-            const int row = m0 + lg * 32 + lane;
+            const int we = warp - 2;
+            const int rloc = lg * 32 + lane;
             mbar_wait(tfull, 0);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 unsigned r[32];
                 tc_ld32(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)c0, r);
-                const int col0 = n0 + c0;
-                if (col0 >= N) continue;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 if (ep.mode == TC_EPI_BIAS_ACT) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        const float b = (ep.bias && col < N) ? __ldg(ep.bias + col) : 0.f;
-                        v[j] = tc_act(v[j] + b, ep.act);
+                        const int col = n0 + c0 + j;
+                        const float bv = (ep.bias && col < N) ? __ldg(ep.bias + col) : 0.f;
+                        Cs[rloc * CS_LD + c0 + j] = tc_act(__uint_as_float(r[j]) + bv, ep.act);
                     }
-                }
-                const bool full_chunk = col0 + 32 <= N;
-                if (ep.mode == TC_EPI_ATOMIC) {
-                    if (row < M) {
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < N)
-                                atomicAdd(ep.out_f32 + (long long)row * ep.ld_f32 + col0 + j, v[j]);
-                    }
-                    continue;
+                    for (int j = 0; j < 32; ++j) Cs[rloc * CS_LD + c0 + j] = __uint_as_float(r[j]);
                 }
-                if (row < M) {
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int rr = we; rr < TC_BM; rr += 4) {
+                const int grow = m0 + rr;
+                if (grow >= M) break;
+#pragma unroll
+                for (int i = 0; i < BN / 32; ++i) {
+                    const int c = lane + 32 * i, gcol = n0 + c;
+                    if (gcol >= N) continue;
+                    float v = Cs[rr * CS_LD + c];
+                    if (ep.mode == TC_EPI_DGRAD_ACT) {
+                        const float yy = __bfloat162float(ep.yprev[(long long)grow * ep.ld_yprev + gcol]);
+                        switch (ep.act) {
+                            case 1: v *= yy * (1.f - yy); break;
+                            case 2: v *= 1.f - yy * yy; break;
+                            case 3: v = yy > 0.f ? v : 0.f; break;
+                            default: break;
+                        }
+                        Cs[rr * CS_LD + c] = v;
+                    }
                     if (ep.out_f32) {
-                        float *dst = ep.out_f32 + (long long)row * ep.ld_f32 + col0;
-                        if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4 *>(dst + j) =
-                                    make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < N) dst[j] = v[j];
-                        }
+                        float *dst = ep.out_f32 + (long long)grow * ep.ld_f32 + gcol;
+                        if (ep.mode == TC_EPI_ATOMIC) atomicAdd(dst, v);
+                        else *dst = v;
                     }
-                    if (ep.out_bf16) {
-                        __nv_bfloat16 *dst = ep.out_bf16 + (long long)row * ep.ld_bf16 + col0;
-                        if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                                uint4 q;
-                                q.x = *reinterpret_cast<unsigned *>(&p0);
-                                q.y = *reinterpret_cast<unsigned *>(&p1);
-                                q.z = *reinterpret_cast<unsigned *>(&p2);
-                                q.w = *reinterpret_cast<unsigned *>(&p3);
-                                *reinterpret_cast<uint4 *>(dst + j) = q;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < N) dst[j] = __float2bfloat16_rn(v[j]);
-                        }
-                    }
+                    if (ep.out_bf16)
+                        ep.out_bf16[(long long)grow * ep.ld_bf16 + gcol] = __float2bfloat16_rn(v);
                 }
-                if (ep.outT_bf16) {      // transposed copy: lanes = consecutive rows -> coalesced
+            }
+            if (ep.outT_bf16 || ep.db) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = we; c < BN; c += 4) {
+                    const int gcol = n0 + c;
+                    if (gcol >= N) break;
+                    float sum = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < N && row < M)
-                            ep.outT_bf16[(long long)(col0 + j) * ep.ld_T + row] =
-                                __float2bfloat16_rn(v[j]);
+                    for (int i = 0; i < TC_BM / 32; ++i) {
+                        const int rr = lane + 32 * i, grow = m0 + rr;
+                        if (grow < M) {
+                            const float v = Cs[rr * CS_LD + c];
+                            sum += v;
+                            if (ep.outT_bf16)
+                                ep.outT_bf16[(long long)gcol * ep.ld_T + grow] = __float2bfloat16_rn(v);
+                        }
+                    }
+                    if (ep.db) {
+                        sum = warp_sum(sum);
+                        if (lane == 0) atomicAdd(ep.db + gcol, sum);
+                    }
                 }
             }
         }
@@ -435,11 +441,14 @@ using namespace abn;
 extern "C" int abn_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb, int M, int N,
                                 int K, int epilogue, const float *bias, int act, float *out_f32,
                                 int64_t ld_f32, void *out_bf16, int64_t ld_bf16, void *outT_bf16,
-                                int64_t ld_T, int split_k, abn_stream_t stream) {
+                                int64_t ld_T, const void *yprev, int64_t ld_yprev, float *db,
+                                int split_k, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (M == 0 || N == 0) return ABN_OK;
-    if (!A || !B || M < 0 || N < 0 || K <= 0 || epilogue < 0 || epilogue > 2 || act < 0 || act > 3)
+    if (!A || !B || M < 0 || N < 0 || K <= 0 || epilogue < 0 || epilogue > 3 || act < 0 || act > 3)
         return set_error(ABN_EINVAL, "abn_gemm_bf16_tn: bad argument");
+    if (epilogue == TC_EPI_DGRAD_ACT && !yprev)
+        return set_error(ABN_EINVAL, "abn_gemm_bf16_tn: dgrad epilogue needs yprev");
     if (epilogue == TC_EPI_ATOMIC && !out_f32)
         return set_error(ABN_EINVAL, "abn_gemm_bf16_tn: atomic epilogue needs out_f32");
     if (epilogue != TC_EPI_ATOMIC) split_k = 1;
@@ -452,6 +461,7 @@ extern "C" int abn_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64
     ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
     ep.out_bf16 = static_cast<__nv_bfloat16 *>(out_bf16); ep.ld_bf16 = ld_bf16;
     ep.outT_bf16 = static_cast<__nv_bfloat16 *>(outT_bf16); ep.ld_T = ld_T;
+    ep.yprev = static_cast<const __nv_bfloat16 *>(yprev); ep.ld_yprev = ld_yprev; ep.db = db;
     cudaStream_t st = (cudaStream_t)stream;
     if (bn == 64) return launch_tc<64>(ma, mb, M, N, K, split_k, ep, st);
     return launch_tc<128>(ma, mb, M, N, K, split_k, ep, st);

@@ -8,12 +8,21 @@ All parameters of the network are re-pointed at views of ONE flat float32
 buffer (and their ``.grad`` at views of one flat gradient buffer), so
 
 * the backward kernels write dW / db straight into the bucket (no autograd
-  accumulation kernels, no ``zero_grad``: every slot is overwritten each step;
-  parameters the reference never trains -- the multitask ``hidden_layers_spk`` /
-  ``hidden_layers_phn`` stacks -- sit outside the trained range);
+  accumulation kernels; parameters the reference never trains -- the multitask
+  ``hidden_layers_spk`` / ``hidden_layers_phn`` stacks -- sit outside the trained
+  range);
 * the all-reduce is one call on one contiguous tensor (2.77 MB for the
   280-500-500-500-100 network): latency bound, so it is never split;
 * the optimizer is one elementwise kernel (abn_optimizer_step) over the bucket.
+
+Two kernel paths, selected by ``network.precision``:
+
+``fp32``  SIMT GEMMs (abn_linear_forward / backward): the 1e-4 parity path.
+``bf16``  tcgen05 tensor cores (abn_gemm_bf16_tn): activations live in bf16 (plus
+          a transposed bf16 copy written by the same epilogue for the weight-
+          gradient GEMM), the dgrad epilogue applies act'(y) of the layer below
+          and emits that layer's dz directly, the two multitask heads run as one
+          200-wide layer; master weights, loss, embeddings and gradients stay fp32.
 
 ``state_dict`` / ``.pth`` interchange is unaffected: the module tree and the
 parameter shapes are those of the reference.
@@ -25,6 +34,7 @@ from . import ops
 from .model import SiameseNetwork, SiameseMultitaskNetwork, PRECISIONS
 
 OPTIMIZERS = ("sgd", "adadelta", "adam")
+GEMM_CTA_SLOTS = 2 * 148       # resident tcgen05 GEMM CTAs on one B200 (2 per SM)
 
 
 def _trained_layers(network):
@@ -45,7 +55,8 @@ def _trained_layers(network):
 
 class FlatBucket(object):
     """Re-point the parameters at views of one flat buffer (trained parameters
-    first, never-trained ones after) and give them flat gradient views."""
+    first, in the given order; never-trained ones after) and give the trained
+    ones flat gradient views."""
 
     def __init__(self, network, trained):
         dev = next(network.parameters()).device
@@ -57,6 +68,7 @@ class FlatBucket(object):
         self.param = torch.empty(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.n_trained = n_trained
+        self.offset = {}
         o = 0
         with torch.no_grad():
             for p in order:
@@ -65,6 +77,7 @@ class FlatBucket(object):
                 p.data = self.param[o:o + n].view_as(p.data)
                 if id(p) in trained_ids:
                     p.grad = self.grad[o:o + n].view_as(p.data)
+                self.offset[id(p)] = o
                 o += n
 
     @property
@@ -74,6 +87,11 @@ class FlatBucket(object):
     @property
     def trained_grad(self):
         return self.grad[:self.n_trained]
+
+
+class _Layer(object):
+    """One GEMM layer of the tensor-core chain: fp32 master views + bf16 operands."""
+    __slots__ = ("W", "b", "gW", "gb", "act", "n_out", "n_in", "wb", "wtb")
 
 
 class SiameseTrainStep(object):
@@ -94,8 +112,10 @@ class SiameseTrainStep(object):
         self.kind, self.lr, self.momentum = optimizer_type, float(lr), float(momentum or 0.0)
         self.trunk, self.heads = _trained_layers(network)
         trained = []
-        for W, b, _ in self.trunk + [l for h in self.heads for l in h]:
+        for W, b, _ in self.trunk:
             trained += [W, b]
+        if self.heads:      # weights adjacent, biases adjacent: the two heads form one 2d-wide layer
+            trained += [h[0][0] for h in self.heads] + [h[0][1] for h in self.heads]
         self.bucket = FlatBucket(network, trained)
         dev = self.bucket.param.device
         n = self.bucket.n_trained
@@ -109,30 +129,11 @@ class SiameseTrainStep(object):
         self.world = dist.get_world_size(process_group) if dist.is_available() and \
             dist.is_initialized() else 1
         self._rows = -1
-        self.wgrad_split_k = 8
+        self._static_n = None
         if self.precision == 1:
-            self._alloc_bf16_weights()
+            self._build_chain()
 
-    # ---- bf16 tensor-core path: operand copies of the weights -----------------
-    def _all_layers(self):
-        return self.trunk + [l for h in self.heads for l in h]
-
-    def _alloc_bf16_weights(self):
-        dev = self.bucket.param.device
-        self.wb, self.wtb = {}, {}
-        for W, _, _ in self._all_layers():
-            n_out, n_in = W.shape
-            self.wb[id(W)] = torch.zeros((n_out, ops.pad8(n_in)), dtype=torch.bfloat16, device=dev)
-            self.wtb[id(W)] = torch.zeros((n_in, ops.pad8(n_out)), dtype=torch.bfloat16, device=dev)
-        self.refresh_bf16_weights()
-
-    def refresh_bf16_weights(self):
-        """bf16 W and W^T operand copies of the fp32 master weights (after every
-        optimizer step, or after load_state_dict)."""
-        for W, _, _ in self._all_layers():
-            ops.cast_bf16(W.data, self.wb[id(W)], self.wtb[id(W)])
-
-    # buffers for a given number of rows (2B): activations and their gradients
+    # ------------------------------------------------------------ fp32 path ---
     def _reserve(self, rows):
         if rows == self._rows:
             return
@@ -141,117 +142,28 @@ class SiameseTrainStep(object):
         def buf(width):
             return torch.empty((rows, width), dtype=torch.float32, device=dev)
 
-        self.acts = [buf(W.shape[0]) for W, _, _ in self.trunk]
-        self.dacts = [buf(W.shape[0]) for W, _, _ in self.trunk]
-        self.head_acts = [[buf(W.shape[0]) for W, _, _ in h] for h in self.heads]
-        self.head_dacts = [[buf(W.shape[0]) for W, _, _ in h] for h in self.heads]
-        if self.precision == 1:
-            ldm = ops.pad8(rows)
-
-            def b16(r, c):
-                return torch.zeros((r, c), dtype=torch.bfloat16, device=dev)
-
-            d_in = self.trunk[0][0].shape[1]
-            self.xb, self.xbT = b16(rows, ops.pad8(d_in)), b16(d_in, ldm)
-            mk = lambda layers: [(b16(rows, ops.pad8(W.shape[0])), b16(W.shape[0], ldm))
-                                 for W, _, _ in layers]
-            self.actb = mk(self.trunk)              # (a bf16, a^T bf16) per trunk layer
-            self.dzb = mk(self.trunk)               # (dz bf16, dz^T bf16)
-            self.head_actb = [mk(h) for h in self.heads]
-            self.head_dzb = [mk(h) for h in self.heads]
+        if self.precision == 0:
+            self.acts = [buf(W.shape[0]) for W, _, _ in self.trunk]
+            self.dacts = [buf(W.shape[0]) for W, _, _ in self.trunk]
+            self.head_acts = [[buf(W.shape[0]) for W, _, _ in h] for h in self.heads]
+            self.head_dacts = [[buf(W.shape[0]) for W, _, _ in h] for h in self.heads]
+        else:
+            self._reserve_bf16(rows)
         self._rows = rows
 
-    def _forward_bf16(self, x):
-        rows = x.shape[0]
-        ops.cast_bf16(x, self.xb, self.xbT)
-        hb = self.xb
-        for l, (W, b, act) in enumerate(self.trunk):
-            n_out, n_in = W.shape
-            ops.gemm_bf16_tn(hb, self.wb[id(W)], rows, n_out, n_in, ops.EPI_BIAS_ACT, b.data, act,
-                             out_f32=self.acts[l], out_bf16=self.actb[l][0],
-                             outT_bf16=self.actb[l][1])
-            hb = self.actb[l][0]
-        outs = []
-        for hi, head in enumerate(self.heads):
-            gb = hb
-            for l, (W, b, act) in enumerate(head):
-                n_out, n_in = W.shape
-                ops.gemm_bf16_tn(gb, self.wb[id(W)], rows, n_out, n_in, ops.EPI_BIAS_ACT, b.data,
-                                 act, out_f32=self.head_acts[hi][l],
-                                 out_bf16=self.head_actb[hi][l][0],
-                                 outT_bf16=self.head_actb[hi][l][1])
-                gb = self.head_actb[hi][l][0]
-            outs.append(self.head_acts[hi][-1])
-        return outs if self.heads else self.acts[-1]
-
-    def _layer_backward_bf16(self, rows, W, b, act, y, dy, dzb, in_bT, dx, dx_accumulate):
-        """One layer: dz (bf16 + transposed), db, dgrad into dx (fp32), wgrad into W.grad."""
-        n_out, n_in = W.shape
-        ops.act_backward_bf16(y, dy, act, dz=dzb[0], dzT=dzb[1], db=b.grad)
-        if dx is not None:
-            ops.gemm_bf16_tn(dzb[0], self.wtb[id(W)], rows, n_in, n_out,
-                             ops.EPI_ATOMIC if dx_accumulate else ops.EPI_STORE, out_f32=dx)
-        ops.gemm_bf16_tn(dzb[1], in_bT, n_out, n_in, rows, ops.EPI_ATOMIC, out_f32=W.grad,
-                         split_k=self.wgrad_split_k)
-
-    def _backward_bf16(self, x):
-        rows = x.shape[0]
-        self.bucket.trained_grad.zero_()       # db / dW are accumulated with atomics
-        if self.heads:
-            first = True
-            for hi, head in enumerate(self.heads):
-                for l in reversed(range(len(head))):
-                    W, b, act = head[l]
-                    in_bT = self.head_actb[hi][l - 1][1] if l > 0 else self.actb[-1][1]
-                    dx = self.head_dacts[hi][l - 1] if l > 0 else self.dacts[-1]
-                    self._layer_backward_bf16(rows, W, b, act, self.head_acts[hi][l],
-                                              self.head_dacts[hi][l], self.head_dzb[hi][l], in_bT,
-                                              dx, l == 0 and not first)
-                first = False
-        for l in reversed(range(len(self.trunk))):
-            W, b, act = self.trunk[l]
-            in_bT = self.actb[l - 1][1] if l > 0 else self.xbT
-            self._layer_backward_bf16(rows, W, b, act, self.acts[l], self.dacts[l], self.dzb[l],
-                                      in_bT, self.dacts[l - 1] if l > 0 else None, False)
-
-    def forward(self, x):
-        """x [rows, input_dim] -> embeddings (last trunk act, or the two heads)."""
-        self._reserve(x.shape[0])
-        if self.precision == 1:
-            return self._forward_bf16(x)
+    def _forward_fp32(self, x):
         h = x
         for l, (W, b, act) in enumerate(self.trunk):
-            h = ops.linear_forward(h, W.data, b.data, act, self.precision, out=self.acts[l])
+            h = ops.linear_forward(h, W.data, b.data, act, 0, out=self.acts[l])
         outs = []
         for hi, head in enumerate(self.heads):
             g = h
             for l, (W, b, act) in enumerate(head):
-                g = ops.linear_forward(g, W.data, b.data, act, self.precision,
-                                       out=self.head_acts[hi][l])
+                g = ops.linear_forward(g, W.data, b.data, act, 0, out=self.head_acts[hi][l])
             outs.append(g)
         return outs if self.heads else h
 
-    def _loss_and_seed(self, out, n, labels):
-        """loss into self.loss_buf, d(loss)/d(embeddings) into the dact buffers."""
-        self.loss_buf.zero_()
-        if not self.heads:
-            kind, margin, avg = self.loss_spec
-            de = self.dacts[-1]
-            ops.pair_loss(out[:n], out[n:], labels[0], kind, margin, 1.0 / n if avg else 1.0,
-                          loss_out=self.loss_buf, grads=(de[:n], de[n:]))
-            return
-        spec_spk, spec_phn, weight = self.loss_spec
-        for hi, (spec, w, y) in enumerate(((spec_spk, weight, labels[0]),
-                                           (spec_phn, 1.0 - weight, labels[1]))):
-            kind, margin, avg = spec
-            de = self.head_dacts[hi][-1]
-            ops.pair_loss(out[hi][:n], out[hi][n:], y, kind, margin,
-                          w * (1.0 / n if avg else 1.0), loss_out=self.loss_buf,
-                          grads=(de[:n], de[n:]))
-
-    def backward(self, x):
-        if self.precision == 1:
-            return self._backward_bf16(x)
+    def _backward_fp32(self, x):
         trunk = self.trunk
         if self.heads:
             first = True
@@ -261,24 +173,160 @@ class SiameseTrainStep(object):
                     xin = self.head_acts[hi][l - 1] if l > 0 else self.acts[-1]
                     dx = self.head_dacts[hi][l - 1] if l > 0 else self.dacts[-1]
                     ops.linear_backward(xin, W.data, self.head_acts[hi][l], self.head_dacts[hi][l],
-                                        act, self.precision, dW=W.grad, db=b.grad, accumulate=False,
+                                        act, 0, dW=W.grad, db=b.grad, accumulate=False,
                                         dx=dx, accumulate_dx=(l == 0 and not first))
                 first = False
         for l in reversed(range(len(trunk))):
             W, b, act = trunk[l]
             xin = self.acts[l - 1] if l > 0 else x
-            ops.linear_backward(xin, W.data, self.acts[l], self.dacts[l], act, self.precision,
+            ops.linear_backward(xin, W.data, self.acts[l], self.dacts[l], act, 0,
                                 need_dx=(l > 0), dW=W.grad, db=b.grad, accumulate=False,
                                 dx=self.dacts[l - 1] if l > 0 else None)
 
-    # ---- CUDA graphs ------------------------------------------------------------
-    # The step is ~40 small launches on fixed buffers; replaying them as two graphs
-    # (forward+loss+backward | optimizer) removes the launch latency that otherwise
-    # dominates a 0.1-0.3 ms step.  The NCCL all-reduce stays between the two graphs.
+    # ------------------------------------------------- bf16 tensor-core path ---
+    def _build_chain(self):
+        """Trunk layers, then (multitask) the two heads as ONE layer whose weight
+        is the [2d, hidden] block they occupy side by side in the flat bucket."""
+        dev = self.bucket.param.device
+        P, G, off = self.bucket.param, self.bucket.grad, self.bucket.offset
+        self.chain = []
+
+        def add(W_view, b_view, gW, gb, act):
+            L = _Layer()
+            L.W, L.b, L.gW, L.gb, L.act = W_view, b_view, gW, gb, act
+            L.n_out, L.n_in = W_view.shape
+            L.wb = torch.zeros((L.n_out, ops.pad8(L.n_in)), dtype=torch.bfloat16, device=dev)
+            L.wtb = torch.zeros((L.n_in, ops.pad8(L.n_out)), dtype=torch.bfloat16, device=dev)
+            self.chain.append(L)
+
+        for W, b, act in self.trunk:
+            add(W.data, b.data, W.grad, b.grad, act)
+        if self.heads:
+            Ws = [h[0][0] for h in self.heads]
+            bs = [h[0][1] for h in self.heads]
+            d, hid = Ws[0].shape
+            ow, ob = off[id(Ws[0])], off[id(bs[0])]
+            assert off[id(Ws[1])] == ow + d * hid and off[id(bs[1])] == ob + d
+            add(P[ow:ow + 2 * d * hid].view(2 * d, hid), P[ob:ob + 2 * d],
+                G[ow:ow + 2 * d * hid].view(2 * d, hid), G[ob:ob + 2 * d], self.heads[0][0][2])
+            self.head_dim = d
+        self.refresh_bf16_weights()
+
+    def refresh_bf16_weights(self):
+        """bf16 W and W^T operand copies of the fp32 master weights (after every
+        optimizer step, or after load_state_dict)."""
+        for L in self.chain:
+            ops.cast_bf16(L.W, L.wb, L.wtb)
+
+    def _reserve_bf16(self, rows):
+        dev = self.bucket.param.device
+        ldm = ops.pad8(rows)
+
+        def b16(r, c):
+            return torch.zeros((r, c), dtype=torch.bfloat16, device=dev)
+
+        d_in = self.chain[0].n_in
+        self.xb, self.xbT = b16(rows, ops.pad8(d_in)), b16(d_in, ldm)
+        # hidden activations: bf16 + transposed bf16 only; the last layer: fp32 only
+        self.actb = [(b16(rows, ops.pad8(L.n_out)), b16(L.n_out, ldm)) for L in self.chain[:-1]]
+        self.dzb = [(b16(rows, ops.pad8(L.n_out)), b16(L.n_out, ldm)) for L in self.chain]
+        n_last = self.chain[-1].n_out
+        self.out_last = torch.empty((rows, n_last), dtype=torch.float32, device=dev)
+        self.de_last = torch.zeros((rows, n_last), dtype=torch.float32, device=dev)
+        self.acts = [None] * (len(self.chain) - 1) + [self.out_last]
+
+    def _forward_bf16(self, x):
+        rows = x.shape[0]
+        ops.cast_bf16(x, self.xb, self.xbT)
+        hb = self.xb
+        last = len(self.chain) - 1
+        for l, L in enumerate(self.chain):
+            if l < last:
+                ops.gemm_bf16_tn(hb, L.wb, rows, L.n_out, L.n_in, ops.EPI_BIAS_ACT, L.b, L.act,
+                                 out_bf16=self.actb[l][0], outT_bf16=self.actb[l][1])
+                hb = self.actb[l][0]
+            else:
+                ops.gemm_bf16_tn(hb, L.wb, rows, L.n_out, L.n_in, ops.EPI_BIAS_ACT, L.b, L.act,
+                                 out_f32=self.out_last)
+        if self.heads:
+            d = self.head_dim
+            return [self.out_last[:, :d], self.out_last[:, d:]]
+        return self.out_last
+
+    def _split_k(self, L):
+        tiles = ((L.n_out + 127) // 128) * ((L.n_in + 127) // 128)
+        return max(1, GEMM_CTA_SLOTS // tiles)
+
+    def _backward_bf16(self, x):
+        rows = x.shape[0]
+        self.bucket.trained_grad.zero_()       # dW / db are accumulated with atomics
+        last = len(self.chain) - 1
+        Ll = self.chain[last]
+        ops.act_backward_bf16(self.out_last, self.de_last, Ll.act, dz=self.dzb[last][0],
+                              dzT=self.dzb[last][1], db=Ll.gb)
+        for l in range(last, -1, -1):
+            L = self.chain[l]
+            if l > 0:
+                Lb = self.chain[l - 1]
+                # dgrad fused with act'(y) of the layer below: emits that layer's dz, dz^T, db
+                ops.gemm_bf16_tn(self.dzb[l][0], L.wtb, rows, L.n_in, L.n_out, ops.EPI_DGRAD_ACT,
+                                 act=Lb.act, yprev=self.actb[l - 1][0],
+                                 out_bf16=self.dzb[l - 1][0], outT_bf16=self.dzb[l - 1][1],
+                                 db=Lb.gb)
+            in_bT = self.actb[l - 1][1] if l > 0 else self.xbT
+            ops.gemm_bf16_tn(self.dzb[l][1], in_bT, L.n_out, L.n_in, rows, ops.EPI_ATOMIC,
+                             out_f32=L.gW, split_k=self._split_k(L))
+
+    # -------------------------------------------------------------- common ---
+    def forward(self, x):
+        """x [rows, input_dim] -> embeddings (last layer, or the two heads)."""
+        self._reserve(x.shape[0])
+        return self._forward_bf16(x) if self.precision == 1 else self._forward_fp32(x)
+
+    def backward(self, x):
+        return self._backward_bf16(x) if self.precision == 1 else self._backward_fp32(x)
+
+    def _loss_and_seed(self, out, n, labels):
+        """loss into self.loss_buf, d(loss)/d(embeddings) into the seed buffers."""
+        self.loss_buf.zero_()
+        if not self.heads:
+            kind, margin, avg = self.loss_spec
+            de = self.de_last if self.precision == 1 else self.dacts[-1]
+            ops.pair_loss(out[:n], out[n:], labels[0], kind, margin, 1.0 / n if avg else 1.0,
+                          loss_out=self.loss_buf, grads=(de[:n], de[n:]))
+            return
+        spec_spk, spec_phn, weight = self.loss_spec
+        d = out[0].shape[1]
+        for hi, (spec, w, y) in enumerate(((spec_spk, weight, labels[0]),
+                                           (spec_phn, 1.0 - weight, labels[1]))):
+            kind, margin, avg = spec
+            if self.precision == 1:
+                de = self.de_last[:, hi * d:(hi + 1) * d]
+            else:
+                de = self.head_dacts[hi][-1]
+            ops.pair_loss(out[hi][:n], out[hi][n:], y, kind, margin,
+                          w * (1.0 / n if avg else 1.0), loss_out=self.loss_buf,
+                          grads=(de[:n], de[n:]))
+
+    def _grad_scale(self):
+        avg = self.loss_spec[2] if not self.heads else self.loss_spec[0][2]
+        return 1.0 / self.world if (self.world > 1 and avg) else 1.0
+
+    def _optimizer(self, scale, step):
+        ops.optimizer_step(self.bucket.trained_param, self.bucket.trained_grad, self.state0,
+                           self.state1, self.kind, self.lr, self.momentum, scale, step)
+        if self.precision == 1:
+            self.refresh_bf16_weights()
+
+    # ---- CUDA graphs ----------------------------------------------------------
+    # The step is a few dozen small launches on fixed buffers; replaying them as two
+    # graphs (forward+loss+backward | optimizer) removes the launch latency that
+    # otherwise dominates a sub-millisecond step.  The NCCL all-reduce stays between
+    # the two graphs.
     def input_buffers(self, n):
         """Static (x [2n, D], labels...) buffers of the graphed step: producers
         (abn_gather_batch) may write straight into them."""
-        if getattr(self, "_static_n", None) != n:
+        if self._static_n != n:
             dev = self.bucket.param.device
             d_in = self.trunk[0][0].shape[1]
             self._sx = torch.empty((2 * n, d_in), dtype=torch.float32, device=dev)
@@ -294,27 +342,20 @@ class SiameseTrainStep(object):
         self._loss_and_seed(out, self._static_n, self._sy)
         self.backward(self._sx)
 
-    def _optimizer(self, scale):
-        ops.optimizer_step(self.bucket.trained_param, self.bucket.trained_grad, self.state0,
-                           self.state1, self.kind, self.lr, self.momentum, scale, 1)
-        if self.precision == 1:
-            self.refresh_bf16_weights()
-
     def step_graphed(self, x, n, *labels):
         """Same as step(do_training=True) through CUDA graphs (SGD / Adadelta)."""
         bufs = self.input_buffers(n)
         for dst, src in zip(bufs, (x,) + tuple(labels)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        avg = self.loss_spec[2] if not self.heads else self.loss_spec[0][2]
-        scale = 1.0 / self.world if (self.world > 1 and avg) else 1.0
+        scale = self._grad_scale()
         if self._graph_fb is None:
-            if self._eager_warm < 2:           # warm-up: lazy attribute setup must not be captured
+            if self._eager_warm < 2:           # lazy one-time setup must not be captured
                 self._eager_warm += 1
                 self._fwd_loss_bwd()
                 if self.world > 1:
                     dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM, group=self.group)
-                self._optimizer(scale)
+                self._optimizer(scale, 1)
                 self.step_count += 1
                 return self.loss_buf
             torch.cuda.synchronize()
@@ -322,7 +363,7 @@ class SiameseTrainStep(object):
             with torch.cuda.graph(self._graph_fb):
                 self._fwd_loss_bwd()
             with torch.cuda.graph(self._graph_opt):
-                self._optimizer(scale)
+                self._optimizer(scale, 1)
         self._graph_fb.replay()
         if self.world > 1:
             dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM, group=self.group)
@@ -342,15 +383,8 @@ class SiameseTrainStep(object):
         if not do_training:
             return self.loss_buf
         self.backward(x)
-        grad = self.bucket.trained_grad
-        scale = 1.0
         if self.world > 1:
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
-            avg = self.loss_spec[2] if not self.heads else self.loss_spec[0][2]
-            scale = 1.0 / self.world if avg else 1.0
+            dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM, group=self.group)
         self.step_count += 1
-        ops.optimizer_step(self.bucket.trained_param, grad, self.state0, self.state1, self.kind,
-                           self.lr, self.momentum, scale, self.step_count)
-        if self.precision == 1:
-            self.refresh_bf16_weights()
+        self._optimizer(self._grad_scale(), self.step_count)
         return self.loss_buf

@@ -174,10 +174,14 @@ def pair_loss(e1, e2, y, kind="coscos2", margin=0.5, scale=1.0, loss_out=None,
               need_grad=True, grads=None):
     """Fused loss value + gradients (abnet3/loss.py:46-67, :85-105).
     Returns (loss[1], de1, de2); ``loss_out`` is accumulated into when given."""
-    _req(e1, torch.float32, "e1")
-    _req(e2, torch.float32, "e2")
+    for t, nm in ((e1, "e1"), (e2, "e2")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.stride(-1) == 1):
+            raise TypeError("%s must be a CUDA float32 tensor with a contiguous last dim" % nm)
     _req(y, torch.float32, "y")
     n, dim = e1.shape
+    ld = e1.stride(0)
+    if e2.stride(0) != ld:
+        raise ValueError("e1 and e2 must share their row stride")
     loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32,
                                                             device=e1.device)
     if grads is not None:
@@ -185,7 +189,9 @@ def pair_loss(e1, e2, y, kind="coscos2", margin=0.5, scale=1.0, loss_out=None,
     else:
         de1 = torch.empty_like(e1) if need_grad else None
         de2 = torch.empty_like(e2) if need_grad else None
-    check(_lib.lib().abn_pair_loss(ptr(e1), ptr(e2), ptr(y), n, dim, LOSS_KIND[kind],
+    if de1 is not None and (de1.stride(0) != ld or de2.stride(0) != ld):
+        raise ValueError("gradient buffers must share the embeddings' row stride")
+    check(_lib.lib().abn_pair_loss(ptr(e1), ptr(e2), ptr(y), n, dim, ld, LOSS_KIND[kind],
                                    float(margin), float(scale), ptr(loss), ptr(de1), ptr(de2),
                                    stream_ptr()))
     return loss, de1, de2
@@ -234,7 +240,7 @@ def optimizer_step(param, grad, state0, state1, kind, lr, momentum=0.0, grad_sca
 
 
 # ------------------------------------------------------- tensor-core path ---
-EPI_BIAS_ACT, EPI_STORE, EPI_ATOMIC = 0, 1, 2
+EPI_BIAS_ACT, EPI_STORE, EPI_ATOMIC, EPI_DGRAD_ACT = 0, 1, 2, 3
 
 
 def pad8(n):
@@ -242,7 +248,7 @@ def pad8(n):
 
 
 def gemm_bf16_tn(A, B, M, N, K, epilogue, bias=None, act=None, out_f32=None, out_bf16=None,
-                 outT_bf16=None, split_k=1):
+                 outT_bf16=None, split_k=1, yprev=None, db=None):
     """C[M,N] = A[M,K] . B[N,K]^T on tcgen05.  A, B: bf16 2-D tensors whose last
     dimension is contiguous (row stride = leading dimension, a multiple of 8)."""
     for t, nm in ((A, "A"), (B, "B")):
@@ -253,6 +259,7 @@ def gemm_bf16_tn(A, B, M, N, K, epilogue, bias=None, act=None, out_f32=None, out
         ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
         ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
         ptr(outT_bf16), outT_bf16.stride(0) if outT_bf16 is not None else 0,
+        ptr(yprev), yprev.stride(0) if yprev is not None else 0, ptr(db),
         split_k, stream_ptr()))
 
 

@@ -169,9 +169,11 @@ ABN_API int abn_gather_batch(const float *feat, int dim, const int32_t *idx1,
  *          weight, ...)
  *   loss   [1] float32, ACCUMULATED into (caller zeroes it)
  *   de1/2  [n, dim] float32 gradients w.r.t. e1 / e2 (NULL: forward only)
+ *   ld     row stride (elements) of e1, e2, de1, de2 (0 = dim): the two heads of the
+ *          multitask network live side by side in one [n, 2*dim] buffer
  * ---------------------------------------------------------------------- */
 ABN_API int abn_pair_loss(const float *e1, const float *e2, const float *y, int64_t n,
-                  int dim, int kind, float margin, float scale, float *loss,
+                  int dim, int64_t ld, int kind, float margin, float scale, float *loss,
                   float *de1, float *de2, abn_stream_t stream);
 
 /* ------------------------------------------------------------------------
@@ -204,14 +206,18 @@ ABN_API int abn_linear_backward(const float *x, const float *W, const float *y,
  *   forward  A = x [m, n_in],     B = W   [n_out, n_in]   epilogue 0 (bias + act)
  *   dgrad    A = dz [m, n_out],   B = W^T [n_in, n_out]   epilogue 1 (store)
  *   wgrad    A = dz^T [n_out, m], B = x^T [n_in, m]       epilogue 2 (fp32 atomic add, split_k)
+ *   dgrad fused with the layer below:                     epilogue 3: C * act'(yprev), where
+ *            yprev bf16 [M, ld_yprev] is that layer's forward output, i.e. its dz directly
  * A, B: bf16, K contiguous, 16-byte aligned, leading dimensions (elements)
- * multiples of 8.  epilogue 0/1 write any of out_f32 [M, ld_f32], out_bf16
- * [M, ld_bf16] and the TRANSPOSED outT_bf16 [N, ld_T] (NULL to skip).
+ * multiples of 8.  Epilogues write any of out_f32 [M, ld_f32], out_bf16
+ * [M, ld_bf16] and the TRANSPOSED outT_bf16 [N, ld_T] (NULL to skip); db [N]
+ * (NULL to skip) is incremented by the column sums of the written values.
  * ---------------------------------------------------------------------- */
 ABN_API int abn_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb,
                              int M, int N, int K, int epilogue, const float *bias, int act,
                              float *out_f32, int64_t ld_f32, void *out_bf16, int64_t ld_bf16,
-                             void *outT_bf16, int64_t ld_T, int split_k, abn_stream_t stream);
+                             void *outT_bf16, int64_t ld_T, const void *yprev, int64_t ld_yprev,
+                             float *db, int split_k, abn_stream_t stream);
 
 /* fp32 [rows, cols] (ld_src) -> bf16 [rows, ld_dst] and/or transposed bf16
  * [cols, ld_T]: operand preparation for abn_gemm_bf16_tn (weights after every

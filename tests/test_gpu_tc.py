@@ -55,6 +55,28 @@ def test_tcgen05_gemm_bias_act_and_all_outputs():
         assert float(o16[:, N:].abs().max()) == 0 and float(oT[:, M:].abs().max()) == 0
 
 
+def test_tcgen05_gemm_dgrad_epilogue_applies_act_derivative():
+    """epilogue 3: dz_below = (dz W) * act'(y_below), plus its transpose and column sums."""
+    M, N, K = 700, 500, 100
+    A, B, ref = _operands(M, N, K, 5)
+    g = torch.Generator().manual_seed(1)
+    for act, dfn in (("sigmoid", lambda y: y * (1 - y)), ("tanh", lambda y: 1 - y * y),
+                     ("relu", lambda y: (y > 0).double())):
+        yprev = torch.zeros((M, ops.pad8(N)), dtype=torch.bfloat16)
+        raw = torch.randn(M, N, generator=g)
+        yprev[:, :N] = {"sigmoid": torch.sigmoid, "tanh": torch.tanh, "relu": torch.relu}[act](raw).bfloat16()
+        want = ref * dfn(yprev[:, :N].double())
+        o16 = torch.zeros((M, ops.pad8(N)), dtype=torch.bfloat16, device=DEV)
+        oT = torch.zeros((N, ops.pad8(M)), dtype=torch.bfloat16, device=DEV)
+        db = torch.full((N,), 0.5, device=DEV)
+        ops.gemm_bf16_tn(A, B, M, N, K, ops.EPI_DGRAD_ACT, act=act, yprev=yprev.to(DEV),
+                         out_bf16=o16, outT_bf16=oT, db=db)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(o16[:, :N].float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-3)
+        assert torch.equal(oT[:, :M].cpu(), o16[:, :N].cpu().T)
+        np.testing.assert_allclose(db.cpu().numpy(), 0.5 + want.sum(0).numpy(), rtol=2e-3, atol=2e-2)
+
+
 def test_tcgen05_gemm_split_k_atomic_accumulates():
     M, N, K = 500, 280, 16384          # the wgrad shape: contraction over the batch
     A, B, ref = _operands(M, N, K, 9)
