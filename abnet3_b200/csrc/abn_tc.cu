@@ -133,17 +133,25 @@ __host__ __device__ constexpr unsigned umma_idesc_bf16(int m, int n) {
            ((unsigned)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float tc_act(float v, int act) {
-    switch (act) {
-        case 1: return 1.f / (1.f + __expf(-v));
-        case 2: return tanhf(v);
-        case 3: return v > 0.f ? v : 0.f;
-        default: return v;
-    }
+// activation / derivative with the activation id as a compile-time constant;
+// sigmoid = ex2 + rcp (two MUFU ops), well inside the bf16 tolerance of this path
+template <int ACT>
+__device__ __forceinline__ float tc_act(float v) {
+    if (ACT == 1) return __fdividef(1.f, 1.f + __expf(-v));
+    if (ACT == 2) { const float e = __expf(2.f * v); return __fdividef(e - 1.f, e + 1.f); }
+    if (ACT == 3) return v > 0.f ? v : 0.f;
+    return v;
+}
+template <int ACT>
+__device__ __forceinline__ float tc_dact(float g, float y) {
+    if (ACT == 1) return g * (y * (1.f - y));
+    if (ACT == 2) return g * (1.f - y * y);
+    if (ACT == 3) return y > 0.f ? g : 0.f;
+    return g;
 }
 
 // ---------------------------------------------------------------- kernel ---
-template <int BN>
+template <int BN, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int M, int N, int K, int k_blocks_per_split, const TcEpilogue ep) {
@@ -237,7 +245,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int j = 0; j < 32; ++j) {
                         const int col = n0 + c0 + j;
                         const float bv = (ep.bias && col < N) ? __ldg(ep.bias + col) : 0.f;
-                        Cs[rloc * CS_LD + c0 + j] = tc_act(__uint_as_float(r[j]) + bv, ep.act);
+                        Cs[rloc * CS_LD + c0 + j] = tc_act<ACT>(__uint_as_float(r[j]) + bv);
                     }
                 } else {
 #pragma unroll
@@ -245,31 +253,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int rr = we; rr < TC_BM; rr += 4) {
-                const int grow = m0 + rr;
-                if (grow >= M) break;
+            // 4 rows x (BN/32) columns per iteration: all yprev loads are issued before
+            // their first use, so their latency is paid once per 4 rows, not once per row
+            for (int rb = we; rb < TC_BM; rb += 16) {
+                if (m0 + rb >= M) break;
+                float yv[4][BN / 32];
+                if (ep.mode == TC_EPI_DGRAD_ACT) {
 #pragma unroll
-                for (int i = 0; i < BN / 32; ++i) {
-                    const int c = lane + 32 * i, gcol = n0 + c;
-                    if (gcol >= N) continue;
-                    float v = Cs[rr * CS_LD + c];
-                    if (ep.mode == TC_EPI_DGRAD_ACT) {
-                        const float yy = __bfloat162float(ep.yprev[(long long)grow * ep.ld_yprev + gcol]);
-                        switch (ep.act) {
-                            case 1: v *= yy * (1.f - yy); break;
-                            case 2: v *= 1.f - yy * yy; break;
-                            case 3: v = yy > 0.f ? v : 0.f; break;
-                            default: break;
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int i = 0; i < BN / 32; ++i) {
+                            const int grow = m0 + rb + 4 * q, gcol = n0 + lane + 32 * i;
+                            yv[q][i] = (grow < M && gcol < N)
+                                ? __bfloat162float(ep.yprev[(long long)grow * ep.ld_yprev + gcol])
+                                : 0.f;
                         }
-                        Cs[rr * CS_LD + c] = v;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = rb + 4 * q, grow = m0 + rr;
+                    if (grow >= M) break;
+#pragma unroll
+                    for (int i = 0; i < BN / 32; ++i) {
+                        const int c = lane + 32 * i, gcol = n0 + c;
+                        if (gcol >= N) continue;
+                        float v = Cs[rr * CS_LD + c];
+                        if (ep.mode == TC_EPI_DGRAD_ACT) {
+                            v = tc_dact<ACT>(v, yv[q][i]);
+                            Cs[rr * CS_LD + c] = v;
+                        }
+                        if (ep.out_f32) {
+                            float *dst = ep.out_f32 + (long long)grow * ep.ld_f32 + gcol;
+                            if (ep.mode == TC_EPI_ATOMIC) atomicAdd(dst, v);
+                            else *dst = v;
+                        }
+                        if (ep.out_bf16)
+                            ep.out_bf16[(long long)grow * ep.ld_bf16 + gcol] = __float2bfloat16_rn(v);
                     }
-                    if (ep.out_f32) {
-                        float *dst = ep.out_f32 + (long long)grow * ep.ld_f32 + gcol;
-                        if (ep.mode == TC_EPI_ATOMIC) atomicAdd(dst, v);
-                        else *dst = v;
-                    }
-                    if (ep.out_bf16)
-                        ep.out_bf16[(long long)grow * ep.ld_bf16 + gcol] = __float2bfloat16_rn(v);
                 }
             }
             if (ep.outT_bf16 || ep.db) {
@@ -413,13 +433,14 @@ static int make_map(CUtensorMap *map, const void *ptr, long long rows, long long
     return ABN_OK;
 }
 
-template <int BN>
+template <int BN, int ACT>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, int M, int N, int K, int split_k,
                      const TcEpilogue &ep, cudaStream_t st) {
     constexpr unsigned smem = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, ACT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return set_error(ABN_EIO, "tc_gemm: cannot reserve %u bytes of shared memory", smem);
         configured = true;
@@ -430,7 +451,7 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, int M, int N,
     const int per = (total_kb + split_k - 1) / split_k;
     split_k = (total_kb + per - 1) / per;
     dim3 grid((N + BN - 1) / BN, (M + TC_BM - 1) / TC_BM, split_k);
-    tc_gemm_kernel<BN><<<grid, TC_THREADS, smem, st>>>(ma, mb, M, N, K, per, ep);
+    tc_gemm_kernel<BN, ACT><<<grid, TC_THREADS, smem, st>>>(ma, mb, M, N, K, per, ep);
     return check_launch("abn_gemm_bf16_tn");
 }
 
@@ -463,8 +484,15 @@ extern "C" int abn_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64
     ep.outT_bf16 = static_cast<__nv_bfloat16 *>(outT_bf16); ep.ld_T = ld_T;
     ep.yprev = static_cast<const __nv_bfloat16 *>(yprev); ep.ld_yprev = ld_yprev; ep.db = db;
     cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64) return launch_tc<64>(ma, mb, M, N, K, split_k, ep, st);
-    return launch_tc<128>(ma, mb, M, N, K, split_k, ep, st);
+    const int a = (epilogue == TC_EPI_BIAS_ACT || epilogue == TC_EPI_DGRAD_ACT) ? act : 0;
+#define ABN_TC(BN_, ACT_) return launch_tc<BN_, ACT_>(ma, mb, M, N, K, split_k, ep, st)
+    if (bn == 64) {
+        switch (a) { case 1: ABN_TC(64, 1); case 2: ABN_TC(64, 2); case 3: ABN_TC(64, 3);
+                     default: ABN_TC(64, 0); }
+    }
+    switch (a) { case 1: ABN_TC(128, 1); case 2: ABN_TC(128, 2); case 3: ABN_TC(128, 3);
+                 default: ABN_TC(128, 0); }
+#undef ABN_TC
 }
 
 extern "C" int abn_cast_bf16(const float *src, int64_t rows, int cols, int64_t ld_src, void *dst,
