@@ -52,6 +52,7 @@ struct AlignArgs {
     double *cost; uint8_t *valid;
     const int64_t *dist_off; float *dist_out;      // distance-only mode when dist_out != null
     const int32_t *order; const int32_t *class_off;
+    int stack;     // 0: generic rows; S > 1: rows are S-frame stacks of dim/S-wide frames
 };
 
 __host__ __device__ constexpr unsigned a16(unsigned x) { return (x + 15u) & ~15u; }
@@ -111,6 +112,13 @@ __device__ __forceinline__ float row_sumsq(unsigned row_addr, int kc4) {
         acc = fmaf(v.w, v.w, acc);
     }
     return acc;
+}
+
+// utils.py:47-58 for one cell, in float32: zero-norm rules, divide, arccos / pi
+__device__ __forceinline__ float cell_distance(float dot, float xn, float yn) {
+    if (xn == 0.f || yn == 0.f) return (xn == 0.f && yn == 0.f) ? 0.f : 1.f;
+    const float cs = __fdiv_rn(dot, __fmul_rn(xn, yn));
+    return __fdiv_rn(acosf(cs), PI_F);
 }
 
 // ------------------------------------------------------- distance (kernel 1)
@@ -217,13 +225,7 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const float *
             const int j = tj + 8 * c;
             if (j >= n2) continue;
             const float yn = norms[L::ROWS_A + j];
-            float d;
-            if (xn == 0.f || yn == 0.f) {
-                d = (xn == 0.f && yn == 0.f) ? 0.f : 1.f;
-            } else {
-                const float cs = __fdiv_rn(tot[r][c], __fmul_rn(xn, yn));
-                d = __fdiv_rn(acosf(cs), PI_F);
-            }
+            const float d = cell_distance(tot[r][c], xn, yn);
             if (!(d >= 0.f)) bad = 1;
             if (dist_gmem) dist_gmem[(size_t)i * ld_gmem + j] = d;
             else Ds[i * L::LDD + j] = d;
@@ -352,14 +354,226 @@ align_class_kernel(const AlignArgs a) {
     }
 }
 
+
+// --------------------------------------- stacked-feature fast path
+// When the table is an S = 7 frame stack of 40-wide frames (abnet3/features.py:135-159:
+// row t = [x[t-3] .. x[t+3]], zeros outside the file), the 280-long dot product of
+// rows i and j is a 7-tap DIAGONAL sum of 40-long dot products of un-stacked frames:
+//     <row_i, row_j> = sum_{c=0..6} <x[i+c-3], y[j+c-3]> = sum_c G40[i+c][j+c]
+// over the token's n + 6 "extended" frames, which all live inside the token's own
+// rows (middle block of every row, left blocks of the first row, right blocks of the
+// last one).  The generic kernel accumulates per 40-wide chunk in exactly this order,
+// so this path returns the SAME BITS with 7x fewer FMAs and 6-7x fewer bytes read.
+// The caller vouches for the structure (abn_stack_violations checks a table).
+constexpr int STACK_S = 7, STACK_H = STACK_S / 2, STACK_F = KC;
+constexpr int STACK_MAXN = NM_SHORT - 2 * STACK_H;       // 90: longest token of this path
+
+template <int RA, int NCG>      // extended sizes: 16 RA >= n1 + 6, 16 NCG >= n2 + 6
+struct StackLayout {
+    static constexpr int ROWS_A = 16 * RA, ROWS_B = 16 * NCG;
+    static constexpr int LDG = ROWS_B + 4;   // = 4 or 20 (mod 32): the diagonal reads are conflict-free
+    static constexpr int LDD = ROWS_B + 2;
+    static constexpr unsigned STAGE_BYTES = (ROWS_A + ROWS_B) * KCP * 4u;
+    static constexpr unsigned DIRS_OFF = a16(ROWS_A * LDD * 4u);
+    static constexpr unsigned ALIAS_END = DIRS_OFF + ROWS_A * ROWS_B;
+    static constexpr unsigned REGION0 = STAGE_BYTES > ALIAS_END ? STAGE_BYTES : ALIAS_END;
+    static constexpr unsigned G_OFF = a16(REGION0);
+    static constexpr unsigned N40_OFF = a16(G_OFF + ROWS_A * LDG * 4u);
+    static constexpr unsigned NORMS_OFF = N40_OFF + (ROWS_A + ROWS_B) * 4u;
+    static constexpr unsigned PATH_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
+    static constexpr unsigned MISC_OFF = a16(PATH_OFF + 2u * (ROWS_A + ROWS_B));
+    static constexpr unsigned TOTAL = MISC_OFF + 32u;
+};
+
+// extended frame e (0 .. n+5) of a token whose first row is `base`: where its 40 floats live
+__device__ __forceinline__ const float *ext_frame(const float *base, int n, int dim, int e) {
+    const int row = e < STACK_H ? 0 : (e < n + STACK_H ? e - STACK_H : n - 1);
+    const int blk = e < STACK_H ? e : (e < n + STACK_H ? STACK_H : e - n + 1);
+    return base + (size_t)row * dim + blk * STACK_F;
+}
+
+template <int RA, int NCG>
+__global__ void __launch_bounds__(AL_THREADS)
+align_stack_kernel(const AlignArgs a) {
+    using L = StackLayout<RA, NCG>;
+    constexpr int CLS = (RA - 1) * NCLS_SIDE + (NCG - 1);
+    constexpr int G = (16 * RA - 2 * STACK_H + 31) / 32;      // DTW rows per lane
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ti = (warp >> 1) * 8 + (lane >> 2);
+    const int tj = (warp & 1) * 4 + (lane & 3);
+    const int beg = a.class_off[CLS], end = a.class_off[CLS + 1];
+    const unsigned sbase = smem_u32(smem);
+    float *Ds = reinterpret_cast<float *>(smem);
+    uint8_t *dirs = smem + L::DIRS_OFF;
+    float *Gs = reinterpret_cast<float *>(smem + L::G_OFF);
+    float *n40 = reinterpret_cast<float *>(smem + L::N40_OFF);
+    float *norms = reinterpret_cast<float *>(smem + L::NORMS_OFF);
+    uint8_t *pb_i = smem + L::PATH_OFF;
+    uint8_t *pb_j = pb_i + (L::ROWS_A + L::ROWS_B);
+    int *misc = reinterpret_cast<int *>(smem + L::MISC_OFF);
+
+    for (int it = beg + blockIdx.x; it < end; it += gridDim.x) {
+        const int p = a.order[it];
+        const int4 tk = reinterpret_cast<const int4 *>(a.pair_tok)[p];
+        const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
+        const int n1e = n1 + 2 * STACK_H, n2e = n2 + 2 * STACK_H;
+        const float *g1 = a.feat + (size_t)s1 * a.dim, *g2 = a.feat + (size_t)s2 * a.dim;
+
+        // 1. stage the extended frames of both tokens (160 contiguous bytes each)
+        {
+            const int piece = tid & 15, r0 = tid >> 4;
+            if (piece < STACK_F / 4) {
+                for (int e = r0; e < n1e; e += AL_THREADS / 16)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
+                                 "r"(sbase + e * (KCP * 4) + piece * 16),
+                                 "l"(ext_frame(g1, n1, a.dim, e) + piece * 4) : "memory");
+                for (int e = r0; e < n2e; e += AL_THREADS / 16)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
+                                 "r"(sbase + (L::ROWS_A + e) * (KCP * 4) + piece * 16),
+                                 "l"(ext_frame(g2, n2, a.dim, e) + piece * 4) : "memory");
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        // 2. per-frame sums of squares and the 40-deep Gram tile G40 (register tiled)
+        {
+            const int nq = n1e + n2e;
+            for (int q = tid; q < nq; q += AL_THREADS) {
+                const int row = q < n1e ? q : L::ROWS_A + (q - n1e);
+                n40[row] = row_sumsq(sbase + row * (KCP * 4), STACK_F / 4);
+            }
+        }
+        float acc[RA][2 * NCG];
+#pragma unroll
+        for (int r = 0; r < RA; ++r)
+#pragma unroll
+            for (int c = 0; c < 2 * NCG; ++c) acc[r][c] = 0.f;
+        {
+            const unsigned a_addr = sbase + ti * (KCP * 4);
+            const unsigned b_addr = sbase + (L::ROWS_A + tj) * (KCP * 4);
+#pragma unroll 2
+            for (int k4 = 0; k4 < STACK_F / 4; ++k4) {
+                float4 av[RA];
+#pragma unroll
+                for (int r = 0; r < RA; ++r) av[r] = lds128(a_addr + (16 * r) * (KCP * 4) + k4 * 16);
+#pragma unroll
+                for (int cg = 0; cg < NCG; ++cg) {
+                    float4 bv[2];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        bv[c] = lds128(b_addr + (8 * (2 * cg + c)) * (KCP * 4) + k4 * 16);
+#pragma unroll
+                    for (int r = 0; r < RA; ++r)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            float t = acc[r][2 * cg + c];
+                            t = fmaf(av[r].x, bv[c].x, t);
+                            t = fmaf(av[r].y, bv[c].y, t);
+                            t = fmaf(av[r].z, bv[c].z, t);
+                            t = fmaf(av[r].w, bv[c].w, t);
+                            acc[r][2 * cg + c] = t;
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RA; ++r)
+#pragma unroll
+            for (int c = 0; c < 2 * NCG; ++c) Gs[(ti + 16 * r) * L::LDG + tj + 8 * c] = acc[r][c];
+        __syncthreads();           // G40, n40 complete; the staging area is dead from here on
+
+        // 3. row norms: |row_i|^2 = sum_c |x[i+c-3]|^2, same summation order as the generic kernel
+        for (int q = tid; q < n1 + n2; q += AL_THREADS) {
+            const int r0 = q < n1 ? q : L::ROWS_A + (q - n1);
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < STACK_S; ++c) ss += n40[r0 + c];
+            norms[q < n1 ? q : L::ROWS_A + (q - n1)] = sqrtf(ss);
+        }
+        __syncthreads();
+
+        // 4. 7-tap diagonal sum + epilogue -> D (over the dead staging area)
+        int bad = 0;
+        float *dist_gmem = a.dist_out ? a.dist_out + a.dist_off[p] : nullptr;
+#pragma unroll
+        for (int r = 0; r < RA; ++r) {
+            const int i = ti + 16 * r;
+            if (i >= n1) continue;
+            const float xn = norms[i];
+#pragma unroll
+            for (int c = 0; c < 2 * NCG; ++c) {
+                const int j = tj + 8 * c;
+                if (j >= n2) continue;
+                const float *gp = Gs + i * L::LDG + j;
+                float tot = 0.f;
+#pragma unroll
+                for (int d = 0; d < STACK_S; ++d) tot += gp[d * (L::LDG + 1)];
+                const float dd = cell_distance(tot, xn, norms[L::ROWS_A + j]);
+                if (!(dd >= 0.f)) bad = 1;
+                if (dist_gmem) dist_gmem[(size_t)i * n2 + j] = dd;
+                else Ds[i * L::LDD + j] = dd;
+            }
+        }
+        bad = __syncthreads_or(bad);
+        if (a.dist_out) {
+            if (tid == 0) a.valid[p] = bad ? 0 : 1;
+            continue;
+        }
+        if (bad) {
+            if (tid == 0) { a.path_len[p] = 0; a.cost[p] = nan(""); a.valid[p] = 0; }
+            continue;
+        }
+        if (tid < 32) {
+            const double cst = dtw_wavefront<float, G>(Ds, L::LDD, dirs, L::ROWS_B, n1, n2, tid);
+            __syncwarp();
+            if (tid == 0) {
+                const int len = traceback(dirs, L::ROWS_B, n1, n2, pb_i, pb_j);
+                misc[0] = len;
+                a.path_len[p] = len;
+                a.cost[p] = cst;
+                a.valid[p] = 1;
+            }
+        }
+        __syncthreads();
+        const int len = misc[0];
+        const int64_t off = a.path_off[p];
+        for (int k = tid; k < len; k += AL_THREADS) {
+            a.idx1[off + k] = s1 + (int)pb_i[len - 1 - k];
+            a.idx2[off + k] = s2 + (int)pb_j[len - 1 - k];
+        }
+        __syncthreads();
+    }
+}
+
+// rows r, r+1 of one file must overlap by dim - dim/S columns; counts the rows that do not
+__global__ void stack_violations_kernel(const float *__restrict__ feat, int64_t n_rows, int dim,
+                                        int stack, const uint8_t *__restrict__ last_row_of_file,
+                                        unsigned long long *__restrict__ count) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (r + 1 >= n_rows || (last_row_of_file && last_row_of_file[r])) return;
+    const int lane = threadIdx.x & 31, f = dim / stack;
+    const float *a = feat + (size_t)r * dim + f, *b = feat + (size_t)(r + 1) * dim;
+    int bad = 0;
+    for (int k = lane; k < dim - f; k += 32)
+        bad |= a[k] != b[k];      // value compare: +0 == -0; a NaN is a violation
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0 && bad) atomicAdd(count, 1ull);
+}
+
 // ------------------------------------------------------- size-class bucketing
-__device__ __forceinline__ int pair_class(const int4 tk, int64_t n_rows) {
+__device__ __forceinline__ int pair_class(const int4 tk, int64_t n_rows, int stack) {
     const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
     const bool ok = n1 > 0 && n2 > 0 && n1 <= NM_LIMIT && n2 <= NM_LIMIT && s1 >= 0 && s2 >= 0 &&
                     (int64_t)s1 + n1 <= n_rows && (int64_t)s2 + n2 <= n_rows;
     if (!ok) return CLS_INVALID;
-    if (n1 > NM_SHORT || n2 > NM_SHORT) return CLS_LONG;
-    return ((n1 + 15) / 16 - 1) * NCLS_SIDE + ((n2 + 15) / 16 - 1);
+    const int ext = stack ? 2 * STACK_H : 0;      // stack mode classes are on n + 6
+    if (n1 + ext > NM_SHORT || n2 + ext > NM_SHORT) return CLS_LONG;
+    return ((n1 + ext + 15) / 16 - 1) * NCLS_SIDE + ((n2 + ext + 15) / 16 - 1);
 }
 
 constexpr int BK_THREADS = 256, BK_ITEMS = 4;
@@ -374,7 +588,8 @@ class_count_kernel(const AlignArgs a, int *__restrict__ counts) {
     for (int u = 0; u < BK_ITEMS; ++u) {
         const int p = base + u * BK_THREADS + threadIdx.x;
         if (p < a.n_pairs) {
-            const int c = pair_class(reinterpret_cast<const int4 *>(a.pair_tok)[p], a.n_rows);
+            const int c = pair_class(reinterpret_cast<const int4 *>(a.pair_tok)[p], a.n_rows,
+                                     a.stack);
             atomicAdd(&hist[c], 1);
             if (c == CLS_INVALID) {   // dataloader.py:184 / :188-191: the pair is skipped
                 a.valid[p] = 0;
@@ -409,7 +624,7 @@ class_scatter_kernel(const AlignArgs a, const int *__restrict__ class_off,
         cls[u] = -1;
         rank[u] = 0;
         if (p < a.n_pairs) {
-            cls[u] = pair_class(reinterpret_cast<const int4 *>(a.pair_tok)[p], a.n_rows);
+            cls[u] = pair_class(reinterpret_cast<const int4 *>(a.pair_tok)[p], a.n_rows, a.stack);
             rank[u] = atomicAdd(&hist[cls[u]], 1);
         }
     }
@@ -754,55 +969,63 @@ struct ClassLaunch {
     int grid;      // resident CTAs on the whole device (persistent launch)
 };
 
-template <int RA, int NCG>
-static int prepare_class(ClassLaunch &cl, int sm_count) {
-    using L = ClassLayout<RA, NCG>;
-    cl.kernel = align_class_kernel<RA, NCG>;
-    cl.smem = L::TOTAL;
-    if (cudaFuncSetAttribute(align_class_kernel<RA, NCG>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)L::TOTAL) != cudaSuccess)
-        return set_error(ABN_EIO, "cudaFuncSetAttribute(smem=%u) failed for class %d,%d", L::TOTAL,
-                         RA, NCG);
+static int prepare_kernel(ClassLaunch &cl, void (*kernel)(const AlignArgs), unsigned smem,
+                          int sm_count, const char *what, int ra, int ncg) {
+    cl.kernel = kernel;
+    cl.smem = smem;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+        return set_error(ABN_EIO, "cudaFuncSetAttribute(smem=%u) failed for %s class %d,%d", smem,
+                         what, ra, ncg);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_class_kernel<RA, NCG>,
-                                                      AL_THREADS, L::TOTAL) != cudaSuccess ||
-        per_sm < 1)
-        return set_error(ABN_EIO, "occupancy query failed for class %d,%d", RA, NCG);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, AL_THREADS, smem) !=
+            cudaSuccess || per_sm < 1)
+        return set_error(ABN_EIO, "occupancy query failed for %s class %d,%d", what, ra, ncg);
     cl.grid = per_sm * sm_count;
     return ABN_OK;
 }
 
+template <int RA, int NCG>
+static int prepare_class(ClassLaunch *generic, ClassLaunch *stacked, int sm_count) {
+    constexpr int idx = (RA - 1) * NCLS_SIDE + (NCG - 1);
+    if (int rc = prepare_kernel(generic[idx], align_class_kernel<RA, NCG>,
+                                ClassLayout<RA, NCG>::TOTAL, sm_count, "generic", RA, NCG))
+        return rc;
+    return prepare_kernel(stacked[idx], align_stack_kernel<RA, NCG>, StackLayout<RA, NCG>::TOTAL,
+                          sm_count, "stacked", RA, NCG);
+}
+
 template <int RA>
-static int prepare_row(ClassLaunch *tab, int sm_count) {
+static int prepare_row(ClassLaunch *g, ClassLaunch *s, int sm_count) {
     int rc = ABN_OK;
-    if (!rc) rc = prepare_class<RA, 1>(tab[(RA - 1) * NCLS_SIDE + 0], sm_count);
-    if (!rc) rc = prepare_class<RA, 2>(tab[(RA - 1) * NCLS_SIDE + 1], sm_count);
-    if (!rc) rc = prepare_class<RA, 3>(tab[(RA - 1) * NCLS_SIDE + 2], sm_count);
-    if (!rc) rc = prepare_class<RA, 4>(tab[(RA - 1) * NCLS_SIDE + 3], sm_count);
-    if (!rc) rc = prepare_class<RA, 5>(tab[(RA - 1) * NCLS_SIDE + 4], sm_count);
-    if (!rc) rc = prepare_class<RA, 6>(tab[(RA - 1) * NCLS_SIDE + 5], sm_count);
+    if (!rc) rc = prepare_class<RA, 1>(g, s, sm_count);
+    if (!rc) rc = prepare_class<RA, 2>(g, s, sm_count);
+    if (!rc) rc = prepare_class<RA, 3>(g, s, sm_count);
+    if (!rc) rc = prepare_class<RA, 4>(g, s, sm_count);
+    if (!rc) rc = prepare_class<RA, 5>(g, s, sm_count);
+    if (!rc) rc = prepare_class<RA, 6>(g, s, sm_count);
     return rc;
 }
 
-static int class_table(const ClassLaunch **out) {
-    static ClassLaunch tab[NCLS];
+static int class_table(const ClassLaunch **generic, const ClassLaunch **stacked) {
+    static ClassLaunch gtab[NCLS], stab[NCLS];
     static int state = 0;        // 0 = not built, 1 = ok  (one device per process)
     if (state == 0) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         int rc = ABN_OK;
-        if (!rc) rc = prepare_row<1>(tab, sms);
-        if (!rc) rc = prepare_row<2>(tab, sms);
-        if (!rc) rc = prepare_row<3>(tab, sms);
-        if (!rc) rc = prepare_row<4>(tab, sms);
-        if (!rc) rc = prepare_row<5>(tab, sms);
-        if (!rc) rc = prepare_row<6>(tab, sms);
+        if (!rc) rc = prepare_row<1>(gtab, stab, sms);
+        if (!rc) rc = prepare_row<2>(gtab, stab, sms);
+        if (!rc) rc = prepare_row<3>(gtab, stab, sms);
+        if (!rc) rc = prepare_row<4>(gtab, stab, sms);
+        if (!rc) rc = prepare_row<5>(gtab, stab, sms);
+        if (!rc) rc = prepare_row<6>(gtab, stab, sms);
         if (rc) return rc;
         state = 1;
     }
-    *out = tab;
+    *generic = gtab;
+    *stacked = stab;
     return ABN_OK;
 }
 
@@ -815,8 +1038,14 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
     if (!workspace || workspace_bytes < need)
         return set_error(ABN_ENOMEM, "%s: workspace of %zu bytes needed, %zu given", who, need,
                          workspace_bytes);
-    const ClassLaunch *tab = nullptr;
-    if (int rc = class_table(&tab)) return rc;
+    if (a.stack != 0 && (a.stack != STACK_S || a.dim != STACK_S * STACK_F))
+        return set_error(ABN_EINVAL, "%s: the stacked fast path needs stack == %d and dim == %d "
+                         "(got stack %d, dim %d); pass stack = 0 for the generic kernels", who,
+                         STACK_S, STACK_S * STACK_F, a.stack, a.dim);
+    const ClassLaunch *gtab = nullptr, *stab = nullptr;
+    if (int rc = class_table(&gtab, &stab)) return rc;
+    const ClassLaunch *tab = a.stack ? stab : gtab;
+    const int ext = a.stack ? 2 * STACK_H : 0;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     int *counts = reinterpret_cast<int *>(ws + WS_COUNTS);
     int *class_off = reinterpret_cast<int *>(ws + WS_OFF);
@@ -830,7 +1059,7 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
     class_count_kernel<<<blocks, BK_THREADS, 0, st>>>(a, counts);
     class_scan_kernel<<<1, 32, 0, st>>>(counts, class_off);
     class_scatter_kernel<<<blocks, BK_THREADS, 0, st>>>(a, class_off, cursor, order);
-    if (max_frames > NM_SHORT) {
+    if (max_frames + ext > NM_SHORT) {
         static int long_grid = 0;
         const int nmax = max_frames;
         const LongLayout LL = long_layout(nmax);
@@ -846,7 +1075,7 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
         const int grid = long_grid < a.n_pairs ? long_grid : a.n_pairs;
         align_long_kernel<<<grid, AL_THREADS, LL.total, st>>>(a, nmax);
     }
-    const int side = ((max_frames < NM_SHORT ? max_frames : NM_SHORT) + 15) / 16;
+    const int side = ((max_frames + ext < NM_SHORT ? max_frames + ext : NM_SHORT) + 15) / 16;
     // large classes first: their pairs take longest, the small ones fill the tail
     for (int ra = side; ra >= 1; --ra)
         for (int ncg = side; ncg >= 1; --ncg) {
@@ -867,7 +1096,7 @@ extern "C" size_t abn_align_workspace_bytes(int n_pairs) {
 }
 
 extern "C" int abn_align_pairs(const float *feat, int64_t n_rows, int dim,
-                               const int32_t *pair_tok, int n_pairs, int max_frames,
+                               const int32_t *pair_tok, int n_pairs, int max_frames, int stack,
                                const int64_t *path_off, int32_t *idx1, int32_t *idx2,
                                int32_t *path_len, double *cost, uint8_t *valid, void *workspace,
                                size_t workspace_bytes, abn_stream_t stream) {
@@ -879,13 +1108,13 @@ extern "C" int abn_align_pairs(const float *feat, int64_t n_rows, int dim,
     AlignArgs a{};
     a.feat = feat; a.n_rows = n_rows; a.dim = dim; a.pair_tok = pair_tok; a.n_pairs = n_pairs;
     a.path_off = path_off; a.idx1 = idx1; a.idx2 = idx2; a.path_len = path_len; a.cost = cost;
-    a.valid = valid; a.dist_off = nullptr; a.dist_out = nullptr;
+    a.valid = valid; a.dist_off = nullptr; a.dist_out = nullptr; a.stack = stack;
     return run_align(a, max_frames, workspace, workspace_bytes, (cudaStream_t)stream,
                      "abn_align_pairs");
 }
 
 extern "C" int abn_cosine_distance(const float *feat, int64_t n_rows, int dim,
-                                   const int32_t *pair_tok, int n_pairs, int max_frames,
+                                   const int32_t *pair_tok, int n_pairs, int max_frames, int stack,
                                    const int64_t *dist_off, float *dist, uint8_t *valid,
                                    void *workspace, size_t workspace_bytes, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
@@ -894,9 +1123,23 @@ extern "C" int abn_cosine_distance(const float *feat, int64_t n_rows, int dim,
         return set_error(ABN_EINVAL, "abn_cosine_distance: bad argument");
     AlignArgs a{};
     a.feat = feat; a.n_rows = n_rows; a.dim = dim; a.pair_tok = pair_tok; a.n_pairs = n_pairs;
-    a.valid = valid; a.dist_off = dist_off; a.dist_out = dist;
+    a.valid = valid; a.dist_off = dist_off; a.dist_out = dist; a.stack = stack;
     return run_align(a, max_frames, workspace, workspace_bytes, (cudaStream_t)stream,
                      "abn_cosine_distance");
+}
+
+extern "C" int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int stack,
+                                    const uint8_t *last_row_of_file, unsigned long long *count,
+                                    abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (!feat || !count || n_rows < 0 || dim <= 0 || stack < 2 || dim % stack)
+        return set_error(ABN_EINVAL, "abn_stack_violations: bad argument");
+    if (n_rows < 2) return ABN_OK;
+    const int wpb = 8;
+    stack_violations_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0,
+                              (cudaStream_t)stream>>>(feat, n_rows, dim, stack, last_row_of_file,
+                                                      count);
+    return check_launch("abn_stack_violations");
 }
 
 extern "C" int abn_dtw_from_dist(const double *dist, const int64_t *dist_off, const int32_t *shape,

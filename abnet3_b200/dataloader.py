@@ -54,7 +54,7 @@ class _Aligned(object):
     idx1[off[p]:off[p+1]] / idx2[...]; valid[p] tells whether the reference
     would have kept the pair."""
 
-    def __init__(self, tok, feat, max_frames):
+    def __init__(self, tok, feat, max_frames, stack=0):
         self.tok = tok
         P = tok.shape[0]
         if P == 0:
@@ -63,7 +63,7 @@ class _Aligned(object):
             self.valid = np.zeros(0, bool)
             return
         tok_d = torch.from_numpy(tok).to(feat.device)
-        res = ops.align_pairs(feat, tok_d, max_frames=max_frames)
+        res = ops.align_pairs(feat, tok_d, max_frames=max_frames, stack=stack)
         d1, d2, doff = ops.compact_paths(res)
         self.idx1, self.idx2 = d1.cpu().numpy(), d2.cpu().numpy()
         self.off = doff.cpu().numpy()
@@ -192,7 +192,7 @@ class OriginalDataLoader(DataLoader):
 
     def _align(self, tok):
         longest = int(tok[:, [1, 3]].max()) if len(tok) else 1
-        return _Aligned(tok, self.table.feat, max(longest, 1))
+        return _Aligned(tok, self.table.feat, max(longest, 1), stack=self.table.stack)
 
     # ------------------------------------------------------------- batching
     def _assemble(self, same_plist, same_tok, same_al, same_ids, diff_plist, diff_tok,

@@ -43,7 +43,7 @@ def _workspace(n_pairs, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
-def align_pairs(feat, pair_tok, max_frames=None):
+def align_pairs(feat, pair_tok, max_frames=None, stack=0):
     """Fused cosine distance + DTW + traceback for every pair
     (abnet3/utils.py:147-153 per pair).  Returns an AlignResult whose idx1/idx2
     hold GLOBAL feature rows in per-pair slots of capacity n1+n2-1 starting at
@@ -65,13 +65,13 @@ def align_pairs(feat, pair_tok, max_frames=None):
     valid = torch.zeros(P, dtype=torch.uint8, device=dev)
     ws, ws_bytes = _workspace(P, dev)
     check(_lib.lib().abn_align_pairs(
-        ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1),
+        ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1), int(stack),
         ptr(path_off), ptr(idx1), ptr(idx2), ptr(path_len), ptr(cost), ptr(valid),
         ptr(ws), ws_bytes, stream_ptr()))
     return AlignResult(idx1, idx2, path_off, path_len, cost, valid)
 
 
-def cosine_distance(feat, pair_tok, max_frames=None):
+def cosine_distance(feat, pair_tok, max_frames=None, stack=0):
     """Batched abnet3/utils.py:40-60.  Returns (dist float32 flat, dist_off, valid)."""
     _req(feat, torch.float32, "feat")
     _req(pair_tok, torch.int32, "pair_tok")
@@ -86,9 +86,21 @@ def cosine_distance(feat, pair_tok, max_frames=None):
     valid = torch.zeros(P, dtype=torch.uint8, device=dev)
     ws, ws_bytes = _workspace(P, dev)
     check(_lib.lib().abn_cosine_distance(
-        ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1),
+        ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1), int(stack),
         ptr(dist_off), ptr(dist), ptr(valid), ptr(ws), ws_bytes, stream_ptr()))
     return dist, dist_off, valid
+
+
+def stack_violations(feat, stack=7, last_row_of_file=None):
+    """Number of rows whose overlap with the next row breaks the S-frame stack
+    structure (0 = the table qualifies for the stacked fast path)."""
+    _req(feat, torch.float32, "feat")
+    if last_row_of_file is not None:
+        _req(last_row_of_file, torch.uint8, "last_row_of_file")
+    count = torch.zeros(1, dtype=torch.int64, device=feat.device)
+    check(_lib.lib().abn_stack_violations(ptr(feat), feat.shape[0], feat.shape[1], int(stack),
+                                          ptr(last_row_of_file), ptr(count), stream_ptr()))
+    return int(count.item())
 
 
 def dtw_from_dist(dist, dist_off, shape, max_frames=None):

@@ -39,7 +39,9 @@ def stack_frames(frames, file_id, nframes=7):
         ok = (src >= 0) & (src < T)
         srcc = src.clamp(0, T - 1)
         ok &= file_id[srcc] == file_id
-        out[:, k * dim:(k + 1) * dim] = frames[srcc] * ok.unsqueeze(1).to(frames.dtype)
+        out[:, k * dim:(k + 1) * dim] = torch.where(ok.unsqueeze(1), frames[srcc],
+                                                    torch.zeros((), dtype=frames.dtype,
+                                                                device=frames.device))
     return out
 
 

@@ -96,9 +96,10 @@ class BatchAligner(object):
     synchronises.  The returned AlignResult aliases the internal buffers and
     is valid until the next ``align``."""
 
-    def __init__(self, feat, max_pairs=0, max_frames=ops.MAX_TOKEN_FRAMES):
+    def __init__(self, feat, max_pairs=0, max_frames=ops.MAX_TOKEN_FRAMES, stack=0):
         self.feat = feat
         self.max_frames = int(max_frames)
+        self.stack = int(stack)      # 7: the table is a verified 7x40 stack (fast path)
         self._cap_pairs = 0
         self._cap_rows = 0
         self._off_key = None
@@ -134,7 +135,7 @@ class BatchAligner(object):
         self._reserve(P, max(total, 1))
         _lib.check(_lib.lib().abn_align_pairs(
             _lib.ptr(self.feat), self.feat.shape[0], self.feat.shape[1], _lib.ptr(pair_tok), P,
-            self.max_frames, _lib.ptr(off), _lib.ptr(self.idx1), _lib.ptr(self.idx2),
+            self.max_frames, self.stack, _lib.ptr(off), _lib.ptr(self.idx1), _lib.ptr(self.idx2),
             _lib.ptr(self.path_len), _lib.ptr(self.cost), _lib.ptr(self.valid),
             _lib.ptr(self._ws), self._ws_bytes, _lib.stream_ptr()))
         return ops.AlignResult(self.idx1, self.idx2, off, self.path_len[:P], self.cost[:P],
@@ -202,6 +203,20 @@ class FeatureTable(object):
         self.host = host
         self.device = device if device is not None else _device()
         self.feat = torch.from_numpy(host).to(self.device)
+        self.stack = 0
+        if self.feat.is_cuda:
+            self.stack = self._detect_stack()
+
+    def _detect_stack(self, stack=7):
+        """7 when every file is a 7-frame stack of dim/7-wide frames
+        (abnet3/features.py:135-159), checked row by row on the device; the
+        alignment kernels then take their stacked fast path (same results)."""
+        if self.dim != 280 or self.feat.shape[0] < 2:
+            return 0
+        last = torch.zeros(self.feat.shape[0], dtype=torch.uint8, device=self.device)
+        ends = [self.row0[f] + self.nrows[f] - 1 for f in self.files if self.nrows[f] > 0]
+        last[torch.tensor(ends, dtype=torch.int64, device=self.device)] = 1
+        return stack if ops.stack_violations(self.feat, stack, last) == 0 else 0
 
     def _key(self, f):
         if f in self.row0:

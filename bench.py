@@ -342,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
     max_frames = int(pairs[:, [1, 3]].max().item())
     torch.cuda.synchronize()
 
-    aligner = utils.BatchAligner(feat, max_pairs=P, max_frames=max_frames)
+    aligner = utils.BatchAligner(feat, max_pairs=P, max_frames=max_frames, stack=0)
     stream = torch.cuda.current_stream()
 
     def step():

@@ -64,6 +64,20 @@ ABN_API const char *abn_last_error(void);
 ABN_API int abn_device_info(int *sm_count, int *cc_major, int *cc_minor,
                     size_t *smem_optin_bytes);
 
+/* `stack` argument of abn_align_pairs / abn_cosine_distance.
+ * 0: generic kernels, any table.  7: the caller vouches that `feat` (dim 280) is the
+ * 7-frame stack of 40-wide frames abnet3/features.py:135-159 builds -- row t =
+ * [x[t-3] .. x[t+3]], zeros outside the file -- so consecutive rows of a file overlap
+ * by 240 columns.  The kernels then read each 40-wide frame once and rebuild the
+ * 280-long dot products as 7-tap diagonal sums: 7x fewer FLOPs and bytes, and the
+ * SAME BITS as the generic kernels (which accumulate per 40-wide block in that order).
+ * abn_stack_violations counts the rows r (not flagged in last_row_of_file, NULL = none)
+ * whose columns [dim/stack, dim) differ from row r+1's columns [0, dim - dim/stack);
+ * `count` (device, caller-zeroed) == 0 means the table qualifies. */
+ABN_API int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int stack,
+                                 const uint8_t *last_row_of_file, unsigned long long *count,
+                                 abn_stream_t stream);
+
 /* Device workspace abn_align_pairs / abn_cosine_distance need for a call over
  * n_pairs pairs (they bucket the pairs into token-length classes on the device
  * and keep the per-class pair order there). */
@@ -81,7 +95,7 @@ ABN_API size_t abn_align_workspace_bytes(int n_pairs);
  *            (the reference's `assert np.all(d >= 0)`, utils.py:59).
  * ---------------------------------------------------------------------- */
 ABN_API int abn_cosine_distance(const float *feat, int64_t n_rows, int dim,
-                        const int32_t *pair_tok, int n_pairs, int max_frames,
+                        const int32_t *pair_tok, int n_pairs, int max_frames, int stack,
                         const int64_t *dist_off, float *dist, uint8_t *valid,
                         void *workspace, size_t workspace_bytes,
                         abn_stream_t stream);
@@ -115,7 +129,7 @@ ABN_API int abn_dtw_from_dist(const double *dist, const int64_t *dist_off,
  *             (dataloader.py:188-191); then path_len[p] = 0.
  * ---------------------------------------------------------------------- */
 ABN_API int abn_align_pairs(const float *feat, int64_t n_rows, int dim,
-                    const int32_t *pair_tok, int n_pairs, int max_frames,
+                    const int32_t *pair_tok, int n_pairs, int max_frames, int stack,
                     const int64_t *path_off, int32_t *idx1, int32_t *idx2,
                     int32_t *path_len, double *cost, uint8_t *valid,
                     void *workspace, size_t workspace_bytes,

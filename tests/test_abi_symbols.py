@@ -47,7 +47,7 @@ def test_entry_points_refuse_to_run_without_sm100(so_path):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     lib = _lib.lib()
-    rc = lib.abn_align_pairs(None, 0, 280, None, 1, 80, None, None, None, None, None, None,
+    rc = lib.abn_align_pairs(None, 0, 280, None, 1, 80, 0, None, None, None, None, None, None,
                              None, 0, None)
     assert rc == 38          # ABN_ENOSYS: no CPU fallback by design
     assert b"no" in lib.abn_last_error().lower()

@@ -291,3 +291,52 @@ def test_compact_and_gather(small_corpus):
     torch.cuda.synchronize()
     assert torch.equal(x1, feat_d[d1[sel].long()]) and torch.equal(x2, feat_d[d2[sel].long()])
     assert torch.equal(yo, y[sel].float())
+
+
+def test_stacked_fast_path_is_bit_identical_to_generic_kernels():
+    """on a 7x40 stacked table the fast path (40-deep Gram tile + 7-tap
+    diagonal sums) must return the SAME BITS as the generic 280-deep kernels:
+    distances, costs, paths -- including tokens at file edges (zero-padded context)
+    and tokens of 91-96 frames, which the stacked mode routes to the tiled kernel."""
+    c = synth.make_corpus(500, cluster_size=8, tokens_per_file=60, len_range=(1, 96), seed=13)
+    feat_d = c.feat.to(DEV)
+    last = torch.zeros(c.feat.shape[0], dtype=torch.uint8)
+    last[(c.file_off[1:] - 1).long()] = 1
+    assert ops.stack_violations(feat_d, 7, last.to(DEV)) == 0
+    assert ops.stack_violations(feat_d, 7) > 0            # file boundaries break the overlap
+    assert ops.stack_violations(torch.randn(100, 280, device=DEV), 7) == 99
+    pairs = synth.make_same_pairs(c, 600, seed=14)
+    # force file-edge tokens and long tokens into the list
+    starts, lens = c.tok_start, c.tok_len
+    edge = [0, 59, 60, 119, 120, int(lens.numel()) - 1]
+    extra = torch.tensor([[int(starts[a]), int(lens[a]), int(starts[b]), int(lens[b])]
+                          for a, b in zip(edge, reversed(edge))], dtype=torch.int32)
+    longs = torch.nonzero(lens > 90).squeeze(1)[:6]
+    assert longs.numel() >= 2
+    extra2 = torch.tensor([[int(starts[a]), int(lens[a]), int(starts[b]), int(lens[b])]
+                           for a, b in zip(longs.tolist(), reversed(longs.tolist()))],
+                          dtype=torch.int32)
+    pairs = torch.cat([pairs, extra, extra2]).contiguous().to(DEV)
+    g = ops.align_pairs(feat_d, pairs, stack=0)
+    s = ops.align_pairs(feat_d, pairs, stack=7)
+    dg, og, vg = ops.cosine_distance(feat_d, pairs, stack=0)
+    ds, os_, vs = ops.cosine_distance(feat_d, pairs, stack=7)
+    torch.cuda.synchronize()
+    assert torch.equal(vg, vs) and torch.equal(og, os_)
+    assert torch.equal(dg.view(torch.int32), ds.view(torch.int32))          # same bits
+    assert torch.equal(g.valid, s.valid) and torch.equal(g.path_len, s.path_len)
+    assert torch.equal(g.cost.view(torch.int64), s.cost.view(torch.int64))
+    plen, off = g.path_len.cpu().numpy(), g.path_off.cpu().numpy()
+    g1, g2, s1, s2 = (t.cpu().numpy() for t in (g.idx1, g.idx2, s.idx1, s.idx2))
+    for p in range(len(plen)):
+        sl = slice(off[p], off[p] + plen[p])
+        np.testing.assert_array_equal(g1[sl], s1[sl])
+        np.testing.assert_array_equal(g2[sl], s2[sl])
+    assert int(g.valid.sum()) == pairs.shape[0]
+
+
+def test_stacked_mode_refuses_other_shapes():
+    feat = torch.randn(200, 40, device=DEV)
+    pairs = torch.tensor([[0, 30, 50, 40]], dtype=torch.int32, device=DEV)
+    with pytest.raises(Exception):
+        ops.align_pairs(feat, pairs, stack=7)
