@@ -153,12 +153,13 @@ def _pinned_buf(name, numel, dtype):
     return buf[:numel]
 
 
-def align_pairs_host(feat_host, pair_tok_host, max_frames=None):
+def align_pairs_host(feat_host, pair_tok_host, max_frames=None, stack=0):
     """Host buffers in, host results out -- the call a user of the reference's
     dataloader would make for a whole pair list.
 
     ``feat_host`` [n_rows, dim] float32 and ``pair_tok_host`` [P, 4] int32 are
-    (ideally pinned) CPU tensors.  Copies both to the GPU, aligns every pair,
+    (ideally pinned) CPU tensors; ``stack=7`` when the table is a verified 7x40
+    stack (FeatureTable.stack).  Copies both to the GPU, aligns every pair,
     compacts the paths and copies them back.  Returns CPU tensors
     ``(idx1, idx2, pair_off, path_len, cost, valid)``: pair p's aligned global
     rows are ``idx1[pair_off[p]:pair_off[p+1]]`` / ``idx2[...]``."""
@@ -167,7 +168,7 @@ def align_pairs_host(feat_host, pair_tok_host, max_frames=None):
     tok = pair_tok_host.to(dev, non_blocking=True)
     if max_frames is None:
         max_frames = int(pair_tok_host[:, [1, 3]].max().item()) if tok.shape[0] else 1
-    res = ops.align_pairs(feat, tok, max_frames=max_frames)
+    res = ops.align_pairs(feat, tok, max_frames=max_frames, stack=stack)
     d1, d2, doff = ops.compact_paths(res)
     P = tok.shape[0]
     out = (_pinned_buf("idx1", d1.numel(), torch.int32), _pinned_buf("idx2", d2.numel(), torch.int32),

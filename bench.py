@@ -168,11 +168,12 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """dram bytes per launch of the align kernel from the committed ncu capture
-    (profiles/traffic.json, written when a --set full capture is summarised)."""
+    """dram bytes per PAIR of the align kernels from the committed ncu captures
+    (profiles/traffic.json: {"generic": B, "stacked": B}, written when a --set full
+    capture is summarised)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get("align_pairs_kernel_bytes_per_pair")
+            return json.load(fh)
     except Exception:
         return None
 
@@ -342,45 +343,57 @@ def run_ours(args, rank, world, local_rank):
     max_frames = int(pairs[:, [1, 3]].max().item())
     torch.cuda.synchronize()
 
-    aligner = utils.BatchAligner(feat, max_pairs=P, max_frames=max_frames, stack=0)
+    # the product path picks the stacked fast path when the table is a verified 7x40 stack
+    # (FeatureTable does this check at load); both kernel families are timed
+    last = torch.zeros(feat.shape[0], dtype=torch.uint8, device=dev)
+    last[(corpus.file_off[1:] - 1).long()] = 1
+    stack = 7 if ops.stack_violations(feat, 7, last) == 0 else 0
     stream = torch.cuda.current_stream()
 
-    def step():
-        return aligner.align(pairs)
+    def timed(aligner, steps, sample_clocks):
+        for _ in range(max(args.warmup, 3)):
+            aligner.align(pairs)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        if sample_clocks and rank == 0:
+            sampler.start()
+            time.sleep(0.2)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(steps)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        beg.record(stream)
+        for a, b in evs:
+            a.record(stream)
+            r = aligner.align(pairs)
+            b.record(stream)
+        end.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        total_ms = beg.elapsed_time(end)
+        kern = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        clk = sampler.stop(t0, t1) if (sample_clocks and rank == 0) else None
+        tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        return float(tmax.item()), kern, clk, r
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.2)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    beg.record(stream)
-    for a, b in evs:
-        a.record(stream)
-        res = step()
-        b.record(stream)
-    end.record(stream)
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    if world > 1:
-        dist.barrier()
-    total_ms = beg.elapsed_time(end)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-
-    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
+    generic = utils.BatchAligner(feat, max_pairs=P, max_frames=max_frames, stack=0)
+    g_total_ms, g_kern_ms, g_clocks, res = timed(generic, args.steps, stack == 0)
+    if stack:
+        fast = utils.BatchAligner(feat, max_pairs=P, max_frames=max_frames, stack=stack)
+        total_ms_max, kern_ms, clocks, res_fast = timed(fast, args.steps, True)
+        same_bits = bool(torch.equal(res_fast.cost.view(torch.int64), res.cost.view(torch.int64))
+                         and torch.equal(res_fast.path_len, res.path_len))
+    else:
+        total_ms_max, kern_ms, clocks, same_bits = g_total_ms, g_kern_ms, g_clocks, None
     value = world * P * args.steps / (total_ms_max * 1e-3)
+    value_generic = world * P * args.steps / (g_total_ms * 1e-3)
 
     # algorithmic bytes of one launch (DESIGN.md "Roofline"):
     #   4*dim*(n1+n2) token rows read once + 8*L index pairs written + 16 B/pair
@@ -390,6 +403,7 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = 4 * FEAT_DIM * n12 + 8 * L_total + 16 * P
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    achieved_generic = alg_bytes / (g_kern_ms * 1e-3) / 1e9
     traffic_pp = ncu_traffic()
     flops = 2.0 * FEAT_DIM * (pairs[:, 1].double() * pairs[:, 3].double()).sum().item()
 
@@ -402,7 +416,7 @@ def run_ours(args, rank, world, local_rank):
         host_pairs.copy_(pairs)
         torch.cuda.synchronize()
         e_steps = max(2, min(args.steps, 3))
-        hres = utils.align_pairs_host(host_feat, host_pairs, max_frames=max_frames)   # warm-up
+        hres = utils.align_pairs_host(host_feat, host_pairs, max_frames=max_frames, stack=stack)
         h2d = host_feat.numel() * 4 + host_pairs.numel() * 4
         d2h = sum(t.numel() * t.element_size() for t in hres)
         torch.cuda.synchronize()
@@ -410,7 +424,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         tt0 = time.perf_counter()
         for _ in range(e_steps):
-            hres = utils.align_pairs_host(host_feat, host_pairs, max_frames=max_frames)
+            hres = utils.align_pairs_host(host_feat, host_pairs, max_frames=max_frames, stack=stack)
         torch.cuda.synchronize()
         dt = time.perf_counter() - tt0
         tm = torch.tensor([dt], device=dev, dtype=torch.float64)
@@ -419,7 +433,7 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": world * P * e_steps / float(tm.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": e_steps,
-               "call": "abnet3_b200.utils.align_pairs_host(feat_host, pair_tok_host)"}
+               "call": "abnet3_b200.utils.align_pairs_host(feat_host, pair_tok_host, stack=%d)" % stack}
         del host_feat
 
     # ---- C3 leg: siamese training steps on the aligned frame pairs ---------
@@ -460,10 +474,24 @@ def run_ours(args, rank, world, local_rank):
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
-                         "kernel": "align_pairs_kernel", "kernel_ms": kern_ms,
+                         "kernel": ("align_stack_kernel<RA,NCG> (one launch per size class; stacked "
+                                    "fast path, bit-identical to the generic kernels)" if stack else
+                                    "align_class_kernel<RA,NCG> (one launch per size class)"),
+                         "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "traffic": (traffic_pp * P if traffic_pp else None),
-                         "fp32_tflops": flops / (kern_ms * 1e-3) / 1e12},
+                         "algorithmic_bytes_def": "4*280*(n1+n2) + 8*L + 16 per pair: the stacked rows "
+                                                  "the API is handed, read once (SURVEY 8d)",
+                         "traffic": (traffic_pp.get("stacked" if stack else "generic") * P
+                                     if traffic_pp else None),
+                         "note": ("the stacked path reads each 40-wide frame once (about 1/6 of the "
+                                  "algorithmic bytes), so frac measures work done per second against "
+                                  "the stacked-bytes roofline, not DRAM traffic" if stack else None),
+                         "generic_kernels": {
+                             "value": value_generic, "kernel_ms": g_kern_ms,
+                             "achieved": achieved_generic, "frac": achieved_generic / peak,
+                             "fp32_tflops": flops / (g_kern_ms * 1e-3) / 1e12,
+                             "traffic": (traffic_pp.get("generic") * P if traffic_pp else None),
+                             "same_bits_as_fast_path": same_bits}},
             "e2e": e2e,
             "train": train,
             "cpu_baseline": cpu,
