@@ -53,7 +53,24 @@ struct AlignArgs {
     const int64_t *dist_off; float *dist_out;      // distance-only mode when dist_out != null
     const int32_t *order; const int32_t *class_off;
     int stack;     // 0: generic rows; S > 1: rows are S-frame stacks of dim/S-wide frames
+    // distance -> DTW hand-over: the pair at sorted position `it` of the window [w0, w1)
+    // keeps its distance matrix at dws + (it - w0) * slot_cells, in skew layout (below)
+    float *dws; int w0, w1, slot_cells;
 };
+
+// Skew layout of an n1 x n2 matrix: anti-diagonal t = i + j holds its cells
+// contiguously, rows ascending, diagonals back to back (n1 * n2 floats, no padding);
+// cell (i, j) lives at skew_base(i + j) + i.  The DTW wavefront reads one diagonal per
+// step, one row per lane: a contiguous, coalesced segment.
+__host__ __device__ __forceinline__ int skew_base(int t, int n1, int n2) {
+    const int m = n1 < n2 ? n1 : n2, mx = n1 < n2 ? n2 : n1, T = n1 + n2 - 1;
+    int off;
+    if (t <= m) off = t * (t + 1) / 2;
+    else if (t <= mx) off = m * (m + 1) / 2 + (t - m) * m;
+    else off = n1 * n2 - (T - t) * (T - t + 1) / 2;
+    const int ilo = t - n2 + 1 > 0 ? t - n2 + 1 : 0;
+    return off - ilo;
+}
 
 __host__ __device__ constexpr unsigned a16(unsigned x) { return (x + 15u) & ~15u; }
 
@@ -69,6 +86,19 @@ struct ClassLayout {
     static constexpr unsigned PATH_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
     static constexpr unsigned MISC_OFF = a16(PATH_OFF + 2u * (ROWS_A + ROWS_B));
     static constexpr unsigned TOTAL = MISC_OFF + 32u;
+};
+
+// class kernels: no row-major D, no DTW state -- the matrix leaves in skew layout
+template <int RA, int NCG>
+struct DistLayout {
+    static constexpr int ROWS_A = 16 * RA, ROWS_B = 16 * NCG;
+    static constexpr int LDD = ROWS_B + 2;
+    static constexpr unsigned STAGE_BYTES = (ROWS_A + ROWS_B) * KCP * 4u;
+    static constexpr unsigned D_BYTES = ROWS_A * ROWS_B * 4u;
+    static constexpr unsigned REGION = 2u * STAGE_BYTES > D_BYTES ? 2u * STAGE_BYTES : D_BYTES;
+    static constexpr unsigned NORMS_OFF = a16(REGION);
+    static constexpr unsigned TB_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
+    static constexpr unsigned TOTAL = TB_OFF + (ROWS_A + ROWS_B) * 4u + 16u;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
@@ -127,11 +157,11 @@ __device__ __forceinline__ float cell_distance(float dot, float xn, float yn) {
 // columns, so every LDS.128 is one conflict-free wavefront with broadcast.
 // Every dot product is the sum over the K chunks of a sequential fp32 FMA
 // chain over the chunk: fixed order, and ~3x tighter than one long chain.
-template <int RA, int NCG>
+template <int RA, int NCG, typename L>
 __device__ __forceinline__ void pair_distance(unsigned char *smem, const float *g1,
                                               const float *g2, int n1, int n2, int dim,
-                                              float *dist_gmem, int ld_gmem, int &bad) {
-    using L = ClassLayout<RA, NCG>;
+                                              float *dist_gmem, int ld_gmem, const int *tb,
+                                              int &bad) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int ti = (warp >> 1) * 8 + (lane >> 2);
@@ -228,9 +258,22 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const float *
             const float d = cell_distance(tot[r][c], xn, yn);
             if (!(d >= 0.f)) bad = 1;
             if (dist_gmem) dist_gmem[(size_t)i * ld_gmem + j] = d;
+            else if (tb) Ds[tb[i + j] + i] = d;
             else Ds[i * L::LDD + j] = d;
         }
     }
+}
+
+// every thread: the pair's skew-base table, and after the matrix is complete its
+// contiguous copy to the hand-over slot (128-bit accesses)
+__device__ __forceinline__ void skew_table(int *tb, int n1, int n2, int tid) {
+    for (int t = tid; t < n1 + n2 - 1; t += AL_THREADS) tb[t] = skew_base(t, n1, n2);
+}
+__device__ __forceinline__ void skew_copy_out(const float *Dsk, float *dst, int cells, int tid) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(Dsk);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    for (int e = tid; e < (cells >> 2); e += AL_THREADS) d4[e] = s4[e];
+    for (int e = (cells & ~3) + tid; e < cells; e += AL_THREADS) dst[e] = Dsk[e];
 }
 
 // ------------------------------------------------------------ DTW (kernel 2)
@@ -299,57 +342,160 @@ __device__ __forceinline__ int traceback(const uint8_t *dirs, int ldr, int n1, i
     return L;
 }
 
+// ------------------------------------------------- DTW kernel (one warp per pair)
+// Reads the skew-layout distance matrix a class kernel left in the hand-over slot:
+// at step t lane l needs cells (G l + g, t - G l - g) = skew_base(t) + G l + g, G
+// coalesced 4-byte loads, prefetched one 4-step block ahead.  Same float64 recurrence
+// and tie order as dtw_wavefront above (C[-1][-1] = 0 replaces the (0,0) special case;
+// out-of-range cells carry +inf instead of being skipped -- no in-range cell ever
+// reads them).  Directions: 2 bits per cell, one byte per (row, 4 steps), in this
+// warp's slice of shared memory; lane 0 walks them back, all lanes write the indices.
+constexpr int DTW_WARPS = 4;
+
+template <int G>
+__global__ void __launch_bounds__(DTW_WARPS * 32)
+dtw_skew_kernel(const AlignArgs a, int cls_beg, int cls_end, int t4_cap) {
+    constexpr int R = 32 * G;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *mine = smem + warp * (t4_cap * R + 8 * t4_cap);
+    uint8_t *dirs = mine;
+    uint8_t *pb_i = mine + t4_cap * R;
+    uint8_t *pb_j = pb_i + 4 * t4_cap;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const float INF_F = __int_as_float(0x7f800000);
+    const int beg = max(a.class_off[cls_beg], a.w0), end = min(a.class_off[cls_end], a.w1);
+    const int i0 = lane * G;
+
+    for (int it = beg + blockIdx.x * DTW_WARPS + warp; it < end; it += gridDim.x * DTW_WARPS) {
+        const int p = a.order[it];
+        if (!a.valid[p]) continue;            // NaN in the matrix: the class kernel dropped the pair
+        const int4 tk = reinterpret_cast<const int4 *>(a.pair_tok)[p];
+        const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
+        const float *__restrict__ D = a.dws + (size_t)(it - a.w0) * a.slot_cells;
+        const int T = n1 + n2 - 1, m = min(n1, n2);
+
+        double cur[G], prev[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) cur[g] = prev[g] = INF;
+        double nbprev = lane == 0 ? 0.0 : INF;          // C[-1][-1] = 0 feeds cell (0, 0)
+        float dn[4][G];
+        int pt = 0, pbase = 0;                          // prefetch cursor: step and its skew base
+#define ABN_DTW_PREFETCH()                                                              \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                 \
+            _Pragma("unroll") for (int g = 0; g < G; ++g) {                             \
+                const int i = i0 + g, j = pt - i;                                       \
+                const bool ok = (i < n1) & ((unsigned)j < (unsigned)n2);                \
+                dn[u][g] = ok ? __ldg(D + pbase + i) : INF_F;                           \
+            }                                                                           \
+            pbase += min(min(pt + 1, m), T - pt) - (pt >= n2 - 1 ? 1 : 0);              \
+            ++pt;                                                                       \
+        }
+        ABN_DTW_PREFETCH()
+        for (int t0 = 0; t0 < T; t0 += 4) {
+            float dc[4][G];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int g = 0; g < G; ++g) dc[u][g] = dn[u][g];
+            ABN_DTW_PREFETCH()
+            unsigned bits[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) bits[g] = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (t0 + u < T) {                       // warp-uniform
+                    double up0 = __shfl_up_sync(FULL, cur[G - 1], 1);
+                    up0 = lane == 0 ? INF : up0;
+                    const double dg0 = nbprev;
+                    nbprev = up0;
+                    double nw[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const double d = (double)dc[u][g];
+                        const double up = g == 0 ? up0 : cur[g - 1];
+                        const double dg = g == 0 ? dg0 : prev[g - 1];
+                        const double lf = cur[g];
+                        const bool up_le = up <= lf;
+                        const double m1 = up_le ? up : lf;
+                        const bool use_dg = dg <= m1;          // dg <= up && dg <= lf
+                        const double mm = use_dg ? dg : m1;
+                        const unsigned dir = use_dg ? DIR_DIAG : (up_le ? DIR_UP : DIR_LEFT);
+                        nw[g] = d + mm;
+                        bits[g] |= dir << (2 * u);
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g) { prev[g] = cur[g]; cur[g] = nw[g]; }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) dirs[(t0 >> 2) * R + i0 + g] = (uint8_t)bits[g];
+        }
+#undef ABN_DTW_PREFETCH
+        const int glast = (n1 - 1) % G;
+        double c = cur[0];
+        if (G > 1) c = glast == 1 ? cur[G > 1 ? 1 : 0] : c;
+        if (G > 2) c = glast == 2 ? cur[G > 2 ? 2 : 0] : c;
+        c = __shfl_sync(FULL, c, (n1 - 1) / G);
+        __syncwarp();
+        int len = 0;
+        if (lane == 0) {
+            int i = n1 - 1, j = n2 - 1;
+            len = 1;
+            pb_i[0] = (uint8_t)i; pb_j[0] = (uint8_t)j;
+            while ((i | j) != 0 && len < T) {
+                const int t = i + j;
+                const unsigned d = ((unsigned)dirs[(t >> 2) * R + i] >> (2 * (t & 3))) & 3u;
+                i -= (d != DIR_LEFT);
+                j -= (d != DIR_UP);
+                pb_i[len] = (uint8_t)i; pb_j[len] = (uint8_t)j; ++len;
+            }
+            a.path_len[p] = len;
+            a.cost[p] = c;
+        }
+        len = __shfl_sync(FULL, len, 0);
+        __syncwarp();
+        const int64_t off = a.path_off[p];
+        for (int k = lane; k < len; k += 32) {
+            a.idx1[off + k] = s1 + (int)pb_i[len - 1 - k];
+            a.idx2[off + k] = s2 + (int)pb_j[len - 1 - k];
+        }
+        __syncwarp();          // the slice is reused by this warp's next pair
+    }
+}
+
 // ------------------------------------------------------------ class kernel --
+// distance matrix of every pair of one size class -> skew layout -> hand-over slot
+// (or, for abn_cosine_distance, row-major straight to the caller's buffer)
 template <int RA, int NCG>
 __global__ void __launch_bounds__(AL_THREADS)
 align_class_kernel(const AlignArgs a) {
-    using L = ClassLayout<RA, NCG>;
+    using L = DistLayout<RA, NCG>;
     constexpr int CLS = (RA - 1) * NCLS_SIDE + (NCG - 1);
-    constexpr int G = (RA + 1) / 2;            // DTW rows per lane: ceil(16 RA / 32)
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
-    const int beg = a.class_off[CLS], end = a.class_off[CLS + 1];
-    float *Ds = reinterpret_cast<float *>(smem);
-    uint8_t *dirs = smem + L::DIRS_OFF;
-    uint8_t *pb_i = smem + L::PATH_OFF;
-    uint8_t *pb_j = pb_i + (L::ROWS_A + L::ROWS_B);
-    int *misc = reinterpret_cast<int *>(smem + L::MISC_OFF);
+    const int beg = max(a.class_off[CLS], a.w0), end = min(a.class_off[CLS + 1], a.w1);
+    const float *Dsk = reinterpret_cast<const float *>(smem);
+    int *tb = reinterpret_cast<int *>(smem + L::TB_OFF);
 
     for (int it = beg + blockIdx.x; it < end; it += gridDim.x) {
         const int p = a.order[it];
         const int4 tk = reinterpret_cast<const int4 *>(a.pair_tok)[p];
         const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
+        if (!a.dist_out) skew_table(tb, n1, n2, tid);
         int bad = 0;
-        pair_distance<RA, NCG>(smem, a.feat + (size_t)s1 * a.dim, a.feat + (size_t)s2 * a.dim, n1,
-                               n2, a.dim, a.dist_out ? a.dist_out + a.dist_off[p] : nullptr, n2,
-                               bad);
+        pair_distance<RA, NCG, L>(smem, a.feat + (size_t)s1 * a.dim, a.feat + (size_t)s2 * a.dim,
+                                  n1, n2, a.dim,
+                                  a.dist_out ? a.dist_out + a.dist_off[p] : nullptr, n2,
+                                  a.dist_out ? nullptr : tb, bad);
         bad = __syncthreads_or(bad);
-        if (a.dist_out) {
-            if (tid == 0) a.valid[p] = bad ? 0 : 1;
-            continue;
+        if (tid == 0) {
+            a.valid[p] = bad ? 0 : 1;     // utils.py:59 assert fails -> dataloader.py:190-191 drops the pair
+            if (bad && !a.dist_out) { a.path_len[p] = 0; a.cost[p] = nan(""); }
         }
-        if (bad) {     // utils.py:59 assert fails -> dataloader.py:190-191 drops the pair
-            if (tid == 0) { a.path_len[p] = 0; a.cost[p] = nan(""); a.valid[p] = 0; }
-            continue;
-        }
-        if (tid < 32) {
-            const double c = dtw_wavefront<float, G>(Ds, L::LDD, dirs, L::ROWS_B, n1, n2, tid);
-            __syncwarp();
-            if (tid == 0) {
-                const int len = traceback(dirs, L::ROWS_B, n1, n2, pb_i, pb_j);
-                misc[0] = len;
-                a.path_len[p] = len;
-                a.cost[p] = c;
-                a.valid[p] = 1;
-            }
-        }
-        __syncthreads();
-        const int len = misc[0];
-        const int64_t off = a.path_off[p];
-        for (int k = tid; k < len; k += AL_THREADS) {
-            a.idx1[off + k] = s1 + (int)pb_i[len - 1 - k];
-            a.idx2[off + k] = s2 + (int)pb_j[len - 1 - k];
-        }
+        if (!a.dist_out && !bad)
+            skew_copy_out(Dsk, a.dws + (size_t)(it - a.w0) * a.slot_cells, n1 * n2, tid);
         __syncthreads();   // smem is reused by the next pair
     }
 }
@@ -372,17 +518,14 @@ template <int RA, int NCG>      // extended sizes: 16 RA >= n1 + 6, 16 NCG >= n2
 struct StackLayout {
     static constexpr int ROWS_A = 16 * RA, ROWS_B = 16 * NCG;
     static constexpr int LDG = ROWS_B + 4;   // = 4 or 20 (mod 32): the diagonal reads are conflict-free
-    static constexpr int LDD = ROWS_B + 2;
     static constexpr unsigned STAGE_BYTES = (ROWS_A + ROWS_B) * KCP * 4u;
-    static constexpr unsigned DIRS_OFF = a16(ROWS_A * LDD * 4u);
-    static constexpr unsigned ALIAS_END = DIRS_OFF + ROWS_A * ROWS_B;
-    static constexpr unsigned REGION0 = STAGE_BYTES > ALIAS_END ? STAGE_BYTES : ALIAS_END;
+    static constexpr unsigned D_BYTES = ROWS_A * ROWS_B * 4u;
+    static constexpr unsigned REGION0 = STAGE_BYTES > D_BYTES ? STAGE_BYTES : D_BYTES;
     static constexpr unsigned G_OFF = a16(REGION0);
     static constexpr unsigned N40_OFF = a16(G_OFF + ROWS_A * LDG * 4u);
     static constexpr unsigned NORMS_OFF = N40_OFF + (ROWS_A + ROWS_B) * 4u;
-    static constexpr unsigned PATH_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
-    static constexpr unsigned MISC_OFF = a16(PATH_OFF + 2u * (ROWS_A + ROWS_B));
-    static constexpr unsigned TOTAL = MISC_OFF + 32u;
+    static constexpr unsigned TB_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
+    static constexpr unsigned TOTAL = TB_OFF + (ROWS_A + ROWS_B) * 4u + 16u;
 };
 
 // extended frame e (0 .. n+5) of a token whose first row is `base`: where its 40 floats live
@@ -397,22 +540,18 @@ __global__ void __launch_bounds__(AL_THREADS)
 align_stack_kernel(const AlignArgs a) {
     using L = StackLayout<RA, NCG>;
     constexpr int CLS = (RA - 1) * NCLS_SIDE + (NCG - 1);
-    constexpr int G = (16 * RA - 2 * STACK_H + 31) / 32;      // DTW rows per lane
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int ti = (warp >> 1) * 8 + (lane >> 2);
     const int tj = (warp & 1) * 4 + (lane & 3);
-    const int beg = a.class_off[CLS], end = a.class_off[CLS + 1];
+    const int beg = max(a.class_off[CLS], a.w0), end = min(a.class_off[CLS + 1], a.w1);
     const unsigned sbase = smem_u32(smem);
     float *Ds = reinterpret_cast<float *>(smem);
-    uint8_t *dirs = smem + L::DIRS_OFF;
     float *Gs = reinterpret_cast<float *>(smem + L::G_OFF);
     float *n40 = reinterpret_cast<float *>(smem + L::N40_OFF);
     float *norms = reinterpret_cast<float *>(smem + L::NORMS_OFF);
-    uint8_t *pb_i = smem + L::PATH_OFF;
-    uint8_t *pb_j = pb_i + (L::ROWS_A + L::ROWS_B);
-    int *misc = reinterpret_cast<int *>(smem + L::MISC_OFF);
+    int *tb = reinterpret_cast<int *>(smem + L::TB_OFF);
 
     for (int it = beg + blockIdx.x; it < end; it += gridDim.x) {
         const int p = a.order[it];
@@ -420,6 +559,7 @@ align_stack_kernel(const AlignArgs a) {
         const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
         const int n1e = n1 + 2 * STACK_H, n2e = n2 + 2 * STACK_H;
         const float *g1 = a.feat + (size_t)s1 * a.dim, *g2 = a.feat + (size_t)s2 * a.dim;
+        if (!a.dist_out) skew_table(tb, n1, n2, tid);
 
         // 1. stage the extended frames of both tokens (160 contiguous bytes each)
         {
@@ -515,36 +655,16 @@ align_stack_kernel(const AlignArgs a) {
                 const float dd = cell_distance(tot, xn, norms[L::ROWS_A + j]);
                 if (!(dd >= 0.f)) bad = 1;
                 if (dist_gmem) dist_gmem[(size_t)i * n2 + j] = dd;
-                else Ds[i * L::LDD + j] = dd;
+                else Ds[tb[i + j] + i] = dd;
             }
         }
         bad = __syncthreads_or(bad);
-        if (a.dist_out) {
-            if (tid == 0) a.valid[p] = bad ? 0 : 1;
-            continue;
+        if (tid == 0) {
+            a.valid[p] = bad ? 0 : 1;
+            if (bad && !a.dist_out) { a.path_len[p] = 0; a.cost[p] = nan(""); }
         }
-        if (bad) {
-            if (tid == 0) { a.path_len[p] = 0; a.cost[p] = nan(""); a.valid[p] = 0; }
-            continue;
-        }
-        if (tid < 32) {
-            const double cst = dtw_wavefront<float, G>(Ds, L::LDD, dirs, L::ROWS_B, n1, n2, tid);
-            __syncwarp();
-            if (tid == 0) {
-                const int len = traceback(dirs, L::ROWS_B, n1, n2, pb_i, pb_j);
-                misc[0] = len;
-                a.path_len[p] = len;
-                a.cost[p] = cst;
-                a.valid[p] = 1;
-            }
-        }
-        __syncthreads();
-        const int len = misc[0];
-        const int64_t off = a.path_off[p];
-        for (int k = tid; k < len; k += AL_THREADS) {
-            a.idx1[off + k] = s1 + (int)pb_i[len - 1 - k];
-            a.idx2[off + k] = s2 + (int)pb_j[len - 1 - k];
-        }
+        if (!a.dist_out && !bad)
+            skew_copy_out(Ds, a.dws + (size_t)(it - a.w0) * a.slot_cells, n1 * n2, tid);
         __syncthreads();
     }
 }
@@ -771,11 +891,11 @@ align_long_kernel(const AlignArgs a, int nmax) {
             for (int j0 = 0; j0 < n2; j0 += LT) {
                 const int w = min(LT, n2 - j0);
                 int bad = 0;
-                pair_distance<NCLS_SIDE, NCLS_SIDE>(
+                pair_distance<NCLS_SIDE, NCLS_SIDE, L>(
                     smem, a.feat + (size_t)(s1 + i0) * a.dim, a.feat + (size_t)(s2 + j0) * a.dim, h,
                     w, a.dim,
                     a.dist_out ? a.dist_out + a.dist_off[p] + (size_t)i0 * n2 + j0 : nullptr, n2,
-                    bad);
+                    nullptr, bad);
                 bad = __syncthreads_or(bad);
                 if (bad) { any_bad = 1; break; }
                 if (!a.dist_out && tid < 32)
@@ -989,7 +1109,7 @@ template <int RA, int NCG>
 static int prepare_class(ClassLaunch *generic, ClassLaunch *stacked, int sm_count) {
     constexpr int idx = (RA - 1) * NCLS_SIDE + (NCG - 1);
     if (int rc = prepare_kernel(generic[idx], align_class_kernel<RA, NCG>,
-                                ClassLayout<RA, NCG>::TOTAL, sm_count, "generic", RA, NCG))
+                                DistLayout<RA, NCG>::TOTAL, sm_count, "generic", RA, NCG))
         return rc;
     return prepare_kernel(stacked[idx], align_stack_kernel<RA, NCG>, StackLayout<RA, NCG>::TOTAL,
                           sm_count, "stacked", RA, NCG);
@@ -1029,15 +1149,58 @@ static int class_table(const ClassLaunch **generic, const ClassLaunch **stacked)
     return ABN_OK;
 }
 
+// hand-over slot of one pair (floats): the largest matrix of the fused classes
+static size_t slot_cells_for(int max_frames) {
+    const size_t ns = (size_t)(max_frames < NM_SHORT ? max_frames : NM_SHORT);
+    return (ns * ns + 3) & ~(size_t)3;
+}
+static size_t ws_dist_off(int n_pairs) {
+    return (WS_ORDER + sizeof(int32_t) * (size_t)(n_pairs > 0 ? n_pairs : 0) + 255) & ~(size_t)255;
+}
+
+struct DtwLaunch { int grid; unsigned smem; int t4_cap; };
+
+template <int G>
+static int launch_dtw(const AlignArgs &a, int ra, int ext, cudaStream_t st) {
+    static DtwLaunch tab[2][NCLS_SIDE + 1] = {};
+    DtwLaunch &d = tab[ext ? 1 : 0][ra];
+    if (d.grid == 0) {
+        // longest diagonal count of the row: (16 ra - ext) + (NM_SHORT - ext) - 1 steps
+        d.t4_cap = (16 * ra + NM_SHORT - 2 * ext + 2) / 4;
+        d.smem = DTW_WARPS * (unsigned)(d.t4_cap * 32 * G + 8 * d.t4_cap);
+        // at most 20 KB: below the 48 KB every kernel may use without opting in (and the
+        // opt-in attribute is per kernel, not per launch, so rows sharing a G must not set it)
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_skew_kernel<G>,
+                                                          DTW_WARPS * 32, d.smem) != cudaSuccess ||
+            per_sm < 1)
+            return set_error(ABN_EIO, "occupancy query failed for the DTW kernel (G = %d)", G);
+        d.grid = per_sm * sms;
+    }
+    const int want = (a.w1 - a.w0 + DTW_WARPS - 1) / DTW_WARPS;
+    dtw_skew_kernel<G><<<d.grid < want ? d.grid : want, DTW_WARPS * 32, d.smem, st>>>(
+        a, (ra - 1) * NCLS_SIDE, ra * NCLS_SIDE, d.t4_cap);
+    if (cudaError_t e = cudaGetLastError())
+        return set_error(ABN_EIO, "DTW kernel launch (G %d, row %d, grid %d, smem %u): %s", G, ra,
+                         d.grid < want ? d.grid : want, d.smem, cudaGetErrorString(e));
+    return ABN_OK;
+}
+
 static int run_align(AlignArgs a, int max_frames, void *workspace, size_t workspace_bytes,
                      cudaStream_t st, const char *who) {
     if (max_frames <= 0) return set_error(ABN_EINVAL, "%s: max_frames must be positive", who);
     if (max_frames > NM_LIMIT)
         return set_error(ABN_ERANGE, "%s: token of %d frames exceeds %d", who, max_frames, NM_LIMIT);
-    const size_t need = WS_ORDER + sizeof(int32_t) * (size_t)a.n_pairs;
+    const bool dist_only = a.dist_out != nullptr;
+    const size_t slot = slot_cells_for(max_frames);
+    const size_t d_off = ws_dist_off(a.n_pairs);
+    const size_t need = dist_only ? WS_ORDER + sizeof(int32_t) * (size_t)a.n_pairs
+                                  : d_off + slot * sizeof(float);
     if (!workspace || workspace_bytes < need)
-        return set_error(ABN_ENOMEM, "%s: workspace of %zu bytes needed, %zu given", who, need,
-                         workspace_bytes);
+        return set_error(ABN_ENOMEM, "%s: workspace of at least %zu bytes needed, %zu given", who,
+                         need, workspace_bytes);
     if (a.stack != 0 && (a.stack != STACK_S || a.dim != STACK_S * STACK_F))
         return set_error(ABN_EINVAL, "%s: the stacked fast path needs stack == %d and dim == %d "
                          "(got stack %d, dim %d); pass stack = 0 for the generic kernels", who,
@@ -1053,6 +1216,10 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
     int32_t *order = reinterpret_cast<int32_t *>(ws + WS_ORDER);
     a.order = order;
     a.class_off = class_off;
+    a.w0 = 0;
+    a.w1 = a.n_pairs;
+    a.dws = nullptr;
+    a.slot_cells = (int)slot;
     cudaMemsetAsync(ws, 0, WS_ORDER, st);
     const int per_block = BK_THREADS * BK_ITEMS;
     const int blocks = (a.n_pairs + per_block - 1) / per_block;
@@ -1060,7 +1227,6 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
     class_scan_kernel<<<1, 32, 0, st>>>(counts, class_off);
     class_scatter_kernel<<<blocks, BK_THREADS, 0, st>>>(a, class_off, cursor, order);
     if (max_frames + ext > NM_SHORT) {
-        static int long_grid = 0;
         const int nmax = max_frames;
         const LongLayout LL = long_layout(nmax);
         if (cudaFuncSetAttribute(align_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1071,18 +1237,41 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_long_kernel, AL_THREADS,
                                                       LL.total);
-        long_grid = (per_sm > 0 ? per_sm : 1) * sms;
+        const int long_grid = (per_sm > 0 ? per_sm : 1) * sms;
         const int grid = long_grid < a.n_pairs ? long_grid : a.n_pairs;
         align_long_kernel<<<grid, AL_THREADS, LL.total, st>>>(a, nmax);
+        if (cudaError_t e = cudaGetLastError())
+            return set_error(ABN_EIO, "%s: long-token kernel launch (smem %u): %s", who, LL.total,
+                             cudaGetErrorString(e));
     }
+    // The fused classes run in rounds over windows of the class-sorted pair order, as many
+    // pairs per round as the workspace has hand-over slots for.  Per round and class row:
+    // the row's distance kernels (large classes first), then ONE DTW launch over the row.
     const int side = ((max_frames + ext < NM_SHORT ? max_frames + ext : NM_SHORT) + 15) / 16;
-    // large classes first: their pairs take longest, the small ones fill the tail
-    for (int ra = side; ra >= 1; --ra)
-        for (int ncg = side; ncg >= 1; --ncg) {
-            const ClassLaunch &cl = tab[(ra - 1) * NCLS_SIDE + (ncg - 1)];
-            const int grid = cl.grid < a.n_pairs ? cl.grid : a.n_pairs;
-            cl.kernel<<<grid, AL_THREADS, cl.smem, st>>>(a);
+    size_t chunk = dist_only ? (size_t)a.n_pairs : (workspace_bytes - d_off) / (slot * sizeof(float));
+    if (chunk > (size_t)a.n_pairs) chunk = (size_t)a.n_pairs;
+    if (!dist_only) a.dws = reinterpret_cast<float *>(ws + d_off);
+    for (size_t w0 = 0; w0 < (size_t)a.n_pairs; w0 += chunk) {
+        a.w0 = (int)w0;
+        a.w1 = (int)(w0 + chunk < (size_t)a.n_pairs ? w0 + chunk : (size_t)a.n_pairs);
+        const int span = a.w1 - a.w0;
+        for (int ra = side; ra >= 1; --ra) {
+            for (int ncg = side; ncg >= 1; --ncg) {
+                const ClassLaunch &cl = tab[(ra - 1) * NCLS_SIDE + (ncg - 1)];
+                cl.kernel<<<cl.grid < span ? cl.grid : span, AL_THREADS, cl.smem, st>>>(a);
+                if (cudaError_t e = cudaGetLastError())
+                    return set_error(ABN_EIO, "%s: class (%d,%d) launch (grid %d, smem %u): %s", who,
+                                     ra, ncg, cl.grid < span ? cl.grid : span, cl.smem,
+                                     cudaGetErrorString(e));
+            }
+            if (dist_only) continue;
+            int rc;
+            if (ra <= 2) rc = launch_dtw<1>(a, ra, ext, st);
+            else if (ra <= 4) rc = launch_dtw<2>(a, ra, ext, st);
+            else rc = launch_dtw<3>(a, ra, ext, st);
+            if (rc) return rc;
         }
+    }
     return check_launch(who);
 }
 
@@ -1091,8 +1280,13 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
 // ------------------------------------------------------------------ C ABI --
 using namespace abn;
 
-extern "C" size_t abn_align_workspace_bytes(int n_pairs) {
-    return WS_ORDER + sizeof(int32_t) * (size_t)(n_pairs > 0 ? n_pairs : 0);
+extern "C" size_t abn_align_workspace_bytes(int n_pairs, int max_frames, int rounds) {
+    if (n_pairs < 0) n_pairs = 0;
+    if (max_frames < 1) max_frames = 1;
+    if (rounds < 1) rounds = 1;
+    size_t per_round = ((size_t)n_pairs + rounds - 1) / rounds;
+    if (per_round < 1) per_round = 1;
+    return ws_dist_off(n_pairs) + per_round * slot_cells_for(max_frames) * sizeof(float);
 }
 
 extern "C" int abn_align_pairs(const float *feat, int64_t n_rows, int dim,

@@ -4,6 +4,7 @@ torch is used here for device memory, streams and prefix sums only; all the
 arithmetic of the hot path happens inside libabnet3_b200.so.  Every function
 requires CUDA tensors and raises if the library or an sm_100 device is missing.
 """
+import os
 from collections import namedtuple
 
 import torch
@@ -38,8 +39,20 @@ def _excl_cumsum(counts):
     return off
 
 
-def _workspace(n_pairs, device):
-    nbytes = _lib.lib().abn_align_workspace_bytes(n_pairs)
+ALIGN_WS_BUDGET = int(float(os.environ.get("ABN_ALIGN_WS_GB", "16")) * (1 << 30))
+
+
+def _workspace(n_pairs, device, max_frames=1, budget=None):
+    """Workspace of abn_align_pairs: the class-sorted pair order plus the hand-over
+    slots of the distance matrices.  One slot per pair when that fits `budget` bytes
+    (default ABN_ALIGN_WS_GB = 16), else the fewest rounds that do."""
+    fn = _lib.lib().abn_align_workspace_bytes
+    budget = ALIGN_WS_BUDGET if budget is None else int(budget)
+    rounds = 1
+    nbytes = fn(n_pairs, max_frames, rounds)
+    while nbytes > budget and rounds < max(n_pairs, 1):
+        rounds = min(max(n_pairs, 1), max(rounds + 1, -(-nbytes * rounds // budget)))
+        nbytes = fn(n_pairs, max_frames, rounds)
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
@@ -63,7 +76,7 @@ def align_pairs(feat, pair_tok, max_frames=None, stack=0):
     path_len = torch.zeros(P, dtype=torch.int32, device=dev)
     cost = torch.full((P,), float("nan"), dtype=torch.float64, device=dev)
     valid = torch.zeros(P, dtype=torch.uint8, device=dev)
-    ws, ws_bytes = _workspace(P, dev)
+    ws, ws_bytes = _workspace(P, dev, max(max_frames, 1))
     check(_lib.lib().abn_align_pairs(
         ptr(feat), feat.shape[0], feat.shape[1], ptr(pair_tok), P, max(max_frames, 1), int(stack),
         ptr(path_off), ptr(idx1), ptr(idx2), ptr(path_len), ptr(cost), ptr(valid),

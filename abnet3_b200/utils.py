@@ -116,7 +116,7 @@ class BatchAligner(object):
             self.path_len = torch.empty(n_pairs, dtype=torch.int32, device=dev)
             self.cost = torch.empty(n_pairs, dtype=torch.float64, device=dev)
             self.valid = torch.empty(n_pairs, dtype=torch.uint8, device=dev)
-            self._ws, self._ws_bytes = ops._workspace(n_pairs, dev)
+            self._ws, self._ws_bytes = ops._workspace(n_pairs, dev, self.max_frames)
             self._cap_pairs = n_pairs
 
     def _offsets(self, pair_tok):

@@ -78,10 +78,17 @@ ABN_API int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int
                                  const uint8_t *last_row_of_file, unsigned long long *count,
                                  abn_stream_t stream);
 
-/* Device workspace abn_align_pairs / abn_cosine_distance need for a call over
- * n_pairs pairs (they bucket the pairs into token-length classes on the device
- * and keep the per-class pair order there). */
-ABN_API size_t abn_align_workspace_bytes(int n_pairs);
+/* Device workspace for abn_align_pairs / abn_cosine_distance over n_pairs pairs.
+ * Both bucket the pairs into token-length classes on the device and keep the
+ * class-sorted pair order there.  abn_align_pairs additionally hands every pair's
+ * distance matrix (float32, at most min(max_frames, 96)^2 cells) from the distance
+ * kernels to the DTW kernel through this workspace; it works through the sorted pair
+ * list in `rounds` windows, so a smaller workspace only means more, shorter rounds.
+ * Returns the bytes for the given number of rounds (rounds = 1: every pair has its own
+ * slot).  abn_align_pairs accepts ANY size >= abn_align_workspace_bytes(n_pairs,
+ * max_frames, n_pairs) and derives the round count from what it is given;
+ * abn_cosine_distance needs abn_align_workspace_bytes(n_pairs, 1, n_pairs). */
+ABN_API size_t abn_align_workspace_bytes(int n_pairs, int max_frames, int rounds);
 
 /* ------------------------------------------------------------------------
  * (1) Batched cosine frame distance.
@@ -120,8 +127,11 @@ ABN_API int abn_dtw_from_dist(const double *dist, const int64_t *dist_off,
 /* ------------------------------------------------------------------------
  * (1)+(2) fused: align every 'same' pair of a pair list.
  * Replaces abnet3/utils.py:147-153 `get_dtw_alignment` as called per pair by
- * abnet3/dataloader.py:183-206 and :642-653.  Distances and accumulated costs
- * never leave the SM.
+ * abnet3/dataloader.py:183-206 and :642-653.  Per size class: a distance kernel
+ * (CTA per pair, shared-memory staged) leaves the float32 matrix in the workspace in
+ * anti-diagonal order, then a DTW kernel (one warp per pair) sweeps it; accumulated
+ * costs and traceback directions never leave the SM.  Tokens longer than 96 frames
+ * (up to 512) take a tiled kernel that keeps everything on chip.
  *   idx1/idx2 GLOBAL row ids into feat (row_start + local path index), i.e.
  *             the rows `feat1[path1, :]`, `feat2[path2, :]` gather
  *             (dataloader.py:204-205), at path_off[p] .. +path_len[p].
