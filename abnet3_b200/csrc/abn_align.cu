@@ -144,11 +144,20 @@ __device__ __forceinline__ float row_sumsq(unsigned row_addr, int kc4) {
     return acc;
 }
 
-// utils.py:47-58 for one cell, in float32: zero-norm rules, divide, arccos / pi
-__device__ __forceinline__ float cell_distance(float dot, float xn, float yn) {
-    if (xn == 0.f || yn == 0.f) return (xn == 0.f && yn == 0.f) ? 0.f : 1.f;
-    const float cs = __fdiv_rn(dot, __fmul_rn(xn, yn));
-    return __fdiv_rn(acosf(cs), PI_F);
+// utils.py:47-58 for one cell, in float32.  rx, ry are the RECIPROCAL row norms (0 for
+// a zero row, which is how the zero-norm rules are recognised): cos = dot * (rx * ry)
+// and arccos * (1/pi) replace the reference's two divisions -- at most 2 ulp apart in
+// cos, well inside the parity bound, and ~30 instructions cheaper.
+constexpr float INV_PI_F = 0.318309873342514038f;       // float32(1 / pi)
+__device__ __forceinline__ float recip_norm(float sumsq) {
+    const float n = sqrtf(sumsq);
+    return n == 0.f ? 0.f : __frcp_rn(n);
+}
+__device__ __forceinline__ float cell_distance(float dot, float rx, float ry) {
+    const float cs = __fmul_rn(dot, __fmul_rn(rx, ry));
+    const float d = __fmul_rn(acosf(cs), INV_PI_F);
+    if (rx == 0.f || ry == 0.f) return (rx == 0.f && ry == 0.f) ? 0.f : 1.f;
+    return d;
 }
 
 // ------------------------------------------------------- distance (kernel 1)
@@ -240,8 +249,8 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const float *
             for (int c = 0; c < 2 * NCG; ++c) tot[r][c] += acc[r][c];
         __syncthreads();   // everyone done with this stage before it is refilled
     }
-    if (q0 < nq) norms[row0] = sqrtf(ss0);
-    if (q1 < nq) norms[row1] = sqrtf(ss1);
+    if (q0 < nq) norms[row0] = recip_norm(ss0);
+    if (q1 < nq) norms[row1] = recip_norm(ss1);
     __syncthreads();
 
     // epilogue: utils.py:47-58 in float32; the staging buffers are dead, D may overwrite them
@@ -522,7 +531,8 @@ struct StackLayout {
     static constexpr unsigned D_BYTES = ROWS_A * ROWS_B * 4u;
     static constexpr unsigned REGION0 = STAGE_BYTES > D_BYTES ? STAGE_BYTES : D_BYTES;
     static constexpr unsigned G_OFF = a16(REGION0);
-    static constexpr unsigned N40_OFF = a16(G_OFF + ROWS_A * LDG * 4u);
+    static constexpr int G_ROWS = ROWS_A + 8;      // the epilogue's diagonal runs may read past the tile
+    static constexpr unsigned N40_OFF = a16(G_OFF + G_ROWS * LDG * 4u);
     static constexpr unsigned NORMS_OFF = N40_OFF + (ROWS_A + ROWS_B) * 4u;
     static constexpr unsigned TB_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
     static constexpr unsigned TOTAL = TB_OFF + (ROWS_A + ROWS_B) * 4u + 16u;
@@ -632,30 +642,43 @@ align_stack_kernel(const AlignArgs a) {
             float ss = 0.f;
 #pragma unroll
             for (int c = 0; c < STACK_S; ++c) ss += n40[r0 + c];
-            norms[q < n1 ? q : L::ROWS_A + (q - n1)] = sqrtf(ss);
+            norms[q < n1 ? q : L::ROWS_A + (q - n1)] = recip_norm(ss);
         }
         __syncthreads();
 
-        // 4. 7-tap diagonal sum + epilogue -> D (over the dead staging area)
+        // 4. 7-tap diagonal sums + epilogue -> D (over the dead staging area).  A thread
+        // owns RUNS of 8 cells along a diagonal, (i0 + k, j0 + k): the 14 Gram entries the
+        // run needs are loaded once, consecutive lanes take consecutive j0 (conflict-free).
+        // Every sum adds its 7 taps in stack order, like the generic kernel's chunk loop.
+        // Runs start at rows 8 b and columns -7 .. n2 - 1; cells outside the matrix are
+        // computed on whatever the loads returned and dropped.
         int bad = 0;
         float *dist_gmem = a.dist_out ? a.dist_out + a.dist_off[p] : nullptr;
+        {
+            constexpr int RUN = 8;
+            const int W = n2 + RUN - 1;
+            const int S = ((n1 + RUN - 1) / RUN) * W;
+            const float invW = 1.0f / (float)W;
+            for (int sidx = tid; sidx < S; sidx += AL_THREADS) {
+                const int b = (int)(((float)sidx + 0.5f) * invW);
+                const int i0 = b * RUN, j0 = sidx - b * W - (RUN - 1);
+                const float *gp = Gs + i0 * L::LDG + j0;
+                float g[RUN + STACK_S - 1];
 #pragma unroll
-        for (int r = 0; r < RA; ++r) {
-            const int i = ti + 16 * r;
-            if (i >= n1) continue;
-            const float xn = norms[i];
+                for (int k = 0; k < RUN + STACK_S - 1; ++k) g[k] = gp[k * (L::LDG + 1)];
 #pragma unroll
-            for (int c = 0; c < 2 * NCG; ++c) {
-                const int j = tj + 8 * c;
-                if (j >= n2) continue;
-                const float *gp = Gs + i * L::LDG + j;
-                float tot = 0.f;
+                for (int k = 0; k < RUN; ++k) {
+                    const int i = i0 + k, j = j0 + k;
+                    float tot = 0.f;
 #pragma unroll
-                for (int d = 0; d < STACK_S; ++d) tot += gp[d * (L::LDG + 1)];
-                const float dd = cell_distance(tot, xn, norms[L::ROWS_A + j]);
-                if (!(dd >= 0.f)) bad = 1;
-                if (dist_gmem) dist_gmem[(size_t)i * n2 + j] = dd;
-                else Ds[tb[i + j] + i] = dd;
+                    for (int d = 0; d < STACK_S; ++d) tot += g[k + d];
+                    if (i < n1 && (unsigned)j < (unsigned)n2) {
+                        const float dd = cell_distance(tot, norms[i], norms[L::ROWS_A + j]);
+                        if (!(dd >= 0.f)) bad = 1;
+                        if (dist_gmem) dist_gmem[(size_t)i * n2 + j] = dd;
+                        else Ds[tb[i + j] + i] = dd;
+                    }
+                }
             }
         }
         bad = __syncthreads_or(bad);
