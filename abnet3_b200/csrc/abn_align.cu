@@ -59,9 +59,13 @@ struct AlignArgs {
 };
 
 // Skew layout of an n1 x n2 matrix: anti-diagonal t = i + j holds its cells
-// contiguously, rows ascending, diagonals back to back (n1 * n2 floats, no padding);
-// cell (i, j) lives at skew_base(i + j) + i.  The DTW wavefront reads one diagonal per
-// step, one row per lane: a contiguous, coalesced segment.
+// contiguously, rows ascending, diagonals back to back; cell (i, j) lives at
+// skew_base(i + j) + i.  The DTW wavefront reads one diagonal per step, one row per lane:
+// a contiguous, coalesced segment.  Diagonals 0 .. n1-2 are followed by one +inf GUARD
+// float: it is what the lane of row t + 1 reads at step t -- the cell (t + 1, -1) left of
+// the matrix -- so the wavefront needs no range test on its loads (every other
+// out-of-range read lands on some finite distance or guard of the same slot, and no
+// in-range cell ever consumes what is computed from it).  n1 * n2 + n1 - 1 floats.
 __host__ __device__ __forceinline__ int skew_base(int t, int n1, int n2) {
     const int m = n1 < n2 ? n1 : n2, mx = n1 < n2 ? n2 : n1, T = n1 + n2 - 1;
     int off;
@@ -69,8 +73,11 @@ __host__ __device__ __forceinline__ int skew_base(int t, int n1, int n2) {
     else if (t <= mx) off = m * (m + 1) / 2 + (t - m) * m;
     else off = n1 * n2 - (T - t) * (T - t + 1) / 2;
     const int ilo = t - n2 + 1 > 0 ? t - n2 + 1 : 0;
-    return off - ilo;
+    const int guards = t < n1 - 1 ? t : n1 - 1;          // guards of the diagonals before t
+    return off + guards - ilo;
 }
+__host__ __device__ __forceinline__ int skew_cells(int n1, int n2) { return n1 * n2 + n1 - 1; }
+constexpr int SKEW_SLACK = 128;      // floats a wavefront may read past its matrix
 
 __host__ __device__ constexpr unsigned a16(unsigned x) { return (x + 15u) & ~15u; }
 
@@ -94,7 +101,7 @@ struct DistLayout {
     static constexpr int ROWS_A = 16 * RA, ROWS_B = 16 * NCG;
     static constexpr int LDD = ROWS_B + 2;
     static constexpr unsigned STAGE_BYTES = (ROWS_A + ROWS_B) * KCP * 4u;
-    static constexpr unsigned D_BYTES = ROWS_A * ROWS_B * 4u;
+    static constexpr unsigned D_BYTES = (ROWS_A * ROWS_B + ROWS_A) * 4u;
     static constexpr unsigned REGION = 2u * STAGE_BYTES > D_BYTES ? 2u * STAGE_BYTES : D_BYTES;
     static constexpr unsigned NORMS_OFF = a16(REGION);
     static constexpr unsigned TB_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
@@ -159,6 +166,8 @@ __device__ __forceinline__ float cell_distance(float dot, float rx, float ry) {
     if (rx == 0.f || ry == 0.f) return (rx == 0.f && ry == 0.f) ? 0.f : 1.f;
     return d;
 }
+
+__device__ __forceinline__ void skew_guards(float *Dsk, const int *tb, int n1, int tid);
 
 // ------------------------------------------------------- distance (kernel 1)
 // Thread grid 16 (rows) x 8 (cols): thread (ti, tj) owns rows ti + 16 r and
@@ -254,6 +263,7 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const float *
     __syncthreads();
 
     // epilogue: utils.py:47-58 in float32; the staging buffers are dead, D may overwrite them
+    if (tb) skew_guards(Ds, tb, n1, tid);
 #pragma unroll
     for (int r = 0; r < RA; ++r) {
         const int i = ti + 16 * r;
@@ -277,6 +287,10 @@ __device__ __forceinline__ void pair_distance(unsigned char *smem, const float *
 // contiguous copy to the hand-over slot (128-bit accesses)
 __device__ __forceinline__ void skew_table(int *tb, int n1, int n2, int tid) {
     for (int t = tid; t < n1 + n2 - 1; t += AL_THREADS) tb[t] = skew_base(t, n1, n2);
+}
+// the +inf guards after diagonals 0 .. n1-2 (call once the staging area under D is dead)
+__device__ __forceinline__ void skew_guards(float *Dsk, const int *tb, int n1, int tid) {
+    for (int t = tid; t < n1 - 1; t += AL_THREADS) Dsk[tb[t] + t + 1] = __int_as_float(0x7f800000);
 }
 __device__ __forceinline__ void skew_copy_out(const float *Dsk, float *dst, int cells, int tid) {
     const float4 *s4 = reinterpret_cast<const float4 *>(Dsk);
@@ -389,59 +403,64 @@ dtw_skew_kernel(const AlignArgs a, int cls_beg, int cls_end, int t4_cap) {
 #pragma unroll
         for (int g = 0; g < G; ++g) cur[g] = prev[g] = INF;
         double nbprev = lane == 0 ? 0.0 : INF;          // C[-1][-1] = 0 feeds cell (0, 0)
-        float dn[4][G];
-        int pt = 0, pbase = 0;                          // prefetch cursor: step and its skew base
-#define ABN_DTW_PREFETCH()                                                              \
-        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                 \
-            _Pragma("unroll") for (int g = 0; g < G; ++g) {                             \
-                const int i = i0 + g, j = pt - i;                                       \
-                const bool ok = (i < n1) & ((unsigned)j < (unsigned)n2);                \
-                dn[u][g] = ok ? __ldg(D + pbase + i) : INF_F;                           \
+        const float *Dl = D + i0;                       // this lane's rows
+        asm volatile("" : "+l"(Dl));                    // keep it one register pair: loads are Dl[b + g]
+        // skew bases of 32 consecutive steps live one per lane; a step's base is one shuffle
+        int bases = 0;
+#define ABN_DTW_LOAD(dst, t_first)                                                      \
+        {                                                                               \
+            if (((t_first) & 31) == 0) bases = skew_base(min((t_first) + lane, T - 1), n1, n2); \
+            _Pragma("unroll") for (int u = 0; u < 4; ++u) {                             \
+                const int b = __shfl_sync(FULL, bases, ((t_first) + u) & 31);           \
+                _Pragma("unroll") for (int g = 0; g < G; ++g) dst[u][g] = __ldg(Dl + b + g); \
             }                                                                           \
-            pbase += min(min(pt + 1, m), T - pt) - (pt >= n2 - 1 ? 1 : 0);              \
-            ++pt;                                                                       \
         }
-        ABN_DTW_PREFETCH()
-        for (int t0 = 0; t0 < T; t0 += 4) {
-            float dc[4][G];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int g = 0; g < G; ++g) dc[u][g] = dn[u][g];
-            ABN_DTW_PREFETCH()
-            unsigned bits[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) bits[g] = 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (t0 + u < T) {                       // warp-uniform
-                    double up0 = __shfl_up_sync(FULL, cur[G - 1], 1);
-                    up0 = lane == 0 ? INF : up0;
-                    const double dg0 = nbprev;
-                    nbprev = up0;
-                    double nw[G];
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const double d = (double)dc[u][g];
-                        const double up = g == 0 ? up0 : cur[g - 1];
-                        const double dg = g == 0 ? dg0 : prev[g - 1];
-                        const double lf = cur[g];
-                        const bool up_le = up <= lf;
-                        const double m1 = up_le ? up : lf;
-                        const bool use_dg = dg <= m1;          // dg <= up && dg <= lf
-                        const double mm = use_dg ? dg : m1;
-                        const unsigned dir = use_dg ? DIR_DIAG : (up_le ? DIR_UP : DIR_LEFT);
-                        nw[g] = d + mm;
-                        bits[g] |= dir << (2 * u);
-                    }
-#pragma unroll
-                    for (int g = 0; g < G; ++g) { prev[g] = cur[g]; cur[g] = nw[g]; }
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) dirs[(t0 >> 2) * R + i0 + g] = (uint8_t)bits[g];
+#define ABN_DTW_STEP(dc, u)                                                             \
+        {                                                                               \
+            double up0 = __shfl_up_sync(FULL, cur[G - 1], 1);                           \
+            up0 = lane == 0 ? INF : up0;                                                \
+            const double dg0 = nbprev;                                                  \
+            nbprev = up0;                                                               \
+            double nw[G];                                                               \
+            _Pragma("unroll") for (int g = 0; g < G; ++g) {                             \
+                const double d = (double)dc[u][g];                                      \
+                const double up = g == 0 ? up0 : cur[g > 0 ? g - 1 : 0];                \
+                const double dg = g == 0 ? dg0 : prev[g > 0 ? g - 1 : 0];               \
+                const double lf = cur[g];                                               \
+                const bool up_le = up <= lf;                                            \
+                const double m1 = up_le ? up : lf;                                      \
+                const bool use_dg = dg <= m1;          /* dg <= up && dg <= lf */       \
+                const double mm = use_dg ? dg : m1;                                     \
+                const unsigned dir = use_dg ? DIR_DIAG : (up_le ? DIR_UP : DIR_LEFT);   \
+                nw[g] = d + mm;                                                         \
+                bits[g] |= dir << (2 * (u));                                            \
+            }                                                                           \
+            _Pragma("unroll") for (int g = 0; g < G; ++g) { prev[g] = cur[g]; cur[g] = nw[g]; } \
         }
-#undef ABN_DTW_PREFETCH
+#define ABN_DTW_BLOCK(dc, dnext, t0)                                                    \
+        {                                                                               \
+            ABN_DTW_LOAD(dnext, (t0) + 4)                                               \
+            unsigned bits[G];                                                           \
+            _Pragma("unroll") for (int g = 0; g < G; ++g) bits[g] = 0;                  \
+            if ((t0) + 4 <= T) {          /* warp-uniform: a full block, no per-step test */ \
+                ABN_DTW_STEP(dc, 0) ABN_DTW_STEP(dc, 1) ABN_DTW_STEP(dc, 2) ABN_DTW_STEP(dc, 3) \
+            } else {                      /* the last, partial block */                 \
+                ABN_DTW_STEP(dc, 0)                                                     \
+                if ((t0) + 1 < T) ABN_DTW_STEP(dc, 1)                                   \
+                if ((t0) + 2 < T) ABN_DTW_STEP(dc, 2)                                   \
+            }                                                                           \
+            _Pragma("unroll") for (int g = 0; g < G; ++g)                               \
+                dirs[((t0) >> 2) * R + i0 + g] = (uint8_t)bits[g];                      \
+        }
+        float da[4][G], db[4][G];
+        ABN_DTW_LOAD(da, 0)
+        for (int t0 = 0; t0 < T; t0 += 8) {
+            ABN_DTW_BLOCK(da, db, t0)
+            if (t0 + 4 < T) ABN_DTW_BLOCK(db, da, t0 + 4)
+        }
+#undef ABN_DTW_BLOCK
+#undef ABN_DTW_STEP
+#undef ABN_DTW_LOAD
         const int glast = (n1 - 1) % G;
         double c = cur[0];
         if (G > 1) c = glast == 1 ? cur[G > 1 ? 1 : 0] : c;
@@ -504,7 +523,7 @@ align_class_kernel(const AlignArgs a) {
             if (bad && !a.dist_out) { a.path_len[p] = 0; a.cost[p] = nan(""); }
         }
         if (!a.dist_out && !bad)
-            skew_copy_out(Dsk, a.dws + (size_t)(it - a.w0) * a.slot_cells, n1 * n2, tid);
+            skew_copy_out(Dsk, a.dws + (size_t)(it - a.w0) * a.slot_cells, skew_cells(n1, n2), tid);
         __syncthreads();   // smem is reused by the next pair
     }
 }
@@ -528,14 +547,15 @@ struct StackLayout {
     static constexpr int ROWS_A = 16 * RA, ROWS_B = 16 * NCG;
     static constexpr int LDG = ROWS_B + 4;   // = 4 or 20 (mod 32): the diagonal reads are conflict-free
     static constexpr unsigned STAGE_BYTES = (ROWS_A + ROWS_B) * KCP * 4u;
-    static constexpr unsigned D_BYTES = ROWS_A * ROWS_B * 4u;
+    static constexpr unsigned D_BYTES = (ROWS_A * ROWS_B + ROWS_A) * 4u;
     static constexpr unsigned REGION0 = STAGE_BYTES > D_BYTES ? STAGE_BYTES : D_BYTES;
     static constexpr unsigned G_OFF = a16(REGION0);
     static constexpr int G_ROWS = ROWS_A + 8;      // the epilogue's diagonal runs may read past the tile
     static constexpr unsigned N40_OFF = a16(G_OFF + G_ROWS * LDG * 4u);
     static constexpr unsigned NORMS_OFF = N40_OFF + (ROWS_A + ROWS_B) * 4u;
     static constexpr unsigned TB_OFF = NORMS_OFF + (ROWS_A + ROWS_B) * 4u;
-    static constexpr unsigned TOTAL = TB_OFF + (ROWS_A + ROWS_B) * 4u + 16u;
+    static constexpr unsigned BAR_OFF = a16(TB_OFF + (ROWS_A + ROWS_B) * 4u);
+    static constexpr unsigned TOTAL = BAR_OFF + 16u;
 };
 
 // extended frame e (0 .. n+5) of a token whose first row is `base`: where its 40 floats live
@@ -543,6 +563,64 @@ __device__ __forceinline__ const float *ext_frame(const float *base, int n, int 
     const int row = e < STACK_H ? 0 : (e < n + STACK_H ? e - STACK_H : n - 1);
     const int blk = e < STACK_H ? e : (e < n + STACK_H ? STACK_H : e - n + 1);
     return base + (size_t)row * dim + blk * STACK_F;
+}
+
+// bulk-copy engine (TMA, 1-D): one instruction moves a whole 160-byte frame and signals
+// the CTA's mbarrier with the byte count
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes,
+                                         unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                 "[%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; spin < (1u << 28); ++spin) {      // bounded: a lost copy traps, never hangs
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// 7-tap diagonal sums + utils.py:47-58 -> D.  A thread owns RUNS of 8 cells along a
+// diagonal, (i0 + k, j0 + k): the 14 Gram entries a run needs are loaded once, consecutive
+// lanes take consecutive j0 (conflict-free).  Every sum adds its 7 taps in stack order,
+// like the generic kernel's chunk loop.  Runs start at rows 8 b and columns -7 .. n2 - 1;
+// cells outside the matrix are computed on whatever the loads returned and not stored.
+template <bool TO_GMEM, typename L>
+__device__ __forceinline__ int stack_epilogue(const float *Gs, const float *norms, const int *tb,
+                                              unsigned dsk_addr, float *dist_gmem, int n1, int n2,
+                                              int tid) {
+    constexpr int RUN = 8;
+    int bad = 0;
+    const int W = n2 + RUN - 1;
+    const int S = ((n1 + RUN - 1) / RUN) * W;
+    const float invW = 1.0f / (float)W;
+    for (int sidx = tid; sidx < S; sidx += AL_THREADS) {
+        const int b = (int)(((float)sidx + 0.5f) * invW);
+        const int i0 = b * RUN, j0 = sidx - b * W - (RUN - 1);
+        const int klo = max(0, -j0), khi = min(n1 - i0, n2 - j0);     // valid cells: klo <= k < khi
+        const float *gp = Gs + i0 * L::LDG + j0;
+        float g[RUN + STACK_S - 1];
+#pragma unroll
+        for (int k = 0; k < RUN + STACK_S - 1; ++k) g[k] = gp[k * (L::LDG + 1)];
+#pragma unroll
+        for (int k = 0; k < RUN; ++k) {
+            const int i = i0 + k, j = j0 + k;
+            float tot = g[k];
+#pragma unroll
+            for (int d = 1; d < STACK_S; ++d) tot += g[k + d];
+            const float dd = cell_distance(tot, norms[i], norms[L::ROWS_A + j]);
+            if (k >= klo && k < khi) {
+                if (!(dd >= 0.f)) bad = 1;
+                if (TO_GMEM) dist_gmem[(size_t)i * n2 + j] = dd;
+                else asm volatile("st.shared.f32 [%0], %1;" ::"r"(dsk_addr + 4u * (unsigned)(tb[i + j] + i)),
+                                  "f"(dd) : "memory");
+            }
+        }
+    }
+    return bad;
 }
 
 template <int RA, int NCG>
@@ -557,11 +635,18 @@ align_stack_kernel(const AlignArgs a) {
     const int tj = (warp & 1) * 4 + (lane & 3);
     const int beg = max(a.class_off[CLS], a.w0), end = min(a.class_off[CLS + 1], a.w1);
     const unsigned sbase = smem_u32(smem);
+    const unsigned bar = sbase + L::BAR_OFF;
     float *Ds = reinterpret_cast<float *>(smem);
     float *Gs = reinterpret_cast<float *>(smem + L::G_OFF);
     float *n40 = reinterpret_cast<float *>(smem + L::N40_OFF);
     float *norms = reinterpret_cast<float *>(smem + L::NORMS_OFF);
     int *tb = reinterpret_cast<int *>(smem + L::TB_OFF);
+    unsigned phase = 0;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     for (int it = beg + blockIdx.x; it < end; it += gridDim.x) {
         const int p = a.order[it];
@@ -569,25 +654,20 @@ align_stack_kernel(const AlignArgs a) {
         const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
         const int n1e = n1 + 2 * STACK_H, n2e = n2 + 2 * STACK_H;
         const float *g1 = a.feat + (size_t)s1 * a.dim, *g2 = a.feat + (size_t)s2 * a.dim;
-        if (!a.dist_out) skew_table(tb, n1, n2, tid);
 
-        // 1. stage the extended frames of both tokens (160 contiguous bytes each)
-        {
-            const int piece = tid & 15, r0 = tid >> 4;
-            if (piece < STACK_F / 4) {
-                for (int e = r0; e < n1e; e += AL_THREADS / 16)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
-                                 "r"(sbase + e * (KCP * 4) + piece * 16),
-                                 "l"(ext_frame(g1, n1, a.dim, e) + piece * 4) : "memory");
-                for (int e = r0; e < n2e; e += AL_THREADS / 16)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
-                                 "r"(sbase + (L::ROWS_A + e) * (KCP * 4) + piece * 16),
-                                 "l"(ext_frame(g2, n2, a.dim, e) + piece * 4) : "memory");
-            }
-            cp_async_commit();
-            cp_async_wait<0>();
+        // 1. stage the extended frames of both tokens: one 160-byte bulk copy per frame
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                         "r"((unsigned)(n1e + n2e) * (STACK_F * 4u)) : "memory");
+        for (int e = tid; e < n1e + n2e; e += AL_THREADS) {
+            const bool first = e < n1e;
+            const int ee = first ? e : e - n1e;
+            const float *src = first ? ext_frame(g1, n1, a.dim, ee) : ext_frame(g2, n2, a.dim, ee);
+            bulk_g2s(sbase + ((first ? 0 : L::ROWS_A) + ee) * (KCP * 4), src, STACK_F * 4u, bar);
         }
-        __syncthreads();
+        if (!a.dist_out) skew_table(tb, n1, n2, tid);
+        mbar_wait_parity(bar, phase);
+        phase ^= 1u;
 
         // 2. per-frame sums of squares and the 40-deep Gram tile G40 (register tiled)
         {
@@ -636,58 +716,33 @@ align_stack_kernel(const AlignArgs a) {
             for (int c = 0; c < 2 * NCG; ++c) Gs[(ti + 16 * r) * L::LDG + tj + 8 * c] = acc[r][c];
         __syncthreads();           // G40, n40 complete; the staging area is dead from here on
 
-        // 3. row norms: |row_i|^2 = sum_c |x[i+c-3]|^2, same summation order as the generic kernel
+        // 3. reciprocal row norms: |row_i|^2 = sum_c |x[i+c-3]|^2, summed in stack order
         for (int q = tid; q < n1 + n2; q += AL_THREADS) {
             const int r0 = q < n1 ? q : L::ROWS_A + (q - n1);
             float ss = 0.f;
 #pragma unroll
             for (int c = 0; c < STACK_S; ++c) ss += n40[r0 + c];
-            norms[q < n1 ? q : L::ROWS_A + (q - n1)] = recip_norm(ss);
+            norms[r0] = recip_norm(ss);
         }
         __syncthreads();
 
-        // 4. 7-tap diagonal sums + epilogue -> D (over the dead staging area).  A thread
-        // owns RUNS of 8 cells along a diagonal, (i0 + k, j0 + k): the 14 Gram entries the
-        // run needs are loaded once, consecutive lanes take consecutive j0 (conflict-free).
-        // Every sum adds its 7 taps in stack order, like the generic kernel's chunk loop.
-        // Runs start at rows 8 b and columns -7 .. n2 - 1; cells outside the matrix are
-        // computed on whatever the loads returned and dropped.
-        int bad = 0;
-        float *dist_gmem = a.dist_out ? a.dist_out + a.dist_off[p] : nullptr;
-        {
-            constexpr int RUN = 8;
-            const int W = n2 + RUN - 1;
-            const int S = ((n1 + RUN - 1) / RUN) * W;
-            const float invW = 1.0f / (float)W;
-            for (int sidx = tid; sidx < S; sidx += AL_THREADS) {
-                const int b = (int)(((float)sidx + 0.5f) * invW);
-                const int i0 = b * RUN, j0 = sidx - b * W - (RUN - 1);
-                const float *gp = Gs + i0 * L::LDG + j0;
-                float g[RUN + STACK_S - 1];
-#pragma unroll
-                for (int k = 0; k < RUN + STACK_S - 1; ++k) g[k] = gp[k * (L::LDG + 1)];
-#pragma unroll
-                for (int k = 0; k < RUN; ++k) {
-                    const int i = i0 + k, j = j0 + k;
-                    float tot = 0.f;
-#pragma unroll
-                    for (int d = 0; d < STACK_S; ++d) tot += g[k + d];
-                    if (i < n1 && (unsigned)j < (unsigned)n2) {
-                        const float dd = cell_distance(tot, norms[i], norms[L::ROWS_A + j]);
-                        if (!(dd >= 0.f)) bad = 1;
-                        if (dist_gmem) dist_gmem[(size_t)i * n2 + j] = dd;
-                        else Ds[tb[i + j] + i] = dd;
-                    }
-                }
-            }
-        }
+        // 4. distances -> D in skew layout over the dead staging area (or row-major to gmem)
+        int bad;
+        if (!a.dist_out) skew_guards(Ds, tb, n1, tid);
+        if (a.dist_out)
+            bad = stack_epilogue<true, L>(Gs, norms, tb, sbase, a.dist_out + a.dist_off[p], n1, n2,
+                                          tid);
+        else
+            bad = stack_epilogue<false, L>(Gs, norms, tb, sbase, nullptr, n1, n2, tid);
         bad = __syncthreads_or(bad);
         if (tid == 0) {
             a.valid[p] = bad ? 0 : 1;
             if (bad && !a.dist_out) { a.path_len[p] = 0; a.cost[p] = nan(""); }
         }
         if (!a.dist_out && !bad)
-            skew_copy_out(Ds, a.dws + (size_t)(it - a.w0) * a.slot_cells, n1 * n2, tid);
+            skew_copy_out(Ds, a.dws + (size_t)(it - a.w0) * a.slot_cells, skew_cells(n1, n2), tid);
+        // the next pair's bulk copies (async proxy) overwrite what this pair read and wrote
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
     }
 }
@@ -1175,7 +1230,7 @@ static int class_table(const ClassLaunch **generic, const ClassLaunch **stacked)
 // hand-over slot of one pair (floats): the largest matrix of the fused classes
 static size_t slot_cells_for(int max_frames) {
     const size_t ns = (size_t)(max_frames < NM_SHORT ? max_frames : NM_SHORT);
-    return (ns * ns + 3) & ~(size_t)3;
+    return (ns * ns + ns + SKEW_SLACK + 3) & ~(size_t)3;
 }
 static size_t ws_dist_off(int n_pairs) {
     return (WS_ORDER + sizeof(int32_t) * (size_t)(n_pairs > 0 ? n_pairs : 0) + 255) & ~(size_t)255;
