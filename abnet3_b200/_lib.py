@@ -16,6 +16,21 @@ _I = _c.c_int
 _L = _c.c_int64
 _F = _c.c_float
 
+
+
+class GemmProblem(_c.Structure):
+    """abn_gemm_problem (include/abnet3_b200.h)."""
+    _fields_ = [("A", _P), ("lda", _L), ("a_mn", _I),
+                ("B", _P), ("ldb", _L), ("b_mn", _I),
+                ("M", _I), ("N", _I), ("K", _I),
+                ("epilogue", _I), ("act", _I), ("split_k", _I),
+                ("bias", _P),
+                ("out", _P), ("ldo", _L), ("out_f32", _I),
+                ("yprev", _P), ("ld_yprev", _L),
+                ("ones_col", _I),
+                ("ones_out", _P)]
+
+
 # name -> (restype, argtypes); mirrors include/abnet3_b200.h declaration order
 SIGNATURES = {
     "abn_version": (_I, []),
@@ -35,6 +50,7 @@ SIGNATURES = {
     "abn_linear_backward": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "abn_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _P, _L, _P, _L, _P, _L, _P, _L,
                                _P, _I, _P]),
+    "abn_gemm_bf16_group": (_I, [_P, _I, _P]),
     "abn_cast_bf16": (_I, [_P, _L, _I, _L, _P, _L, _P, _L, _P]),
     "abn_act_backward_bf16": (_I, [_P, _P, _L, _I, _I, _P, _L, _P, _L, _P, _P]),
     "abn_optimizer_step": (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _F, _L, _P]),

@@ -1,0 +1,563 @@
+// abn_tc2.cu -- kernel (3), tensor-core path: every dense contraction of the embedder's
+// training step on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// fed by TMA, as ONE persistent kernel that walks a list of GEMM problems.
+//
+// Reference behaviour served (paths relative to /root/reference):
+//   forward   y = act(x W^T + b)        abnet3/model.py:133-170, :179-186
+//   backward  dz_below = (dz W) * act'(y_below),  dW = dz^T x,  db = colsum(dz)
+//             -- the autograd of those blocks (abnet3/trainer.py:238)
+//
+// All operands are bf16 arrays in their NATURAL row-major layout -- activations and dz
+// [rows, features], weights [n_out, n_in] (nn.Linear) -- no transposed copies exist:
+//   forward  C[rows, n_out] = x[rows, n_in] . W[n_out, n_in]^T     A K-major,  B K-major
+//   dgrad    C[rows, n_in]  = dz[rows, n_out] . W[n_out, n_in]     A K-major,  B MN-major
+//   wgrad    C[n_out, n_in] = dz[rows, n_out]^T . x[rows, n_in]    A MN-major, B MN-major
+// "MN-major" = the operand's M (or N) index is the contiguous one in memory; the UMMA
+// shared-memory descriptor and instruction descriptor express it (cute::UMMA::Major::MN),
+// TMA delivers it as 64-element x 64-row boxes with the 128-byte swizzle.
+// db comes for free: activations carry a column of ones right after their last feature
+// (inside the 8-element row padding), so column n_in of dz^T [x | 1] is colsum(dz).
+//
+// CTA = 192 threads, persistent over 128 x BN output tiles (x split-K):
+//   warp 0      TMA producer (cp.async.bulk.tensor.2d, mbarrier ring of smem stages)
+//   warp 1      MMA issuer: one lane, tcgen05.mma.cta_group::1.kind::f16 M=128 N<=256 K=16
+//   warps 2-5   epilogue: tcgen05.ld (one TMEM lane = one output row per thread) ->
+//               bias + activation | x act'(y_below) -> packed bf16 / fp32 rows, 16-byte
+//               stores; or (wgrad) a shared-memory transpose and coalesced fp32 reds
+// The accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile i
+// overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "abn_common.cuh"
+
+namespace abn {
+
+constexpr int G_BM = 128;          // UMMA_M
+constexpr int G_BK = 64;           // bf16 elements per K block (128-byte swizzle row / 64 K rows)
+constexpr int G_UK = 16;           // UMMA_K
+constexpr int G_THREADS = 192;
+constexpr int G_MAXP = ABN_GEMM_MAX_GROUP;
+
+enum { GE_BIAS_ACT = 0, GE_DACT = 1, GE_ATOMIC = 2 };
+
+struct GProblem {
+    CUtensorMap map_a, map_b;
+    int M, N, K;                    // N includes the ones column of a wgrad problem
+    int a_mn, b_mn;
+    int epi, act, out_f32, ones_col;
+    int n_cap;                      // N + ones_col: the columns a tile row covers
+    int tiles_m, tiles_n, splits, kb_per_split;
+    int tile_beg;
+    const float *bias;
+    void *out; long long ldo;
+    const __nv_bfloat16 *yprev; long long ld_yprev;
+    float *ones_out;
+};
+struct GGroup {
+    GProblem p[G_MAXP];
+    int n_problems, total_tiles;
+};
+
+// ------------------------------------------------------------------- PTX ---
+__device__ __forceinline__ unsigned g_smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void g_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void g_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; spin < (1u << 27); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void g_tma_2d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0,
+                                         int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void g_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void g_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void g_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void g_mma(unsigned d_tmem, unsigned long long a_desc,
+                                      unsigned long long b_desc, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void g_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// cute::UMMA::SmemDescriptor, 128-byte swizzle.
+//   K-major  tile [rows x 64 K]: rows of 128 B, 8-row groups 1024 B apart (SBO); a UMMA_K
+//            step of 16 elements advances the start address by 32 B
+//   MN-major tile [64 K rows x R]: per 64-element column block, 64 rows of 128 B; 8-row
+//            K groups 1024 B apart (SBO), column blocks 8192 B apart (LBO); a UMMA_K step
+//            of 16 rows advances the start address by 2048 B
+__device__ __forceinline__ unsigned long long g_desc(unsigned smem_addr, int mn_major) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (unsigned long long)(mn_major ? (8192 >> 4) : 1) << 16;     // leading byte offset
+    d |= (unsigned long long)(1024 >> 4) << 32;                      // stride byte offset
+    d |= (unsigned long long)1 << 46;                                // descriptor version (Blackwell)
+    d |= (unsigned long long)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D fp32, A/B bf16, majors per operand
+__device__ __forceinline__ unsigned g_idesc(int n, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)a_mn << 15) | ((unsigned)b_mn << 16) |
+           ((unsigned)(n >> 3) << 17) | ((unsigned)(G_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float g_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// one MUFU op per element: sigmoid(v) = 0.5 + 0.5 tanh(v / 2); well inside the bf16 tolerance
+template <int ACT>
+__device__ __forceinline__ float g_act(float v) {
+    if (ACT == 1) return fmaf(0.5f, g_tanh(0.5f * v), 0.5f);
+    if (ACT == 2) return g_tanh(v);
+    if (ACT == 3) return v > 0.f ? v : 0.f;
+    return v;
+}
+template <int ACT>
+__device__ __forceinline__ float g_dact(float g, float y) {
+    if (ACT == 1) return g * (y * (1.f - y));
+    if (ACT == 2) return g * (1.f - y * y);
+    if (ACT == 3) return y > 0.f ? g : 0.f;
+    return g;
+}
+template <int ACT>
+__device__ __forceinline__ void g_bias_act32(float (&v)[32], const float *bs) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = g_act<ACT>(v[j] + bs[j]);
+}
+template <int ACT>
+__device__ __forceinline__ void g_dact32(float (&v)[32], const uint4 (&y)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const unsigned w[4] = {y[q].x, y[q].y, y[q].z, y[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[8 * q + 2 * e] = g_dact<ACT>(v[8 * q + 2 * e], __uint_as_float(w[e] << 16));
+            v[8 * q + 2 * e + 1] = g_dact<ACT>(v[8 * q + 2 * e + 1], __uint_as_float(w[e] & 0xffff0000u));
+        }
+    }
+}
+__device__ __forceinline__ unsigned g_pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<unsigned *>(&h);
+}
+
+struct GTile { int pi, m0, n0, kb0, nkb, n_eff; };
+
+__device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn) {
+    int pi = 0;
+#pragma unroll
+    for (int q = 1; q < G_MAXP; ++q)
+        if (q < g.n_problems && tile >= g.p[q].tile_beg) pi = q;
+    const GProblem &P = g.p[pi];
+    const int local = tile - P.tile_beg;
+    const int per_split = P.tiles_m * P.tiles_n;
+    const int ks = local / per_split, r = local - ks * per_split;
+    const int mt = r / P.tiles_n, nt = r - mt * P.tiles_n;
+    GTile t;
+    t.pi = pi;
+    t.m0 = mt * G_BM;
+    t.n0 = nt * bn;
+    const int total_kb = (P.K + G_BK - 1) / G_BK;
+    t.kb0 = ks * P.kb_per_split;
+    t.nkb = min(total_kb, t.kb0 + P.kb_per_split) - t.kb0;
+    const int rem = P.n_cap - t.n0;
+    t.n_eff = rem >= bn ? bn : ((rem + 15) & ~15);
+    return t;
+}
+
+// ---------------------------------------------------------------- kernel ---
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS, 1)
+tc_group_kernel(const __grid_constant__ GGroup g) {
+    constexpr unsigned A_BYTES = G_BM * G_BK * 2;           // 16 KB
+    constexpr unsigned B_BYTES = BN * G_BK * 2;             // 16 / 32 KB
+    constexpr unsigned STAGE = A_BYTES + B_BYTES;
+    constexpr int STAGES = BN == 256 ? 4 : 6;
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned raw = g_smem_u32(smem_raw);
+    const unsigned base = (raw + 1023u) & ~1023u;           // 128B-swizzle atoms are 1024-byte aligned
+    unsigned char *gen = smem_raw + (base - raw);
+    const unsigned bars = base + STAGES * STAGE;
+    const unsigned full0 = bars, empty0 = bars + 8 * STAGES;
+    const unsigned tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16, tptr = tempty0 + 16;
+    volatile unsigned *tptr_gen = reinterpret_cast<volatile unsigned *>(gen + STAGES * STAGE +
+                                                                        16 * STAGES + 32);
+    float *bias_s = reinterpret_cast<float *>(gen + STAGES * STAGE + 256);      // [2][BN]
+    float *scratch = bias_s + 2 * BN;                                            // [4][32][33]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { g_mbar_init(full0 + 8 * s, 1); g_mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { g_mbar_init(tfull0 + 8 * b, 1); g_mbar_init(tempty0 + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {      // the whole TMEM of the SM is ours (one CTA per SM): two accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(tptr), "n"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    g_fence_before();
+    __syncthreads();
+    g_fence_after();
+    const unsigned tmem = *tptr_gen;
+
+    if (warp == 0) {
+        // ------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            unsigned n = 0;                                  // k-blocks issued so far (ring position)
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                const GTile t = g_decode(g, tile, BN);
+                const GProblem &P = g.p[t.pi];
+                const int nbox_b = (t.n_eff + 63) >> 6;
+                const unsigned bytes = A_BYTES + (P.b_mn ? (unsigned)nbox_b * 8192u : B_BYTES);
+                for (int i = 0; i < t.nkb; ++i, ++n) {
+                    const int s = n % STAGES;
+                    g_mbar_wait(empty0 + 8 * s, ((n / STAGES) & 1) ^ 1);
+                    g_mbar_expect_tx(full0 + 8 * s, bytes);
+                    const unsigned sa = base + s * STAGE, sb = sa + A_BYTES;
+                    const int k0 = (t.kb0 + i) * G_BK;
+                    if (P.a_mn) {
+                        g_tma_2d(sa, &P.map_a, full0 + 8 * s, t.m0, k0);
+                        g_tma_2d(sa + 8192, &P.map_a, full0 + 8 * s, t.m0 + 64, k0);
+                    } else {
+                        g_tma_2d(sa, &P.map_a, full0 + 8 * s, k0, t.m0);
+                    }
+                    if (P.b_mn) {
+                        for (int j = 0; j < nbox_b; ++j)
+                            g_tma_2d(sb + j * 8192, &P.map_b, full0 + 8 * s, t.n0 + 64 * j, k0);
+                    } else {
+                        g_tma_2d(sb, &P.map_b, full0 + 8 * s, k0, t.n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            unsigned n = 0, it = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+                const GTile t = g_decode(g, tile, BN);
+                const GProblem &P = g.p[t.pi];
+                const unsigned ab = it & 1;
+                g_mbar_wait(tempty0 + 8 * ab, ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+                g_fence_after();
+                const unsigned idesc = g_idesc(t.n_eff, P.a_mn, P.b_mn);
+                const unsigned d_tmem = tmem + ab * BN;
+                const unsigned a_step = P.a_mn ? (2048 >> 4) : (32 >> 4);
+                const unsigned b_step = P.b_mn ? (2048 >> 4) : (32 >> 4);
+                for (int i = 0; i < t.nkb; ++i, ++n) {
+                    const int s = n % STAGES;
+                    g_mbar_wait(full0 + 8 * s, (n / STAGES) & 1);
+                    g_fence_after();
+                    const unsigned sa = base + s * STAGE;
+                    const unsigned long long da = g_desc(sa, P.a_mn);
+                    const unsigned long long db = g_desc(sa + A_BYTES, P.b_mn);
+#pragma unroll
+                    for (int k = 0; k < G_BK / G_UK; ++k)
+                        g_mma(d_tmem, da + (unsigned long long)(a_step * k),
+                              db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
+                    g_commit(empty0 + 8 * s);           // frees the smem stage when these MMAs retire
+                }
+                g_commit(tfull0 + 8 * ab);              // accumulator complete
+            }
+        }
+    } else {
+        // ---------------------------------------------------------- epilogue
+        const int wq = warp & 3;                        // TMEM lane quarter of this warp
+        const int et = (warp - 2) * 32 + lane;          // 0..127
+        float *my_scratch = scratch + wq * (32 * 33);
+        unsigned it = 0;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+            const GTile t = g_decode(g, tile, BN);
+            const GProblem &P = g.p[t.pi];
+            const unsigned ab = it & 1;
+            float *bs = bias_s + ab * BN;
+            if (P.epi == GE_BIAS_ACT) {
+                for (int c = et; c < BN; c += 128)
+                    bs[c] = (P.bias && t.n0 + c < P.N) ? __ldg(P.bias + t.n0 + c) : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            g_mbar_wait(tfull0 + 8 * ab, (it >> 1) & 1);
+            g_fence_after();
+            const unsigned taddr = tmem + ((unsigned)(wq * 32) << 16) + ab * BN;
+            const int row = t.m0 + wq * 32 + lane;
+            if (t.nkb <= 0) {
+                // nothing was accumulated (cannot happen with the host's split sizes)
+            } else if (P.epi == GE_ATOMIC) {
+                // fp32 reduction of a split-K partial: transpose 32 x 32 blocks through smem so
+                // that a warp's red instructions cover 128 contiguous bytes of one output row
+                float *out = static_cast<float *>(P.out);
+                const int n_w = P.ones_out ? P.N - 1 : P.N;          // columns that belong to `out`
+                for (int c0 = 0; c0 < t.n_eff; c0 += 32) {
+                    float v[32];
+                    g_ld32(taddr + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) my_scratch[lane * 33 + j] = v[j];
+                    __syncwarp();
+                    const int gcol = t.n0 + c0 + lane;
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        const int grow = t.m0 + wq * 32 + r;
+                        if (grow >= P.M) break;
+                        const float x = my_scratch[r * 33 + lane];
+                        if (gcol < n_w) atomicAdd(out + (long long)grow * P.ldo + gcol, x);
+                        else if (gcol == n_w && P.ones_out) atomicAdd(P.ones_out + grow, x);
+                    }
+                    __syncwarp();
+                }
+            } else {
+                const int n_cap = P.n_cap;
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int gcol0 = t.n0 + c0;
+                    if (gcol0 >= n_cap || c0 >= t.n_eff + 16) break;     // warp-uniform
+                    float v[32];
+                    g_ld32(taddr + c0, v);
+                    if (P.epi == GE_BIAS_ACT) {
+                        switch (P.act) {
+                            case 1: g_bias_act32<1>(v, bs + c0); break;
+                            case 2: g_bias_act32<2>(v, bs + c0); break;
+                            case 3: g_bias_act32<3>(v, bs + c0); break;
+                            default: g_bias_act32<0>(v, bs + c0); break;
+                        }
+                    } else {
+                        // x act'(y_below): 8 bf16 of this row per 16-byte load
+                        const __nv_bfloat16 *yp = P.yprev + (long long)row * P.ld_yprev + gcol0;
+                        uint4 y8[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            y8[q] = make_uint4(0, 0, 0, 0);
+                            if (row < P.M && gcol0 + 8 * q + 8 <= P.ld_yprev)
+                                y8[q] = __ldg(reinterpret_cast<const uint4 *>(yp + 8 * q));
+                        }
+                        switch (P.act) {
+                            case 1: g_dact32<1>(v, y8); break;
+                            case 2: g_dact32<2>(v, y8); break;
+                            case 3: g_dact32<3>(v, y8); break;
+                            default: break;
+                        }
+                    }
+                    if (P.ones_col && P.N >= gcol0 && P.N < gcol0 + 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (gcol0 + j == P.N) ? 1.f : v[j];
+                    }
+                    if (row < P.M) {
+                        if (P.out_f32) {
+                            float *op = static_cast<float *>(P.out) + (long long)row * P.ldo + gcol0;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (gcol0 + 4 * q + 4 <= P.N && (P.ldo & 3) == 0)
+                                    *reinterpret_cast<float4 *>(op + 4 * q) =
+                                        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                                else
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (gcol0 + 4 * q + e < P.N) op[4 * q + e] = v[4 * q + e];
+                            }
+                        } else {
+                            // rows are padded to a multiple of 8 elements: whole 16-byte groups
+                            // up to the padded width (padding columns receive don't-care values)
+                            __nv_bfloat16 *op = static_cast<__nv_bfloat16 *>(P.out) +
+                                                (long long)row * P.ldo + gcol0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (gcol0 + 8 * q + 8 <= P.ldo)
+                                    *reinterpret_cast<uint4 *>(op + 8 * q) = make_uint4(
+                                        g_pack_bf16(v[8 * q], v[8 * q + 1]),
+                                        g_pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                        g_pack_bf16(v[8 * q + 4], v[8 * q + 5]),
+                                        g_pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+                        }
+                    }
+                }
+            }
+            g_fence_before();
+            __syncwarp();
+            if (lane == 0) g_mbar_arrive(tempty0 + 8 * ab);
+        }
+    }
+    g_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        g_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host ---
+typedef CUresult (*GEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                              const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                              const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static GEncodeFn g_encode_fn() {
+    static GEncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<GEncodeFn>(p);
+    }
+    return fn;
+}
+
+// bf16 array [rows, cols] with leading dimension ld (elements), cols contiguous;
+// box = box_cols (inner) x box_rows, 128-byte swizzle, out-of-bounds elements read as 0
+static int g_make_map(CUtensorMap *map, const void *ptr, long long rows, long long cols,
+                      long long ld, int box_cols, int box_rows) {
+    GEncodeFn fn = g_encode_fn();
+    if (!fn) return set_error(ABN_EIO, "cuTensorMapEncodeTiled is not available");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (ld & 7))
+        return set_error(ABN_EINVAL, "bf16 operand must be 16-byte aligned with ld %% 8 == 0");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(ABN_EIO, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return ABN_OK;
+}
+
+template <int BN>
+static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
+    constexpr int STAGES = BN == 256 ? 4 : 6;
+    constexpr unsigned smem = STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 256 + 2 * BN * 4 +
+                              4 * 32 * 33 * 4 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc_group_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return set_error(ABN_EIO, "abn_gemm_bf16_group: cannot reserve %u bytes of shared memory",
+                             smem);
+        configured = true;
+    }
+    const int grid = g.total_tiles < sm_count ? g.total_tiles : sm_count;
+    tc_group_kernel<BN><<<grid, G_THREADS, smem, st>>>(g);
+    return check_launch("abn_gemm_bf16_group");
+}
+
+}  // namespace abn
+
+using namespace abn;
+
+extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_problems,
+                                   abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (n_problems == 0) return ABN_OK;
+    if (!problems || n_problems < 0 || n_problems > G_MAXP)
+        return set_error(ABN_EINVAL, "abn_gemm_bf16_group: 1..%d problems per call", G_MAXP);
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int max_n = 0;
+    for (int i = 0; i < n_problems; ++i) {
+        const abn_gemm_problem &q = problems[i];
+        if (!q.A || !q.B || !q.out || q.M <= 0 || q.N <= 0 || q.K <= 0 || q.epilogue < 0 ||
+            q.epilogue > 2 || q.act < 0 || q.act > 3)
+            return set_error(ABN_EINVAL, "abn_gemm_bf16_group: bad argument in problem %d", i);
+        if (q.epilogue == GE_DACT && !q.yprev)
+            return set_error(ABN_EINVAL, "abn_gemm_bf16_group: problem %d: act' epilogue needs yprev", i);
+        if (q.epilogue == GE_ATOMIC && !q.out_f32)
+            return set_error(ABN_EINVAL, "abn_gemm_bf16_group: problem %d: reduction output is fp32", i);
+        const int n_cols = q.N + ((q.epilogue == GE_ATOMIC ? q.ones_out != nullptr : q.ones_col != 0) ? 1 : 0);
+        if (n_cols > max_n) max_n = n_cols;
+    }
+    const int bn = max_n <= 128 ? 128 : 256;
+    GGroup g;
+    memset(&g, 0, sizeof(g));
+    g.n_problems = n_problems;
+    int tile = 0;
+    for (int i = 0; i < n_problems; ++i) {
+        const abn_gemm_problem &q = problems[i];
+        GProblem &P = g.p[i];
+        const int ones_in = (q.epilogue == GE_ATOMIC && q.ones_out) ? 1 : 0;
+        P.M = q.M; P.N = q.N + ones_in; P.K = q.K;
+        P.a_mn = q.a_mn ? 1 : 0; P.b_mn = q.b_mn ? 1 : 0;
+        P.epi = q.epilogue; P.act = q.act; P.out_f32 = q.out_f32 ? 1 : 0;
+        P.ones_col = (q.epilogue != GE_ATOMIC && q.ones_col) ? 1 : 0;
+        P.bias = q.bias; P.out = q.out; P.ldo = q.ldo;
+        P.yprev = static_cast<const __nv_bfloat16 *>(q.yprev); P.ld_yprev = q.ld_yprev;
+        P.ones_out = ones_in ? q.ones_out : nullptr;
+        if (!P.out_f32 && ((q.ldo & 7) || q.ldo < P.N + P.ones_col))
+            return set_error(ABN_EINVAL, "abn_gemm_bf16_group: problem %d: bf16 output rows must be "
+                             "padded to a multiple of 8 elements covering N%s", i,
+                             P.ones_col ? " + 1" : "");
+        // A: K-major [M, K] or MN-major [K, M];  B: K-major [N, K] or MN-major [K, N]
+        int rc = P.a_mn ? g_make_map(&P.map_a, q.A, q.K, q.M, q.lda, 64, 64)
+                        : g_make_map(&P.map_a, q.A, q.M, q.K, q.lda, G_BK, G_BM);
+        if (rc) return rc;
+        rc = P.b_mn ? g_make_map(&P.map_b, q.B, q.K, P.N, q.ldb, 64, 64)
+                    : g_make_map(&P.map_b, q.B, P.N, q.K, q.ldb, G_BK, bn);
+        if (rc) return rc;
+        P.tiles_m = (P.M + G_BM - 1) / G_BM;
+        P.n_cap = P.N + P.ones_col;
+        P.tiles_n = (P.n_cap + bn - 1) / bn;
+        const int total_kb = (P.K + G_BK - 1) / G_BK;
+        int splits = (q.epilogue == GE_ATOMIC && q.split_k > 1) ? q.split_k : 1;
+        if (splits > total_kb) splits = total_kb;
+        P.kb_per_split = (total_kb + splits - 1) / splits;
+        P.splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
+        P.tile_beg = tile;
+        tile += P.tiles_m * P.tiles_n * P.splits;
+    }
+    g.total_tiles = tile;
+    cudaStream_t st = (cudaStream_t)stream;
+    return bn == 128 ? g_launch<128>(g, sm_count, st) : g_launch<256>(g, sm_count, st);
+}

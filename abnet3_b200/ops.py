@@ -305,3 +305,39 @@ def act_backward_bf16(y, dy, act, dz=None, dzT=None, db=None):
                                            dz.stride(0) if dz is not None else 0, ptr(dzT),
                                            dzT.stride(0) if dzT is not None else 0, ptr(db),
                                            stream_ptr()))
+
+
+# ------------------------------------- persistent grouped tcgen05 GEMM ---
+GE_BIAS_ACT, GE_DACT, GE_ATOMIC = 0, 1, 2
+GEMM_MAX_GROUP = 4
+
+
+def gemm_problem(A, B, M, N, K, epilogue, out, a_mn=False, b_mn=False, act=None, bias=None,
+                 yprev=None, split_k=1, ones_col=False, ones_out=None):
+    """One abn_gemm_problem.  A / B: bf16 2-D CUDA tensors with a contiguous last
+    dimension ([M, K] / [N, K], or [K, M] / [K, N] when a_mn / b_mn); ``out``: bf16 or
+    float32 2-D tensor.  Keeps references to the tensors alive on the returned object."""
+    for t, nm in ((A, "A"), (B, "B")):
+        if not (t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1):
+            raise TypeError("%s must be a CUDA bf16 tensor with a contiguous last dim" % nm)
+    if not (out.is_cuda and out.stride(-1) == 1 and out.dtype in (torch.float32, torch.bfloat16)):
+        raise TypeError("out must be a CUDA float32 / bf16 tensor with a contiguous last dim")
+    q = _lib.GemmProblem()
+    q.A, q.lda, q.a_mn = ptr(A), A.stride(0), int(bool(a_mn))
+    q.B, q.ldb, q.b_mn = ptr(B), B.stride(0), int(bool(b_mn))
+    q.M, q.N, q.K = int(M), int(N), int(K)
+    q.epilogue, q.act, q.split_k = int(epilogue), ACT[act], int(split_k)
+    q.bias = ptr(bias)
+    q.out, q.ldo, q.out_f32 = ptr(out), out.stride(0), int(out.dtype == torch.float32)
+    q.yprev, q.ld_yprev = ptr(yprev), (yprev.stride(0) if yprev is not None else 0)
+    q.ones_col = int(bool(ones_col))
+    q.ones_out = ptr(ones_out)
+    q._keep = (A, B, out, bias, yprev, ones_out)
+    return q
+
+
+def gemm_group(problems):
+    """Run up to GEMM_MAX_GROUP problems in ONE persistent tcgen05 launch."""
+    n = len(problems)
+    arr = (_lib.GemmProblem * n)(*problems)
+    check(_lib.lib().abn_gemm_bf16_group(arr, n, stream_ptr()))

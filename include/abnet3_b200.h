@@ -243,6 +243,42 @@ ABN_API int abn_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t 
                              void *outT_bf16, int64_t ld_T, const void *yprev, int64_t ld_yprev,
                              float *db, int split_k, abn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * (3) tensor-core path, persistent grouped GEMM: up to ABN_GEMM_MAX_GROUP problems
+ * C[M,N] = A . B^T in ONE launch (tcgen05 / TMEM / TMA; one persistent CTA per SM walks
+ * the 128 x 256 output tiles of all problems, the accumulator double buffered in TMEM).
+ * Operands are bf16 arrays in their natural row-major layout, never transposed copies:
+ *   a_mn = 0: A is [M, K] (K contiguous);  a_mn = 1: A is [K, M] (M contiguous)
+ *   b_mn = 0: B is [N, K] (K contiguous);  b_mn = 1: B is [K, N] (N contiguous)
+ * so for one layer of abnet3/model.py:133-170 and its backward:
+ *   forward  A = x [rows, n_in],    B = W [n_out, n_in]            a_mn 0, b_mn 0, epilogue 0
+ *   dgrad    A = dz [rows, n_out],  B = W [n_out, n_in]            a_mn 0, b_mn 1, epilogue 1
+ *   wgrad    A = dz [rows, n_out],  B = x [rows, n_in]  (K = rows) a_mn 1, b_mn 1, epilogue 2
+ * Epilogues: 0  out = act(C + bias)            -> bf16 [M, ldo] or fp32 (out_f32)
+ *            1  out = C * act'(yprev)          -> the dz of the layer below (yprev = its
+ *                                                 forward output, bf16 [M, ld_yprev])
+ *            2  out += C (fp32 reds, split_k)  -> out fp32 [M, ldo]
+ * ones_col (epilogues 0/1): also write 1.0 into column N of every output row (it must lie
+ *   inside the row padding, ldo >= N + 1).  ones_out (epilogue 2): B has such a column of
+ *   ones at index N; its products -- the column sums of A, i.e. the bias gradient -- are
+ *   added to ones_out[M] instead of `out`.
+ * Leading dimensions in elements; bf16 pointers 16-byte aligned, bf16 lds multiples of 8.
+ * ---------------------------------------------------------------------- */
+#define ABN_GEMM_MAX_GROUP 4
+typedef struct {
+    const void *A; int64_t lda; int a_mn;
+    const void *B; int64_t ldb; int b_mn;
+    int M, N, K;
+    int epilogue, act, split_k;
+    const float *bias;
+    void *out; int64_t ldo; int out_f32;
+    const void *yprev; int64_t ld_yprev;
+    int ones_col;
+    float *ones_out;
+} abn_gemm_problem;
+ABN_API int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_problems,
+                                abn_stream_t stream);
+
 /* fp32 [rows, cols] (ld_src) -> bf16 [rows, ld_dst] and/or transposed bf16
  * [cols, ld_T]: operand preparation for abn_gemm_bf16_tn (weights after every
  * optimizer step, the gathered input batch). */
