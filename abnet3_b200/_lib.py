@@ -31,6 +31,11 @@ class GemmProblem(_c.Structure):
                 ("ones_out", _P)]
 
 
+class ParamSegment(_c.Structure):
+    """abn_param_segment (include/abnet3_b200.h)."""
+    _fields_ = [("offset", _L), ("count", _L), ("ld", _L), ("bf16", _P), ("n_in", _I)]
+
+
 # name -> (restype, argtypes); mirrors include/abnet3_b200.h declaration order
 SIGNATURES = {
     "abn_version": (_I, []),
@@ -54,6 +59,9 @@ SIGNATURES = {
     "abn_cast_bf16": (_I, [_P, _L, _I, _L, _P, _L, _P, _L, _P]),
     "abn_act_backward_bf16": (_I, [_P, _P, _L, _I, _I, _P, _L, _P, _L, _P, _P]),
     "abn_optimizer_step": (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _F, _L, _P]),
+    "abn_gather_batch_bf16": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P]),
+    "abn_pair_loss_dz": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _I, _P, _P, _P, _L, _P]),
+    "abn_optimizer_step_fused": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _I, _P]),
 }
 
 _lib = None

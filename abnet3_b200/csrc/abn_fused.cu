@@ -1,0 +1,220 @@
+// abn_fused.cu -- the memory-bound companions of the tensor-core training step, each
+// fused with the format conversion its consumer needs so that no fp32 intermediate makes
+// a round trip through HBM:
+//   abn_gather_batch_bf16    batch generation (abnet3/dataloader.py:204-205, :673-684)
+//                            straight into the bf16 A operand of the first layer
+//   abn_pair_loss_dz         coscos2 / cosmargin value (abnet3/loss.py:46-67, :85-105) and
+//                            the gradient w.r.t. the PRE-activation of the output layer,
+//                            dz = dL/de * act'(e), as bf16 rows (the wgrad / dgrad operand)
+//   abn_optimizer_step_fused optimizer.step() of abnet3/trainer.py:240 over the flat
+//                            bucket + the bf16 operand copy of every weight matrix + the
+//                            zeroing of the gradient bucket for the next step's reductions
+#include <cuda_bf16.h>
+
+#include "abn_common.cuh"
+
+namespace abn {
+
+// one warp per gathered row; 16-byte loads, 8-byte bf16x4 stores
+__global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
+                                   const int32_t *__restrict__ idx1,
+                                   const int32_t *__restrict__ idx2,
+                                   const int8_t *__restrict__ y_in,
+                                   const int64_t *__restrict__ sel, int64_t n,
+                                   __nv_bfloat16 *__restrict__ xb, int64_t ldx,
+                                   float *__restrict__ y_out, float *__restrict__ zero_me) {
+    if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0.f;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t w = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (w >= 2 * n) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t k = w >> 1;
+    const int side = (int)(w & 1);
+    const int64_t pos = sel ? sel[k] : k;
+    const int32_t row = side ? idx2[pos] : idx1[pos];
+    const float4 *src = reinterpret_cast<const float4 *>(feat + (size_t)row * dim);
+    uint2 *dst = reinterpret_cast<uint2 *>(xb + (size_t)(side ? n + k : k) * ldx);
+    for (int c = lane; c < dim / 4; c += 32) {
+        const float4 v = __ldg(src + c);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        dst[c] = make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+    }
+    if (side == 0 && lane == 0 && y_out) y_out[k] = y_in ? (float)y_in[pos] : 1.f;
+}
+
+constexpr int LZ_WARPS = 8;
+constexpr float LZ_EPS = 1e-6f;      // nn.CosineSimilarity(eps=1e-6), loss.py:44
+
+__device__ __forceinline__ float dact_of(float y, int act) {
+    if (act == 1) return y * (1.f - y);
+    if (act == 2) return 1.f - y * y;
+    if (act == 3) return y > 0.f ? 1.f : 0.f;
+    return 1.f;
+}
+
+// one warp per frame pair (same arithmetic as pair_loss_kernel in abn_nn.cu)
+__global__ void __launch_bounds__(LZ_WARPS * 32)
+pair_loss_dz_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
+                    const float *__restrict__ y, int64_t n, int dim, int64_t ld, int kind,
+                    float margin, float scale, int act, float *__restrict__ loss,
+                    __nv_bfloat16 *__restrict__ dz1, __nv_bfloat16 *__restrict__ dz2,
+                    int64_t ld_dz) {
+    __shared__ float wsum[LZ_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float local = 0.f;
+    for (int64_t row = (int64_t)blockIdx.x * LZ_WARPS + warp; row < n;
+         row += (int64_t)gridDim.x * LZ_WARPS) {
+        const float *a = e1 + row * ld, *b = e2 + row * ld;
+        float dot = 0.f, na = 0.f, nb = 0.f;
+        for (int k = lane; k < dim; k += 32) {
+            const float x = a[k], z = b[k];
+            dot = fmaf(x, z, dot); na = fmaf(x, x, na); nb = fmaf(z, z, nb);
+        }
+        dot = warp_sum(dot); na = warp_sum(na); nb = warp_sum(nb);
+        const float ra = sqrtf(na), rb = sqrtf(nb);
+        const float an = fmaxf(ra, LZ_EPS), bn = fmaxf(rb, LZ_EPS);
+        const float inv = 1.f / (an * bn);
+        const float c = dot * inv;
+        const float lab = y[row];
+        float term, dldc;
+        if (kind == 0) {          // coscos2, loss.py:59-62
+            if (lab == 1.f)       { term = 0.5f * (1.f - c); dldc = -0.5f; }
+            else if (lab == -1.f) { term = c * c;            dldc = 2.f * c; }
+            else                  { term = c;                dldc = 1.f; }
+        } else {                  // cosmargin, loss.py:98-101
+            if (lab == 1.f)       { term = 1.f - c;          dldc = -1.f; }
+            else if (lab == -1.f) { const float h = c - margin;
+                                    term = fmaxf(h, 0.f);    dldc = h > 0.f ? 1.f : 0.f; }
+            else                  { term = c;                dldc = 1.f; }
+        }
+        if (lane == 0) local += term;
+        const float g = dldc * scale;
+        const float ka = ra > LZ_EPS ? c / (an * an) : 0.f;
+        const float kb = rb > LZ_EPS ? c / (bn * bn) : 0.f;
+        __nv_bfloat16 *ga = dz1 + row * ld_dz, *gb = dz2 + row * ld_dz;
+        for (int k = lane; k < dim; k += 32) {
+            const float x = a[k], z = b[k];      // L1 hits: read a moment ago
+            ga[k] = __float2bfloat16_rn(g * (z * inv - ka * x) * dact_of(x, act));
+            gb[k] = __float2bfloat16_rn(g * (x * inv - kb * z) * dact_of(z, act));
+        }
+    }
+    if (lane == 0) wsum[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LZ_WARPS; ++w) s += wsum[w];
+        if (s != 0.f) atomicAdd(loss, s * scale);
+    }
+}
+
+struct SegTable { abn_param_segment s[ABN_MAX_PARAM_SEGMENTS]; int n; };
+
+// grid.y = segment; same update rules as optimizer_kernel (abn_nn.cu)
+__global__ void optimizer_fused_kernel(float *__restrict__ p, float *__restrict__ g,
+                                       float *__restrict__ s0, float *__restrict__ s1, int kind,
+                                       float lr, float momentum, float gscale, float bc1,
+                                       float bc2_sqrt, int zero_grad, const SegTable tab) {
+    const abn_param_segment sg = tab.s[blockIdx.y];
+    __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < sg.count;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = sg.offset + j;
+        const float grad = g[i] * gscale;
+        float w = p[i];
+        if (kind == 0) {            // torch.optim.SGD(momentum, dampening=0)
+            float buf = grad;
+            if (momentum != 0.f) { buf = momentum * s0[i] + grad; s0[i] = buf; }
+            w -= lr * buf;
+        } else if (kind == 1) {     // torch.optim.Adadelta(rho=0.9, eps=1e-6)
+            const float rho = 0.9f, eps = 1e-6f;
+            const float sq = rho * s0[i] + (1.f - rho) * grad * grad;
+            const float stdv = sqrtf(sq + eps);
+            const float delta = sqrtf(s1[i] + eps) / stdv * grad;
+            s0[i] = sq;
+            s1[i] = rho * s1[i] + (1.f - rho) * delta * delta;
+            w -= lr * delta;
+        } else {                    // torch.optim.Adam(betas=(0.9, 0.999), eps=1e-8)
+            const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+            const float m = b1 * s0[i] + (1.f - b1) * grad;
+            const float v = b2 * s1[i] + (1.f - b2) * grad * grad;
+            s0[i] = m; s1[i] = v;
+            const float denom = sqrtf(v) / bc2_sqrt + eps;
+            w -= (lr / bc1) * (m / denom);
+        }
+        p[i] = w;
+        if (zero_grad) g[i] = 0.f;
+        if (wb) {
+            const int64_t r = j / sg.n_in;
+            wb[r * sg.ld + (j - r * sg.n_in)] = __float2bfloat16_rn(w);
+        }
+    }
+}
+
+}  // namespace abn
+
+using namespace abn;
+
+extern "C" int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *idx1,
+                                     const int32_t *idx2, const int8_t *y_in, const int64_t *sel,
+                                     int64_t n, void *xb, int64_t ldx, float *y_out,
+                                     float *zero_me, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (n == 0) return ABN_OK;
+    if (!feat || !idx1 || !idx2 || !xb || n < 0 || dim <= 0 || (dim & 3) || ldx < dim || (ldx & 3))
+        return set_error(ABN_EINVAL, "abn_gather_batch_bf16: bad argument");
+    const int wpb = 8;
+    const int64_t warps = 2 * n;
+    gather_bf16_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        feat, dim, idx1, idx2, y_in, sel, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out, zero_me);
+    return check_launch("abn_gather_batch_bf16");
+}
+
+extern "C" int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,
+                                int64_t ld, int kind, float margin, float scale, int act,
+                                float *loss, void *dz1, void *dz2, int64_t ld_dz,
+                                abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (n == 0) return ABN_OK;
+    if (ld == 0) ld = dim;
+    if (!e1 || !e2 || !y || !loss || !dz1 || !dz2 || n < 0 || dim <= 0 || ld < dim ||
+        ld_dz < dim || (kind != 0 && kind != 1) || act < 0 || act > 3)
+        return set_error(ABN_EINVAL, "abn_pair_loss_dz: bad argument");
+    int64_t blocks = (n + LZ_WARPS - 1) / LZ_WARPS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pair_loss_dz_kernel<<<(unsigned)blocks, LZ_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        e1, e2, y, n, dim, ld, kind, margin, scale, act, loss, static_cast<__nv_bfloat16 *>(dz1),
+        static_cast<__nv_bfloat16 *>(dz2), ld_dz);
+    return check_launch("abn_pair_loss_dz");
+}
+
+extern "C" int abn_optimizer_step_fused(float *param, float *grad, float *state0, float *state1,
+                                        int kind, float lr, float momentum, float grad_scale,
+                                        int64_t step, const abn_param_segment *segments,
+                                        int n_segments, int zero_grad, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (n_segments == 0) return ABN_OK;
+    if (!param || !grad || !segments || n_segments < 0 || n_segments > ABN_MAX_PARAM_SEGMENTS ||
+        kind < 0 || kind > 2 || (kind == 0 && momentum != 0.f && !state0) ||
+        (kind >= 1 && (!state0 || !state1)) || step < 1)
+        return set_error(ABN_EINVAL, "abn_optimizer_step_fused: bad argument (at most %d segments)",
+                         ABN_MAX_PARAM_SEGMENTS);
+    SegTable tab;
+    tab.n = n_segments;
+    int64_t longest = 0;
+    for (int i = 0; i < n_segments; ++i) {
+        tab.s[i] = segments[i];
+        if (segments[i].count < 0 || (segments[i].bf16 && segments[i].n_in <= 0))
+            return set_error(ABN_EINVAL, "abn_optimizer_step_fused: bad segment %d", i);
+        if (segments[i].count > longest) longest = segments[i].count;
+    }
+    const float bc1 = 1.f - powf(0.9f, (float)step);
+    const float bc2s = sqrtf(1.f - powf(0.999f, (float)step));
+    int64_t bx = (longest + 255) / 256;
+    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)n_segments);
+    optimizer_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        param, grad, state0, state1, kind, lr, momentum, grad_scale, bc1, bc2s, zero_grad, tab);
+    return check_launch("abn_optimizer_step_fused");
+}

@@ -57,6 +57,7 @@ struct GProblem {
 struct GGroup {
     GProblem p[G_MAXP];
     int n_problems, total_tiles;
+    long long *trace;               // debug: per-CTA role timestamps (NULL in production)
 };
 
 // ------------------------------------------------------------------- PTX ---
@@ -194,6 +195,14 @@ __device__ __forceinline__ unsigned g_pack_bf16(float lo, float hi) {
 
 struct GTile { int pi, m0, n0, kb0, nkb, n_eff; };
 
+__device__ __forceinline__ void g_trace(const GGroup &g, unsigned it, int slot) {
+    if (g.trace && it < 4) {
+        long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g.trace[((size_t)blockIdx.x * 4 + it) * 8 + slot] = t;
+    }
+}
+
 __device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn) {
     int pi = 0;
 #pragma unroll
@@ -255,9 +264,10 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer
         if (lane == 0) {
-            unsigned n = 0;                                  // k-blocks issued so far (ring position)
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            unsigned n = 0, pit = 0;                         // k-blocks issued so far (ring position)
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++pit) {
                 const GTile t = g_decode(g, tile, BN);
+                g_trace(g, pit, 0);
                 const GProblem &P = g.p[t.pi];
                 const int nbox_b = (t.n_eff + 63) >> 6;
                 const unsigned bytes = A_BYTES + (P.b_mn ? (unsigned)nbox_b * 8192u : B_BYTES);
@@ -280,6 +290,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                         g_tma_2d(sb, &P.map_b, full0 + 8 * s, k0, t.n0);
                     }
                 }
+                g_trace(g, pit, 1);
             }
         }
     } else if (warp == 1) {
@@ -290,8 +301,10 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                 const GTile t = g_decode(g, tile, BN);
                 const GProblem &P = g.p[t.pi];
                 const unsigned ab = it & 1;
+                g_trace(g, it, 2);
                 g_mbar_wait(tempty0 + 8 * ab, ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
                 g_fence_after();
+                g_trace(g, it, 3);
                 const unsigned idesc = g_idesc(t.n_eff, P.a_mn, P.b_mn);
                 const unsigned d_tmem = tmem + ab * BN;
                 const unsigned a_step = P.a_mn ? (2048 >> 4) : (32 >> 4);
@@ -310,6 +323,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                     g_commit(empty0 + 8 * s);           // frees the smem stage when these MMAs retire
                 }
                 g_commit(tfull0 + 8 * ab);              // accumulator complete
+                g_trace(g, it, 4);
             }
         }
     } else {
@@ -328,8 +342,10 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                     bs[c] = (P.bias && t.n0 + c < P.N) ? __ldg(P.bias + t.n0 + c) : 0.f;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+            if (et == 0) g_trace(g, it, 5);
             g_mbar_wait(tfull0 + 8 * ab, (it >> 1) & 1);
             g_fence_after();
+            if (et == 0) g_trace(g, it, 6);
             const unsigned taddr = tmem + ((unsigned)(wq * 32) << 16) + ab * BN;
             const int row = t.m0 + wq * 32 + lane;
             if (t.nkb <= 0) {
@@ -424,6 +440,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
             g_fence_before();
             __syncwarp();
             if (lane == 0) g_mbar_arrive(tempty0 + 8 * ab);
+            if (et == 0) g_trace(g, it, 7);
         }
     }
     g_fence_before();
@@ -494,6 +511,9 @@ static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
 
 using namespace abn;
 
+// debug hook (not in the public header): device buffer of 148 * 4 * 8 int64 timestamps
+extern "C" { __attribute__((visibility("default"))) void *abn_gemm_trace_buffer = nullptr; }
+
 extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_problems,
                                    abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
@@ -558,6 +578,7 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
         tile += P.tiles_m * P.tiles_n * P.splits;
     }
     g.total_tiles = tile;
+    g.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
     cudaStream_t st = (cudaStream_t)stream;
     return bn == 128 ? g_launch<128>(g, sm_count, st) : g_launch<256>(g, sm_count, st);
 }

@@ -34,7 +34,7 @@ from . import ops
 from .model import SiameseNetwork, SiameseMultitaskNetwork, PRECISIONS
 
 OPTIMIZERS = ("sgd", "adadelta", "adam")
-GEMM_CTA_SLOTS = 2 * 148       # resident tcgen05 GEMM CTAs on one B200 (2 per SM)
+GEMM_CTAS = 148                # persistent tcgen05 GEMM CTAs on one B200 (one per SM)
 
 
 def _trained_layers(network):
@@ -91,7 +91,7 @@ class FlatBucket(object):
 
 class _Layer(object):
     """One GEMM layer of the tensor-core chain: fp32 master views + bf16 operands."""
-    __slots__ = ("W", "b", "gW", "gb", "act", "n_out", "n_in", "wb", "wtb")
+    __slots__ = ("W", "b", "gW", "gb", "act", "n_out", "n_in", "wb")
 
 
 class SiameseTrainStep(object):
@@ -130,6 +130,8 @@ class SiameseTrainStep(object):
             dist.is_initialized() else 1
         self._rows = -1
         self._static_n = None
+        self._loss_cleared = False
+        self._grads_clean = False
         if self.precision == 1:
             self._build_chain()
 
@@ -184,23 +186,29 @@ class SiameseTrainStep(object):
                                 dx=self.dacts[l - 1] if l > 0 else None)
 
     # ------------------------------------------------- bf16 tensor-core path ---
+    # Every contraction is one problem of the persistent grouped tcgen05 GEMM
+    # (abn_gemm_bf16_group) on bf16 arrays in their natural layout: activations and dz
+    # [rows, features] (+ a column of ones inside the row padding: the wgrad GEMM's extra
+    # output column is the bias gradient), weights [n_out, n_in].
     def _build_chain(self):
         """Trunk layers, then (multitask) the two heads as ONE layer whose weight
         is the [2d, hidden] block they occupy side by side in the flat bucket."""
         dev = self.bucket.param.device
         P, G, off = self.bucket.param, self.bucket.grad, self.bucket.offset
         self.chain = []
+        entries = []
 
-        def add(W_view, b_view, gW, gb, act):
+        def add(W_view, b_view, gW, gb, act, w_off, b_off):
             L = _Layer()
             L.W, L.b, L.gW, L.gb, L.act = W_view, b_view, gW, gb, act
             L.n_out, L.n_in = W_view.shape
             L.wb = torch.zeros((L.n_out, ops.pad8(L.n_in)), dtype=torch.bfloat16, device=dev)
-            L.wtb = torch.zeros((L.n_in, ops.pad8(L.n_out)), dtype=torch.bfloat16, device=dev)
             self.chain.append(L)
+            entries.append((w_off, L.n_out * L.n_in, L.wb, L.n_in))
+            entries.append((b_off, L.n_out, None, 0))
 
         for W, b, act in self.trunk:
-            add(W.data, b.data, W.grad, b.grad, act)
+            add(W.data, b.data, W.grad, b.grad, act, off[id(W)], off[id(b)])
         if self.heads:
             Ws = [h[0][0] for h in self.heads]
             bs = [h[0][1] for h in self.heads]
@@ -208,74 +216,79 @@ class SiameseTrainStep(object):
             ow, ob = off[id(Ws[0])], off[id(bs[0])]
             assert off[id(Ws[1])] == ow + d * hid and off[id(bs[1])] == ob + d
             add(P[ow:ow + 2 * d * hid].view(2 * d, hid), P[ob:ob + 2 * d],
-                G[ow:ow + 2 * d * hid].view(2 * d, hid), G[ob:ob + 2 * d], self.heads[0][0][2])
+                G[ow:ow + 2 * d * hid].view(2 * d, hid), G[ob:ob + 2 * d], self.heads[0][0][2],
+                ow, ob)
             self.head_dim = d
+        self._segments = ops.param_segments(entries)
+        self._grads_clean = False
         self.refresh_bf16_weights()
 
     def refresh_bf16_weights(self):
-        """bf16 W and W^T operand copies of the fp32 master weights (after every
-        optimizer step, or after load_state_dict)."""
+        """bf16 operand copies of the fp32 master weights (after load_state_dict; the
+        fused optimizer keeps them current during training)."""
         for L in self.chain:
-            ops.cast_bf16(L.W, L.wb, L.wtb)
+            ops.cast_bf16(L.W, L.wb, None)
 
     def _reserve_bf16(self, rows):
         dev = self.bucket.param.device
-        ldm = ops.pad8(rows)
 
-        def b16(r, c):
-            return torch.zeros((r, c), dtype=torch.bfloat16, device=dev)
+        def b16(r, c, ones_at=None):
+            t = torch.zeros((r, c), dtype=torch.bfloat16, device=dev)
+            if ones_at is not None:
+                t[:, ones_at] = 1.0
+            return t
 
         d_in = self.chain[0].n_in
-        self.xb, self.xbT = b16(rows, ops.pad8(d_in)), b16(d_in, ldm)
-        # hidden activations: bf16 + transposed bf16 only; the last layer: fp32 only
-        self.actb = [(b16(rows, ops.pad8(L.n_out)), b16(L.n_out, ldm)) for L in self.chain[:-1]]
-        self.dzb = [(b16(rows, ops.pad8(L.n_out)), b16(L.n_out, ldm)) for L in self.chain]
+        self.xb = b16(rows, ops.pad8(d_in + 1), d_in)
+        # hidden activations and every layer's dz: bf16; the embeddings: fp32
+        self.actb = [b16(rows, ops.pad8(L.n_out + 1)) for L in self.chain[:-1]]
+        self.dzb = [b16(rows, ops.pad8(L.n_out)) for L in self.chain]
         n_last = self.chain[-1].n_out
         self.out_last = torch.empty((rows, n_last), dtype=torch.float32, device=dev)
-        self.de_last = torch.zeros((rows, n_last), dtype=torch.float32, device=dev)
         self.acts = [None] * (len(self.chain) - 1) + [self.out_last]
+        last = len(self.chain) - 1
+        self._fwd_problems, self._dgrad_problems, wgrad = [], [], []
+        hb = self.xb
+        for l, L in enumerate(self.chain):
+            out = self.actb[l] if l < last else self.out_last
+            self._fwd_problems.append(ops.gemm_problem(
+                hb, L.wb, rows, L.n_out, L.n_in, ops.GE_BIAS_ACT, out, act=L.act, bias=L.b,
+                ones_col=(l < last)))
+            if l > 0:       # dz of the layer below = (dz W) * act'(its output)
+                self._dgrad_problems.append(ops.gemm_problem(
+                    self.dzb[l], L.wb, rows, L.n_in, L.n_out, ops.GE_DACT, self.dzb[l - 1], b_mn=True,
+                    act=self.chain[l - 1].act, yprev=self.actb[l - 1]))
+            wgrad.append((L, hb))
+            hb = out
+        # weight + bias gradients of ALL layers: one launch per group of 4 problems, split
+        # over the batch so that the group fills the machine about twice
+        tiles = sum(((L.n_out + 127) // 128) * ((L.n_in + 1 + 255) // 256) for L, _ in wgrad)
+        split = max(1, min((rows + 63) // 64, (2 * GEMM_CTAS + tiles - 1) // tiles))
+        self._wgrad_groups = []
+        probs = [ops.gemm_problem(self.dzb[l], xin, L.n_out, L.n_in, rows, ops.GE_ATOMIC, L.gW,
+                                  a_mn=True, b_mn=True, split_k=split, ones_out=L.gb)
+                 for l, (L, xin) in enumerate(wgrad)]
+        for i in range(0, len(probs), ops.GEMM_MAX_GROUP):
+            self._wgrad_groups.append(probs[i:i + ops.GEMM_MAX_GROUP])
 
     def _forward_bf16(self, x):
-        rows = x.shape[0]
-        ops.cast_bf16(x, self.xb, self.xbT)
-        hb = self.xb
-        last = len(self.chain) - 1
-        for l, L in enumerate(self.chain):
-            if l < last:
-                ops.gemm_bf16_tn(hb, L.wb, rows, L.n_out, L.n_in, ops.EPI_BIAS_ACT, L.b, L.act,
-                                 out_bf16=self.actb[l][0], outT_bf16=self.actb[l][1])
-                hb = self.actb[l][0]
-            else:
-                ops.gemm_bf16_tn(hb, L.wb, rows, L.n_out, L.n_in, ops.EPI_BIAS_ACT, L.b, L.act,
-                                 out_f32=self.out_last)
+        if x is not None:       # fp32 batch -> bf16 A operand (the gather can also write it directly)
+            ops.cast_bf16(x, self.xb, None)
+        for p in self._fwd_problems:
+            ops.gemm_group([p])
         if self.heads:
             d = self.head_dim
             return [self.out_last[:, :d], self.out_last[:, d:]]
         return self.out_last
 
-    def _split_k(self, L):
-        tiles = ((L.n_out + 127) // 128) * ((L.n_in + 127) // 128)
-        return max(1, GEMM_CTA_SLOTS // tiles)
-
     def _backward_bf16(self, x):
-        rows = x.shape[0]
-        self.bucket.trained_grad.zero_()       # dW / db are accumulated with atomics
-        last = len(self.chain) - 1
-        Ll = self.chain[last]
-        ops.act_backward_bf16(self.out_last, self.de_last, Ll.act, dz=self.dzb[last][0],
-                              dzT=self.dzb[last][1], db=Ll.gb)
-        for l in range(last, -1, -1):
-            L = self.chain[l]
-            if l > 0:
-                Lb = self.chain[l - 1]
-                # dgrad fused with act'(y) of the layer below: emits that layer's dz, dz^T, db
-                ops.gemm_bf16_tn(self.dzb[l][0], L.wtb, rows, L.n_in, L.n_out, ops.EPI_DGRAD_ACT,
-                                 act=Lb.act, yprev=self.actb[l - 1][0],
-                                 out_bf16=self.dzb[l - 1][0], outT_bf16=self.dzb[l - 1][1],
-                                 db=Lb.gb)
-            in_bT = self.actb[l - 1][1] if l > 0 else self.xbT
-            ops.gemm_bf16_tn(self.dzb[l][1], in_bT, L.n_out, L.n_in, rows, ops.EPI_ATOMIC,
-                             out_f32=L.gW, split_k=self._split_k(L))
+        if not self._grads_clean:
+            self.bucket.trained_grad.zero_()       # dW / db are accumulated with reds
+        self._grads_clean = False
+        for p in reversed(self._dgrad_problems):
+            ops.gemm_group([p])
+        for grp in self._wgrad_groups:
+            ops.gemm_group(grp)
 
     # -------------------------------------------------------------- common ---
     def forward(self, x):
@@ -288,10 +301,14 @@ class SiameseTrainStep(object):
 
     def _loss_and_seed(self, out, n, labels):
         """loss into self.loss_buf, d(loss)/d(embeddings) into the seed buffers."""
-        self.loss_buf.zero_()
+        if not self._loss_cleared:
+            self.loss_buf.zero_()
+        self._loss_cleared = False
+        if self.precision == 1:
+            return self._loss_and_seed_bf16(out, n, labels)
         if not self.heads:
             kind, margin, avg = self.loss_spec
-            de = self.de_last if self.precision == 1 else self.dacts[-1]
+            de = self.dacts[-1]
             ops.pair_loss(out[:n], out[n:], labels[0], kind, margin, 1.0 / n if avg else 1.0,
                           loss_out=self.loss_buf, grads=(de[:n], de[n:]))
             return
@@ -300,23 +317,42 @@ class SiameseTrainStep(object):
         for hi, (spec, w, y) in enumerate(((spec_spk, weight, labels[0]),
                                            (spec_phn, 1.0 - weight, labels[1]))):
             kind, margin, avg = spec
-            if self.precision == 1:
-                de = self.de_last[:, hi * d:(hi + 1) * d]
-            else:
-                de = self.head_dacts[hi][-1]
+            de = self.head_dacts[hi][-1]
             ops.pair_loss(out[hi][:n], out[hi][n:], y, kind, margin,
                           w * (1.0 / n if avg else 1.0), loss_out=self.loss_buf,
                           grads=(de[:n], de[n:]))
+
+    def _loss_and_seed_bf16(self, out, n, labels):
+        """Tensor-core path: the loss kernel writes the output layer's dz (bf16) directly."""
+        dz = self.dzb[-1]
+        act = self.chain[-1].act
+        if not self.heads:
+            kind, margin, avg = self.loss_spec
+            ops.pair_loss_dz(out[:n], out[n:], labels[0], dz[:n], dz[n:], kind, margin,
+                             1.0 / n if avg else 1.0, act, loss_out=self.loss_buf)
+            return
+        spec_spk, spec_phn, weight = self.loss_spec
+        d = self.head_dim
+        for hi, (spec, w, y) in enumerate(((spec_spk, weight, labels[0]),
+                                           (spec_phn, 1.0 - weight, labels[1]))):
+            kind, margin, avg = spec
+            dzh = dz[:, hi * d:(hi + 1) * d]
+            ops.pair_loss_dz(out[hi][:n], out[hi][n:], y, dzh[:n], dzh[n:], kind, margin,
+                             w * (1.0 / n if avg else 1.0), act, loss_out=self.loss_buf)
 
     def _grad_scale(self):
         avg = self.loss_spec[2] if not self.heads else self.loss_spec[0][2]
         return 1.0 / self.world if (self.world > 1 and avg) else 1.0
 
     def _optimizer(self, scale, step):
+        if self.precision == 1:     # update + bf16 operand copies + gradient reset in one kernel
+            ops.optimizer_step_fused(self.bucket.param, self.bucket.grad, self.state0, self.state1,
+                                     self.kind, self.lr, self.momentum, scale, step,
+                                     self._segments, zero_grad=True)
+            self._grads_clean = True
+            return
         ops.optimizer_step(self.bucket.trained_param, self.bucket.trained_grad, self.state0,
                            self.state1, self.kind, self.lr, self.momentum, scale, step)
-        if self.precision == 1:
-            self.refresh_bf16_weights()
 
     # ---- CUDA graphs ----------------------------------------------------------
     # The step is a few dozen small launches on fixed buffers; replaying them as two
@@ -369,6 +405,65 @@ class SiameseTrainStep(object):
             dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM, group=self.group)
         self._graph_opt.replay()
         self.step_count += 1
+        return self.loss_buf
+
+    # ---- batch generation fused in front (tensor-core path, single-label networks) ----
+    def gather_buffers(self, n):
+        """Static ``sel`` [n] int64 buffer of step_gather: write the batch's positions
+        in the frame-pair table into it (e.g. ``sel.copy_(perm[lo:lo + n])``)."""
+        if getattr(self, "_gsel_n", None) != n:
+            dev = self.bucket.param.device
+            self._gsel = torch.zeros(n, dtype=torch.int64, device=dev)
+            self._gy = torch.empty(n, dtype=torch.float32, device=dev)
+            self._gsel_n = n
+            self._graph_g = None
+            self._g_warm = 0
+        return self._gsel
+
+    def _gather_fwd_loss_bwd(self, feat, idx1, idx2, y, n):
+        self._reserve(2 * n)
+        # abn_gather_batch_bf16 writes the first layer's bf16 operand and clears the loss
+        ops.gather_batch_bf16(feat, idx1, idx2, y, self._gsel, n, self.xb, y_out=self._gy,
+                              zero=self.loss_buf)
+        self._loss_cleared = True
+        out = self._forward_bf16(None)
+        self._loss_and_seed(out, n, [self._gy])
+        self.backward(None)
+
+    def step_gather(self, feat, idx1, idx2, y, n, graph=True):
+        """One training step on the batch ``sel`` (gather_buffers) of the device-resident
+        frame-pair table (idx1, idx2, y int8) over ``feat``: gather -> forward -> loss ->
+        backward [-> all-reduce] -> optimizer, replayed as CUDA graphs after two eager
+        steps.  What FramesDataLoader.load_batch + TrainerSiamese.optimize_model do per
+        batch (abnet3/dataloader.py:673-684, abnet3/trainer.py:226-243)."""
+        if self.precision != 1 or self.heads:
+            raise ValueError("step_gather serves the bf16 path of SiameseNetwork")
+        self.gather_buffers(n)
+        scale = self._grad_scale()
+        key = (feat.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), y.data_ptr())
+        use_graph = graph and self.kind != "adam"
+        if use_graph and self._graph_g is not None and self._graph_g[0] == key:
+            self._graph_g[1].replay()
+            if self.world > 1:
+                dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self._graph_g[2].replay()
+            self.step_count += 1
+            return self.loss_buf
+        if use_graph and self._g_warm >= 2:
+            torch.cuda.synchronize()
+            g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fb):
+                self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)
+            with torch.cuda.graph(g_opt):
+                self._optimizer(scale, 1)
+            self._graph_g = (key, g_fb, g_opt)
+            return self.step_gather(feat, idx1, idx2, y, n, graph=True)
+        self._g_warm += 1
+        self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)
+        if self.world > 1:
+            dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM, group=self.group)
+        self.step_count += 1
+        self._optimizer(scale, self.step_count)
         return self.loss_buf
 
     def step(self, x, n, *labels, do_training=True, graph=False):

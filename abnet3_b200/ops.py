@@ -341,3 +341,57 @@ def gemm_group(problems):
     n = len(problems)
     arr = (_lib.GemmProblem * n)(*problems)
     check(_lib.lib().abn_gemm_bf16_group(arr, n, stream_ptr()))
+
+
+# ------------------------------- fused companions of the tensor-core step ---
+def gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=None, zero=None):
+    """xb[:n] = bf16(feat[idx1[sel]]), xb[n:2n] = bf16(feat[idx2[sel]]), y_out = float(y[sel]);
+    ``zero`` (1-element float32 tensor) is cleared by the same kernel."""
+    _req(feat, torch.float32, "feat")
+    _req(idx1, torch.int32, "idx1")
+    _req(idx2, torch.int32, "idx2")
+    if sel is not None:
+        _req(sel, torch.int64, "sel")
+    if y is not None:
+        _req(y, torch.int8, "y")
+    if not (xb.is_cuda and xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and xb.shape[0] >= 2 * n):
+        raise TypeError("xb must be a CUDA bf16 [>= 2n, ld] tensor")
+    check(_lib.lib().abn_gather_batch_bf16(ptr(feat), feat.shape[1], ptr(idx1), ptr(idx2), ptr(y),
+                                           ptr(sel), n, ptr(xb), xb.stride(0), ptr(y_out), ptr(zero),
+                                           stream_ptr()))
+
+
+def pair_loss_dz(e1, e2, y, dz1, dz2, kind="coscos2", margin=0.5, scale=1.0, act=None,
+                 loss_out=None):
+    """Loss value (accumulated into loss_out) and dz = dL/de * act'(e) as bf16 rows."""
+    _req(y, torch.float32, "y")
+    n, dim = e1.shape
+    ld = e1.stride(0)
+    if e2.stride(0) != ld or dz1.stride(0) != dz2.stride(0):
+        raise ValueError("e1/e2 and dz1/dz2 must share their row strides")
+    loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=e1.device)
+    check(_lib.lib().abn_pair_loss_dz(ptr(e1), ptr(e2), ptr(y), n, dim, ld, LOSS_KIND[kind],
+                                      float(margin), float(scale), ACT[act], ptr(loss), ptr(dz1),
+                                      ptr(dz2), dz1.stride(0), stream_ptr()))
+    return loss
+
+
+def param_segments(entries):
+    """entries: [(offset, count, bf16 tensor [rows, ld] or None, n_in)] -> ctypes array."""
+    arr = (_lib.ParamSegment * len(entries))()
+    for a, (off, cnt, wb, n_in) in zip(arr, entries):
+        a.offset, a.count = int(off), int(cnt)
+        a.ld = wb.stride(0) if wb is not None else 0
+        a.bf16 = ptr(wb)
+        a.n_in = int(n_in)
+    return arr
+
+
+def optimizer_step_fused(param, grad, state0, state1, kind, lr, momentum, grad_scale, step,
+                         segments, zero_grad=True):
+    _req(param, torch.float32, "param")
+    _req(grad, torch.float32, "grad")
+    check(_lib.lib().abn_optimizer_step_fused(ptr(param), ptr(grad), ptr(state0), ptr(state1),
+                                              OPT_KIND[kind], float(lr), float(momentum),
+                                              float(grad_scale), int(step), segments,
+                                              len(segments), int(bool(zero_grad)), stream_ptr()))

@@ -261,10 +261,19 @@ def bench_train(args, corpus, pairs, res, world, rank, dev):
 
         sx, sy = step.input_buffers(B)
 
-        def one(i):
-            lo = (i * B) % max(n_fp - B, 1)
-            ops.gather_batch(feat, idx1, idx2, y, perm[lo:lo + B], B, out=(sx[:B], sx[B:], sy))
-            return step.step(sx, B, sy, graph=True)
+        if prec == "bf16":
+            # gather -> bf16 operand -> forward -> loss -> backward -> optimizer, graph replayed
+            sel = step.gather_buffers(B)
+
+            def one(i):
+                lo = (i * B) % max(n_fp - B, 1)
+                sel.copy_(perm[lo:lo + B], non_blocking=True)
+                return step.step_gather(feat, idx1, idx2, y, B, graph=True)
+        else:
+            def one(i):
+                lo = (i * B) % max(n_fp - B, 1)
+                ops.gather_batch(feat, idx1, idx2, y, perm[lo:lo + B], B, out=(sx[:B], sx[B:], sy))
+                return step.step(sx, B, sy, graph=True)
 
         for i in range(5):
             one(i)
@@ -289,19 +298,26 @@ def bench_train(args, corpus, pairs, res, world, rank, dev):
         if prec == "bf16":
             # e2e: the batch's index pairs and labels come from pinned host memory and the
             # loss is read back every step (the reference's `.data[0]`, trainer.py:242)
-            h1 = idx1[perm[:B * 8]].cpu().pin_memory()
-            h2 = idx2[perm[:B * 8]].cpu().pin_memory()
-            hy = y[perm[:B * 8]].cpu().pin_memory()
-            e_steps = 8
+            h1 = idx1[perm[:B * 40]].cpu().pin_memory()
+            h2 = idx2[perm[:B * 40]].cpu().pin_memory()
+            hy = y[perm[:B * 40]].cpu().pin_memory()
+            e_steps = 40
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e1 = torch.empty(B, dtype=torch.int32, device=dev)
+            e2 = torch.empty(B, dtype=torch.int32, device=dev)
+            ey = torch.empty(B, dtype=torch.int8, device=dev)
+            sel.copy_(torch.arange(B, device=dev))
+            for i in range(3):          # new table pointers: two eager steps, then a fresh graph
+                step.step_gather(feat, e1.copy_(h1[:B]), e2.copy_(h2[:B]), ey.copy_(hy[:B]), B)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for i in range(e_steps):
                 sl = slice(i * B, (i + 1) * B)
-                a = h1[sl].to(dev, non_blocking=True)
-                b = h2[sl].to(dev, non_blocking=True)
-                c = hy[sl].to(dev, non_blocking=True)
-                ops.gather_batch(feat, a, b, c, None, B, out=(sx[:B], sx[B:], sy))
-                lv = float(step.step(sx, B, sy, graph=True).item())
+                e1.copy_(h1[sl], non_blocking=True)
+                e2.copy_(h2[sl], non_blocking=True)
+                ey.copy_(hy[sl], non_blocking=True)
+                lv = float(step.step_gather(feat, e1, e2, ey, B, graph=True).item())
             dt = time.perf_counter() - t0
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             if world > 1:

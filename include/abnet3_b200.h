@@ -306,6 +306,40 @@ ABN_API int abn_optimizer_step(float *param, const float *grad, float *state0,
                        float momentum, float grad_scale, int64_t step,
                        abn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Memory-bound companions of the tensor-core step, fused with the conversion their
+ * consumer needs (no fp32 intermediate makes a round trip through HBM).
+ *
+ * abn_gather_batch_bf16: abn_gather_batch writing bf16 rows -- X1 = rows 0..n-1,
+ *   X2 = rows n..2n-1 of xb [2n, ldx] -- i.e. the first layer's A operand.  zero_me
+ *   (nullable) is a float the kernel clears (the step's loss accumulator).
+ * abn_pair_loss_dz: abn_pair_loss whose gradient output is dz = dL/de * act'(e) as bf16
+ *   rows [n, ld_dz] (act = the output layer's activation; e1/e2 are its outputs): the
+ *   operand of the output layer's dgrad / wgrad GEMMs.
+ * abn_optimizer_step_fused: abn_optimizer_step over `segments` of the flat bucket; a
+ *   segment with bf16 != NULL is a weight matrix [count / n_in, n_in] whose updated values
+ *   are also written as bf16 rows of leading dimension ld; zero_grad clears the gradient
+ *   after use (the next step's wgrad reductions accumulate into it).
+ * ---------------------------------------------------------------------- */
+ABN_API int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *idx1,
+                                  const int32_t *idx2, const int8_t *y_in, const int64_t *sel,
+                                  int64_t n, void *xb, int64_t ldx, float *y_out, float *zero_me,
+                                  abn_stream_t stream);
+ABN_API int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,
+                             int64_t ld, int kind, float margin, float scale, int act, float *loss,
+                             void *dz1, void *dz2, int64_t ld_dz, abn_stream_t stream);
+#define ABN_MAX_PARAM_SEGMENTS 24
+typedef struct {
+    int64_t offset, count;      /* range of the flat bucket */
+    int64_t ld;                 /* bf16 copy: leading dimension (elements) */
+    void *bf16;                 /* NULL: no bf16 copy (biases) */
+    int n_in;                   /* bf16 copy: row length of the matrix */
+} abn_param_segment;
+ABN_API int abn_optimizer_step_fused(float *param, float *grad, float *state0, float *state1,
+                                     int kind, float lr, float momentum, float grad_scale,
+                                     int64_t step, const abn_param_segment *segments,
+                                     int n_segments, int zero_grad, abn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
