@@ -18,15 +18,18 @@
 // db comes for free: activations carry a column of ones right after their last feature
 // (inside the 8-element row padding), so column n_in of dz^T [x | 1] is colsum(dz).
 //
-// CTA = 192 threads, persistent over 128 x BN output tiles (x split-K):
+// CTA = 320 threads, persistent over 128 x BN output tiles (x split-K):
 //   warp 0      TMA producer (cp.async.bulk.tensor.2d, mbarrier ring of smem stages)
 //   warp 1      MMA issuer: one lane, tcgen05.mma.cta_group::1.kind::f16 M=128 N<=256 K=16
-//   warps 2-5   epilogue: tcgen05.ld (one TMEM lane = one output row per thread) ->
-//               bias + activation | x act'(y_below) -> packed bf16 / fp32 rows, 16-byte
-//               stores; or (wgrad) a shared-memory transpose and coalesced fp32 reds
+//   warps 2-9   epilogue: tcgen05.ld (one TMEM lane = one output row per thread, two warps
+//               per lane quarter taking alternate 32-column chunks) -> bias + activation |
+//               x act'(y_below) -> packed bf16 / fp32 rows, 16-byte stores; or (wgrad)
+//               16-byte vector fp32 reds straight from the registers
 // The accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile i
 // overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <cuda_bf16.h>
 
 #include "abn_common.cuh"
@@ -36,16 +39,17 @@ namespace abn {
 constexpr int G_BM = 128;          // UMMA_M
 constexpr int G_BK = 64;           // bf16 elements per K block (128-byte swizzle row / 64 K rows)
 constexpr int G_UK = 16;           // UMMA_K
-constexpr int G_THREADS = 192;
+constexpr int G_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes every other 32-column chunk
+constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
 constexpr int G_MAXP = ABN_GEMM_MAX_GROUP;
 
 enum { GE_BIAS_ACT = 0, GE_DACT = 1, GE_ATOMIC = 2 };
 
 struct GProblem {
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_c;     // map_c: bf16 output [M, ldo], 64 x 128 boxes (TMA store)
     int M, N, K;                    // N includes the ones column of a wgrad problem
     int a_mn, b_mn;
-    int epi, act, out_f32, ones_col;
+    int epi, act, out_f32, ones_col, tma_store;
     int n_cap;                      // N + ones_col: the columns a tile row covers
     int tiles_m, tiles_n, splits, kb_per_split;
     int tile_beg;
@@ -146,11 +150,12 @@ __device__ __forceinline__ unsigned long long g_desc(unsigned smem_addr, int mn_
     return d;
 }
 // cute::UMMA::InstrDescriptor for kind::f16: D fp32, A/B bf16, majors per operand
-__device__ __forceinline__ unsigned g_idesc(int n, int a_mn, int b_mn) {
+__device__ __forceinline__ unsigned g_idesc(int m, int n, int a_mn, int b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)a_mn << 15) | ((unsigned)b_mn << 16) |
-           ((unsigned)(n >> 3) << 17) | ((unsigned)(G_BM >> 4) << 24);
+           ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ unsigned g_pack_bf16(float lo, float hi);
 __device__ __forceinline__ float g_tanh(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -170,6 +175,32 @@ __device__ __forceinline__ float g_dact(float g, float y) {
     if (ACT == 2) return g * (1.f - y * y);
     if (ACT == 3) return y > 0.f ? g : 0.f;
     return g;
+}
+// bf16 outputs of sigmoid / tanh layers: two activations per MUFU op (tanh.approx.bf16x2);
+// the argument is rounded to bf16 first, an error of the order of the output rounding
+__device__ __forceinline__ unsigned g_tanh_bf16x2(unsigned x) {
+    unsigned y;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+template <int ACT>      // ACT 1: sigmoid, 2: tanh;  out[16] = packed bf16 pairs of act(v + bias)
+__device__ __forceinline__ void g_bias_act32_packed(const float (&v)[32], const float *bs,
+                                                    unsigned (&out)[16]) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(bs);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 b = b4[q];
+        const float sc = ACT == 1 ? 0.5f : 1.f;
+        const unsigned p0 = g_pack_bf16(sc * (v[4 * q] + b.x), sc * (v[4 * q + 1] + b.y));
+        const unsigned p1 = g_pack_bf16(sc * (v[4 * q + 2] + b.z), sc * (v[4 * q + 3] + b.w));
+        unsigned t0 = g_tanh_bf16x2(p0), t1 = g_tanh_bf16x2(p1);
+        if (ACT == 1) {         // 0.5 t + 0.5 on both halves (bf16 0.5 = 0x3f00)
+            asm("fma.rn.bf16x2 %0, %1, %2, %2;" : "=r"(t0) : "r"(t0), "r"(0x3f003f00u));
+            asm("fma.rn.bf16x2 %0, %1, %2, %2;" : "=r"(t1) : "r"(t1), "r"(0x3f003f00u));
+        }
+        out[2 * q] = t0;
+        out[2 * q + 1] = t1;
+    }
 }
 template <int ACT>
 __device__ __forceinline__ void g_bias_act32(float (&v)[32], const float *bs) {
@@ -193,17 +224,66 @@ __device__ __forceinline__ unsigned g_pack_bf16(float lo, float hi) {
     return *reinterpret_cast<unsigned *>(&h);
 }
 
+// ---- CTA-pair (cta_group::2) helpers: the two CTAs of a cluster share every B tile (each
+// loads half of its columns), one thread of the leader CTA issues the 256-row MMAs
+constexpr unsigned G_PEER_MASK = 0xFEFFFFFFu;      // shared-window address of the same object in CTA 0 of the pair
+__device__ __forceinline__ unsigned g_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void g_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void g_tma_2d_pair(unsigned dst, const CUtensorMap *map, unsigned bar_cta0,
+                                              int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar_cta0), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void g_mma_pair(unsigned d_tmem, unsigned long long a_desc,
+                                           unsigned long long b_desc, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void g_commit_pair(unsigned bar) {      // arrives on `bar` in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+                 "[%0], %1;" ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive_cta0(unsigned bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+                 ::"r"(bar & G_PEER_MASK) : "memory");
+}
+
+__device__ __forceinline__ void g_tma_store_2d(const CUtensorMap *map, unsigned src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void g_store_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void g_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 struct GTile { int pi, m0, n0, kb0, nkb, n_eff; };
 
 __device__ __forceinline__ void g_trace(const GGroup &g, unsigned it, int slot) {
     if (g.trace && it < 4) {
         long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        g.trace[((size_t)blockIdx.x * 4 + it) * 8 + slot] = t;
+        g.trace[((size_t)blockIdx.x * 4 + it) * 16 + slot] = t;
     }
 }
 
-__device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn) {
+__device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn, int ncta = 1, int rank = 0) {
     int pi = 0;
 #pragma unroll
     for (int q = 1; q < G_MAXP; ++q)
@@ -215,7 +295,7 @@ __device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn) {
     const int mt = r / P.tiles_n, nt = r - mt * P.tiles_n;
     GTile t;
     t.pi = pi;
-    t.m0 = mt * G_BM;
+    t.m0 = (mt * ncta + rank) * G_BM;
     t.n0 = nt * bn;
     const int total_kb = (P.K + G_BK - 1) / G_BK;
     t.kb0 = ks * P.kb_per_split;
@@ -226,38 +306,50 @@ __device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn) {
 }
 
 // ---------------------------------------------------------------- kernel ---
-template <int BN>
+template <int BN, int NCTA>
 __global__ void __launch_bounds__(G_THREADS, 1)
 tc_group_kernel(const __grid_constant__ GGroup g) {
-    constexpr unsigned A_BYTES = G_BM * G_BK * 2;           // 16 KB
-    constexpr unsigned B_BYTES = BN * G_BK * 2;             // 16 / 32 KB
+    constexpr unsigned A_BYTES = G_BM * G_BK * 2;           // 16 KB: this CTA's 128 rows
+    constexpr unsigned B_BYTES = (BN / NCTA) * G_BK * 2;    // this CTA's share of the B tile
     constexpr unsigned STAGE = A_BYTES + B_BYTES;
-    constexpr int STAGES = BN == 256 ? 4 : 6;
+    constexpr int STAGES = STAGE > 32768 ? 3 : 5;
+    constexpr unsigned OUT_BYTES = 2u * 16384u;             // two 128 x 64 bf16 boxes staged for TMA stores
+    const int rank = NCTA == 2 ? (int)g_cluster_rank() : 0;
+    const int tile0 = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
     extern __shared__ unsigned char smem_raw[];
     const unsigned raw = g_smem_u32(smem_raw);
     const unsigned base = (raw + 1023u) & ~1023u;           // 128B-swizzle atoms are 1024-byte aligned
     unsigned char *gen = smem_raw + (base - raw);
-    const unsigned bars = base + STAGES * STAGE;
+    const unsigned outs = base + STAGES * STAGE;            // 1024-byte aligned (stages are multiples of 16 KB)
+    const unsigned bars = outs + OUT_BYTES;
     const unsigned full0 = bars, empty0 = bars + 8 * STAGES;
     const unsigned tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16, tptr = tempty0 + 16;
-    volatile unsigned *tptr_gen = reinterpret_cast<volatile unsigned *>(gen + STAGES * STAGE +
-                                                                        16 * STAGES + 32);
-    float *bias_s = reinterpret_cast<float *>(gen + STAGES * STAGE + 256);      // [2][BN]
-    float *scratch = bias_s + 2 * BN;                                            // [4][32][33]
+    volatile unsigned *tptr_gen = reinterpret_cast<volatile unsigned *>(
+        gen + STAGES * STAGE + OUT_BYTES + 16 * STAGES + 32);
+    float *bias_s = reinterpret_cast<float *>(gen + STAGES * STAGE + OUT_BYTES + 256);      // [2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { g_mbar_init(full0 + 8 * s, 1); g_mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { g_mbar_init(tfull0 + 8 * b, 1); g_mbar_init(tempty0 + 8 * b, 4); }
+        for (int b = 0; b < 2; ++b) {
+            g_mbar_init(tfull0 + 8 * b, 1);
+            g_mbar_init(tempty0 + 8 * b, NCTA * G_EPI_WARPS);      // the pair's epilogues report to the leader
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {      // the whole TMEM of the SM is ours (one CTA per SM): two accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(tptr), "n"(2 * BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(tptr), "n"(2 * BN) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(tptr), "n"(2 * BN) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     g_fence_before();
-    __syncthreads();
+    if (NCTA == 2) g_cluster_sync(); else __syncthreads();
     g_fence_after();
     const unsigned tmem = *tptr_gen;
 
@@ -265,29 +357,49 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
         // ------------------------------------------------------ TMA producer
         if (lane == 0) {
             unsigned n = 0, pit = 0;                         // k-blocks issued so far (ring position)
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++pit) {
-                const GTile t = g_decode(g, tile, BN);
-                g_trace(g, pit, 0);
+            for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++pit) {
+                const GTile t = g_decode(g, tile, BN, NCTA, rank);
                 const GProblem &P = g.p[t.pi];
-                const int nbox_b = (t.n_eff + 63) >> 6;
+                g_trace(g, pit, 0);
+                // this CTA's share of the B tile: n_eff / NCTA columns from nb0 on
+                const int nb_cols = t.n_eff / NCTA, nb0 = t.n0 + rank * nb_cols;
+                const int nbox_b = (nb_cols + 63) >> 6;
                 const unsigned bytes = A_BYTES + (P.b_mn ? (unsigned)nbox_b * 8192u : B_BYTES);
                 for (int i = 0; i < t.nkb; ++i, ++n) {
                     const int s = n % STAGES;
                     g_mbar_wait(empty0 + 8 * s, ((n / STAGES) & 1) ^ 1);
-                    g_mbar_expect_tx(full0 + 8 * s, bytes);
                     const unsigned sa = base + s * STAGE, sb = sa + A_BYTES;
                     const int k0 = (t.kb0 + i) * G_BK;
-                    if (P.a_mn) {
-                        g_tma_2d(sa, &P.map_a, full0 + 8 * s, t.m0, k0);
-                        g_tma_2d(sa + 8192, &P.map_a, full0 + 8 * s, t.m0 + 64, k0);
+                    if (NCTA == 2) {
+                        // both CTAs' copies complete on the LEADER's barrier, which expects them all
+                        const unsigned fb = (full0 + 8 * s) & G_PEER_MASK;
+                        if (rank == 0) g_mbar_expect_tx(full0 + 8 * s, 2u * bytes);
+                        if (P.a_mn) {
+                            g_tma_2d_pair(sa, &P.map_a, fb, t.m0, k0);
+                            g_tma_2d_pair(sa + 8192, &P.map_a, fb, t.m0 + 64, k0);
+                        } else {
+                            g_tma_2d_pair(sa, &P.map_a, fb, k0, t.m0);
+                        }
+                        if (P.b_mn) {
+                            for (int j = 0; j < nbox_b; ++j)
+                                g_tma_2d_pair(sb + j * 8192, &P.map_b, fb, nb0 + 64 * j, k0);
+                        } else {
+                            g_tma_2d_pair(sb, &P.map_b, fb, k0, nb0);
+                        }
                     } else {
-                        g_tma_2d(sa, &P.map_a, full0 + 8 * s, k0, t.m0);
-                    }
-                    if (P.b_mn) {
-                        for (int j = 0; j < nbox_b; ++j)
-                            g_tma_2d(sb + j * 8192, &P.map_b, full0 + 8 * s, t.n0 + 64 * j, k0);
-                    } else {
-                        g_tma_2d(sb, &P.map_b, full0 + 8 * s, k0, t.n0);
+                        g_mbar_expect_tx(full0 + 8 * s, bytes);
+                        if (P.a_mn) {
+                            g_tma_2d(sa, &P.map_a, full0 + 8 * s, t.m0, k0);
+                            g_tma_2d(sa + 8192, &P.map_a, full0 + 8 * s, t.m0 + 64, k0);
+                        } else {
+                            g_tma_2d(sa, &P.map_a, full0 + 8 * s, k0, t.m0);
+                        }
+                        if (P.b_mn) {
+                            for (int j = 0; j < nbox_b; ++j)
+                                g_tma_2d(sb + j * 8192, &P.map_b, full0 + 8 * s, nb0 + 64 * j, k0);
+                        } else {
+                            g_tma_2d(sb, &P.map_b, full0 + 8 * s, k0, nb0);
+                        }
                     }
                 }
                 g_trace(g, pit, 1);
@@ -295,17 +407,17 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {       // of a pair, only the leader CTA issues
             unsigned n = 0, it = 0;
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
-                const GTile t = g_decode(g, tile, BN);
+            for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++it) {
+                const GTile t = g_decode(g, tile, BN, NCTA, rank);
                 const GProblem &P = g.p[t.pi];
                 const unsigned ab = it & 1;
                 g_trace(g, it, 2);
-                g_mbar_wait(tempty0 + 8 * ab, ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+                g_mbar_wait(tempty0 + 8 * ab, ((it >> 1) & 1) ^ 1);      // epilogue(s) drained this accumulator
                 g_fence_after();
                 g_trace(g, it, 3);
-                const unsigned idesc = g_idesc(t.n_eff, P.a_mn, P.b_mn);
+                const unsigned idesc = g_idesc(G_BM * NCTA, t.n_eff, P.a_mn, P.b_mn);
                 const unsigned d_tmem = tmem + ab * BN;
                 const unsigned a_step = P.a_mn ? (2048 >> 4) : (32 >> 4);
                 const unsigned b_step = P.b_mn ? (2048 >> 4) : (32 >> 4);
@@ -317,97 +429,172 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                     const unsigned long long da = g_desc(sa, P.a_mn);
                     const unsigned long long db = g_desc(sa + A_BYTES, P.b_mn);
 #pragma unroll
-                    for (int k = 0; k < G_BK / G_UK; ++k)
-                        g_mma(d_tmem, da + (unsigned long long)(a_step * k),
-                              db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
-                    g_commit(empty0 + 8 * s);           // frees the smem stage when these MMAs retire
+                    for (int k = 0; k < G_BK / G_UK; ++k) {
+                        if (NCTA == 2)
+                            g_mma_pair(d_tmem, da + (unsigned long long)(a_step * k),
+                                       db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
+                        else
+                            g_mma(d_tmem, da + (unsigned long long)(a_step * k),
+                                  db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
+                    }
+                    // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                    if (NCTA == 2) g_commit_pair(empty0 + 8 * s); else g_commit(empty0 + 8 * s);
                 }
-                g_commit(tfull0 + 8 * ab);              // accumulator complete
+                // accumulator complete (each CTA's epilogue watches its own barrier)
+                if (NCTA == 2) g_commit_pair(tfull0 + 8 * ab); else g_commit(tfull0 + 8 * ab);
                 g_trace(g, it, 4);
             }
         }
     } else {
         // ---------------------------------------------------------- epilogue
         const int wq = warp & 3;                        // TMEM lane quarter of this warp
-        const int et = (warp - 2) * 32 + lane;          // 0..127
-        float *my_scratch = scratch + wq * (32 * 33);
-        unsigned it = 0;
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
-            const GTile t = g_decode(g, tile, BN);
+        const int half = (warp - 2) >> 2;               // which of the quarter's two warps
+        const int et = (warp - 2) * 32 + lane;          // 0 .. 255
+        unsigned it = 0, nbox = 0;                      // boxes handed to the TMA store engine so far
+        for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++it) {
+            const GTile t = g_decode(g, tile, BN, NCTA, rank);
             const GProblem &P = g.p[t.pi];
             const unsigned ab = it & 1;
             float *bs = bias_s + ab * BN;
+            const int row = t.m0 + wq * 32 + lane;
+            const int c_first = half * 32;
+            uint4 y8[4];
             if (P.epi == GE_BIAS_ACT) {
-                for (int c = et; c < BN; c += 128)
+                for (int c = et; c < BN; c += 32 * G_EPI_WARPS)
                     bs[c] = (P.bias && t.n0 + c < P.N) ? __ldg(P.bias + t.n0 + c) : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
+            } else if (P.epi == GE_DACT) {
+                // the first chunk's y_below does not depend on the accumulator: fetch it now
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    y8[q] = make_uint4(0, 0, 0, 0);
+                    if (row < P.M && t.n0 + c_first + 8 * q + 8 <= P.ld_yprev)
+                        y8[q] = __ldg(reinterpret_cast<const uint4 *>(
+                            P.yprev + (long long)row * P.ld_yprev + t.n0 + c_first + 8 * q));
+                }
             }
             if (et == 0) g_trace(g, it, 5);
             g_mbar_wait(tfull0 + 8 * ab, (it >> 1) & 1);
             g_fence_after();
             if (et == 0) g_trace(g, it, 6);
             const unsigned taddr = tmem + ((unsigned)(wq * 32) << 16) + ab * BN;
-            const int row = t.m0 + wq * 32 + lane;
             if (t.nkb <= 0) {
                 // nothing was accumulated (cannot happen with the host's split sizes)
             } else if (P.epi == GE_ATOMIC) {
-                // fp32 reduction of a split-K partial: transpose 32 x 32 blocks through smem so
-                // that a warp's red instructions cover 128 contiguous bytes of one output row
+                // fp32 reduction of a split-K partial: 16-byte vector reds, one output row per
+                // thread (REDG issue is per lane-op: the vector form is 4x cheaper than scalars)
                 float *out = static_cast<float *>(P.out);
                 const int n_w = P.ones_out ? P.N - 1 : P.N;          // columns that belong to `out`
-                for (int c0 = 0; c0 < t.n_eff; c0 += 32) {
+                const bool vec_ok = (P.ldo & 3) == 0;
+                for (int c0 = c_first; c0 < t.n_eff; c0 += 64) {
                     float v[32];
                     g_ld32(taddr + c0, v);
+                    const int gcol0 = t.n0 + c0;
+                    if (row < P.M) {
+                        float *op = out + (long long)row * P.ldo + gcol0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) my_scratch[lane * 33 + j] = v[j];
-                    __syncwarp();
-                    const int gcol = t.n0 + c0 + lane;
-#pragma unroll 4
-                    for (int r = 0; r < 32; ++r) {
-                        const int grow = t.m0 + wq * 32 + r;
-                        if (grow >= P.M) break;
-                        const float x = my_scratch[r * 33 + lane];
-                        if (gcol < n_w) atomicAdd(out + (long long)grow * P.ldo + gcol, x);
-                        else if (gcol == n_w && P.ones_out) atomicAdd(P.ones_out + grow, x);
+                        for (int q = 0; q < 8; ++q) {
+                            if (vec_ok && gcol0 + 4 * q + 4 <= n_w) {
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                             ::"l"(op + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                                               "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int gcol = gcol0 + 4 * q + e;
+                                    if (gcol < n_w) atomicAdd(op + 4 * q + e, v[4 * q + e]);
+                                    else if (gcol == n_w && P.ones_out)
+                                        atomicAdd(P.ones_out + row, v[4 * q + e]);
+                                }
+                            }
+                        }
                     }
-                    __syncwarp();
                 }
             } else {
                 const int n_cap = P.n_cap;
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = c_first; c0 < BN; c0 += 64) {
                     const int gcol0 = t.n0 + c0;
-                    if (gcol0 >= n_cap || c0 >= t.n_eff + 16) break;     // warp-uniform
+                    // uniform over the whole epilogue (boxes of 64 columns): both halves of a box
+                    // take part in its barrier
+                    if (t.n0 + (c0 & ~63) >= n_cap || (c0 & ~63) >= t.n_eff + 16) break;
                     float v[32];
+                    if (et == 0 && c0 == c_first) g_trace(g, it, 8);
                     g_ld32(taddr + c0, v);
+                    if (et == 0 && c0 == c_first) g_trace(g, it, 9);
+                    unsigned pk[16];
+                    bool packed = false;
                     if (P.epi == GE_BIAS_ACT) {
-                        switch (P.act) {
-                            case 1: g_bias_act32<1>(v, bs + c0); break;
-                            case 2: g_bias_act32<2>(v, bs + c0); break;
-                            case 3: g_bias_act32<3>(v, bs + c0); break;
-                            default: g_bias_act32<0>(v, bs + c0); break;
+                        if (P.tma_store && (P.act == 1 || P.act == 2)) {
+                            if (P.act == 1) g_bias_act32_packed<1>(v, bs + c0, pk);
+                            else g_bias_act32_packed<2>(v, bs + c0, pk);
+                            packed = true;
+                        } else {
+                            switch (P.act) {
+                                case 1: g_bias_act32<1>(v, bs + c0); break;
+                                case 2: g_bias_act32<2>(v, bs + c0); break;
+                                case 3: g_bias_act32<3>(v, bs + c0); break;
+                                default: g_bias_act32<0>(v, bs + c0); break;
+                            }
                         }
                     } else {
-                        // x act'(y_below): 8 bf16 of this row per 16-byte load
-                        const __nv_bfloat16 *yp = P.yprev + (long long)row * P.ld_yprev + gcol0;
-                        uint4 y8[4];
+                        // x act'(y_below); the next chunk's 8-bf16 loads are issued first
+                        uint4 yc[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) yc[q] = y8[q];
+                        const int gn = gcol0 + 64;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             y8[q] = make_uint4(0, 0, 0, 0);
-                            if (row < P.M && gcol0 + 8 * q + 8 <= P.ld_yprev)
-                                y8[q] = __ldg(reinterpret_cast<const uint4 *>(yp + 8 * q));
+                            if (row < P.M && gn < n_cap && gn + 8 * q + 8 <= P.ld_yprev)
+                                y8[q] = __ldg(reinterpret_cast<const uint4 *>(
+                                    P.yprev + (long long)row * P.ld_yprev + gn + 8 * q));
                         }
                         switch (P.act) {
-                            case 1: g_dact32<1>(v, y8); break;
-                            case 2: g_dact32<2>(v, y8); break;
-                            case 3: g_dact32<3>(v, y8); break;
+                            case 1: g_dact32<1>(v, yc); break;
+                            case 2: g_dact32<2>(v, yc); break;
+                            case 3: g_dact32<3>(v, yc); break;
                             default: break;
                         }
                     }
-                    if (P.ones_col && P.N >= gcol0 && P.N < gcol0 + 32) {
+                    if (!packed) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = (gcol0 + j == P.N) ? 1.f : v[j];
+                        for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
                     }
-                    if (row < P.M) {
+                    if (P.ones_col && P.N >= gcol0 && P.N < gcol0 + 32) {
+                        const int jo = P.N - gcol0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (2 * j == jo) pk[j] = (pk[j] & 0xffff0000u) | 0x3f80u;
+                            if (2 * j + 1 == jo) pk[j] = (pk[j] & 0x0000ffffu) | 0x3f800000u;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (j == jo) ? 1.f : v[j];
+                    }
+                    if (et == 0 && c0 == c_first) g_trace(g, it, 10);
+                    if (P.tma_store) {
+                        // bf16 rows -> the 128-byte-swizzled 128 x 64 box in smem -> one TMA store
+                        // per box (full-line writes, clipped at M rows / ldo columns by the map)
+                        const unsigned sbuf = outs + (nbox & 1u) * 16384u;
+                        const int rr = wq * 32 + lane;
+                        const unsigned rowa = sbuf + rr * 128;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const unsigned phys = (unsigned)((4 * half + q) ^ (rr & 7)) * 16u;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(rowa + phys), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                                           "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (et == 0 && c0 == c_first) g_trace(g, it, 11);
+                        // the previous box's store must have finished reading the OTHER buffer
+                        // before anybody starts filling it again after this barrier
+                        if (et == 0) g_store_wait_read0();
+                        asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
+                        if (et == 0 && c0 == c_first) g_trace(g, it, 12);
+                        if (et == 0) g_tma_store_2d(&P.map_c, sbuf, t.n0 + (c0 & ~63), t.m0);
+                        if (et == 0 && c0 == c_first) g_trace(g, it, 13);
+                        ++nbox;
+                    } else if (row < P.M) {
                         if (P.out_f32) {
                             float *op = static_cast<float *>(P.out) + (long long)row * P.ldo + gcol0;
 #pragma unroll
@@ -439,16 +626,23 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
             }
             g_fence_before();
             __syncwarp();
-            if (lane == 0) g_mbar_arrive(tempty0 + 8 * ab);
+            if (lane == 0) {
+                if (NCTA == 2) g_mbar_arrive_cta0(tempty0 + 8 * ab); else g_mbar_arrive(tempty0 + 8 * ab);
+            }
             if (et == 0) g_trace(g, it, 7);
         }
     }
+    if (warp == 2 && lane == 0) g_store_wait_all();            // staged boxes are on their way out of smem
     g_fence_before();
-    __syncthreads();
+    if (NCTA == 2) g_cluster_sync(); else __syncthreads();     // nobody leaves while the peer may still signal it
     if (warp == 2) {
         g_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN)
-                     : "memory");
+        if (NCTA == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN)
+                         : "memory");
     }
 }
 
@@ -489,21 +683,35 @@ static int g_make_map(CUtensorMap *map, const void *ptr, long long rows, long lo
     return ABN_OK;
 }
 
-template <int BN>
+template <int BN, int NCTA>
 static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
-    constexpr int STAGES = BN == 256 ? 4 : 6;
-    constexpr unsigned smem = STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 256 + 2 * BN * 4 +
-                              4 * 32 * 33 * 4 + 1024;
+    constexpr unsigned stage = G_BM * G_BK * 2 + (BN / NCTA) * G_BK * 2;
+    constexpr int STAGES = stage > 32768 ? 3 : 5;
+    constexpr unsigned smem = STAGES * stage + 2 * 16384 + 256 + 2 * BN * 4 + 1024;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(tc_group_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(tc_group_kernel<BN, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return set_error(ABN_EIO, "abn_gemm_bf16_group: cannot reserve %u bytes of shared memory",
                              smem);
         configured = true;
     }
-    const int grid = g.total_tiles < sm_count ? g.total_tiles : sm_count;
-    tc_group_kernel<BN><<<grid, G_THREADS, smem, st>>>(g);
+    int grid = g.total_tiles * NCTA < sm_count ? g.total_tiles * NCTA : sm_count;
+    grid -= grid % NCTA;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_group_kernel<BN, NCTA>, g) != cudaSuccess)
+        return check_launch("abn_gemm_bf16_group");
     return check_launch("abn_gemm_bf16_group");
 }
 
@@ -540,6 +748,12 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
         if (n_cols > max_n) max_n = n_cols;
     }
     const int bn = max_n <= 128 ? 128 : 256;
+    // CTA pairs (cta_group::2) halve the B traffic per MMA; ABN_GEMM_1CTA=1 keeps single CTAs
+    static int ncta = 0;
+    if (!ncta) {
+        const char *e = getenv("ABN_GEMM_1CTA");
+        ncta = (e && e[0] == '1') ? 1 : 2;
+    }
     GGroup g;
     memset(&g, 0, sizeof(g));
     g.n_problems = n_problems;
@@ -564,9 +778,14 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
                         : g_make_map(&P.map_a, q.A, q.M, q.K, q.lda, G_BK, G_BM);
         if (rc) return rc;
         rc = P.b_mn ? g_make_map(&P.map_b, q.B, q.K, P.N, q.ldb, 64, 64)
-                    : g_make_map(&P.map_b, q.B, P.N, q.K, q.ldb, G_BK, bn);
+                    : g_make_map(&P.map_b, q.B, P.N, q.K, q.ldb, G_BK, bn / ncta);
         if (rc) return rc;
-        P.tiles_m = (P.M + G_BM - 1) / G_BM;
+        P.tma_store = (!P.out_f32 && q.epilogue != GE_ATOMIC) ? 1 : 0;
+        if (P.tma_store) {
+            rc = g_make_map(&P.map_c, q.out, q.M, q.ldo, q.ldo, 64, G_BM);
+            if (rc) return rc;
+        }
+        P.tiles_m = (P.M + G_BM * ncta - 1) / (G_BM * ncta);
         P.n_cap = P.N + P.ones_col;
         P.tiles_n = (P.n_cap + bn - 1) / bn;
         const int total_kb = (P.K + G_BK - 1) / G_BK;
@@ -580,5 +799,7 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
     g.total_tiles = tile;
     g.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
     cudaStream_t st = (cudaStream_t)stream;
-    return bn == 128 ? g_launch<128>(g, sm_count, st) : g_launch<256>(g, sm_count, st);
+    if (ncta == 2)
+        return bn == 128 ? g_launch<128, 2>(g, sm_count, st) : g_launch<256, 2>(g, sm_count, st);
+    return bn == 128 ? g_launch<128, 1>(g, sm_count, st) : g_launch<256, 1>(g, sm_count, st);
 }

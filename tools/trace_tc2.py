@@ -6,21 +6,33 @@ DEV = "cuda"
 rows = 16384
 def bf(r, c):
     return (torch.randn(r, ops.pad8(c + 1), device=DEV) * 0.05).bfloat16()
-x, a1 = bf(rows, 500), bf(rows, 500)
-W = bf(500, 500)
+dims = [280, 500, 500, 500, 100]
+acts = [bf(rows, d) for d in dims]
+dzs = [bf(rows, d) for d in dims]
+Ws = [bf(dims[i + 1], dims[i]) for i in range(4)]
 bias = torch.zeros(500, device=DEV)
-fwd = ops.gemm_problem(x, W, rows, 500, 500, ops.GE_BIAS_ACT, a1, act="sigmoid", bias=bias, ones_col=True)
-for _ in range(3): ops.gemm_group([fwd])
+gW = [torch.zeros(dims[i + 1], dims[i], device=DEV) for i in range(4)]
+gb = [torch.zeros(dims[i + 1], device=DEV) for i in range(4)]
+which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+split = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+if which == "fwd":
+    probs = [ops.gemm_problem(acts[1], Ws[1], rows, 500, 500, ops.GE_BIAS_ACT, acts[2], act="sigmoid", bias=bias, ones_col=True)]
+elif which == "dgrad":
+    probs = [ops.gemm_problem(dzs[3], Ws[2], rows, 500, 500, ops.GE_DACT, dzs[2], b_mn=True, act="sigmoid", yprev=acts[2])]
+else:
+    probs = [ops.gemm_problem(dzs[l + 1], acts[l], dims[l + 1], dims[l], rows, ops.GE_ATOMIC, gW[l], a_mn=True, b_mn=True, split_k=split, ones_out=gb[l]) for l in range(4)]
+for _ in range(3): ops.gemm_group(probs)
 torch.cuda.synchronize()
-tr = torch.zeros(148 * 4 * 8, dtype=torch.int64, device=DEV)
+tr = torch.zeros(148 * 4 * 16, dtype=torch.int64, device=DEV)
 ctypes.c_void_p.in_dll(_lib.lib(), "abn_gemm_trace_buffer").value = tr.data_ptr()
-ops.gemm_group([fwd])
+ops.gemm_group(probs)
 torch.cuda.synchronize()
 ctypes.c_void_p.in_dll(_lib.lib(), "abn_gemm_trace_buffer").value = None
-t = tr.cpu().view(148, 4, 8)
+t = tr.cpu().view(148, 4, 16)
 t0 = int(t[t > 0].min())
-names = ["prod_start", "prod_done", "mma_start", "mma_acc_free", "mma_commit", "epi_start", "epi_tfull", "epi_done"]
-for cta in (0, 1, 73, 147):
-    for it in range(2):
+names = ["p0", "p1", "m0", "mfree", "mcommit", "e0", "etfull", "edone", "c_ld0", "c_ld1", "c_math", "c_sts", "c_bar", "c_tma", "-", "-"]
+for cta in (0, 1, 50, 100, 147):
+    for it in range(4):
+        if int(t[cta, it].max()) == 0: continue
         print("cta %3d tile %d: " % (cta, it) + "  ".join("%s %6.2f" % (n, (int(v) - t0) / 1e3) if v > 0 else "%s    -  " % n for n, v in zip(names, t[cta, it])))
 print("last event us", (int(t.max()) - t0) / 1e3)
