@@ -41,12 +41,14 @@ constexpr int G_BK = 64;           // bf16 elements per K block (128-byte swizzl
 constexpr int G_UK = 16;           // UMMA_K
 constexpr int G_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes every other 32-column chunk
 constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
+constexpr int G_OBUF = 4;          // output boxes in flight per epilogue warp (TMA store latency ~1 us)
 constexpr int G_MAXP = ABN_GEMM_MAX_GROUP;
 
 enum { GE_BIAS_ACT = 0, GE_DACT = 1, GE_ATOMIC = 2 };
 
 struct GProblem {
-    CUtensorMap map_a, map_b, map_c;     // map_c: bf16 output [M, ldo], 64 x 128 boxes (TMA store)
+    CUtensorMap map_a, map_b;
+    CUtensorMap map_c, map_y;            // bf16 output / y_below [M, ld]: 32 x 32 boxes, 64-byte swizzle
     int M, N, K;                    // N includes the ones column of a wgrad problem
     int a_mn, b_mn;
     int epi, act, out_f32, ones_col, tma_store;
@@ -257,7 +259,7 @@ __device__ __forceinline__ void g_commit_pair(unsigned bar) {      // arrives on
                  "[%0], %1;" ::"r"(bar), "h"((unsigned short)3) : "memory");
 }
 __device__ __forceinline__ void g_mbar_arrive_cta0(unsigned bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];"
                  ::"r"(bar & G_PEER_MASK) : "memory");
 }
 
@@ -305,6 +307,79 @@ __device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn, int
     return t;
 }
 
+// One warp's share of a bf16-output tile (forward: bias + activation; dgrad: x act'(y_below)).
+// Everything the chunk loop needs sits in registers; EPI / ACT are compile-time so that the
+// loop body is straight-line code (the problem descriptor lives in constant memory: reading
+// it field by field inside the loop costs a dependent LDC + branch per decision).
+struct GEpi {
+    const CUtensorMap *map_c, *map_y;
+    const float *bs;                // staged bias of this tile (forward)
+    unsigned taddr, my_out, my_y, ybar;
+    int n0, row0, n_eff, n_cap, N, ones_col, c_first, lane;
+};
+template <int EPI, int ACT, int BN>
+__device__ __forceinline__ void g_epi_bf16_tile(const GEpi &e, unsigned &nbox, unsigned &ycount) {
+    const unsigned swz = (unsigned)((e.lane >> 1) & 3);      // 64-byte swizzle of row `lane`
+    const int lane = e.lane;
+#pragma unroll 1
+    for (int c0 = e.c_first; c0 < BN; c0 += 64) {
+        const int gcol0 = e.n0 + c0;
+        if (gcol0 >= e.n_cap || c0 >= e.n_eff + 16) break;     // warp-uniform
+        uint4 yc[4];
+        if (EPI == GE_DACT) {
+            // this warp's 32 x 32 box of y_below: TMA -> smem -> one row per lane; the next
+            // chunk's box is requested as soon as this one has been read
+            g_mbar_wait(e.ybar, ycount & 1u);
+            ++ycount;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(yc[q].x), "=r"(yc[q].y), "=r"(yc[q].z), "=r"(yc[q].w)
+                             : "r"(e.my_y + lane * 64 + (((unsigned)q ^ swz) << 4)) : "memory");
+            __syncwarp();
+            const int gn = gcol0 + 64;
+            if (lane == 0 && gn < e.n_cap && c0 + 64 < e.n_eff + 16 && c0 + 64 < BN) {
+                g_mbar_expect_tx(e.ybar, 2048u);
+                g_tma_2d(e.my_y, e.map_y, e.ybar, gn, e.row0);
+            }
+        }
+        float v[32];
+        g_ld32(e.taddr + c0, v);
+        unsigned pk[16];
+        if (EPI == GE_BIAS_ACT && (ACT == 1 || ACT == 2)) {
+            g_bias_act32_packed<ACT>(v, e.bs + c0, pk);
+        } else {
+            if (EPI == GE_BIAS_ACT) g_bias_act32<ACT>(v, e.bs + c0);
+            else g_dact32<ACT>(v, yc);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
+        }
+        if (e.ones_col && e.N >= gcol0 && e.N < gcol0 + 32) {
+            const int jo = e.N - gcol0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (2 * j == jo) pk[j] = (pk[j] & 0xffff0000u) | 0x3f80u;
+                if (2 * j + 1 == jo) pk[j] = (pk[j] & 0x0000ffffu) | 0x3f800000u;
+            }
+        }
+        // bf16 rows -> this warp's 64-byte-swizzled 32 x 32 box in smem -> one TMA store
+        // (full-line writes, clipped at M rows / ldo columns by the map); the box filled
+        // G_OBUF chunks ago must have left smem before it is reused
+        const unsigned sbuf = e.my_out + (nbox % G_OBUF) * 2048u;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(G_OBUF - 1) : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(sbuf + lane * 64 + (((unsigned)q ^ swz) << 4)), "r"(pk[4 * q]),
+                           "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) g_tma_store_2d(e.map_c, sbuf, gcol0, e.row0);
+        ++nbox;
+    }
+}
+
 // ---------------------------------------------------------------- kernel ---
 template <int BN, int NCTA>
 __global__ void __launch_bounds__(G_THREADS, 1)
@@ -312,8 +387,9 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     constexpr unsigned A_BYTES = G_BM * G_BK * 2;           // 16 KB: this CTA's 128 rows
     constexpr unsigned B_BYTES = (BN / NCTA) * G_BK * 2;    // this CTA's share of the B tile
     constexpr unsigned STAGE = A_BYTES + B_BYTES;
-    constexpr int STAGES = STAGE > 32768 ? 3 : 5;
-    constexpr unsigned OUT_BYTES = 2u * 16384u;             // two 128 x 64 bf16 boxes staged for TMA stores
+    constexpr int STAGES = STAGE > 32768 ? 3 : 4;
+    // per epilogue warp: G_OBUF 32 x 32 bf16 boxes staged for TMA stores, one for y_below loads
+    constexpr unsigned OUT_BYTES = G_EPI_WARPS * (G_OBUF * 2048u + 2048u);
     const int rank = NCTA == 2 ? (int)g_cluster_rank() : 0;
     const int tile0 = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
     extern __shared__ unsigned char smem_raw[];
@@ -324,6 +400,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     const unsigned bars = outs + OUT_BYTES;
     const unsigned full0 = bars, empty0 = bars + 8 * STAGES;
     const unsigned tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16, tptr = tempty0 + 16;
+    const unsigned ybar0 = bars + 16 * STAGES + 64;          // one mbarrier per epilogue warp
     volatile unsigned *tptr_gen = reinterpret_cast<volatile unsigned *>(
         gen + STAGES * STAGE + OUT_BYTES + 16 * STAGES + 32);
     float *bias_s = reinterpret_cast<float *>(gen + STAGES * STAGE + OUT_BYTES + 256);      // [2][BN]
@@ -331,6 +408,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { g_mbar_init(full0 + 8 * s, 1); g_mbar_init(empty0 + 8 * s, 1); }
+        for (int w = 0; w < G_EPI_WARPS; ++w) g_mbar_init(ybar0 + 8 * w, 1);
         for (int b = 0; b < 2; ++b) {
             g_mbar_init(tfull0 + 8 * b, 1);
             g_mbar_init(tempty0 + 8 * b, NCTA * G_EPI_WARPS);      // the pair's epilogues report to the leader
@@ -450,7 +528,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
         const int wq = warp & 3;                        // TMEM lane quarter of this warp
         const int half = (warp - 2) >> 2;               // which of the quarter's two warps
         const int et = (warp - 2) * 32 + lane;          // 0 .. 255
-        unsigned it = 0, nbox = 0;                      // boxes handed to the TMA store engine so far
+        unsigned it = 0, nbox = 0, ycount = 0;          // boxes stored / y_below boxes consumed by this warp
         for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++it) {
             const GTile t = g_decode(g, tile, BN, NCTA, rank);
             const GProblem &P = g.p[t.pi];
@@ -458,19 +536,20 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
             float *bs = bias_s + ab * BN;
             const int row = t.m0 + wq * 32 + lane;
             const int c_first = half * 32;
-            uint4 y8[4];
+            const int ew = warp - 2;
+            const unsigned my_out = outs + ew * (G_OBUF * 2048u);
+            const unsigned my_y = outs + G_EPI_WARPS * (G_OBUF * 2048u) + ew * 2048u;
+            const unsigned ybar = ybar0 + 8 * ew;
+            const int row0 = t.m0 + wq * 32;                 // first row of this warp's 32 x 32 boxes
             if (P.epi == GE_BIAS_ACT) {
                 for (int c = et; c < BN; c += 32 * G_EPI_WARPS)
                     bs[c] = (P.bias && t.n0 + c < P.N) ? __ldg(P.bias + t.n0 + c) : 0.f;
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
             } else if (P.epi == GE_DACT) {
                 // the first chunk's y_below does not depend on the accumulator: fetch it now
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    y8[q] = make_uint4(0, 0, 0, 0);
-                    if (row < P.M && t.n0 + c_first + 8 * q + 8 <= P.ld_yprev)
-                        y8[q] = __ldg(reinterpret_cast<const uint4 *>(
-                            P.yprev + (long long)row * P.ld_yprev + t.n0 + c_first + 8 * q));
+                if (lane == 0 && t.n0 + c_first < P.n_cap) {
+                    g_mbar_expect_tx(ybar, 2048u);
+                    g_tma_2d(my_y, &P.map_y, ybar, t.n0 + c_first, row0);
                 }
             }
             if (et == 0) g_trace(g, it, 5);
@@ -510,116 +589,51 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                         }
                     }
                 }
+            } else if (P.tma_store) {
+                GEpi e;
+                e.map_c = &P.map_c; e.map_y = &P.map_y; e.bs = bs;
+                e.taddr = taddr; e.my_out = my_out; e.my_y = my_y; e.ybar = ybar;
+                e.n0 = t.n0; e.row0 = row0; e.n_eff = t.n_eff; e.n_cap = P.n_cap; e.N = P.N;
+                e.ones_col = P.ones_col; e.c_first = c_first; e.lane = lane;
+                const int mode = P.epi * 4 + P.act;
+                switch (mode) {
+                    case 0: g_epi_bf16_tile<GE_BIAS_ACT, 0, BN>(e, nbox, ycount); break;
+                    case 1: g_epi_bf16_tile<GE_BIAS_ACT, 1, BN>(e, nbox, ycount); break;
+                    case 2: g_epi_bf16_tile<GE_BIAS_ACT, 2, BN>(e, nbox, ycount); break;
+                    case 3: g_epi_bf16_tile<GE_BIAS_ACT, 3, BN>(e, nbox, ycount); break;
+                    case 4: g_epi_bf16_tile<GE_DACT, 0, BN>(e, nbox, ycount); break;
+                    case 5: g_epi_bf16_tile<GE_DACT, 1, BN>(e, nbox, ycount); break;
+                    case 6: g_epi_bf16_tile<GE_DACT, 2, BN>(e, nbox, ycount); break;
+                    default: g_epi_bf16_tile<GE_DACT, 3, BN>(e, nbox, ycount); break;
+                }
             } else {
-                const int n_cap = P.n_cap;
+                // fp32 rows (the embeddings): bias + activation, 16-byte stores
+                const int n_cap = P.n_cap, N = P.N, act = P.act;
+                const long long ldo = P.ldo;
+                float *outp = static_cast<float *>(P.out);
+                const bool row_ok = row < P.M;
                 for (int c0 = c_first; c0 < BN; c0 += 64) {
                     const int gcol0 = t.n0 + c0;
-                    // uniform over the whole epilogue (boxes of 64 columns): both halves of a box
-                    // take part in its barrier
-                    if (t.n0 + (c0 & ~63) >= n_cap || (c0 & ~63) >= t.n_eff + 16) break;
+                    if (gcol0 >= n_cap || c0 >= t.n_eff + 16) break;     // warp-uniform
                     float v[32];
-                    if (et == 0 && c0 == c_first) g_trace(g, it, 8);
                     g_ld32(taddr + c0, v);
-                    if (et == 0 && c0 == c_first) g_trace(g, it, 9);
-                    unsigned pk[16];
-                    bool packed = false;
-                    if (P.epi == GE_BIAS_ACT) {
-                        if (P.tma_store && (P.act == 1 || P.act == 2)) {
-                            if (P.act == 1) g_bias_act32_packed<1>(v, bs + c0, pk);
-                            else g_bias_act32_packed<2>(v, bs + c0, pk);
-                            packed = true;
-                        } else {
-                            switch (P.act) {
-                                case 1: g_bias_act32<1>(v, bs + c0); break;
-                                case 2: g_bias_act32<2>(v, bs + c0); break;
-                                case 3: g_bias_act32<3>(v, bs + c0); break;
-                                default: g_bias_act32<0>(v, bs + c0); break;
-                            }
-                        }
-                    } else {
-                        // x act'(y_below); the next chunk's 8-bf16 loads are issued first
-                        uint4 yc[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) yc[q] = y8[q];
-                        const int gn = gcol0 + 64;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            y8[q] = make_uint4(0, 0, 0, 0);
-                            if (row < P.M && gn < n_cap && gn + 8 * q + 8 <= P.ld_yprev)
-                                y8[q] = __ldg(reinterpret_cast<const uint4 *>(
-                                    P.yprev + (long long)row * P.ld_yprev + gn + 8 * q));
-                        }
-                        switch (P.act) {
-                            case 1: g_dact32<1>(v, yc); break;
-                            case 2: g_dact32<2>(v, yc); break;
-                            case 3: g_dact32<3>(v, yc); break;
-                            default: break;
-                        }
+                    switch (act) {
+                        case 1: g_bias_act32<1>(v, bs + c0); break;
+                        case 2: g_bias_act32<2>(v, bs + c0); break;
+                        case 3: g_bias_act32<3>(v, bs + c0); break;
+                        default: g_bias_act32<0>(v, bs + c0); break;
                     }
-                    if (!packed) {
+                    if (row_ok) {
+                        float *op = outp + (long long)row * ldo + gcol0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
-                    }
-                    if (P.ones_col && P.N >= gcol0 && P.N < gcol0 + 32) {
-                        const int jo = P.N - gcol0;
+                        for (int q = 0; q < 8; ++q) {
+                            if (gcol0 + 4 * q + 4 <= N && (ldo & 3) == 0)
+                                *reinterpret_cast<float4 *>(op + 4 * q) =
+                                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            else
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (2 * j == jo) pk[j] = (pk[j] & 0xffff0000u) | 0x3f80u;
-                            if (2 * j + 1 == jo) pk[j] = (pk[j] & 0x0000ffffu) | 0x3f800000u;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = (j == jo) ? 1.f : v[j];
-                    }
-                    if (et == 0 && c0 == c_first) g_trace(g, it, 10);
-                    if (P.tma_store) {
-                        // bf16 rows -> the 128-byte-swizzled 128 x 64 box in smem -> one TMA store
-                        // per box (full-line writes, clipped at M rows / ldo columns by the map)
-                        const unsigned sbuf = outs + (nbox & 1u) * 16384u;
-                        const int rr = wq * 32 + lane;
-                        const unsigned rowa = sbuf + rr * 128;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const unsigned phys = (unsigned)((4 * half + q) ^ (rr & 7)) * 16u;
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                         ::"r"(rowa + phys), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                                           "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        if (et == 0 && c0 == c_first) g_trace(g, it, 11);
-                        // the previous box's store must have finished reading the OTHER buffer
-                        // before anybody starts filling it again after this barrier
-                        if (et == 0) g_store_wait_read0();
-                        asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
-                        if (et == 0 && c0 == c_first) g_trace(g, it, 12);
-                        if (et == 0) g_tma_store_2d(&P.map_c, sbuf, t.n0 + (c0 & ~63), t.m0);
-                        if (et == 0 && c0 == c_first) g_trace(g, it, 13);
-                        ++nbox;
-                    } else if (row < P.M) {
-                        if (P.out_f32) {
-                            float *op = static_cast<float *>(P.out) + (long long)row * P.ldo + gcol0;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                if (gcol0 + 4 * q + 4 <= P.N && (P.ldo & 3) == 0)
-                                    *reinterpret_cast<float4 *>(op + 4 * q) =
-                                        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                                else
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e)
-                                        if (gcol0 + 4 * q + e < P.N) op[4 * q + e] = v[4 * q + e];
-                            }
-                        } else {
-                            // rows are padded to a multiple of 8 elements: whole 16-byte groups
-                            // up to the padded width (padding columns receive don't-care values)
-                            __nv_bfloat16 *op = static_cast<__nv_bfloat16 *>(P.out) +
-                                                (long long)row * P.ldo + gcol0;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (gcol0 + 8 * q + 8 <= P.ldo)
-                                    *reinterpret_cast<uint4 *>(op + 8 * q) = make_uint4(
-                                        g_pack_bf16(v[8 * q], v[8 * q + 1]),
-                                        g_pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                        g_pack_bf16(v[8 * q + 4], v[8 * q + 5]),
-                                        g_pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+                                for (int e2 = 0; e2 < 4; ++e2)
+                                    if (gcol0 + 4 * q + e2 < N) op[4 * q + e2] = v[4 * q + e2];
                         }
                     }
                 }
@@ -632,7 +646,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
             if (et == 0) g_trace(g, it, 7);
         }
     }
-    if (warp == 2 && lane == 0) g_store_wait_all();            // staged boxes are on their way out of smem
+    if (warp >= 2 && lane == 0) g_store_wait_all();            // staged boxes are on their way out of smem
     g_fence_before();
     if (NCTA == 2) g_cluster_sync(); else __syncthreads();     // nobody leaves while the peer may still signal it
     if (warp == 2) {
@@ -667,7 +681,8 @@ static GEncodeFn g_encode_fn() {
 // bf16 array [rows, cols] with leading dimension ld (elements), cols contiguous;
 // box = box_cols (inner) x box_rows, 128-byte swizzle, out-of-bounds elements read as 0
 static int g_make_map(CUtensorMap *map, const void *ptr, long long rows, long long cols,
-                      long long ld, int box_cols, int box_rows) {
+                      long long ld, int box_cols, int box_rows,
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     GEncodeFn fn = g_encode_fn();
     if (!fn) return set_error(ABN_EIO, "cuTensorMapEncodeTiled is not available");
     if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (ld & 7))
@@ -677,7 +692,7 @@ static int g_make_map(CUtensorMap *map, const void *ptr, long long rows, long lo
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(ABN_EIO, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return ABN_OK;
@@ -686,8 +701,8 @@ static int g_make_map(CUtensorMap *map, const void *ptr, long long rows, long lo
 template <int BN, int NCTA>
 static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
     constexpr unsigned stage = G_BM * G_BK * 2 + (BN / NCTA) * G_BK * 2;
-    constexpr int STAGES = stage > 32768 ? 3 : 5;
-    constexpr unsigned smem = STAGES * stage + 2 * 16384 + 256 + 2 * BN * 4 + 1024;
+    constexpr int STAGES = stage > 32768 ? 3 : 4;
+    constexpr unsigned smem = STAGES * stage + G_EPI_WARPS * (G_OBUF + 1) * 2048 + 256 + 2 * BN * 4 + 1024;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(tc_group_kernel<BN, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -782,7 +797,15 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
         if (rc) return rc;
         P.tma_store = (!P.out_f32 && q.epilogue != GE_ATOMIC) ? 1 : 0;
         if (P.tma_store) {
-            rc = g_make_map(&P.map_c, q.out, q.M, q.ldo, q.ldo, 64, G_BM);
+            rc = g_make_map(&P.map_c, q.out, q.M, q.ldo, q.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+            if (rc) return rc;
+        }
+        if (q.epilogue == GE_DACT) {
+            if (P.out_f32)
+                return set_error(ABN_EINVAL, "abn_gemm_bf16_group: problem %d: the act' epilogue "
+                                 "writes bf16", i);
+            rc = g_make_map(&P.map_y, q.yprev, q.M, q.ld_yprev, q.ld_yprev, 32, 32,
+                            CU_TENSOR_MAP_SWIZZLE_64B);
             if (rc) return rc;
         }
         P.tiles_m = (P.M + G_BM * ncta - 1) / (G_BM * ncta);
