@@ -430,6 +430,10 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     if (NCTA == 2) g_cluster_sync(); else __syncthreads();
     g_fence_after();
     const unsigned tmem = *tptr_gen;
+    // programmatic dependent launch: everything above overlapped the predecessor's tail; its
+    // results are needed from here on, and our own successor may start its prologue now
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer
@@ -698,6 +702,12 @@ static int g_make_map(CUtensorMap *map, const void *ptr, long long rows, long lo
     return ABN_OK;
 }
 
+static bool g_use_pdl() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("ABN_GEMM_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
 template <int BN, int NCTA>
 static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
     constexpr unsigned stage = G_BM * G_BK * 2 + (BN / NCTA) * G_BK * 2;
@@ -718,13 +728,15 @@ static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
     cfg.blockDim = dim3(G_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NCTA;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_use_pdl() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, tc_group_kernel<BN, NCTA>, g) != cudaSuccess)
         return check_launch("abn_gemm_bf16_group");
     return check_launch("abn_gemm_bf16_group");

@@ -27,6 +27,8 @@ Two kernel paths, selected by ``network.precision``:
 ``state_dict`` / ``.pth`` interchange is unaffected: the module tree and the
 parameter shapes are those of the reference.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -263,7 +265,8 @@ class SiameseTrainStep(object):
         # weight + bias gradients of ALL layers: one launch per group of 4 problems, split
         # over the batch so that the group fills the machine about twice
         tiles = sum(((L.n_out + 127) // 128) * ((L.n_in + 1 + 255) // 256) for L, _ in wgrad)
-        split = max(1, min((rows + 63) // 64, (2 * GEMM_CTAS + tiles - 1) // tiles))
+        split = max(1, min((rows + 63) // 64, int(os.environ.get("ABN_WGRAD_SPLIT", "0")) or
+                           max(1, (GEMM_CTAS // 2) // max(1, tiles // 2))))
         self._wgrad_groups = []
         probs = [ops.gemm_problem(self.dzb[l], xin, L.n_out, L.n_in, rows, ops.GE_ATOMIC, L.gW,
                                   a_mn=True, b_mn=True, split_k=split, ones_out=L.gb)
