@@ -447,19 +447,31 @@ class SiameseTrainStep(object):
         use_graph = graph and self.kind != "adam"
         if use_graph and self._graph_g is not None and self._graph_g[0] == key:
             self._graph_g[1].replay()
-            if self.world > 1:
+            if self._graph_g[2] is not None:        # all-reduce outside the graphs
                 dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM, group=self.group)
-            self._graph_g[2].replay()
+                self._graph_g[2].replay()
             self.step_count += 1
             return self.loss_buf
         if use_graph and self._g_warm >= 2:
             torch.cuda.synchronize()
-            g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_fb):
-                self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)
-            with torch.cuda.graph(g_opt):
-                self._optimizer(scale, 1)
-            self._graph_g = (key, g_fb, g_opt)
+            fused_ar = self.world > 1 and os.environ.get("ABN_GRAPH_ALLREDUCE", "1") == "1"
+            g_fb = torch.cuda.CUDAGraph()
+            if self.world == 1 or fused_ar:
+                # ONE graph: gather .. backward, the NCCL all-reduce (captured), optimizer
+                with torch.cuda.graph(g_fb):
+                    self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)
+                    if self.world > 1:
+                        dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM,
+                                        group=self.group)
+                    self._optimizer(scale, 1)
+                self._graph_g = (key, g_fb, None)
+            else:
+                g_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_fb):
+                    self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)
+                with torch.cuda.graph(g_opt):
+                    self._optimizer(scale, 1)
+                self._graph_g = (key, g_fb, g_opt)
             return self.step_gather(feat, idx1, idx2, y, n, graph=True)
         self._g_warm += 1
         self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)

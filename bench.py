@@ -189,11 +189,16 @@ def run_reference(args, rank):
     from abnet3_b200 import synth
     cores = os.cpu_count() or 1
     corpus = synth.make_corpus(min(args.tokens, 8000), seed=0, device="cpu")
-    per_step = args.cpu_sample or 256 * cores
-    pairs = synth.make_same_pairs(corpus, per_step, seed=1).numpy()
     feat = corpus.feat.numpy()
+    # size a step for ~4 s of CPU work (calibrated on a short run), unless told otherwise
+    per_step = args.cpu_sample
+    if not per_step:
+        probe = synth.make_same_pairs(corpus, 512 * cores, seed=2).numpy()
+        rate, _, _ = cpu_align_rate(feat, probe, cores)
+        per_step = int(max(2048 * cores, min(rate * 4.0, 4_000_000)))
+    pairs = synth.make_same_pairs(corpus, per_step, seed=1).numpy()
     for _ in range(args.warmup):
-        cpu_align_rate(feat, pairs[:max(cores * 8, 64)], cores)
+        cpu_align_rate(feat, pairs[:max(cores * 64, 64)], cores)
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
         rate, dt, _ = cpu_align_rate(feat, pairs, cores)
@@ -461,11 +466,14 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_s = args.cpu_sample or 8192 * cores
-        n_s = min(n_s, P)
-        sp = pairs[:n_s].cpu().numpy()
-        # the sample's tokens live in the first rows it touches; copy the whole table once
         feat_h = feat.cpu().numpy()
+        pairs_h = pairs.cpu().numpy()
+        n_s = args.cpu_sample
+        if not n_s:         # ~15 s of CPU work, calibrated on a short run
+            rate0, _, _ = cpu_align_rate(feat_h, pairs_h[:min(P, 1024 * cores)], cores)
+            n_s = int(max(8192 * cores, rate0 * 15.0))
+        n_s = min(n_s, P)
+        sp = pairs_h[:n_s]
         rate, dt, _ = cpu_align_rate(feat_h, sp, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d pairs of the step's pair list, %.1f s on %d processes "
