@@ -48,8 +48,8 @@ class _LinearActFn(torch.autograd.Function):
             ops.cast_bf16(x, xb)
             ops.cast_bf16(weight.detach(), wb)
             y = torch.empty((m, n_out), dtype=torch.float32, device=x.device)
-            ops.gemm_bf16_tn(xb, wb, m, n_out, n_in, ops.EPI_BIAS_ACT, bias.detach(), act,
-                             out_f32=y)
+            ops.gemm_group([ops.gemm_problem(xb, wb, m, n_out, n_in, ops.GE_BIAS_ACT, y, act=act,
+                                             bias=bias.detach())])
         else:
             y = ops.linear_forward(x, weight, bias, act, 0)
         ctx.save_for_backward(x, weight, y)

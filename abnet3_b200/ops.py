@@ -265,27 +265,8 @@ def optimizer_step(param, grad, state0, state1, kind, lr, momentum=0.0, grad_sca
 
 
 # ------------------------------------------------------- tensor-core path ---
-EPI_BIAS_ACT, EPI_STORE, EPI_ATOMIC, EPI_DGRAD_ACT = 0, 1, 2, 3
-
-
 def pad8(n):
     return (n + 7) // 8 * 8
-
-
-def gemm_bf16_tn(A, B, M, N, K, epilogue, bias=None, act=None, out_f32=None, out_bf16=None,
-                 outT_bf16=None, split_k=1, yprev=None, db=None):
-    """C[M,N] = A[M,K] . B[N,K]^T on tcgen05.  A, B: bf16 2-D tensors whose last
-    dimension is contiguous (row stride = leading dimension, a multiple of 8)."""
-    for t, nm in ((A, "A"), (B, "B")):
-        if not (t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1):
-            raise TypeError("%s must be a CUDA bf16 tensor with a contiguous last dim" % nm)
-    check(_lib.lib().abn_gemm_bf16_tn(
-        ptr(A), A.stride(0), ptr(B), B.stride(0), M, N, K, epilogue, ptr(bias), ACT[act],
-        ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
-        ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
-        ptr(outT_bf16), outT_bf16.stride(0) if outT_bf16 is not None else 0,
-        ptr(yprev), yprev.stride(0) if yprev is not None else 0, ptr(db),
-        split_k, stream_ptr()))
 
 
 def cast_bf16(src, dst=None, dstT=None):
@@ -295,16 +276,6 @@ def cast_bf16(src, dst=None, dstT=None):
     check(_lib.lib().abn_cast_bf16(ptr(src), rows, cols, src.stride(0), ptr(dst),
                                    dst.stride(0) if dst is not None else 0, ptr(dstT),
                                    dstT.stride(0) if dstT is not None else 0, stream_ptr()))
-
-
-def act_backward_bf16(y, dy, act, dz=None, dzT=None, db=None):
-    _req(y, torch.float32, "y")
-    _req(dy, torch.float32, "dy")
-    m, n = y.shape
-    check(_lib.lib().abn_act_backward_bf16(ptr(y), ptr(dy), m, n, ACT[act], ptr(dz),
-                                           dz.stride(0) if dz is not None else 0, ptr(dzT),
-                                           dzT.stride(0) if dzT is not None else 0, ptr(db),
-                                           stream_ptr()))
 
 
 # ------------------------------------- persistent grouped tcgen05 GEMM ---

@@ -224,26 +224,6 @@ ABN_API int abn_linear_backward(const float *x, const float *W, const float *y,
                         abn_stream_t stream);
 
 /* ------------------------------------------------------------------------
- * (3) tensor-core path: C[M,N] = A[M,K] . B[N,K]^T on tcgen05 (bf16 operands,
- * fp32 accumulation in TMEM, TMA-fed), the contraction behind every embedder
- * layer (abnet3/model.py:133-170) and its backward:
- *   forward  A = x [m, n_in],     B = W   [n_out, n_in]   epilogue 0 (bias + act)
- *   dgrad    A = dz [m, n_out],   B = W^T [n_in, n_out]   epilogue 1 (store)
- *   wgrad    A = dz^T [n_out, m], B = x^T [n_in, m]       epilogue 2 (fp32 atomic add, split_k)
- *   dgrad fused with the layer below:                     epilogue 3: C * act'(yprev), where
- *            yprev bf16 [M, ld_yprev] is that layer's forward output, i.e. its dz directly
- * A, B: bf16, K contiguous, 16-byte aligned, leading dimensions (elements)
- * multiples of 8.  Epilogues write any of out_f32 [M, ld_f32], out_bf16
- * [M, ld_bf16] and the TRANSPOSED outT_bf16 [N, ld_T] (NULL to skip); db [N]
- * (NULL to skip) is incremented by the column sums of the written values.
- * ---------------------------------------------------------------------- */
-ABN_API int abn_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb,
-                             int M, int N, int K, int epilogue, const float *bias, int act,
-                             float *out_f32, int64_t ld_f32, void *out_bf16, int64_t ld_bf16,
-                             void *outT_bf16, int64_t ld_T, const void *yprev, int64_t ld_yprev,
-                             float *db, int split_k, abn_stream_t stream);
-
-/* ------------------------------------------------------------------------
  * (3) tensor-core path, persistent grouped GEMM: up to ABN_GEMM_MAX_GROUP problems
  * C[M,N] = A . B^T in ONE launch (tcgen05 / TMEM / TMA; one persistent CTA per SM walks
  * the 128 x 256 output tiles of all problems, the accumulator double buffered in TMEM).
@@ -280,16 +260,10 @@ ABN_API int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_problems
                                 abn_stream_t stream);
 
 /* fp32 [rows, cols] (ld_src) -> bf16 [rows, ld_dst] and/or transposed bf16
- * [cols, ld_T]: operand preparation for abn_gemm_bf16_tn (weights after every
- * optimizer step, the gathered input batch). */
+ * [cols, ld_T]: operand preparation for abn_gemm_bf16_group (the weights after
+ * load_state_dict, an fp32 input batch). */
 ABN_API int abn_cast_bf16(const float *src, int64_t rows, int cols, int64_t ld_src, void *dst,
                           int64_t ld_dst, void *dstT, int64_t ld_T, abn_stream_t stream);
-
-/* dz = dy * act'(y) (fp32 in) -> dz bf16 [m, ld], dz^T bf16 [n, ldT], db += colsum(dz):
- * the elementwise half of abn_linear_backward for the tensor-core path. */
-ABN_API int abn_act_backward_bf16(const float *y, const float *dy, int64_t m, int n, int act,
-                                  void *dz, int64_t ld, void *dzT, int64_t ldT, float *db,
-                                  abn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Fused optimizer step over one flat parameter bucket.

@@ -14,94 +14,67 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _operands(M, N, K, seed):
-    g = torch.Generator().manual_seed(seed)
-    A = torch.zeros((M, ops.pad8(K)), dtype=torch.bfloat16)
-    B = torch.zeros((N, ops.pad8(K)), dtype=torch.bfloat16)
-    A[:, :K] = (torch.randn(M, K, generator=g) / np.sqrt(K)).bfloat16()
-    B[:, :K] = torch.randn(N, K, generator=g).bfloat16()
-    A[:, K:] = 7.0            # padding columns must never be read (TMA bounds = true K)
-    B[:, K:] = 7.0
-    ref = A[:, :K].double() @ B[:, :K].double().T
-    return A.to(DEV), B.to(DEV), ref
-
-
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 64, 64), (256, 500, 280), (1000, 100, 500),
-                                   (16384, 500, 500), (300, 100, 24), (130, 36, 8), (2048, 280, 500)])
-def test_tcgen05_gemm_store(M, N, K):
-    A, B, ref = _operands(M, N, K, M + N + K)
-    out = torch.full((M, N), float("nan"), device=DEV)
-    ops.gemm_bf16_tn(A, B, M, N, K, ops.EPI_STORE, out_f32=out)
-    torch.cuda.synchronize()
-    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-4)
-
-
-def test_tcgen05_gemm_bias_act_and_all_outputs():
-    M, N, K = 700, 500, 280
-    A, B, ref = _operands(M, N, K, 3)
-    bias = torch.randn(N) * 0.1
-    for act, fn in (("sigmoid", torch.sigmoid), ("tanh", torch.tanh), ("relu", torch.relu),
-                    ("none", lambda v: v)):
-        want = fn(ref + bias.double())
-        o32 = torch.zeros((M, N), device=DEV)
-        o16 = torch.zeros((M, ops.pad8(N)), dtype=torch.bfloat16, device=DEV)
-        oT = torch.zeros((N, ops.pad8(M)), dtype=torch.bfloat16, device=DEV)
-        ops.gemm_bf16_tn(A, B, M, N, K, ops.EPI_BIAS_ACT, bias.to(DEV), act, out_f32=o32,
-                         out_bf16=o16, outT_bf16=oT)
-        torch.cuda.synchronize()
-        np.testing.assert_allclose(o32.cpu().numpy(), want.numpy(), rtol=3e-4, atol=3e-4)
-        assert torch.equal(o16[:, :N].cpu(), o32.cpu().bfloat16())            # same values, rounded once
-        assert torch.equal(oT[:, :M].cpu(), o32.cpu().bfloat16().T)
-        assert float(o16[:, N:].abs().max()) == 0 and float(oT[:, M:].abs().max()) == 0
-
-
-def test_tcgen05_gemm_dgrad_epilogue_applies_act_derivative():
-    """epilogue 3: dz_below = (dz W) * act'(y_below), plus its transpose and column sums."""
-    M, N, K = 700, 500, 100
-    A, B, ref = _operands(M, N, K, 5)
-    g = torch.Generator().manual_seed(1)
-    for act, dfn in (("sigmoid", lambda y: y * (1 - y)), ("tanh", lambda y: 1 - y * y),
-                     ("relu", lambda y: (y > 0).double())):
-        yprev = torch.zeros((M, ops.pad8(N)), dtype=torch.bfloat16)
-        raw = torch.randn(M, N, generator=g)
-        yprev[:, :N] = {"sigmoid": torch.sigmoid, "tanh": torch.tanh, "relu": torch.relu}[act](raw).bfloat16()
-        want = ref * dfn(yprev[:, :N].double())
-        o16 = torch.zeros((M, ops.pad8(N)), dtype=torch.bfloat16, device=DEV)
-        oT = torch.zeros((N, ops.pad8(M)), dtype=torch.bfloat16, device=DEV)
-        db = torch.full((N,), 0.5, device=DEV)
-        ops.gemm_bf16_tn(A, B, M, N, K, ops.EPI_DGRAD_ACT, act=act, yprev=yprev.to(DEV),
-                         out_bf16=o16, outT_bf16=oT, db=db)
-        torch.cuda.synchronize()
-        np.testing.assert_allclose(o16[:, :N].float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-3)
-        assert torch.equal(oT[:, :M].cpu(), o16[:, :N].cpu().T)
-        np.testing.assert_allclose(db.cpu().numpy(), 0.5 + want.sum(0).numpy(), rtol=2e-3, atol=2e-2)
-
-
-def test_tcgen05_gemm_split_k_atomic_accumulates():
-    M, N, K = 500, 280, 16384          # the wgrad shape: contraction over the batch
-    A, B, ref = _operands(M, N, K, 9)
-    out = torch.ones((M, N), device=DEV)
-    ops.gemm_bf16_tn(A, B, M, N, K, ops.EPI_ATOMIC, out_f32=out, split_k=8)
-    torch.cuda.synchronize()
-    np.testing.assert_allclose(out.cpu().numpy(), 1.0 + ref.numpy(), rtol=3e-4, atol=3e-4)
-
-
-def test_cast_and_act_backward_bf16():
+def test_cast_bf16_and_fused_companions():
     torch.manual_seed(0)
     x = torch.randn(333, 280, device=DEV)
     xb = torch.zeros((333, 280), dtype=torch.bfloat16, device=DEV)
     xT = torch.zeros((280, ops.pad8(333)), dtype=torch.bfloat16, device=DEV)
     ops.cast_bf16(x, xb, xT)
     assert torch.equal(xb, x.bfloat16()) and torch.equal(xT[:, :333], x.bfloat16().T)
-    y = torch.sigmoid(torch.randn(333, 100, device=DEV))
-    dy = torch.randn(333, 100, device=DEV)
-    dz = torch.zeros((333, ops.pad8(100)), dtype=torch.bfloat16, device=DEV)
-    dzT = torch.zeros((100, ops.pad8(333)), dtype=torch.bfloat16, device=DEV)
-    db = torch.zeros(100, device=DEV)
-    ops.act_backward_bf16(y, dy, "sigmoid", dz, dzT, db)
-    want = dy * y * (1 - y)
-    assert torch.equal(dz[:, :100], want.bfloat16()) and torch.equal(dzT[:, :333], want.bfloat16().T)
-    np.testing.assert_allclose(db.cpu().numpy(), want.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_gather_batch_bf16_writes_the_first_layers_operand():
+    torch.manual_seed(1)
+    feat = torch.randn(5000, 280, device=DEV)
+    n = 777
+    idx1 = torch.randint(0, 5000, (3000,), device=DEV, dtype=torch.int32)
+    idx2 = torch.randint(0, 5000, (3000,), device=DEV, dtype=torch.int32)
+    y = (torch.randint(0, 2, (3000,), device=DEV) * 2 - 1).to(torch.int8)
+    sel = torch.randperm(3000, device=DEV)[:n]
+    xb = torch.full((2 * n, ops.pad8(281)), 3.0, dtype=torch.bfloat16, device=DEV)
+    yo = torch.zeros(n, device=DEV)
+    acc = torch.full((1,), 5.0, device=DEV)
+    ops.gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=yo, zero=acc)
+    assert torch.equal(xb[:n, :280], feat[idx1[sel].long()].bfloat16())
+    assert torch.equal(xb[n:, :280], feat[idx2[sel].long()].bfloat16())
+    assert bool((xb[:, 280:] == 3.0).all())            # row padding (the ones column lives there) untouched
+    assert torch.equal(yo, y[sel].float()) and float(acc) == 0.0
+
+
+def test_pair_loss_dz_matches_pair_loss_times_activation_derivative():
+    torch.manual_seed(2)
+    n, d = 1000, 100
+    e = torch.sigmoid(torch.randn(2 * n, d, device=DEV))
+    y = (torch.randint(0, 2, (n,), device=DEV) * 2 - 1).float()
+    for kind in ("coscos2", "cosmargin"):
+        loss_ref, de1, de2 = ops.pair_loss(e[:n], e[n:], y, kind, 0.5, 1.0)
+        dz = torch.zeros((2 * n, ops.pad8(d)), dtype=torch.bfloat16, device=DEV)
+        loss = ops.pair_loss_dz(e[:n], e[n:], y, dz[:n], dz[n:], kind, 0.5, 1.0, "sigmoid")
+        want = torch.cat([de1, de2]) * e * (1 - e)
+        assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+        np.testing.assert_allclose(dz[:, :d].float().cpu().numpy(), want.cpu().numpy(), rtol=1e-2, atol=1e-7)
+
+
+def test_fused_optimizer_matches_plain_step_and_refreshes_bf16_weights():
+    torch.manual_seed(3)
+    n_out, n_in = 60, 44
+    nw, nb = n_out * n_in, n_out
+    for kind in ("sgd", "adadelta", "adam"):
+        p0 = torch.randn(nw + nb, device=DEV)
+        g0 = torch.randn(nw + nb, device=DEV) * 0.1
+        pa, pb = p0.clone(), p0.clone()
+        ga, gb = g0.clone(), g0.clone()
+        sa = [torch.zeros_like(p0), torch.zeros_like(p0)]
+        sb = [torch.zeros_like(p0), torch.zeros_like(p0)]
+        wb = torch.zeros((n_out, ops.pad8(n_in)), dtype=torch.bfloat16, device=DEV)
+        seg = ops.param_segments([(0, nw, wb, n_in), (nw, nb, None, 0)])
+        for step in (1, 2):
+            ops.optimizer_step(pa, ga, sa[0], sa[1], kind, 0.1, 0.9, 0.5, step)
+            ops.optimizer_step_fused(pb, gb, sb[0], sb[1], kind, 0.1, 0.9, 0.5, step, seg, zero_grad=True)
+            assert torch.equal(pa, pb)
+            assert torch.equal(wb[:, :n_in], pb[:nw].view(n_out, n_in).bfloat16())
+            assert float(gb.abs().max()) == 0.0
+            gb.copy_(g0)
 
 
 def _rel(a, b):
