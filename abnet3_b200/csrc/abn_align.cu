@@ -1367,6 +1367,19 @@ extern "C" size_t abn_align_workspace_bytes(int n_pairs, int max_frames, int rou
     return ws_dist_off(n_pairs) + per_round * slot_cells_for(max_frames) * sizeof(float);
 }
 
+// kernels one abn_align_pairs call enqueues (for launch accounting in benchmarks)
+extern "C" int abn_align_launches(int n_pairs, int max_frames, int stack, size_t workspace_bytes) {
+    if (n_pairs <= 0 || max_frames <= 0) return 0;
+    const int ext = stack ? 2 * STACK_H : 0;
+    const size_t slot = slot_cells_for(max_frames) * sizeof(float), d_off = ws_dist_off(n_pairs);
+    size_t chunk = workspace_bytes > d_off ? (workspace_bytes - d_off) / slot : 0;
+    if (chunk < 1) return 0;
+    if (chunk > (size_t)n_pairs) chunk = (size_t)n_pairs;
+    const int rounds = (int)(((size_t)n_pairs + chunk - 1) / chunk);
+    const int side = ((max_frames + ext < NM_SHORT ? max_frames + ext : NM_SHORT) + 15) / 16;
+    return 3 + (max_frames + ext > NM_SHORT ? 1 : 0) + rounds * (side * side + side);
+}
+
 extern "C" int abn_align_pairs(const float *feat, int64_t n_rows, int dim,
                                const int32_t *pair_tok, int n_pairs, int max_frames, int stack,
                                const int64_t *path_off, int32_t *idx1, int32_t *idx2,

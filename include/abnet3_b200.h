@@ -89,6 +89,9 @@ ABN_API int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int
  * max_frames, n_pairs) and derives the round count from what it is given;
  * abn_cosine_distance needs abn_align_workspace_bytes(n_pairs, 1, n_pairs). */
 ABN_API size_t abn_align_workspace_bytes(int n_pairs, int max_frames, int rounds);
+/* Number of kernels one abn_align_pairs call with this workspace enqueues (bucketing +
+ * per round: one distance kernel per size class and one DTW kernel per class row). */
+ABN_API int abn_align_launches(int n_pairs, int max_frames, int stack, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------
  * (1) Batched cosine frame distance.
