@@ -36,6 +36,11 @@ class ParamSegment(_c.Structure):
     _fields_ = [("offset", _L), ("count", _L), ("ld", _L), ("bf16", _P), ("n_in", _I)]
 
 
+class DpPeers(_c.Structure):
+    """abn_dp_peers (include/abnet3_b200.h)."""
+    _fields_ = [("grad", _P * 8), ("flags", _P * 8), ("rank", _I), ("world", _I)]
+
+
 # name -> (restype, argtypes); mirrors include/abnet3_b200.h declaration order
 SIGNATURES = {
     "abn_version": (_I, []),
@@ -60,6 +65,10 @@ SIGNATURES = {
     "abn_gather_batch_bf16": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P]),
     "abn_pair_loss_dz": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _I, _P, _P, _P, _L, _P]),
     "abn_optimizer_step_fused": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _I, _P]),
+    "abn_ipc_export": (_I, [_P, _P, _P]),
+    "abn_ipc_import": (_I, [_P, _L, _P]),
+    "abn_dp_optimizer_step": (_I, [_P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _P, _P]),
+    "abn_dp_grad_reset": (_I, [_P, _L, _P, _P]),
 }
 
 _lib = None

@@ -9,7 +9,9 @@
 //   abn_optimizer_step_fused optimizer.step() of abnet3/trainer.py:240 over the flat
 //                            bucket + the bf16 operand copy of every weight matrix + the
 //                            zeroing of the gradient bucket for the next step's reductions
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "abn_common.cuh"
 
@@ -217,4 +219,277 @@ extern "C" int abn_optimizer_step_fused(float *param, float *grad, float *state0
     optimizer_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         param, grad, state0, state1, kind, lr, momentum, grad_scale, bc1, bc2s, zero_grad, tab);
     return check_launch("abn_optimizer_step_fused");
+}
+
+// ------------------------------------------------------------------------
+// Data-parallel step without a library collective: the gradient all-reduce is FUSED into
+// the optimizer kernel over NVLink peer memory.  Every rank maps its peers' gradient
+// buckets (CUDA IPC) and a small flag block; per step
+//   dp_optimizer_kernel            block 0 sets ready[rank] = step (= done[rank] + 1) in every peer's
+//                                  flags; all blocks wait until ready[p] >= step for all p, then every thread
+//                                  sums its elements over the local + peer buckets (one-shot
+//                                  reads over NVLink / NVSwitch), applies the update, writes
+//                                  the bf16 weight copy; the last block sets done[rank] = step
+//                                  in every peer's flags
+//   dp_grad_reset_kernel           (before the next step's wgrad reductions) waits until
+//                                  done[p] >= done[rank] for all p -- nobody still reads this
+//                                  rank's bucket -- and clears it
+// The flags are monotonically increasing step numbers kept on the device, so the whole
+// sequence replays inside a CUDA graph.  Replaces dist.all_reduce + optimizer.step().
+namespace abn {
+
+constexpr int DP_MAX_WORLD = ABN_DP_MAX_WORLD;
+enum { DPF_READY = 0, DPF_DONE = DP_MAX_WORLD, DPF_COUNTER = 2 * DP_MAX_WORLD, DPF_TICKET = 2 * DP_MAX_WORLD + 1 };
+
+struct DpPeers {
+    const float *grad[DP_MAX_WORLD];          // every rank's gradient bucket (own one included)
+    unsigned long long *flags[DP_MAX_WORLD];  // every rank's flag block
+    int rank, world;
+};
+
+__device__ __forceinline__ unsigned long long dp_ld_acquire(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dp_st_release(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// bounded spin: a missing peer must trap, not hang the GPU forever
+__device__ __forceinline__ void dp_wait_all(const unsigned long long *slots, int world,
+                                            unsigned long long want) {
+    for (int p = 0; p < world; ++p) {
+        unsigned long long spins = 0;
+        while (dp_ld_acquire(slots + p) < want) {
+            if (++spins > (1ull << 31)) __trap();
+        }
+    }
+}
+
+// 16-byte uncached loads from a (peer) bucket
+__device__ __forceinline__ float4 dp_ld4(const float *p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ float dp_update(float w, float grad, float *s0, float *s1, int64_t i,
+                                           int kind, float lr, float momentum, float bc1,
+                                           float bc2_sqrt) {
+    if (kind == 0) {            // torch.optim.SGD(momentum, dampening=0)
+        float buf = grad;
+        if (momentum != 0.f) { buf = momentum * s0[i] + grad; s0[i] = buf; }
+        return w - lr * buf;
+    }
+    if (kind == 1) {            // torch.optim.Adadelta(rho=0.9, eps=1e-6)
+        const float rho = 0.9f, eps = 1e-6f;
+        const float sq = rho * s0[i] + (1.f - rho) * grad * grad;
+        const float stdv = sqrtf(sq + eps);
+        const float delta = sqrtf(s1[i] + eps) / stdv * grad;
+        s0[i] = sq;
+        s1[i] = rho * s1[i] + (1.f - rho) * delta * delta;
+        return w - lr * delta;
+    }
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;     // torch.optim.Adam
+    const float m = b1 * s0[i] + (1.f - b1) * grad;
+    const float v = b2 * s1[i] + (1.f - b2) * grad * grad;
+    s0[i] = m; s1[i] = v;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    return w - (lr / bc1) * (m / denom);
+}
+
+__global__ void dp_optimizer_kernel(float *__restrict__ p, float *__restrict__ s0,
+                                    float *__restrict__ s1, int kind, float lr, float momentum,
+                                    float gscale, float bc1, float bc2_sqrt, const SegTable tab,
+                                    const DpPeers pe) {
+    unsigned long long *mine = pe.flags[pe.rank];
+    __shared__ unsigned long long step_s;
+    if (threadIdx.x == 0) {
+        // this step's number: one more than the last step this rank completed (done[rank] is
+        // only advanced by the LAST block of a launch, after every block has read it)
+        const unsigned long long step = dp_ld_acquire(mine + DPF_DONE + pe.rank) + 1;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            // the stream order put every gradient reduction of this rank before this kernel
+            __threadfence_system();
+            for (int q = 0; q < pe.world; ++q) dp_st_release(pe.flags[q] + DPF_READY + pe.rank, step);
+        }
+        dp_wait_all(mine + DPF_READY, pe.world, step);       // every rank's gradients are complete
+        step_s = step;
+    }
+    __syncthreads();
+    const abn_param_segment sg = tab.s[blockIdx.y];
+    __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
+    const bool vec = ((sg.offset | sg.count) & 3) == 0 && (!wb || (sg.n_in & 3) == 0);
+    if (vec) {
+        // 4 consecutive elements per thread: 16-byte loads from every bucket, all in flight
+        for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j < sg.count;
+             j += (int64_t)gridDim.x * blockDim.x * 4) {
+            const int64_t i = sg.offset + j;
+            float4 part[DP_MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r)
+                if (r < pe.world) part[r] = dp_ld4(pe.grad[r] + i);
+            float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r)       // rank order: the same sum on every rank
+                if (r < pe.world) { gs.x += part[r].x; gs.y += part[r].y; gs.z += part[r].z; gs.w += part[r].w; }
+            const float4 w4 = *reinterpret_cast<const float4 *>(p + i);
+            float w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float g[4] = {gs.x * gscale, gs.y * gscale, gs.z * gscale, gs.w * gscale};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                w[e] = dp_update(w[e], g[e], s0, s1, i + e, kind, lr, momentum, bc1, bc2_sqrt);
+            *reinterpret_cast<float4 *>(p + i) = make_float4(w[0], w[1], w[2], w[3]);
+            if (wb) {
+                const int64_t r = j / sg.n_in;
+                __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]), hi = __floats2bfloat162_rn(w[2], w[3]);
+                *reinterpret_cast<uint2 *>(wb + r * sg.ld + (j - r * sg.n_in)) =
+                    make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+            }
+        }
+    } else {
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < sg.count;
+             j += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t i = sg.offset + j;
+            float gsum = 0.f;
+            for (int r = 0; r < pe.world; ++r) gsum += __ldcv(pe.grad[r] + i);
+            const float w = dp_update(p[i], gsum * gscale, s0, s1, i, kind, lr, momentum, bc1, bc2_sqrt);
+            p[i] = w;
+            if (wb) {
+                const int64_t r = j / sg.n_in;
+                wb[r * sg.ld + (j - r * sg.n_in)] = __float2bfloat16_rn(w);
+            }
+        }
+    }
+    // the last block to finish tells every peer that this rank no longer reads their buckets
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long total = (unsigned long long)gridDim.x * gridDim.y;
+        const unsigned long long t = atomicAdd(mine + DPF_TICKET, 1ull);
+        if (t == total - 1) {
+            mine[DPF_TICKET] = 0;
+            __threadfence_system();
+            for (int q = 0; q < pe.world; ++q)
+                dp_st_release(pe.flags[q] + DPF_DONE + pe.rank, step_s);
+        }
+    }
+}
+
+__global__ void dp_grad_reset_kernel(float *__restrict__ g, int64_t n, const DpPeers pe) {
+    const unsigned long long *mine = pe.flags[pe.rank];
+    if (threadIdx.x == 0) dp_wait_all(mine + DPF_DONE, pe.world, dp_ld_acquire(mine + DPF_DONE + pe.rank));
+    __syncthreads();
+    float4 *g4 = reinterpret_cast<float4 *>(g);
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x)
+        g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        g[i] = 0.f;
+}
+
+static int dp_fill(DpPeers &pe, const abn_dp_peers *peers) {
+    if (!peers || peers->world < 2 || peers->world > DP_MAX_WORLD || peers->rank < 0 ||
+        peers->rank >= peers->world)
+        return set_error(ABN_EINVAL, "data-parallel peers: world must be 2..%d", DP_MAX_WORLD);
+    pe.rank = peers->rank;
+    pe.world = peers->world;
+    for (int r = 0; r < peers->world; ++r) {
+        if (!peers->grad[r] || !peers->flags[r])
+            return set_error(ABN_EINVAL, "data-parallel peers: rank %d is not mapped", r);
+        pe.grad[r] = static_cast<const float *>(peers->grad[r]);
+        pe.flags[r] = static_cast<unsigned long long *>(peers->flags[r]);
+    }
+    return ABN_OK;
+}
+
+}  // namespace abn
+
+extern "C" int abn_ipc_export(const void *ptr, unsigned char *handle64, int64_t *offset) {
+    if (int rc = require_sm100()) return rc;
+    if (!ptr || !handle64 || !offset) return set_error(ABN_EINVAL, "abn_ipc_export: bad argument");
+    typedef CUresult (*RangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+    static RangeFn fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return set_error(ABN_EIO, "abn_ipc_export: cuMemGetAddressRange is not available");
+        fn = reinterpret_cast<RangeFn>(f);
+    }
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS)
+        return set_error(ABN_EIO, "abn_ipc_export: cannot find the allocation of %p", ptr);
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void *>(base));
+    if (e != cudaSuccess)
+        return set_error(ABN_EIO, "abn_ipc_export: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &h, 64);
+    *offset = (int64_t)((CUdeviceptr)ptr - base);
+    return ABN_OK;
+}
+
+extern "C" int abn_ipc_import(const unsigned char *handle64, int64_t offset, void **ptr) {
+    if (int rc = require_sm100()) return rc;
+    if (!handle64 || !ptr) return set_error(ABN_EINVAL, "abn_ipc_import: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(ABN_EIO, "abn_ipc_import: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    }
+    *ptr = static_cast<unsigned char *>(base) + offset;
+    return ABN_OK;
+}
+
+extern "C" int abn_dp_optimizer_step(float *param, float *state0, float *state1, int kind, float lr,
+                                     float momentum, float grad_scale, int64_t step,
+                                     const abn_param_segment *segments, int n_segments,
+                                     const abn_dp_peers *peers, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (n_segments == 0) return ABN_OK;
+    if (!param || !segments || n_segments < 0 || n_segments > ABN_MAX_PARAM_SEGMENTS || kind < 0 ||
+        kind > 2 || (kind == 0 && momentum != 0.f && !state0) || (kind >= 1 && (!state0 || !state1)) ||
+        step < 1)
+        return set_error(ABN_EINVAL, "abn_dp_optimizer_step: bad argument");
+    DpPeers pe;
+    if (int rc = dp_fill(pe, peers)) return rc;
+    SegTable tab;
+    tab.n = n_segments;
+    int64_t longest = 0;
+    for (int i = 0; i < n_segments; ++i) {
+        tab.s[i] = segments[i];
+        if (segments[i].count > longest) longest = segments[i].count;
+    }
+    const float bc1 = 1.f - powf(0.9f, (float)step);
+    const float bc2s = sqrtf(1.f - powf(0.999f, (float)step));
+    int64_t bx = (longest / 4 + 255) / 256;
+    if (bx > 148 * 2) bx = 148 * 2;
+    if (bx < 1) bx = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)bx, (unsigned)n_segments);
+    dp_optimizer_kernel<<<grid, 256, 0, st>>>(param, state0, state1, kind, lr, momentum, grad_scale,
+                                              bc1, bc2s, tab, pe);
+    return check_launch("abn_dp_optimizer_step");
+}
+
+extern "C" int abn_dp_grad_reset(float *grad, int64_t n, const abn_dp_peers *peers,
+                                 abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (!grad || n < 0) return set_error(ABN_EINVAL, "abn_dp_grad_reset: bad argument");
+    DpPeers pe;
+    if (int rc = dp_fill(pe, peers)) return rc;
+    int64_t bx = (n / 4 + 255) / 256;
+    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx < 1) bx = 1;
+    dp_grad_reset_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(grad, n, pe);
+    return check_launch("abn_dp_grad_reset");
 }

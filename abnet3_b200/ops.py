@@ -366,3 +366,57 @@ def optimizer_step_fused(param, grad, state0, state1, kind, lr, momentum, grad_s
                                               OPT_KIND[kind], float(lr), float(momentum),
                                               float(grad_scale), int(step), segments,
                                               len(segments), int(bool(zero_grad)), stream_ptr()))
+
+
+# ------------------------- data parallelism over NVLink peer memory (no NCCL) ---
+def dp_setup(grad, group=None):
+    """Map every rank's gradient bucket and flag block into this process (CUDA IPC).
+    Collective over ``group``; returns an opaque peers object for dp_optimizer_step /
+    dp_grad_reset, or raises if the buffers cannot be shared (then use NCCL)."""
+    import ctypes
+    import torch.distributed as dist
+    lib = _lib.lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world > 8:
+        raise RuntimeError("peer-memory data parallelism serves one box (world <= 8)")
+    flags = torch.zeros(32, dtype=torch.int64, device=grad.device)
+    torch.cuda.synchronize()
+
+    def export(t):
+        h = (ctypes.c_ubyte * 64)()
+        off = ctypes.c_int64(0)
+        check(lib.abn_ipc_export(ptr(t), h, ctypes.byref(off)))
+        return bytes(h), int(off.value)
+
+    mine = {"grad": export(grad), "flags": export(flags), "numel": grad.numel()}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    peers = _lib.DpPeers()
+    peers.rank, peers.world = rank, world
+    for r, info in enumerate(everyone):
+        if info["numel"] != grad.numel():
+            raise RuntimeError("rank %d has a different gradient bucket" % r)
+        if r == rank:
+            peers.grad[r], peers.flags[r] = ptr(grad), ptr(flags)
+            continue
+        for key, arr in (("grad", peers.grad), ("flags", peers.flags)):
+            hb, off = info[key]
+            h = (ctypes.c_ubyte * 64).from_buffer_copy(hb)
+            out = ctypes.c_void_p()
+            check(lib.abn_ipc_import(h, off, ctypes.byref(out)))
+            arr[r] = out.value
+    dist.barrier(group=group)
+    peers._keep = (grad, flags)
+    return peers
+
+
+def dp_optimizer_step(param, state0, state1, kind, lr, momentum, grad_scale, step, segments, peers):
+    import ctypes
+    check(_lib.lib().abn_dp_optimizer_step(ptr(param), ptr(state0), ptr(state1), OPT_KIND[kind],
+                                           float(lr), float(momentum), float(grad_scale), int(step),
+                                           segments, len(segments), ctypes.byref(peers), stream_ptr()))
+
+
+def dp_grad_reset(grad, peers):
+    import ctypes
+    check(_lib.lib().abn_dp_grad_reset(ptr(grad), grad.numel(), ctypes.byref(peers), stream_ptr()))

@@ -317,6 +317,37 @@ ABN_API int abn_optimizer_step_fused(float *param, float *grad, float *state0, f
                                      int64_t step, const abn_param_segment *segments,
                                      int n_segments, int zero_grad, abn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Data parallelism without a library collective (new: the reference is single-GPU,
+ * abnet3/trainer.py:59-61): the gradient all-reduce fused into the optimizer over NVLink /
+ * NVSwitch peer memory, one process per GPU on one box.
+ *   abn_ipc_export / abn_ipc_import: CUDA IPC handle (64 bytes) + byte offset of a device
+ *     buffer, and the mapping of a peer's buffer into this process (peer access enabled).
+ *   abn_dp_peers: every rank's gradient bucket and flag block (ABN_DP_FLAG_WORDS uint64,
+ *     zero-initialised once) as mapped in THIS process; entry `rank` is the local one.
+ *   abn_dp_optimizer_step: abn_optimizer_step_fused on grad = sum over ranks (read straight
+ *     from the peers' buckets once every rank has signalled that its gradients are complete).
+ *   abn_dp_grad_reset: clears the local bucket once every peer has finished reading it
+ *     (enqueue before the next step's gradient reductions).
+ * Every rank must enqueue the same sequence of steps; the flags are device-side step
+ * counters, so the sequence may be captured in a CUDA graph and replayed.
+ * ---------------------------------------------------------------------- */
+#define ABN_DP_MAX_WORLD 8
+#define ABN_DP_FLAG_WORDS 32
+typedef struct {
+    void *grad[ABN_DP_MAX_WORLD];
+    void *flags[ABN_DP_MAX_WORLD];
+    int rank, world;
+} abn_dp_peers;
+ABN_API int abn_ipc_export(const void *ptr, unsigned char *handle64, int64_t *offset);
+ABN_API int abn_ipc_import(const unsigned char *handle64, int64_t offset, void **ptr);
+ABN_API int abn_dp_optimizer_step(float *param, float *state0, float *state1, int kind, float lr,
+                                  float momentum, float grad_scale, int64_t step,
+                                  const abn_param_segment *segments, int n_segments,
+                                  const abn_dp_peers *peers, abn_stream_t stream);
+ABN_API int abn_dp_grad_reset(float *grad, int64_t n, const abn_dp_peers *peers,
+                              abn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
