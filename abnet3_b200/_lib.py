@@ -28,7 +28,8 @@ class GemmProblem(_c.Structure):
                 ("out", _P), ("ldo", _L), ("out_f32", _I),
                 ("yprev", _P), ("ld_yprev", _L),
                 ("ones_col", _I),
-                ("ones_out", _P)]
+                ("ones_out", _P),
+                ("signal", _P), ("wait", _P), ("wait_count", _I)]
 
 
 class ParamSegment(_c.Structure):

@@ -41,7 +41,7 @@ constexpr int G_BK = 64;           // bf16 elements per K block (128-byte swizzl
 constexpr int G_UK = 16;           // UMMA_K
 constexpr int G_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes every other 32-column chunk
 constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
-constexpr int G_OBUF = 4;          // output boxes in flight per epilogue warp (TMA store latency ~1 us)
+constexpr int G_OBUF = 2;          // output boxes in flight per epilogue warp (TMA store latency ~1 us)
 constexpr int G_MAXP = ABN_GEMM_MAX_GROUP;
 
 enum { GE_BIAS_ACT = 0, GE_DACT = 1, GE_ATOMIC = 2 };
@@ -59,6 +59,8 @@ struct GProblem {
     void *out; long long ldo;
     const __nv_bfloat16 *yprev; long long ld_yprev;
     float *ones_out;
+    int *signal;                    // [tiles_m]: +1 per CTA when a tile's output rows are in global memory
+    const int *wait; int wait_count; // A rows of m-tile mt may be loaded once wait[mt] >= wait_count
 };
 struct GGroup {
     GProblem p[G_MAXP];
@@ -275,13 +277,13 @@ __device__ __forceinline__ void g_store_wait_all() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-struct GTile { int pi, m0, n0, kb0, nkb, n_eff; };
+struct GTile { int pi, m0, n0, kb0, nkb, n_eff, mt; };
 
 __device__ __forceinline__ void g_trace(const GGroup &g, unsigned it, int slot) {
-    if (g.trace && it < 4) {
+    if (g.trace && it < 8) {
         long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        g.trace[((size_t)blockIdx.x * 4 + it) * 16 + slot] = t;
+        g.trace[((size_t)blockIdx.x * 8 + it) * 16 + slot] = t;
     }
 }
 
@@ -298,6 +300,7 @@ __device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn, int
     GTile t;
     t.pi = pi;
     t.m0 = (mt * ncta + rank) * G_BM;
+    t.mt = mt;
     t.n0 = nt * bn;
     const int total_kb = (P.K + G_BK - 1) / G_BK;
     t.kb0 = ks * P.kb_per_split;
@@ -387,7 +390,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     constexpr unsigned A_BYTES = G_BM * G_BK * 2;           // 16 KB: this CTA's 128 rows
     constexpr unsigned B_BYTES = (BN / NCTA) * G_BK * 2;    // this CTA's share of the B tile
     constexpr unsigned STAGE = A_BYTES + B_BYTES;
-    constexpr int STAGES = STAGE > 32768 ? 3 : 4;
+    constexpr int STAGES = STAGE > 32768 ? 3 : 5;
     // per epilogue warp: G_OBUF 32 x 32 bf16 boxes staged for TMA stores, one for y_below loads
     constexpr unsigned OUT_BYTES = G_EPI_WARPS * (G_OBUF * 2048u + 2048u);
     const int rank = NCTA == 2 ? (int)g_cluster_rank() : 0;
@@ -443,6 +446,18 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                 const GTile t = g_decode(g, tile, BN, NCTA, rank);
                 const GProblem &P = g.p[t.pi];
                 g_trace(g, pit, 0);
+                if (P.wait) {
+                    // in-launch dependency: the rows of A are the output of an earlier problem of
+                    // this group (possibly computed by other CTAs) -- wait for all of its tiles
+                    // over these rows, then order the TMA reads after the observation
+                    unsigned spins = 0;
+                    int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(P.wait + t.mt) : "memory");
+                        if (++spins > (1u << 28)) __trap();
+                    } while (seen < P.wait_count);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
                 // this CTA's share of the B tile: n_eff / NCTA columns from nb0 on
                 const int nb_cols = t.n_eff / NCTA, nb0 = t.n0 + rank * nb_cols;
                 const int nbox_b = (nb_cols + 63) >> 6;
@@ -647,6 +662,17 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
             if (lane == 0) {
                 if (NCTA == 2) g_mbar_arrive_cta0(tempty0 + 8 * ab); else g_mbar_arrive(tempty0 + 8 * ab);
             }
+            if (P.signal) {
+                // publish this CTA's rows of the tile: every warp's stores have landed, then one
+                // release-increment of the m-tile's counter (consumers: producers of later problems)
+                if (lane == 0) g_store_wait_all();
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
+                if (et == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(P.signal + t.mt) : "memory");
+                }
+            }
             if (et == 0) g_trace(g, it, 7);
         }
     }
@@ -711,7 +737,7 @@ static bool g_use_pdl() {
 template <int BN, int NCTA>
 static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
     constexpr unsigned stage = G_BM * G_BK * 2 + (BN / NCTA) * G_BK * 2;
-    constexpr int STAGES = stage > 32768 ? 3 : 4;
+    constexpr int STAGES = stage > 32768 ? 3 : 5;
     constexpr unsigned smem = STAGES * stage + G_EPI_WARPS * (G_OBUF + 1) * 2048 + 256 + 2 * BN * 4 + 1024;
     static bool configured = false;
     if (!configured) {
@@ -796,6 +822,7 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
         P.bias = q.bias; P.out = q.out; P.ldo = q.ldo;
         P.yprev = static_cast<const __nv_bfloat16 *>(q.yprev); P.ld_yprev = q.ld_yprev;
         P.ones_out = ones_in ? q.ones_out : nullptr;
+        P.signal = q.signal; P.wait = q.wait; P.wait_count = q.wait_count;
         if (!P.out_f32 && ((q.ldo & 7) || q.ldo < P.N + P.ones_col))
             return set_error(ABN_EINVAL, "abn_gemm_bf16_group: problem %d: bf16 output rows must be "
                              "padded to a multiple of 8 elements covering N%s", i,
@@ -830,6 +857,16 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
         P.splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
         P.tile_beg = tile;
         tile += P.tiles_m * P.tiles_n * P.splits;
+    }
+    // wait_count 0 = "all tiles of the problem of this group that signals what I wait for"
+    for (int i = 0; i < n_problems; ++i) {
+        GProblem &P = g.p[i];
+        if (!P.wait || P.wait_count > 0) continue;
+        for (int j = 0; j < i; ++j)
+            if (g.p[j].signal == P.wait) P.wait_count = g.p[j].tiles_n * g.p[j].splits * ncta;
+        if (P.wait_count <= 0)
+            return set_error(ABN_EINVAL, "abn_gemm_bf16_group: problem %d waits for a counter no "
+                             "earlier problem of the group signals", i);
     }
     g.total_tiles = tile;
     g.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);

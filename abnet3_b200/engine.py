@@ -262,19 +262,33 @@ class SiameseTrainStep(object):
         self.out_last = torch.empty((rows, n_last), dtype=torch.float32, device=dev)
         self.acts = [None] * (len(self.chain) - 1) + [self.out_last]
         last = len(self.chain) - 1
+        # Layers are chained INSIDE a launch: a problem's tiles signal per 256-row block when
+        # their output rows are in global memory, the next layer's tiles wait for their block
+        # only -- no grid-wide barrier, no launch per layer (groups of up to 4 problems).
+        tiles_m = (rows + 255) // 256
+        self._dep = torch.zeros((2 * len(self.chain) + 2, tiles_m), dtype=torch.int32, device=dev)
         self._fwd_problems, self._dgrad_problems, wgrad = [], [], []
         hb = self.xb
+        G = ops.GEMM_MAX_GROUP
         for l, L in enumerate(self.chain):
             out = self.actb[l] if l < last else self.out_last
             self._fwd_problems.append(ops.gemm_problem(
                 hb, L.wb, rows, L.n_out, L.n_in, ops.GE_BIAS_ACT, out, act=L.act, bias=L.b,
-                ones_col=(l < last)))
-            if l > 0:       # dz of the layer below = (dz W) * act'(its output)
-                self._dgrad_problems.append(ops.gemm_problem(
-                    self.dzb[l], L.wb, rows, L.n_in, L.n_out, ops.GE_DACT, self.dzb[l - 1], b_mn=True,
-                    act=self.chain[l - 1].act, yprev=self.actb[l - 1]))
+                ones_col=(l < last),
+                signal=self._dep[l] if (l < last and (l + 1) % G != 0) else None,
+                wait=self._dep[l - 1] if (l > 0 and l % G != 0) else None))
             wgrad.append((L, hb))
             hb = out
+        n_d = 0
+        for l in range(last, 0, -1):       # dz of the layer below = (dz W) * act'(its output)
+            L = self.chain[l]
+            base = len(self.chain)
+            self._dgrad_problems.append(ops.gemm_problem(
+                self.dzb[l], L.wb, rows, L.n_in, L.n_out, ops.GE_DACT, self.dzb[l - 1], b_mn=True,
+                act=self.chain[l - 1].act, yprev=self.actb[l - 1],
+                signal=self._dep[base + n_d] if (l > 1 and (n_d + 1) % G != 0) else None,
+                wait=self._dep[base + n_d - 1] if (n_d > 0 and n_d % G != 0) else None))
+            n_d += 1
         # weight + bias gradients of ALL layers: one launch per group of 4 problems, split
         # over the batch so that the group fills the machine about twice
         tiles = sum(((L.n_out + 127) // 128) * ((L.n_in + 1 + 255) // 256) for L, _ in wgrad)
@@ -290,8 +304,10 @@ class SiameseTrainStep(object):
     def _forward_bf16(self, x):
         if x is not None:       # fp32 batch -> bf16 A operand (the gather can also write it directly)
             ops.cast_bf16(x, self.xb, None)
-        for p in self._fwd_problems:
-            ops.gemm_group([p])
+        self._dep.zero_()
+        G = ops.GEMM_MAX_GROUP
+        for i in range(0, len(self._fwd_problems), G):
+            ops.gemm_group(self._fwd_problems[i:i + G])
         if self.heads:
             d = self.head_dim
             return [self.out_last[:, :d], self.out_last[:, d:]]
@@ -303,8 +319,9 @@ class SiameseTrainStep(object):
         elif not self._grads_clean:
             self.bucket.trained_grad.zero_()       # dW / db are accumulated with reds
         self._grads_clean = False
-        for p in reversed(self._dgrad_problems):
-            ops.gemm_group([p])
+        G = ops.GEMM_MAX_GROUP
+        for i in range(0, len(self._dgrad_problems), G):
+            ops.gemm_group(self._dgrad_problems[i:i + G])
         for grp in self._wgrad_groups:
             ops.gemm_group(grp)
 

@@ -284,7 +284,8 @@ GEMM_MAX_GROUP = 4
 
 
 def gemm_problem(A, B, M, N, K, epilogue, out, a_mn=False, b_mn=False, act=None, bias=None,
-                 yprev=None, split_k=1, ones_col=False, ones_out=None):
+                 yprev=None, split_k=1, ones_col=False, ones_out=None, signal=None, wait=None,
+                 wait_count=0):
     """One abn_gemm_problem.  A / B: bf16 2-D CUDA tensors with a contiguous last
     dimension ([M, K] / [N, K], or [K, M] / [K, N] when a_mn / b_mn); ``out``: bf16 or
     float32 2-D tensor.  Keeps references to the tensors alive on the returned object."""
@@ -303,7 +304,8 @@ def gemm_problem(A, B, M, N, K, epilogue, out, a_mn=False, b_mn=False, act=None,
     q.yprev, q.ld_yprev = ptr(yprev), (yprev.stride(0) if yprev is not None else 0)
     q.ones_col = int(bool(ones_col))
     q.ones_out = ptr(ones_out)
-    q._keep = (A, B, out, bias, yprev, ones_out)
+    q.signal, q.wait, q.wait_count = ptr(signal), ptr(wait), int(wait_count)
+    q._keep = (A, B, out, bias, yprev, ones_out, signal, wait)
     return q
 
 

@@ -241,6 +241,7 @@ ABN_API int abn_linear_backward(const float *x, const float *W, const float *y,
  *            1  out = C * act'(yprev)          -> the dz of the layer below (yprev = its
  *                                                 forward output, bf16 [M, ld_yprev])
  *            2  out += C (fp32 reds, split_k)  -> out fp32 [M, ldo]
+ * Problems of one group are independent unless chained with signal / wait below.
  * ones_col (epilogues 0/1): also write 1.0 into column N of every output row (it must lie
  *   inside the row padding, ldo >= N + 1).  ones_out (epilogue 2): B has such a column of
  *   ones at index N; its products -- the column sums of A, i.e. the bias gradient -- are
@@ -258,6 +259,15 @@ typedef struct {
     const void *yprev; int64_t ld_yprev;
     int ones_col;
     float *ones_out;
+    /* in-launch dependencies between the problems of one group (NULL: none).  signal
+     * [ceil(M / 256)] int32, caller-zeroed: every CTA adds 1 per finished tile of that
+     * 256-row block once its output rows are in global memory.  wait / wait_count: the A
+     * rows of a block are loaded only once wait[block] >= wait_count -- point `wait` at an
+     * earlier problem's `signal` and leave wait_count 0 (= all of that problem's tiles over
+     * the block) to chain layers inside one launch (list the problems in dependency order). */
+    int32_t *signal;
+    const int32_t *wait;
+    int wait_count;
 } abn_gemm_problem;
 ABN_API int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_problems,
                                 abn_stream_t stream);

@@ -51,3 +51,26 @@ for split in (2, 3, 4, 6, 8, 12):
     fl = sum(2.0 * rows * dims[l] * dims[l + 1] for l in range(4))
     print("wgrad group split %2d  %7.1f us  %6.1f TFLOP/s" % (split, us, fl / us / 1e6))
 print("fwd+dgrad total us", tot)
+
+# chained groups (layers linked inside one launch by per-row-block counters)
+tiles_m = (rows + 255) // 256
+dep = torch.zeros((8, tiles_m), dtype=torch.int32, device=DEV)
+fw = []
+for l in range(4):
+    n_in, n_out = dims[l], dims[l + 1]
+    out = acts[l + 1] if l < 3 else out_last
+    fw.append(ops.gemm_problem(acts[l], Ws[l], rows, n_out, n_in, ops.GE_BIAS_ACT, out, act="sigmoid", bias=bias[l],
+                               ones_col=(l < 3), signal=dep[l] if l < 3 else None, wait=dep[l - 1] if l > 0 else None))
+def run_fw():
+    dep.zero_(); ops.gemm_group(fw)
+print("fwd chain (4 layers, one launch)   %7.1f us" % timeit(run_fw))
+dg = []
+k = 0
+for l in range(3, 0, -1):
+    n_in, n_out = dims[l], dims[l + 1]
+    dg.append(ops.gemm_problem(dzs[l + 1], Ws[l], rows, n_in, n_out, ops.GE_DACT, dzs[l], b_mn=True, act="sigmoid", yprev=acts[l],
+                               signal=dep[4 + k] if l > 1 else None, wait=dep[4 + k - 1] if k > 0 else None))
+    k += 1
+def run_dg():
+    dep.zero_(); ops.gemm_group(dg)
+print("dgrad chain (3 layers, one launch) %7.1f us" % timeit(run_dg))
