@@ -763,6 +763,30 @@ __global__ void stack_violations_kernel(const float *__restrict__ feat, int64_t 
     if (lane == 0 && bad) atomicAdd(count, 1ull);
 }
 
+// Rebuild the S-frame stack on the device from its middle blocks (the only part a host ->
+// device upload of a verified stack needs to carry: S x fewer bytes over PCIe): block c of
+// row t is the middle block of row t + c - S/2 when that row belongs to the same file, zeros
+// otherwise (abnet3/features.py:135-159 pads with zeros at the file edges).
+__global__ void restack_kernel(float *__restrict__ feat, int64_t n_rows, int dim, int stack,
+                               const uint8_t *__restrict__ last_row_of_file) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (t >= n_rows) return;
+    const int lane = threadIdx.x & 31, f = dim / stack, h = stack / 2;
+    // file extent around t, looking at most h rows each way
+    int back = 0, fwd = 0;
+    while (back < h && t - back - 1 >= 0 && !(last_row_of_file && last_row_of_file[t - back - 1])) ++back;
+    while (fwd < h && t + fwd + 1 < n_rows && !(last_row_of_file && last_row_of_file[t + fwd])) ++fwd;
+    float *row = feat + (size_t)t * dim;
+    for (int c = 0; c < stack; ++c) {
+        if (c == h) continue;
+        const int d = c - h;
+        const bool inside = d < 0 ? -d <= back : d <= fwd;
+        const float *src = feat + (size_t)(t + d) * dim + h * f;
+        for (int k = lane; k < f; k += 32) row[c * f + k] = inside ? src[k] : 0.f;
+    }
+}
+
 // ------------------------------------------------------- size-class bucketing
 __device__ __forceinline__ int pair_class(const int4 tk, int64_t n_rows, int stack) {
     const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
@@ -1411,6 +1435,26 @@ extern "C" int abn_cosine_distance(const float *feat, int64_t n_rows, int dim,
     a.valid = valid; a.dist_off = dist_off; a.dist_out = dist; a.stack = stack;
     return run_align(a, max_frames, workspace, workspace_bytes, (cudaStream_t)stream,
                      "abn_cosine_distance");
+}
+
+extern "C" int abn_stack_upload(float *feat_dev, const float *feat_host, int64_t n_rows, int dim,
+                                int stack, const uint8_t *last_row_of_file, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (!feat_dev || !feat_host || n_rows < 0 || dim <= 0 || stack < 3 || !(stack & 1) || dim % stack ||
+        ((dim / stack) & 3))
+        return set_error(ABN_EINVAL, "abn_stack_upload: bad argument (odd stack >= 3 dividing dim)");
+    if (n_rows == 0) return ABN_OK;
+    const int f = dim / stack, h = stack / 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpy2DAsync(feat_dev + h * f, (size_t)dim * 4, feat_host + h * f,
+                                      (size_t)dim * 4, (size_t)f * 4, (size_t)n_rows,
+                                      cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess)
+        return set_error(ABN_EIO, "abn_stack_upload: cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+    const int wpb = 8;
+    restack_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(feat_dev, n_rows, dim,
+                                                                              stack, last_row_of_file);
+    return check_launch("abn_stack_upload");
 }
 
 extern "C" int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int stack,

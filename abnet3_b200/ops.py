@@ -116,6 +116,21 @@ def stack_violations(feat, stack=7, last_row_of_file=None):
     return int(count.item())
 
 
+def stack_upload(feat_host, stack=7, last_row_of_file=None, out=None):
+    """Device copy of a HOST table that is a verified S-frame stack: uploads the middle
+    blocks only (S x fewer PCIe bytes) and rebuilds the rest on the device."""
+    if feat_host.is_cuda or feat_host.dtype != torch.float32 or not feat_host.is_contiguous():
+        raise TypeError("feat_host must be a contiguous float32 CPU tensor")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if last_row_of_file is not None:
+        _req(last_row_of_file, torch.uint8, "last_row_of_file")
+    feat = out if out is not None else torch.empty(feat_host.shape, dtype=torch.float32, device=dev)
+    check(_lib.lib().abn_stack_upload(ptr(feat), feat_host.data_ptr(), feat_host.shape[0],
+                                      feat_host.shape[1], int(stack), ptr(last_row_of_file),
+                                      stream_ptr()))
+    return feat
+
+
 def dtw_from_dist(dist, dist_off, shape, max_frames=None):
     """Batched DTW on given float64 matrices (the call at abnet3/utils.py:149-151).
     Returns (path1, path2, path_off, path_len, cost, valid) with LOCAL indices."""

@@ -77,6 +77,13 @@ ABN_API int abn_device_info(int *sm_count, int *cc_major, int *cc_minor,
 ABN_API int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int stack,
                                  const uint8_t *last_row_of_file, unsigned long long *count,
                                  abn_stream_t stream);
+/* Host -> device upload of a table the caller vouches to be such a stack: only the middle
+ * block of every row crosses PCIe (a strided 2-D copy from the HOST pointer feat_host,
+ * ideally pinned: `stack` x fewer bytes), then a kernel rebuilds the other blocks from the
+ * neighbouring rows' middle blocks, with zeros across file edges (last_row_of_file: device,
+ * [n_rows] uint8, NULL = one file).  feat_dev [n_rows, dim] ends up identical to feat_host. */
+ABN_API int abn_stack_upload(float *feat_dev, const float *feat_host, int64_t n_rows, int dim,
+                             int stack, const uint8_t *last_row_of_file, abn_stream_t stream);
 
 /* Device workspace for abn_align_pairs / abn_cosine_distance over n_pairs pairs.
  * Both bucket the pairs into token-length classes on the device and keep the
