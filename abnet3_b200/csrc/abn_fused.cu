@@ -24,8 +24,10 @@ __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
                                    const int8_t *__restrict__ y_in,
                                    const int64_t *__restrict__ sel, int64_t n,
                                    __nv_bfloat16 *__restrict__ xb, int64_t ldx,
-                                   float *__restrict__ y_out, float *__restrict__ zero_me) {
-    if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0.f;
+                                   float *__restrict__ y_out, unsigned *__restrict__ zero_me,
+                                   int zero_words) {
+    if (zero_me && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < zero_words; i += blockDim.x) zero_me[i] = 0u;
     const int warps_per_block = blockDim.x >> 5;
     const int64_t w = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (w >= 2 * n) return;
@@ -160,7 +162,7 @@ using namespace abn;
 extern "C" int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *idx1,
                                      const int32_t *idx2, const int8_t *y_in, const int64_t *sel,
                                      int64_t n, void *xb, int64_t ldx, float *y_out,
-                                     float *zero_me, abn_stream_t stream) {
+                                     void *zero_me, int zero_words, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (n == 0) return ABN_OK;
     if (!feat || !idx1 || !idx2 || !xb || n < 0 || dim <= 0 || (dim & 3) || ldx < dim || (ldx & 3))
@@ -168,7 +170,8 @@ extern "C" int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *
     const int wpb = 8;
     const int64_t warps = 2 * n;
     gather_bf16_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        feat, dim, idx1, idx2, y_in, sel, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out, zero_me);
+        feat, dim, idx1, idx2, y_in, sel, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out,
+        static_cast<unsigned *>(zero_me), zero_me ? zero_words : 0);
     return check_launch("abn_gather_batch_bf16");
 }
 

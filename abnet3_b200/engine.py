@@ -124,7 +124,8 @@ class SiameseTrainStep(object):
         self.state0 = torch.zeros(n, dtype=torch.float32, device=dev)
         self.state1 = torch.zeros(n, dtype=torch.float32, device=dev) \
             if optimizer_type != "sgd" else None
-        self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._zbuf = torch.zeros(1, dtype=torch.int32, device=dev)     # [loss | dependency counters]
+        self.loss_buf = self._zbuf[:1].view(torch.float32)
         self.step_count = 0
         self.precision = PRECISIONS[network.precision]
         self.group = process_group
@@ -266,7 +267,12 @@ class SiameseTrainStep(object):
         # their output rows are in global memory, the next layer's tiles wait for their block
         # only -- no grid-wide barrier, no launch per layer (groups of up to 4 problems).
         tiles_m = (rows + 255) // 256
-        self._dep = torch.zeros((2 * len(self.chain) + 2, tiles_m), dtype=torch.int32, device=dev)
+        n_dep = 2 * len(self.chain) + 2
+        zbuf = torch.zeros(1 + n_dep * tiles_m, dtype=torch.int32, device=dev)
+        zbuf[:1].copy_(self._zbuf[:1])
+        self._zbuf = zbuf                  # one contiguous block: the gather kernel clears it
+        self.loss_buf = zbuf[:1].view(torch.float32)
+        self._dep = zbuf[1:].view(n_dep, tiles_m)
         self._fwd_problems, self._dgrad_problems, wgrad = [], [], []
         hb = self.xb
         G = ops.GEMM_MAX_GROUP
@@ -304,7 +310,8 @@ class SiameseTrainStep(object):
     def _forward_bf16(self, x):
         if x is not None:       # fp32 batch -> bf16 A operand (the gather can also write it directly)
             ops.cast_bf16(x, self.xb, None)
-        self._dep.zero_()
+        if not self._loss_cleared:          # (the gather kernel clears loss + counters together)
+            self._dep.zero_()
         G = ops.GEMM_MAX_GROUP
         for i in range(0, len(self._fwd_problems), G):
             ops.gemm_group(self._fwd_problems[i:i + G])
@@ -470,7 +477,7 @@ class SiameseTrainStep(object):
         self._reserve(2 * n)
         # abn_gather_batch_bf16 writes the first layer's bf16 operand and clears the loss
         ops.gather_batch_bf16(feat, idx1, idx2, y, self._gsel, n, self.xb, y_out=self._gy,
-                              zero=self.loss_buf)
+                              zero=self._zbuf)
         self._loss_cleared = True
         out = self._forward_bf16(None)
         self._loss_and_seed(out, n, [self._gy])

@@ -334,7 +334,7 @@ def gemm_group(problems):
 # ------------------------------- fused companions of the tensor-core step ---
 def gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=None, zero=None):
     """xb[:n] = bf16(feat[idx1[sel]]), xb[n:2n] = bf16(feat[idx2[sel]]), y_out = float(y[sel]);
-    ``zero`` (1-element float32 tensor) is cleared by the same kernel."""
+    ``zero`` (contiguous 4-byte-element tensor) is cleared by the same kernel."""
     _req(feat, torch.float32, "feat")
     _req(idx1, torch.int32, "idx1")
     _req(idx2, torch.int32, "idx2")
@@ -346,7 +346,7 @@ def gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=None, zero=None):
         raise TypeError("xb must be a CUDA bf16 [>= 2n, ld] tensor")
     check(_lib.lib().abn_gather_batch_bf16(ptr(feat), feat.shape[1], ptr(idx1), ptr(idx2), ptr(y),
                                            ptr(sel), n, ptr(xb), xb.stride(0), ptr(y_out), ptr(zero),
-                                           stream_ptr()))
+                                           zero.numel() if zero is not None else 0, stream_ptr()))
 
 
 def pair_loss_dz(e1, e2, y, dz1, dz2, kind="coscos2", margin=0.5, scale=1.0, act=None,

@@ -306,7 +306,8 @@ ABN_API int abn_optimizer_step(float *param, const float *grad, float *state0,
  *
  * abn_gather_batch_bf16: abn_gather_batch writing bf16 rows -- X1 = rows 0..n-1,
  *   X2 = rows n..2n-1 of xb [2n, ldx] -- i.e. the first layer's A operand.  zero_me
- *   (nullable) is a float the kernel clears (the step's loss accumulator).
+ *   (nullable): zero_words 4-byte words the kernel clears (the step's loss accumulator and
+ *   the dependency counters of the chained GEMM launches).
  * abn_pair_loss_dz: abn_pair_loss whose gradient output is dz = dL/de * act'(e) as bf16
  *   rows [n, ld_dz] (act = the output layer's activation; e1/e2 are its outputs): the
  *   operand of the output layer's dgrad / wgrad GEMMs.
@@ -317,8 +318,8 @@ ABN_API int abn_optimizer_step(float *param, const float *grad, float *state0,
  * ---------------------------------------------------------------------- */
 ABN_API int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *idx1,
                                   const int32_t *idx2, const int8_t *y_in, const int64_t *sel,
-                                  int64_t n, void *xb, int64_t ldx, float *y_out, float *zero_me,
-                                  abn_stream_t stream);
+                                  int64_t n, void *xb, int64_t ldx, float *y_out, void *zero_me,
+                                  int zero_words, abn_stream_t stream);
 ABN_API int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,
                              int64_t ld, int kind, float margin, float scale, int act, float *loss,
                              void *dz1, void *dz2, int64_t ld_dz, abn_stream_t stream);
