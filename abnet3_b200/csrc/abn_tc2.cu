@@ -665,10 +665,11 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
             if (P.signal) {
                 // publish this CTA's rows of the tile: every warp's stores have landed, then one
                 // release-increment of the m-tile's counter (consumers: producers of later problems)
-                if (lane == 0) g_store_wait_all();
-                __threadfence();
+                if (lane == 0) g_store_wait_all();          // TMA-stored boxes (lane 0 issued them)
+                if (!P.tma_store) __threadfence();           // rows stored directly from registers
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
                 if (et == 0) {
+                    __threadfence();
                     asm volatile("fence.proxy.async;" ::: "memory");
                     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(P.signal + t.mt) : "memory");
                 }
