@@ -48,7 +48,7 @@ enum { GE_BIAS_ACT = 0, GE_DACT = 1, GE_ATOMIC = 2 };
 
 struct GProblem {
     CUtensorMap map_a, map_b;
-    CUtensorMap map_c, map_y;            // bf16 output / y_below [M, ld]: 32 x 32 boxes, 64-byte swizzle
+    CUtensorMap map_c, map_y;            // bf16 output / y_below [M, ld]: 64 x 32 boxes, 128-byte swizzle
     int M, N, K;                    // N includes the ones column of a wgrad problem
     int a_mn, b_mn;
     int epi, act, out_f32, ones_col, tma_store;
@@ -322,60 +322,75 @@ struct GEpi {
 };
 template <int EPI, int ACT, int BN>
 __device__ __forceinline__ void g_epi_bf16_tile(const GEpi &e, unsigned &nbox, unsigned &ycount) {
-    const unsigned swz = (unsigned)((e.lane >> 1) & 3);      // 64-byte swizzle of row `lane`
+    // A warp works in steps of 64 columns: its 32 x 64 bf16 box has 128-byte rows (128-byte
+    // swizzle) -- half as many, twice as large TMA requests as 32-column boxes, which matter
+    // because the stores share the TMA path with the operand loads of the next tile.
     const int lane = e.lane;
+    const unsigned swz = (unsigned)(lane & 7);          // 128-byte swizzle of row `lane`
 #pragma unroll 1
-    for (int c0 = e.c_first; c0 < BN; c0 += 64) {
+    for (int c0 = e.c_first; c0 < BN; c0 += 128) {
         const int gcol0 = e.n0 + c0;
         if (gcol0 >= e.n_cap || c0 >= e.n_eff + 16) break;     // warp-uniform
-        uint4 yc[4];
+        const unsigned sbuf = e.my_out + (nbox & 1u) * 4096u;
+        uint4 yc[8];
         if (EPI == GE_DACT) {
-            // this warp's 32 x 32 box of y_below: TMA -> smem -> one row per lane; the next
-            // chunk's box is requested as soon as this one has been read
+            // this warp's 32 x 64 box of y_below arrived in the SAME buffer its outputs will
+            // use (read it into registers first); the next step's box goes to the other
+            // buffer once the store that last used it has been read out
             g_mbar_wait(e.ybar, ycount & 1u);
             ++ycount;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 8; ++q)
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(yc[q].x), "=r"(yc[q].y), "=r"(yc[q].z), "=r"(yc[q].w)
-                             : "r"(e.my_y + lane * 64 + (((unsigned)q ^ swz) << 4)) : "memory");
+                             : "r"(sbuf + lane * 128 + (((unsigned)q ^ swz) << 4)) : "memory");
             __syncwarp();
-            const int gn = gcol0 + 64;
-            if (lane == 0 && gn < e.n_cap && c0 + 64 < e.n_eff + 16 && c0 + 64 < BN) {
-                g_mbar_expect_tx(e.ybar, 2048u);
-                g_tma_2d(e.my_y, e.map_y, e.ybar, gn, e.row0);
+            const int gn = gcol0 + 128;
+            if (lane == 0 && gn < e.n_cap && c0 + 128 < e.n_eff + 16 && c0 + 128 < BN) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                g_mbar_expect_tx(e.ybar, 4096u);
+                g_tma_2d(e.my_out + ((nbox + 1) & 1u) * 4096u, e.map_y, e.ybar, gn, e.row0);
             }
-        }
-        float v[32];
-        g_ld32(e.taddr + c0, v);
-        unsigned pk[16];
-        if (EPI == GE_BIAS_ACT && (ACT == 1 || ACT == 2)) {
-            g_bias_act32_packed<ACT>(v, e.bs + c0, pk);
         } else {
-            if (EPI == GE_BIAS_ACT) g_bias_act32<ACT>(v, e.bs + c0);
-            else g_dact32<ACT>(v, yc);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
+            // the store issued two steps ago must have left this buffer
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
         }
-        if (e.ones_col && e.N >= gcol0 && e.N < gcol0 + 32) {
-            const int jo = e.N - gcol0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (2 * j == jo) pk[j] = (pk[j] & 0xffff0000u) | 0x3f80u;
-                if (2 * j + 1 == jo) pk[j] = (pk[j] & 0x0000ffffu) | 0x3f800000u;
+        for (int hseg = 0; hseg < 2; ++hseg) {             // the two 32-column halves of the step
+            const int cc = c0 + 32 * hseg, gc = gcol0 + 32 * hseg;
+            float v[32];
+            g_ld32(e.taddr + cc, v);
+            unsigned pk[16];
+            if (EPI == GE_BIAS_ACT && (ACT == 1 || ACT == 2)) {
+                g_bias_act32_packed<ACT>(v, e.bs + cc, pk);
+            } else {
+                if (EPI == GE_BIAS_ACT) {
+                    g_bias_act32<ACT>(v, e.bs + cc);
+                } else {
+                    const uint4 yh[4] = {yc[4 * hseg], yc[4 * hseg + 1], yc[4 * hseg + 2], yc[4 * hseg + 3]};
+                    g_dact32<ACT>(v, yh);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
             }
-        }
-        // bf16 rows -> this warp's 64-byte-swizzled 32 x 32 box in smem -> one TMA store
-        // (full-line writes, clipped at M rows / ldo columns by the map); the box filled
-        // G_OBUF chunks ago must have left smem before it is reused
-        const unsigned sbuf = e.my_out + (nbox % G_OBUF) * 2048u;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(G_OBUF - 1) : "memory");
-        __syncwarp();
+            if (e.ones_col && e.N >= gc && e.N < gc + 32) {
+                const int jo = e.N - gc;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                         ::"r"(sbuf + lane * 64 + (((unsigned)q ^ swz) << 4)), "r"(pk[4 * q]),
-                           "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                for (int j = 0; j < 16; ++j) {
+                    if (2 * j == jo) pk[j] = (pk[j] & 0xffff0000u) | 0x3f80u;
+                    if (2 * j + 1 == jo) pk[j] = (pk[j] & 0x0000ffffu) | 0x3f800000u;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(sbuf + lane * 128 + (((unsigned)(4 * hseg + q) ^ swz) << 4)),
+                               "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                             : "memory");
+        }
+        // bf16 rows -> one TMA store of the box (full-line writes, clipped at M rows / ldo
+        // columns by the tensor map)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) g_tma_store_2d(e.map_c, sbuf, gcol0, e.row0);
@@ -390,9 +405,9 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     constexpr unsigned A_BYTES = G_BM * G_BK * 2;           // 16 KB: this CTA's 128 rows
     constexpr unsigned B_BYTES = (BN / NCTA) * G_BK * 2;    // this CTA's share of the B tile
     constexpr unsigned STAGE = A_BYTES + B_BYTES;
-    constexpr int STAGES = STAGE > 32768 ? 3 : 5;
-    // per epilogue warp: G_OBUF 32 x 32 bf16 boxes staged for TMA stores, one for y_below loads
-    constexpr unsigned OUT_BYTES = G_EPI_WARPS * (G_OBUF * 2048u + 2048u);
+    constexpr int STAGES = STAGE > 32768 ? 3 : 4;
+    // per epilogue warp: two 32 x 64 bf16 boxes staged for TMA stores (y_below boxes land in them too)
+    constexpr unsigned OUT_BYTES = G_EPI_WARPS * 2u * 4096u;
     const int rank = NCTA == 2 ? (int)g_cluster_rank() : 0;
     const int tile0 = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
     extern __shared__ unsigned char smem_raw[];
@@ -556,8 +571,8 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
             const int row = t.m0 + wq * 32 + lane;
             const int c_first = half * 32;
             const int ew = warp - 2;
-            const unsigned my_out = outs + ew * (G_OBUF * 2048u);
-            const unsigned my_y = outs + G_EPI_WARPS * (G_OBUF * 2048u) + ew * 2048u;
+            const unsigned my_out = outs + ew * 8192u;
+            const unsigned my_y = my_out;
             const unsigned ybar = ybar0 + 8 * ew;
             const int row0 = t.m0 + wq * 32;                 // first row of this warp's 32 x 32 boxes
             if (P.epi == GE_BIAS_ACT) {
@@ -566,9 +581,10 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
             } else if (P.epi == GE_DACT) {
                 // the first chunk's y_below does not depend on the accumulator: fetch it now
-                if (lane == 0 && t.n0 + c_first < P.n_cap) {
-                    g_mbar_expect_tx(ybar, 2048u);
-                    g_tma_2d(my_y, &P.map_y, ybar, t.n0 + c_first, row0);
+                if (lane == 0 && t.n0 + 2 * c_first < P.n_cap && 2 * c_first < t.n_eff + 16) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    g_mbar_expect_tx(ybar, 4096u);
+                    g_tma_2d(my_out + (nbox & 1u) * 4096u, &P.map_y, ybar, t.n0 + 2 * c_first, row0);
                 }
             }
             if (et == 0) g_trace(g, it, 5);
@@ -613,7 +629,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                 e.map_c = &P.map_c; e.map_y = &P.map_y; e.bs = bs;
                 e.taddr = taddr; e.my_out = my_out; e.my_y = my_y; e.ybar = ybar;
                 e.n0 = t.n0; e.row0 = row0; e.n_eff = t.n_eff; e.n_cap = P.n_cap; e.N = P.N;
-                e.ones_col = P.ones_col; e.c_first = c_first; e.lane = lane;
+                e.ones_col = P.ones_col; e.c_first = 2 * c_first; e.lane = lane;      // 64-column steps
                 const int mode = P.epi * 4 + P.act;
                 switch (mode) {
                     case 0: g_epi_bf16_tile<GE_BIAS_ACT, 0, BN>(e, nbox, ycount); break;
@@ -738,8 +754,8 @@ static bool g_use_pdl() {
 template <int BN, int NCTA>
 static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
     constexpr unsigned stage = G_BM * G_BK * 2 + (BN / NCTA) * G_BK * 2;
-    constexpr int STAGES = stage > 32768 ? 3 : 5;
-    constexpr unsigned smem = STAGES * stage + G_EPI_WARPS * (G_OBUF + 1) * 2048 + 256 + 2 * BN * 4 + 1024;
+    constexpr int STAGES = stage > 32768 ? 3 : 4;
+    constexpr unsigned smem = STAGES * stage + G_EPI_WARPS * 8192 + 256 + 2 * BN * 4 + 1024;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(tc_group_kernel<BN, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -837,15 +853,14 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
         if (rc) return rc;
         P.tma_store = (!P.out_f32 && q.epilogue != GE_ATOMIC) ? 1 : 0;
         if (P.tma_store) {
-            rc = g_make_map(&P.map_c, q.out, q.M, q.ldo, q.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+            rc = g_make_map(&P.map_c, q.out, q.M, q.ldo, q.ldo, 64, 32);
             if (rc) return rc;
         }
         if (q.epilogue == GE_DACT) {
             if (P.out_f32)
                 return set_error(ABN_EINVAL, "abn_gemm_bf16_group: problem %d: the act' epilogue "
                                  "writes bf16", i);
-            rc = g_make_map(&P.map_y, q.yprev, q.M, q.ld_yprev, q.ld_yprev, 32, 32,
-                            CU_TENSOR_MAP_SWIZZLE_64B);
+            rc = g_make_map(&P.map_y, q.yprev, q.M, q.ld_yprev, q.ld_yprev, 64, 32);
             if (rc) return rc;
         }
         P.tiles_m = (P.M + G_BM * ncta - 1) / (G_BM * ncta);

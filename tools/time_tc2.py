@@ -55,12 +55,13 @@ print("fwd+dgrad total us", tot)
 # chained groups (layers linked inside one launch by per-row-block counters)
 tiles_m = (rows + 255) // 256
 dep = torch.zeros((8, tiles_m), dtype=torch.int32, device=DEV)
+NODEP = os.environ.get('ABN_NODEP') == '1'
 fw = []
 for l in range(4):
     n_in, n_out = dims[l], dims[l + 1]
     out = acts[l + 1] if l < 3 else out_last
     fw.append(ops.gemm_problem(acts[l], Ws[l], rows, n_out, n_in, ops.GE_BIAS_ACT, out, act="sigmoid", bias=bias[l],
-                               ones_col=(l < 3), signal=dep[l] if l < 3 else None, wait=dep[l - 1] if l > 0 else None))
+                               ones_col=(l < 3), signal=dep[l] if (l < 3 and not NODEP) else None, wait=dep[l - 1] if (l > 0 and not NODEP) else None))
 def run_fw():
     dep.zero_(); ops.gemm_group(fw)
 print("fwd chain (4 layers, one launch)   %7.1f us" % timeit(run_fw))
