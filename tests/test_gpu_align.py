@@ -362,3 +362,49 @@ def test_stack_upload_rebuilds_the_table_from_its_middle_blocks():
     a = [t.clone() for t in utils.align_pairs_host(host, pairs, stack=7, last_row_of_file=last, chunks=1)]
     for x, y in zip(a, c):
         assert torch.equal(x, y)
+
+
+def test_alignment_invariants_at_scale():
+    """Size-independent properties on a large pair list (BASELINE C2 shapes, 200 k pairs):
+    every path starts at (0, 0), ends at (n1-1, n2-1), moves by (1,0) / (0,1) / (1,1), has
+    max(n1, n2) <= L <= n1 + n2 - 1; the cost is the float64 sum of the kernel's own
+    distances along the path; the stacked and the generic kernels agree bit for bit; a
+    second run returns the same bits (no run-to-run variation)."""
+    corpus = synth.make_corpus(8000, seed=11, device=DEV)
+    pairs = synth.make_same_pairs(corpus, 200_000, seed=12)
+    feat = corpus.feat
+    res = ops.align_pairs(feat, pairs, stack=0)
+    d1, d2, off = ops.compact_paths(res)
+    torch.cuda.synchronize()
+    assert bool((res.valid == 1).all())
+    L = res.path_len.long()
+    n1, n2 = pairs[:, 1].long(), pairs[:, 3].long()
+    assert bool((L >= torch.maximum(n1, n2)).all()) and bool((L <= n1 + n2 - 1).all())
+    first, last = off[:-1], off[1:] - 1
+    assert torch.equal(d1[first].long(), pairs[:, 0].long()) and torch.equal(d2[first].long(), pairs[:, 2].long())
+    assert torch.equal(d1[last].long(), pairs[:, 0].long() + n1 - 1)
+    assert torch.equal(d2[last].long(), pairs[:, 2].long() + n2 - 1)
+    di, dj = d1[1:] - d1[:-1], d2[1:] - d2[:-1]
+    inner = torch.ones(d1.numel() - 1, dtype=torch.bool, device=DEV)
+    inner[last[:-1]] = False                      # steps across pair boundaries do not count
+    assert bool((((di == 0) | (di == 1)) & ((dj == 0) | (dj == 1)) & (di + dj >= 1))[inner].all())
+    # stacked fast path and a second run: same bits
+    res7 = ops.align_pairs(feat, pairs, stack=7)
+    e1, e2, _ = ops.compact_paths(res7)
+    assert torch.equal(res7.cost.view(torch.int64), res.cost.view(torch.int64))
+    assert torch.equal(e1, d1) and torch.equal(e2, d2)
+    res_b = ops.align_pairs(feat, pairs, stack=7)
+    assert torch.equal(res_b.cost.view(torch.int64), res7.cost.view(torch.int64))
+    # cost == float64 sum of the kernel's own distances along the path (first 500 pairs)
+    sub = pairs[:500].contiguous()
+    dist, doff, _ = ops.cosine_distance(feat, sub)
+    dist, doff = dist.double().cpu().numpy(), doff.cpu().numpy()
+    offc, d1c, d2c = off.cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy()
+    cost = res.cost.cpu().numpy()
+    for p, (s1, a, s2, b) in enumerate(sub.cpu().numpy().tolist()):
+        i = d1c[offc[p]:offc[p + 1]] - s1
+        j = d2c[offc[p]:offc[p + 1]] - s2
+        acc = 0.0
+        for v in dist[doff[p] + i * b + j]:
+            acc += v
+        assert acc == cost[p], (p, acc, cost[p])
