@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libabnet3_b200.so")
+# ABN_LIB: an experiment build of the same library (tools/build_dbg.sh); never a fallback
+SO_PATH = os.environ.get("ABN_LIB") or os.path.join(_HERE, "libabnet3_b200.so")
 
 _c = ctypes
 _P = _c.c_void_p
@@ -42,6 +43,12 @@ class DpPeers(_c.Structure):
     _fields_ = [("grad", _P * 8), ("flags", _P * 8), ("rank", _I), ("world", _I)]
 
 
+class DpPush(_c.Structure):
+    """abn_dp_push (include/abnet3_b200.h)."""
+    _fields_ = [("param", _P * 8), ("recv", _P * 8), ("flags", _P * 8), ("rank", _I), ("world", _I),
+                ("n", _L), ("slice_cap", _L)]
+
+
 # name -> (restype, argtypes); mirrors include/abnet3_b200.h declaration order
 SIGNATURES = {
     "abn_version": (_I, []),
@@ -71,6 +78,7 @@ SIGNATURES = {
     "abn_ipc_import": (_I, [_P, _L, _P]),
     "abn_dp_optimizer_step": (_I, [_P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _P, _P]),
     "abn_dp_grad_reset": (_I, [_P, _L, _P, _P]),
+    "abn_dp_push_step": (_I, [_P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _P, _P]),
 }
 
 _lib = None

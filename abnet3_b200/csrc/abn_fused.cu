@@ -496,3 +496,166 @@ extern "C" int abn_dp_grad_reset(float *grad, int64_t n, const abn_dp_peers *pee
     dp_grad_reset_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(grad, n, pe);
     return check_launch("abn_dp_grad_reset");
 }
+
+// ------------------------------------------------------------------------
+// Two-shot variant, all transfers are WRITES over NVLink (posted, no round trips):
+//   phase 0  every rank pushes slice j of its gradient bucket into owner j's receive
+//            buffer (recv[j][rank]) and then raises pushed[rank] = step on every peer
+//   phase 1  the owner of slice r sums its own slice and the W-1 received ones in rank
+//            order, applies the optimizer to that slice and pushes the updated fp32
+//            parameters into EVERY rank's parameter bucket; raises updated[rank] = step
+//   phase 2  once all slices have arrived: bf16 operand copies of the weights, gradient
+//            bucket cleared for the next step's reductions
+// One kernel, one block per SM (every block must be resident: they wait on flags that
+// other blocks of the same grid help to raise).  Per rank and step: 2 (W-1)/W x the bucket
+// leaves over NVLink, as in a ring all-reduce, in two hops instead of 2 (W-1).
+namespace abn {
+
+enum { DPF_PUSHED = 0, DPF_UPDATED = DP_MAX_WORLD, DPF_STEP = 2 * DP_MAX_WORLD,
+       DPF_TICKET_A = 2 * DP_MAX_WORLD + 1, DPF_TICKET_B = 2 * DP_MAX_WORLD + 2,
+       DPF_TICKET_C = 2 * DP_MAX_WORLD + 3 };
+
+struct DpPush {
+    float *param[DP_MAX_WORLD];
+    float *recv[DP_MAX_WORLD];
+    unsigned long long *flags[DP_MAX_WORLD];
+    int rank, world;
+    long long n, cap;
+};
+
+__device__ __forceinline__ void dp_st4(float *p, float4 v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+// all blocks have passed: the last one to arrive raises `slot` = step on every rank
+__device__ __forceinline__ void dp_grid_raise(const DpPush &pp, int ticket, int slot,
+                                              unsigned long long step) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long *mine = pp.flags[pp.rank];
+        const unsigned long long t = atomicAdd(mine + ticket, 1ull);
+        if (t == (unsigned long long)gridDim.x - 1) {
+            mine[ticket] = 0;
+            __threadfence_system();
+            for (int q = 0; q < pp.world; ++q) dp_st_release(pp.flags[q] + slot + pp.rank, step);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512)
+dp_push_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restrict__ s1, int kind,
+               float lr, float momentum, float gscale, float bc1, float bc2_sqrt,
+               const SegTable tab, const DpPush pp) {
+    unsigned long long *mine = pp.flags[pp.rank];
+    __shared__ unsigned long long step_s;
+    if (threadIdx.x == 0) step_s = dp_ld_acquire(mine + DPF_STEP) + 1;
+    __syncthreads();
+    const unsigned long long step = step_s;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    const int W = pp.world, R = pp.rank;
+
+    // phase 0: my slice j -> owner j's receive row R
+    for (int j = 0; j < W; ++j) {
+        if (j == R) continue;
+        const long long lo = j * pp.cap, hi = min(pp.n, lo + pp.cap);
+        float *dst = pp.recv[j] + (long long)R * pp.cap;
+        for (long long i = lo + 4 * gtid; i < hi; i += 4 * gstride)
+            dp_st4(dst + (i - lo), *reinterpret_cast<const float4 *>(grad + i));
+    }
+    dp_grid_raise(pp, DPF_TICKET_A, DPF_PUSHED, step);
+
+    // phase 1: reduce + update my slice, push the new parameters to everybody
+    if (threadIdx.x == 0) dp_wait_all(mine + DPF_PUSHED, W, step);
+    __syncthreads();
+    {
+        const long long lo = R * pp.cap, hi = min(pp.n, lo + pp.cap);
+        const float *rv = pp.recv[R];
+        for (long long i = lo + 4 * gtid; i < hi; i += 4 * gstride) {
+            float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = 0; p < W; ++p) {         // rank order
+                const float4 v = p == R ? *reinterpret_cast<const float4 *>(grad + i)
+                                        : dp_ld4(rv + (long long)p * pp.cap + (i - lo));
+                gs.x += v.x; gs.y += v.y; gs.z += v.z; gs.w += v.w;
+            }
+            const float4 w4 = *reinterpret_cast<const float4 *>(pp.param[R] + i);
+            float w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float g[4] = {gs.x * gscale, gs.y * gscale, gs.z * gscale, gs.w * gscale};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i + e < pp.n)
+                    w[e] = dp_update(w[e], g[e], s0, s1, i + e, kind, lr, momentum, bc1, bc2_sqrt);
+            const float4 out = make_float4(w[0], w[1], w[2], w[3]);
+            for (int q = 0; q < W; ++q) dp_st4(pp.param[q] + i, out);
+        }
+    }
+    dp_grid_raise(pp, DPF_TICKET_B, DPF_UPDATED, step);
+
+    // phase 2: all slices are in: bf16 operand copies, gradient bucket cleared
+    if (threadIdx.x == 0) dp_wait_all(mine + DPF_UPDATED, W, step);
+    __syncthreads();
+    const float *pl = pp.param[R];
+    for (int sidx = 0; sidx < tab.n; ++sidx) {
+        const abn_param_segment sg = tab.s[sidx];
+        __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
+        if (!wb) continue;
+        for (long long j = gtid; j < sg.count; j += gstride) {
+            const long long r = j / sg.n_in;
+            wb[r * sg.ld + (j - r * sg.n_in)] = __float2bfloat16_rn(__ldcv(pl + sg.offset + j));
+        }
+    }
+    for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride)
+        *reinterpret_cast<float4 *>(grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the step counter advances once every block has read it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(mine + DPF_TICKET_C, 1ull);
+        if (t == (unsigned long long)gridDim.x - 1) {
+            mine[DPF_TICKET_C] = 0;
+            __threadfence();
+            mine[DPF_STEP] = step;
+        }
+    }
+}
+
+}  // namespace abn
+
+extern "C" int abn_dp_push_step(float *grad, float *state0, float *state1, int kind, float lr,
+                                float momentum, float grad_scale, int64_t step,
+                                const abn_param_segment *segments, int n_segments,
+                                const abn_dp_push *peers, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (!grad || !segments || !peers || n_segments <= 0 || n_segments > ABN_MAX_PARAM_SEGMENTS ||
+        kind < 0 || kind > 2 || (kind == 0 && momentum != 0.f && !state0) ||
+        (kind >= 1 && (!state0 || !state1)) || step < 1)
+        return set_error(ABN_EINVAL, "abn_dp_push_step: bad argument");
+    if (peers->world < 2 || peers->world > DP_MAX_WORLD || peers->rank < 0 ||
+        peers->rank >= peers->world || peers->n <= 0 || (peers->n & 3) || (peers->slice_cap & 3) ||
+        peers->slice_cap * peers->world < peers->n)
+        return set_error(ABN_EINVAL, "abn_dp_push_step: world 2..%d, n and slice_cap multiples of 4, "
+                         "world * slice_cap >= n", DP_MAX_WORLD);
+    DpPush pp;
+    pp.rank = peers->rank; pp.world = peers->world; pp.n = peers->n; pp.cap = peers->slice_cap;
+    for (int r = 0; r < peers->world; ++r) {
+        if (!peers->param[r] || !peers->recv[r] || !peers->flags[r])
+            return set_error(ABN_EINVAL, "abn_dp_push_step: rank %d is not mapped", r);
+        pp.param[r] = static_cast<float *>(peers->param[r]);
+        pp.recv[r] = static_cast<float *>(peers->recv[r]);
+        pp.flags[r] = static_cast<unsigned long long *>(peers->flags[r]);
+    }
+    SegTable tab;
+    tab.n = n_segments;
+    for (int i = 0; i < n_segments; ++i) tab.s[i] = segments[i];
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const float bc1 = 1.f - powf(0.9f, (float)step);
+    const float bc2s = sqrtf(1.f - powf(0.999f, (float)step));
+    dp_push_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
+                                                          grad_scale, bc1, bc2s, tab, pp);
+    return check_launch("abn_dp_push_step");
+}

@@ -65,8 +65,18 @@ struct GProblem {
 struct GGroup {
     GProblem p[G_MAXP];
     int n_problems, total_tiles;
+    int rot;                        // tile of CTA pair q in wave k: k * pairs + (q + rot * k) % pairs
     long long *trace;               // debug: per-CTA role timestamps (NULL in production)
+#ifdef ABN_TC_DEBUG
+    int dbg;                        // experiments (tools/build_dbg.sh): 1 no epilogue work, 2 no TMA
+                                    // stores, 4 no tcgen05.ld, 8 no tcgen05.mma
+#endif
 };
+#ifdef ABN_TC_DEBUG
+#define G_DBG(g, bit) (((g).dbg & (bit)) != 0)
+#else
+#define G_DBG(g, bit) false
+#endif
 
 // ------------------------------------------------------------------- PTX ---
 __device__ __forceinline__ unsigned g_smem_u32(const void *p) {
@@ -310,6 +320,13 @@ __device__ __forceinline__ GTile g_decode(const GGroup &g, int tile, int bn, int
     return t;
 }
 
+// Static schedule: wave k hands position (q + rot k) mod pairs to CTA pair q.  With chained
+// problems the positions whose dependency sits in the wave just before stall for an epilogue;
+// rot != 0 rotates that bad luck over the pairs instead of charging the same ones every wave.
+__device__ __forceinline__ int g_tile_of(const GGroup &g, int q, int pairs, unsigned k) {
+    return (int)k * pairs + (q + g.rot * (int)k) % pairs;
+}
+
 // One warp's share of a bf16-output tile (forward: bias + activation; dgrad: x act'(y_below)).
 // Everything the chunk loop needs sits in registers; EPI / ACT are compile-time so that the
 // loop body is straight-line code (the problem descriptor lives in constant memory: reading
@@ -319,6 +336,7 @@ struct GEpi {
     const float *bs;                // staged bias of this tile (forward)
     unsigned taddr, my_out, my_y, ybar;
     int n0, row0, n_eff, n_cap, N, ones_col, c_first, lane;
+    int dbg;
 };
 template <int EPI, int ACT, int BN>
 __device__ __forceinline__ void g_epi_bf16_tile(const GEpi &e, unsigned &nbox, unsigned &ycount) {
@@ -360,7 +378,12 @@ __device__ __forceinline__ void g_epi_bf16_tile(const GEpi &e, unsigned &nbox, u
         for (int hseg = 0; hseg < 2; ++hseg) {             // the two 32-column halves of the step
             const int cc = c0 + 32 * hseg, gc = gcol0 + 32 * hseg;
             float v[32];
-            g_ld32(e.taddr + cc, v);
+            if (G_DBG(e, 4)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (float)(cc + j);
+            } else {
+                g_ld32(e.taddr + cc, v);
+            }
             unsigned pk[16];
             if (EPI == GE_BIAS_ACT && (ACT == 1 || ACT == 2)) {
                 g_bias_act32_packed<ACT>(v, e.bs + cc, pk);
@@ -393,7 +416,7 @@ __device__ __forceinline__ void g_epi_bf16_tile(const GEpi &e, unsigned &nbox, u
         // columns by the tensor map)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) g_tma_store_2d(e.map_c, sbuf, gcol0, e.row0);
+        if (lane == 0 && !G_DBG(e, 2)) g_tma_store_2d(e.map_c, sbuf, gcol0, e.row0);
         ++nbox;
     }
 }
@@ -456,8 +479,10 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer
         if (lane == 0) {
-            unsigned n = 0, pit = 0;                         // k-blocks issued so far (ring position)
-            for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++pit) {
+            unsigned n = 0;                                  // k-blocks issued so far (ring position)
+            for (unsigned pit = 0;; ++pit) {
+                const int tile = g_tile_of(g, tile0, tile_step, pit);
+                if (tile >= g.total_tiles) break;
                 const GTile t = g_decode(g, tile, BN, NCTA, rank);
                 const GProblem &P = g.p[t.pi];
                 g_trace(g, pit, 0);
@@ -520,8 +545,10 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer
         if (lane == 0 && rank == 0) {       // of a pair, only the leader CTA issues
-            unsigned n = 0, it = 0;
-            for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++it) {
+            unsigned n = 0;
+            for (unsigned it = 0;; ++it) {
+                const int tile = g_tile_of(g, tile0, tile_step, it);
+                if (tile >= g.total_tiles) break;
                 const GTile t = g_decode(g, tile, BN, NCTA, rank);
                 const GProblem &P = g.p[t.pi];
                 const unsigned ab = it & 1;
@@ -542,6 +569,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                     const unsigned long long db = g_desc(sa + A_BYTES, P.b_mn);
 #pragma unroll
                     for (int k = 0; k < G_BK / G_UK; ++k) {
+                        if (G_DBG(g, 8)) continue;
                         if (NCTA == 2)
                             g_mma_pair(d_tmem, da + (unsigned long long)(a_step * k),
                                        db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
@@ -562,8 +590,10 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
         const int wq = warp & 3;                        // TMEM lane quarter of this warp
         const int half = (warp - 2) >> 2;               // which of the quarter's two warps
         const int et = (warp - 2) * 32 + lane;          // 0 .. 255
-        unsigned it = 0, nbox = 0, ycount = 0;          // boxes stored / y_below boxes consumed by this warp
-        for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++it) {
+        unsigned nbox = 0, ycount = 0;                  // boxes stored / y_below boxes consumed by this warp
+        for (unsigned it = 0;; ++it) {
+            const int tile = g_tile_of(g, tile0, tile_step, it);
+            if (tile >= g.total_tiles) break;
             const GTile t = g_decode(g, tile, BN, NCTA, rank);
             const GProblem &P = g.p[t.pi];
             const unsigned ab = it & 1;
@@ -592,7 +622,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
             g_fence_after();
             if (et == 0) g_trace(g, it, 6);
             const unsigned taddr = tmem + ((unsigned)(wq * 32) << 16) + ab * BN;
-            if (t.nkb <= 0) {
+            if (t.nkb <= 0 || (G_DBG(g, 1) && P.epi != GE_DACT)) {
                 // nothing was accumulated (cannot happen with the host's split sizes)
             } else if (P.epi == GE_ATOMIC) {
                 // fp32 reduction of a split-K partial: 16-byte vector reds, one output row per
@@ -630,6 +660,11 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
                 e.taddr = taddr; e.my_out = my_out; e.my_y = my_y; e.ybar = ybar;
                 e.n0 = t.n0; e.row0 = row0; e.n_eff = t.n_eff; e.n_cap = P.n_cap; e.N = P.N;
                 e.ones_col = P.ones_col; e.c_first = 2 * c_first; e.lane = lane;      // 64-column steps
+#ifdef ABN_TC_DEBUG
+                e.dbg = g.dbg;
+#else
+                e.dbg = 0;
+#endif
                 const int mode = P.epi * 4 + P.act;
                 switch (mode) {
                     case 0: g_epi_bf16_tile<GE_BIAS_ACT, 0, BN>(e, nbox, ycount); break;
@@ -766,6 +801,10 @@ static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
     }
     int grid = g.total_tiles * NCTA < sm_count ? g.total_tiles * NCTA : sm_count;
     grid -= grid % NCTA;
+    if (const char *e = getenv("ABN_GEMM_GRID")) {       // experiments: fewer CTAs
+        const int lim = atoi(e);
+        if (lim >= NCTA && lim < grid) grid = lim - lim % NCTA;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(G_THREADS);
@@ -886,6 +925,10 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
     }
     g.total_tiles = tile;
     g.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
+    { const char *e = getenv("ABN_GEMM_ROT"); g.rot = e ? atoi(e) : 0; }
+#ifdef ABN_TC_DEBUG
+    { const char *e = getenv("ABN_GEMM_DBG"); g.dbg = e ? atoi(e) : 0; }
+#endif
     cudaStream_t st = (cudaStream_t)stream;
     if (ncta == 2)
         return bn == 128 ? g_launch<128, 2>(g, sm_count, st) : g_launch<256, 2>(g, sm_count, st);

@@ -136,6 +136,7 @@ class SiameseTrainStep(object):
         self._loss_cleared = False
         self._grads_clean = False
         self._dp = None
+        self._dp_push = None
         if self.precision == 1:
             self._build_chain()
             # One-shot peer reads move (world - 1) x the bucket per rank: measured 203 us/step
@@ -143,7 +144,14 @@ class SiameseTrainStep(object):
             # exchange); beyond 2 ranks NCCL's NVLS / tree all-reduce moves fewer bytes, so the
             # peer-memory path is the default at world == 2 only (ABN_DP_P2P=1 forces, 0 disables).
             p2p = os.environ.get("ABN_DP_P2P", "auto")
-            if self.world > 1 and (p2p == "1" or (p2p == "auto" and self.world == 2)):
+            if self.world > 1 and p2p in ("push", "auto") and self.bucket.n_trained % 4 == 0:
+                try:        # two-shot, write-only exchange fused with the optimizer (any world size)
+                    self._dp_push = ops.dp_push_setup(self.bucket.param, self.bucket.n_trained, self.group)
+                except Exception as exc:
+                    import warnings
+                    warnings.warn("peer-memory data parallelism unavailable (%s); using NCCL" % exc)
+                    self._dp_push = None
+            elif self.world > 1 and p2p == "1":
                 try:
                     self._dp = ops.dp_setup(self.bucket.grad, self.group)
                 except Exception as exc:       # buffers not shareable: the NCCL all-reduce remains
@@ -218,7 +226,7 @@ class SiameseTrainStep(object):
             L = _Layer()
             L.W, L.b, L.gW, L.gb, L.act = W_view, b_view, gW, gb, act
             L.n_out, L.n_in = W_view.shape
-            L.wb = torch.zeros((L.n_out, ops.pad8(L.n_in)), dtype=torch.bfloat16, device=dev)
+            L.wb = torch.zeros((L.n_out, ops.pad_row(L.n_in)), dtype=torch.bfloat16, device=dev)
             self.chain.append(L)
             entries.append((w_off, L.n_out * L.n_in, L.wb, L.n_in))
             entries.append((b_off, L.n_out, None, 0))
@@ -255,10 +263,10 @@ class SiameseTrainStep(object):
             return t
 
         d_in = self.chain[0].n_in
-        self.xb = b16(rows, ops.pad8(d_in + 1), d_in)
+        self.xb = b16(rows, ops.pad_row(d_in + 1), d_in)
         # hidden activations and every layer's dz: bf16; the embeddings: fp32
-        self.actb = [b16(rows, ops.pad8(L.n_out + 1)) for L in self.chain[:-1]]
-        self.dzb = [b16(rows, ops.pad8(L.n_out)) for L in self.chain]
+        self.actb = [b16(rows, ops.pad_row(L.n_out + 1)) for L in self.chain[:-1]]
+        self.dzb = [b16(rows, ops.pad_row(L.n_out)) for L in self.chain]
         n_last = self.chain[-1].n_out
         self.out_last = torch.empty((rows, n_last), dtype=torch.float32, device=dev)
         self.acts = [None] * (len(self.chain) - 1) + [self.out_last]
@@ -389,10 +397,17 @@ class SiameseTrainStep(object):
     def _allreduce(self):
         """Sum the gradient bucket over the ranks -- unless the optimizer kernel does it
         itself over NVLink peer memory (self._dp)."""
-        if self.world > 1 and self._dp is None:
+        if self.world > 1 and self._dp is None and self._dp_push is None:
             dist.all_reduce(self.bucket.trained_grad, op=dist.ReduceOp.SUM, group=self.group)
 
     def _optimizer(self, scale, step):
+        if self.precision == 1 and self._dp_push is not None:
+            # reduce-scatter + update + all-gather of the parameters as NVLink writes, bf16
+            # weight copies and the gradient reset: one kernel
+            ops.dp_push_step(self.bucket.grad, self.state0, self.state1, self.kind, self.lr,
+                             self.momentum, scale, step, self._segments, self._dp_push)
+            self._grads_clean = True
+            return
         if self.precision == 1 and self._dp is not None:
             # all-reduce fused into the update: every rank reads its peers' buckets directly
             ops.dp_optimizer_step(self.bucket.param, self.state0, self.state1, self.kind, self.lr,

@@ -43,8 +43,8 @@ class _LinearActFn(torch.autograd.Function):
             # training engine keeps them resident instead (abnet3_b200.engine)
             m, n_in = x.shape
             n_out = weight.shape[0]
-            xb = torch.empty((m, ops.pad8(n_in)), dtype=torch.bfloat16, device=x.device)
-            wb = torch.empty((n_out, ops.pad8(n_in)), dtype=torch.bfloat16, device=x.device)
+            xb = torch.empty((m, ops.pad_row(n_in)), dtype=torch.bfloat16, device=x.device)
+            wb = torch.empty((n_out, ops.pad_row(n_in)), dtype=torch.bfloat16, device=x.device)
             ops.cast_bf16(x, xb)
             ops.cast_bf16(weight.detach(), wb)
             y = torch.empty((m, n_out), dtype=torch.float32, device=x.device)

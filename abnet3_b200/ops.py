@@ -284,6 +284,14 @@ def pad8(n):
     return (n + 7) // 8 * 8
 
 
+def pad_row(n):
+    """Leading dimension (bf16 elements) of a GEMM operand / output array: rows start on
+    128-byte lines.  The kernel only needs a multiple of 8; with 1008-byte rows (504 elements)
+    every 128-byte TMA row segment straddles two L2 lines and a half sector -- measured
+    40.7 -> 32.3 us for the forward chain (tools/time_chain.py, PADTO=8 vs 64)."""
+    return (n + 63) // 64 * 64
+
+
 def cast_bf16(src, dst=None, dstT=None):
     """fp32 [rows, cols] -> bf16 copy and/or transposed bf16 copy (padded leading dims)."""
     _req(src, torch.float32, "src")
@@ -437,3 +445,55 @@ def dp_optimizer_step(param, state0, state1, kind, lr, momentum, grad_scale, ste
 def dp_grad_reset(grad, peers):
     import ctypes
     check(_lib.lib().abn_dp_grad_reset(ptr(grad), grad.numel(), ctypes.byref(peers), stream_ptr()))
+
+
+def dp_push_setup(param, n_trained, group=None):
+    """Two-shot, write-only exchange: share the parameter bucket, a receive buffer and a
+    flag block with every rank of ``group`` (CUDA IPC).  Collective."""
+    import ctypes
+    import torch.distributed as dist
+    lib = _lib.lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world > 8:
+        raise RuntimeError("peer-memory data parallelism serves one box (world <= 8)")
+    if n_trained % 4:
+        raise RuntimeError("the trained parameter count must be a multiple of 4")
+    cap = ((n_trained + world - 1) // world + 3) // 4 * 4
+    recv = torch.zeros(world * cap, dtype=torch.float32, device=param.device)
+    flags = torch.zeros(32, dtype=torch.int64, device=param.device)
+    torch.cuda.synchronize()
+
+    def export(t):
+        h = (ctypes.c_ubyte * 64)()
+        off = ctypes.c_int64(0)
+        check(lib.abn_ipc_export(ptr(t), h, ctypes.byref(off)))
+        return bytes(h), int(off.value)
+
+    mine = {"param": export(param), "recv": export(recv), "flags": export(flags), "n": n_trained}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    pp = _lib.DpPush()
+    pp.rank, pp.world, pp.n, pp.slice_cap = rank, world, n_trained, cap
+    local = {"param": param, "recv": recv, "flags": flags}
+    for r, info in enumerate(everyone):
+        if info["n"] != n_trained:
+            raise RuntimeError("rank %d trains a different number of parameters" % r)
+        for key, arr in (("param", pp.param), ("recv", pp.recv), ("flags", pp.flags)):
+            if r == rank:
+                arr[r] = ptr(local[key])
+                continue
+            hb, off = info[key]
+            h = (ctypes.c_ubyte * 64).from_buffer_copy(hb)
+            out = ctypes.c_void_p()
+            check(lib.abn_ipc_import(h, off, ctypes.byref(out)))
+            arr[r] = out.value
+    dist.barrier(group=group)
+    pp._keep = (param, recv, flags)
+    return pp
+
+
+def dp_push_step(grad, state0, state1, kind, lr, momentum, grad_scale, step, segments, pp):
+    import ctypes
+    check(_lib.lib().abn_dp_push_step(ptr(grad), ptr(state0), ptr(state1), OPT_KIND[kind], float(lr),
+                                      float(momentum), float(grad_scale), int(step), segments,
+                                      len(segments), ctypes.byref(pp), stream_ptr()))

@@ -365,6 +365,24 @@ ABN_API int abn_dp_optimizer_step(float *param, float *state0, float *state1, in
                                   const abn_dp_peers *peers, abn_stream_t stream);
 ABN_API int abn_dp_grad_reset(float *grad, int64_t n, const abn_dp_peers *peers,
                               abn_stream_t stream);
+/* Two-shot variant in which every transfer is a WRITE over NVLink (posted, no round trips):
+ * each rank pushes slice j of its gradient bucket to owner j, the owner reduces in rank
+ * order, applies the optimizer to its slice and pushes the updated fp32 parameters into
+ * every rank's parameter bucket; then bf16 weight copies and the gradient reset, all in ONE
+ * kernel (one resident block per SM).  param[r] / recv[r] / flags[r]: rank r's parameter
+ * bucket (n trained floats first), receive buffer (world x slice_cap floats) and flag block
+ * as mapped in this process.  n and slice_cap are multiples of 4, world * slice_cap >= n. */
+typedef struct {
+    void *param[ABN_DP_MAX_WORLD];
+    void *recv[ABN_DP_MAX_WORLD];
+    void *flags[ABN_DP_MAX_WORLD];
+    int rank, world;
+    int64_t n, slice_cap;
+} abn_dp_push;
+ABN_API int abn_dp_push_step(float *grad, float *state0, float *state1, int kind, float lr,
+                             float momentum, float grad_scale, int64_t step,
+                             const abn_param_segment *segments, int n_segments,
+                             const abn_dp_push *peers, abn_stream_t stream);
 
 #ifdef __cplusplus
 }

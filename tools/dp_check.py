@@ -20,7 +20,7 @@ idx2 = torch.randint(0, feat.shape[0], (n_fp,), device=dev, dtype=torch.int32, g
 y = (torch.randint(0, 2, (n_fp,), device=dev, generator=g) * 2 - 1).to(torch.int8)
 
 def run(p2p, steps=12, graph=True, opt="adadelta", no_comm=False):
-    os.environ["ABN_DP_P2P"] = "1" if p2p else "0"      # "1" forces the peer-memory path at any world size
+    os.environ["ABN_DP_P2P"] = p2p if isinstance(p2p, str) else ("1" if p2p else "0")
     torch.manual_seed(0)
     net = SiameseNetwork(input_dim=280, num_hidden_layers=2, hidden_dim=500, output_dim=100, p_dropout=0.0,
                          activation_layer="sigmoid", precision="bf16").to(dev)
@@ -28,7 +28,9 @@ def run(p2p, steps=12, graph=True, opt="adadelta", no_comm=False):
         step = SiameseTrainStep(net, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
     else:
         step = SiameseTrainStep(net, ("coscos2", 0.0, False), "sgd", lr=1e-4, momentum=0.9)
-    assert (step._dp is not None) == p2p, "p2p setup state %s" % (step._dp is not None)
+    mode = "push" if step._dp_push is not None else ("read" if step._dp is not None else "nccl")
+    if rank == 0:
+        print("   exchange: %s" % mode, flush=True)
     if no_comm:
         step._allreduce = lambda: None
     sel = step.gather_buffers(B)
@@ -56,16 +58,16 @@ def run(p2p, steps=12, graph=True, opt="adadelta", no_comm=False):
 l0, w0, dt0 = run(False, no_comm=True)
 if rank == 0:
     print("no communication at all: us/step %.1f" % (dt0 * 1e6), flush=True)
-for p2p in (True, False):
+for p2p in (("push", "0") if world > 2 else ("push", "1", "0")):
     losses, w, dt = run(p2p, opt="sgd")
     # every rank must hold the same weights
     ws = [torch.empty_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
     same = all(torch.equal(ws[0], x) for x in ws)
     if rank == 0:
-        print("p2p=%d  us/step %.1f  ranks identical: %s  losses %s" % (p2p, dt * 1e6, same, ["%.1f" % l for l in losses[:6]]), flush=True)
-    if p2p: w_p2p, l_p2p = w, losses
-    else: w_nccl, l_nccl = w, losses
+        print("p2p=%s  us/step %.1f  ranks identical: %s  losses %s" % (p2p, dt * 1e6, same, ["%.1f" % l for l in losses[:6]]), flush=True)
+    if p2p == "push": w_p2p, l_p2p = w, losses
+    elif p2p == "0": w_nccl, l_nccl = w, losses
 rel = float((w_p2p - w_nccl).norm() / w_nccl.norm())
 if rank == 0:
     print("weights p2p vs nccl: rel diff %.3e; loss[5] %.2f vs %.2f" % (rel, l_p2p[5], l_nccl[5]), flush=True)

@@ -4,8 +4,9 @@ import torch
 from abnet3_b200 import ops, _lib
 DEV = "cuda"
 rows = 16384
+PAD = int(os.environ.get("PADTO", "8"))
 def bf(r, c):
-    return (torch.randn(r, ops.pad8(c + 1), device=DEV) * 0.05).bfloat16()
+    return (torch.randn(r, (c + 1 + PAD - 1) // PAD * PAD, device=DEV) * 0.05).bfloat16()
 dims = [280, 500, 500, 500, 100]
 acts = [bf(rows, d) for d in dims]
 dzs = [bf(rows, d) for d in dims]
@@ -44,8 +45,8 @@ ctypes.c_void_p.in_dll(_lib.lib(), "abn_gemm_trace_buffer").value = None
 t = tr.cpu().view(148, 8, 16)
 t0 = int(t[t > 0].min())
 names = ["p0", "p1", "m0", "mfree", "mcommit", "e0", "etfull", "edone", "c_ld0", "c_ld1", "c_math", "c_sts", "c_bar", "c_tma", "-", "-"]
-for cta in (0, 1, 50, 100, 147):
+for cta in (0, 2, 64, 100, 126):
     for it in range(8):
         if int(t[cta, it].max()) == 0: continue
-        print("cta %3d tile %d: " % (cta, it) + "  ".join("%s %6.2f" % (n, (int(v) - t0) / 1e3) if v > 0 else "%s    -  " % n for n, v in zip(names, t[cta, it])))
+        print("cta %3d tile %d: " % (cta, it) + "  ".join("%s %6.2f" % (n, (int(v) - t0) / 1e3) if v > 0 else "%s    -  " % n for n, v in list(zip(names, t[cta, it]))[:8]))
 print("last event us", (int(t.max()) - t0) / 1e3)
