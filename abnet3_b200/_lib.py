@@ -33,6 +33,18 @@ class GemmProblem(_c.Structure):
                 ("signal", _P), ("wait", _P), ("wait_count", _I)]
 
 
+class MlpLayer(_c.Structure):
+    """abn_mlp_layer (include/abnet3_b200.h)."""
+    _fields_ = [("W", _P), ("ldw", _L), ("bias", _P), ("n_in", _I), ("n_out", _I), ("act", _I),
+                ("out", _P), ("ldo", _L), ("out_f32", _I), ("ones_col", _I)]
+
+
+class MlpDLayer(_c.Structure):
+    """abn_mlp_dlayer (include/abnet3_b200.h)."""
+    _fields_ = [("W", _P), ("ldw", _L), ("n_in", _I), ("n_out", _I), ("act_below", _I),
+                ("y_below", _P), ("ld_y", _L), ("dz_below", _P), ("ld_dz", _L)]
+
+
 class ParamSegment(_c.Structure):
     """abn_param_segment (include/abnet3_b200.h)."""
     _fields_ = [("offset", _L), ("count", _L), ("ld", _L), ("bf16", _P), ("n_in", _I)]
@@ -69,6 +81,8 @@ SIGNATURES = {
     "abn_linear_forward": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P, _P]),
     "abn_linear_backward": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "abn_gemm_bf16_group": (_I, [_P, _I, _P]),
+    "abn_mlp_forward_fused": (_I, [_P, _L, _L, _P, _I, _P]),
+    "abn_mlp_dgrad_fused": (_I, [_P, _L, _L, _P, _I, _P]),
     "abn_cast_bf16": (_I, [_P, _L, _I, _L, _P, _L, _P, _L, _P]),
     "abn_optimizer_step": (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _F, _L, _P]),
     "abn_gather_batch_bf16": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _I, _P]),

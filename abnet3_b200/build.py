@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libabnet3_b200.so")
-SOURCES = ["abn_capi.cu", "abn_align.cu", "abn_nn.cu", "abn_tc.cu", "abn_tc2.cu", "abn_fused.cu"]
+SOURCES = ["abn_capi.cu", "abn_align.cu", "abn_nn.cu", "abn_tc.cu", "abn_tc2.cu", "abn_tc3.cu", "abn_fused.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
     "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

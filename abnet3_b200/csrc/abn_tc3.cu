@@ -1,0 +1,536 @@
+// abn_tc3.cu -- kernel (3b): the embedder's FORWARD pass with the activations resident on
+// chip.  One launch runs every layer of  y = act(x W^T + b)  (abnet3/model.py:133-170,
+// :179-186) for a 256-row block per CTA pair:
+//
+//   * the block's activations live in shared memory as the A operand of the next layer
+//     ("slab": 8 k-blocks of 128 rows x 64 bf16, 128-byte swizzle = the layout TMA would have
+//     produced), written there by the epilogue of the layer before -- they are never re-read
+//     from L2, and the next layer does not wait for a global round trip;
+//   * only the weights stream (TMA ring, this CTA's half of every 256-column B tile);
+//   * the accumulators of a layer's two 256-column halves fill the 512 TMEM columns; the
+//     epilogue drains them k-block by k-block and the next layer's MMAs start on a k-block
+//     as soon as both CTAs have written it (per-k-block mbarriers on the leader CTA);
+//   * every hidden layer's rows also leave through TMA stores from the slab (the backward
+//     pass needs them), the last layer's rows as fp32 (the embeddings).
+//
+// Why (measured, tools/time_chain.py + tools/trace_tc2.py): the chained grouped GEMM is bound
+// by L2 -> SM operand delivery (196 MB per forward pass at ~11 TB/s) and, with the layers'
+// dependencies, by the latency of store -> signal -> load between layers (44 us against 31 us
+// without dependencies).  Keeping A on chip removes half of the operand traffic and all of
+// that latency.
+//
+// Serves networks whose layer widths fit the slab: n_in <= 512, n_out (+ the ones column)
+// <= 512; anything else takes the chained launch of abn_tc2.cu.
+#include <stdlib.h>
+#include <string.h>
+
+#include "abn_tc_ptx.cuh"
+
+namespace abn {
+
+constexpr int F_MAXL = ABN_MLP_MAX_LAYERS;
+constexpr int F_KB = 8;                         // slab k-blocks (8 x 64 = 512 features)
+constexpr int F_STAGES = 4;                     // B ring
+constexpr unsigned F_SLAB_KB_BYTES = 128 * 64 * 2;      // 16 KB: this CTA's 128 rows of one k-block
+constexpr unsigned F_B_BYTES = 128 * 64 * 2;            // this CTA's half of a 256-column B tile
+
+struct FLayer {
+    CUtensorMap map_w;              // forward: W [n_out, n_in], box {64 k, 128 rows};  dgrad: box {64 cols, 64 k rows}
+    CUtensorMap map_out;            // bf16 output [rows, ld], box {64 cols, 32 rows}
+    CUtensorMap map_y;              // dgrad: y_below [rows, ld] bf16, box {64 cols, 32 rows}
+    const float *bias;
+    float *out32; long long ld32;   // last layer: fp32 rows
+    int n_in, n_out, act, ones_col, out_f32;
+    int nkb, tiles_n, n_cap;        // GEMM view: K = 64 nkb, N = n_cap (forward: n_out + ones_col; dgrad: n_in)
+};
+struct FChain {
+    CUtensorMap map_x;              // x [rows, n_in0] bf16, box {64, 128}
+    FLayer L[F_MAXL];
+    int n_layers, rows, tiles_m;
+};
+
+__device__ __forceinline__ void f_mbar_wait_cluster(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; spin < (1u << 27); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// arrive on the LEADER CTA's copy of `bar` (own copy when this CTA is the leader)
+__device__ __forceinline__ void f_arrive_leader_release(unsigned bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+                 ::"r"(bar & G_PEER_MASK) : "memory");
+}
+
+__device__ __forceinline__ int f_n_eff(const FLayer &L, int nt) {
+    const int rem = L.n_cap - nt * 256;        // (the ones column is computed as a zero and overwritten)
+    return rem >= 256 ? 256 : ((rem + 15) & ~15);
+}
+
+// One 64-column block of a hidden layer: TMEM -> bias + activation -> bf16 -> this warp's 32
+// rows of slab k-block cb (the next layer's A operand), then a TMA store of the same box.
+template <int ACT>
+__device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, unsigned dst, int lane,
+                                            int ones_at) {
+    const unsigned swz = (unsigned)(lane & 7);
+#pragma unroll
+    for (int hseg = 0; hseg < 2; ++hseg) {
+        float v[32];
+        g_ld32(taddr + 32 * hseg, v);
+        unsigned pk[16];
+        if (ACT == 1 || ACT == 2) {
+            g_bias_act32_packed<ACT>(v, bs + 32 * hseg, pk);
+        } else {
+            g_bias_act32<ACT>(v, bs + 32 * hseg);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
+        }
+        const int jo = ones_at - 32 * hseg;             // the column of ones, if it is in this half
+        if (jo >= 0 && jo < 32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (2 * j == jo) pk[j] = (pk[j] & 0xffff0000u) | 0x3f80u;
+                if (2 * j + 1 == jo) pk[j] = (pk[j] & 0x0000ffffu) | 0x3f800000u;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(dst + lane * 128 + (((unsigned)(4 * hseg + q) ^ swz) << 4)),
+                           "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                         : "memory");
+    }
+}
+
+// dgrad: TMEM -> x act'(y_below) -> bf16 -> slab rows (y_below's box sits in `ybuf`)
+template <int ACT>
+__device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[8], unsigned dst, int lane) {
+    const unsigned swz = (unsigned)(lane & 7);
+#pragma unroll
+    for (int hseg = 0; hseg < 2; ++hseg) {
+        float v[32];
+        g_ld32(taddr + 32 * hseg, v);
+        const uint4 yh[4] = {yc[4 * hseg], yc[4 * hseg + 1], yc[4 * hseg + 2], yc[4 * hseg + 3]};
+        g_dact32<ACT>(v, yh);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(dst + lane * 128 + (((unsigned)(4 * hseg + q) ^ swz) << 4)),
+                           "r"(g_pack_bf16(v[8 * q], v[8 * q + 1])), "r"(g_pack_bf16(v[8 * q + 2], v[8 * q + 3])),
+                           "r"(g_pack_bf16(v[8 * q + 4], v[8 * q + 5])), "r"(g_pack_bf16(v[8 * q + 6], v[8 * q + 7]))
+                         : "memory");
+    }
+}
+
+// MODE 0: forward (B = W K-major, bias + activation, last layer fp32)
+// MODE 1: dgrad   (B = W MN-major, x act'(y_below) with y_below fetched per warp by TMA)
+template <int MODE>
+__global__ void __launch_bounds__(G_THREADS, 1)
+mlp_chain_kernel(const __grid_constant__ FChain ch) {
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned raw = g_smem_u32(smem_raw);
+    const unsigned base = (raw + 1023u) & ~1023u;
+    unsigned char *gen = smem_raw + (base - raw);
+    const unsigned slab = base;                                         // F_KB x 16 KB
+    const unsigned ring = slab + F_KB * F_SLAB_KB_BYTES;                // F_STAGES x 16 KB
+    const unsigned bars = ring + F_STAGES * F_B_BYTES;
+    const unsigned bfull0 = bars, bempty0 = bars + 8 * F_STAGES;
+    const unsigned xfull0 = bars + 16 * F_STAGES;                       // [F_KB] layer 0: TMA
+    const unsigned sfull0 = xfull0 + 8 * F_KB;                          // [F_KB] later layers: epilogue
+    const unsigned afull0 = sfull0 + 8 * F_KB, aempty0 = afull0 + 16;   // [2] accumulators
+    const unsigned slab_free = aempty0 + 16, drained = slab_free + 8;
+    const unsigned tptr = drained + 8;
+    const unsigned ybar0 = tptr + 8;                                    // [G_EPI_WARPS] dgrad: y_below boxes
+    constexpr unsigned BAR_BYTES = 16 * F_STAGES + 16 * F_KB + 32 + 16 + 16 + 8 * G_EPI_WARPS;
+    volatile unsigned *tptr_gen = reinterpret_cast<volatile unsigned *>(
+        gen + F_KB * F_SLAB_KB_BYTES + F_STAGES * F_B_BYTES + (tptr - bars));
+    float *bias_s = reinterpret_cast<float *>(
+        gen + F_KB * F_SLAB_KB_BYTES + F_STAGES * F_B_BYTES + ((BAR_BYTES + 127u) & ~127u));  // [2][512] (forward)
+    // dgrad: one 32 x 64 bf16 box of y_below per epilogue warp, 1024-byte aligned (128-byte swizzle)
+    const unsigned ybuf0 = (bars + BAR_BYTES + 1023u) & ~1023u;
+
+    const int rank = (int)g_cluster_rank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < F_STAGES; ++s) { g_mbar_init(bfull0 + 8 * s, 1); g_mbar_init(bempty0 + 8 * s, 1); }
+        for (int k = 0; k < F_KB; ++k) {
+            g_mbar_init(xfull0 + 8 * k, 1);
+            g_mbar_init(sfull0 + 8 * k, 8);          // 4 row-quarter warps x 2 CTAs
+        }
+        for (int a = 0; a < 2; ++a) {
+            g_mbar_init(afull0 + 8 * a, 1);
+            g_mbar_init(aempty0 + 8 * a, 2 * G_EPI_WARPS);
+        }
+        g_mbar_init(slab_free, 1);
+        g_mbar_init(drained, G_EPI_WARPS);
+        for (int w = 0; w < G_EPI_WARPS; ++w) g_mbar_init(ybar0 + 8 * w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(tptr), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    g_fence_before();
+    g_cluster_sync();
+    g_fence_after();
+    const unsigned tmem = *tptr_gen;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0) {
+        // -------------------------------------------------- TMA producer: x, then the weights
+        if (lane == 0) {
+            unsigned n = 0, iter = 0;
+            for (int rb = pair; rb < ch.tiles_m; rb += npairs, ++iter) {
+                const int m0 = (rb * 2 + rank) * G_BM;
+                if (iter > 0) {          // the slab is reused: MMAs and output stores of the last block are done
+                    g_mbar_wait(slab_free, (iter - 1) & 1);
+                    g_mbar_wait(drained, (iter - 1) & 1);
+                }
+                const FLayer &L0 = ch.L[0];
+                for (int kb = 0; kb < L0.nkb; ++kb) {
+                    if (rank == 0) g_mbar_expect_tx(xfull0 + 8 * kb, 2u * F_SLAB_KB_BYTES);
+                    g_tma_2d_pair(slab + kb * F_SLAB_KB_BYTES, &ch.map_x, (xfull0 + 8 * kb) & G_PEER_MASK,
+                                  kb * G_BK, m0);
+                }
+                for (int l = 0; l < ch.n_layers; ++l) {
+                    const FLayer &L = ch.L[l];
+                    for (int nt = 0; nt < L.tiles_n; ++nt) {
+                        const int nb_cols = f_n_eff(L, nt) >> 1, nb0 = nt * 256 + rank * nb_cols;
+                        const int nbox = (nb_cols + 63) >> 6;
+                        for (int kb = 0; kb < L.nkb; ++kb, ++n) {
+                            const int s = n % F_STAGES;
+                            g_mbar_wait(bempty0 + 8 * s, ((n / F_STAGES) & 1) ^ 1);
+                            const unsigned fb = (bfull0 + 8 * s) & G_PEER_MASK;
+                            if (MODE == 0) {
+                                if (rank == 0) g_mbar_expect_tx(bfull0 + 8 * s, 2u * F_B_BYTES);
+                                g_tma_2d_pair(ring + s * F_B_BYTES, &L.map_w, fb, kb * G_BK, nb0);
+                            } else {
+                                if (rank == 0) g_mbar_expect_tx(bfull0 + 8 * s, 2u * (unsigned)nbox * 8192u);
+                                for (int j = 0; j < nbox; ++j)
+                                    g_tma_2d_pair(ring + s * F_B_BYTES + j * 8192, &L.map_w, fb,
+                                                  nb0 + 64 * j, kb * G_BK);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA)
+        if (lane == 0 && rank == 0) {
+            unsigned n = 0, iter = 0, sphase = 0, aphase = 0;     // phase bits per barrier
+            for (int rb = pair; rb < ch.tiles_m; rb += npairs, ++iter) {
+                for (int l = 0; l < ch.n_layers; ++l) {
+                    const FLayer &L = ch.L[l];
+                    for (int nt = 0; nt < L.tiles_n; ++nt) {
+                        g_mbar_wait(aempty0 + 8 * nt, ((aphase >> nt) & 1) ^ 1);     // epilogues drained it
+                        aphase ^= 1u << nt;
+                        g_fence_after();
+                        const unsigned idesc = g_idesc(2 * G_BM, f_n_eff(L, nt), 0, MODE);
+                        const unsigned d_tmem = tmem + nt * 256;
+                        for (int kb = 0; kb < L.nkb; ++kb, ++n) {
+                            if (nt == 0) {          // this k-block of the layer's input is in both slabs
+                                if (l == 0) {
+                                    g_mbar_wait(xfull0 + 8 * kb, iter & 1);
+                                } else {
+                                    f_mbar_wait_cluster(sfull0 + 8 * kb, (sphase >> kb) & 1);
+                                    sphase ^= 1u << kb;
+                                }
+                            }
+                            const int s = n % F_STAGES;
+                            g_mbar_wait(bfull0 + 8 * s, (n / F_STAGES) & 1);
+                            g_fence_after();
+                            const unsigned long long da = g_desc(slab + kb * F_SLAB_KB_BYTES, 0);
+                            const unsigned long long db = g_desc(ring + s * F_B_BYTES, MODE);
+                            constexpr unsigned b_step = MODE ? (2048 >> 4) : (32 >> 4);
+#pragma unroll
+                            for (int k = 0; k < G_BK / G_UK; ++k)
+                                g_mma_pair(d_tmem, da + (unsigned long long)(2 * k),
+                                           db + (unsigned long long)(b_step * k), idesc, (kb | k) != 0);
+                            g_commit_pair(bempty0 + 8 * s);
+                        }
+                        g_commit_pair(afull0 + 8 * nt);
+                    }
+                }
+                g_commit_pair(slab_free);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------- epilogue
+        const int ew = warp - 2;
+        const int wq = warp & 3;                        // TMEM lane quarter of this warp
+        const int half = ew >> 2;                       // takes the 64-column blocks cb = half, half + 2, ..
+        const int et = ew * 32 + lane;
+        unsigned afphase = 0, lcount = 0, ycount = 0;
+        for (int rb = pair; rb < ch.tiles_m; rb += npairs) {
+            const int m0 = (rb * 2 + rank) * G_BM;
+            const int row0 = m0 + wq * 32;
+            for (int l = 0; l < ch.n_layers; ++l, ++lcount) {
+                const FLayer &L = ch.L[l];
+                float *bs = bias_s + (lcount & 1u) * 512;
+                const int nblk = (L.n_cap + 63) >> 6;
+                const unsigned ybuf = ybuf0 + ew * 4096u, ybar = ybar0 + 8 * ew;
+                if (MODE == 0) {
+                    for (int c = et; c < 512; c += 32 * G_EPI_WARPS)
+                        bs[c] = (L.bias && c < L.n_out) ? __ldg(L.bias + c) : 0.f;
+                }
+                // this warp's earlier output boxes have left the slab rows it is about to rewrite
+                if (lane == 0) {
+                    g_store_wait_read0();
+                    if (MODE == 1 && half < nblk) {      // the first block's y_below does not depend on the MMAs
+                        g_mbar_expect_tx(ybar, 4096u);
+                        g_tma_2d(ybuf, &L.map_y, ybar, half * 64, row0);
+                    }
+                }
+                if (MODE == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
+                else __syncwarp();
+                // the layer's MMAs read the whole slab: nothing may be written before the last
+                // accumulator is complete (tcgen05.commit covers every MMA issued before it)
+                for (int a = 0; a < L.tiles_n; ++a) {
+                    g_mbar_wait(afull0 + 8 * a, (afphase >> a) & 1);
+                    afphase ^= 1u << a;
+                }
+                g_fence_after();
+                for (int a = 0; a < L.tiles_n; ++a) {
+                    for (int cb = 4 * a + half; cb < 4 * a + 4 && cb < nblk; cb += 2) {
+                        const unsigned taddr = tmem + ((unsigned)(wq * 32) << 16) + cb * 64;
+                        if (MODE == 1 || !L.out_f32) {
+                            const unsigned dst = slab + cb * F_SLAB_KB_BYTES + wq * 4096u;
+                            if (MODE == 0) {
+                                const int ones_at = L.ones_col ? L.n_out - cb * 64 : -1;
+                                switch (L.act) {
+                                    case 1: f_epi_block<1>(taddr, bs + cb * 64, dst, lane, ones_at); break;
+                                    case 2: f_epi_block<2>(taddr, bs + cb * 64, dst, lane, ones_at); break;
+                                    case 3: f_epi_block<3>(taddr, bs + cb * 64, dst, lane, ones_at); break;
+                                    default: f_epi_block<0>(taddr, bs + cb * 64, dst, lane, ones_at); break;
+                                }
+                            } else {
+                                g_mbar_wait(ybar, ycount & 1u);
+                                ++ycount;
+                                uint4 yc[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=r"(yc[q].x), "=r"(yc[q].y), "=r"(yc[q].z), "=r"(yc[q].w)
+                                                 : "r"(ybuf + lane * 128 + (((unsigned)q ^ (unsigned)(lane & 7)) << 4))
+                                                 : "memory");
+                                __syncwarp();               // every lane holds its y_below row: fetch the next box
+                                if (lane == 0 && cb + 2 < nblk) {
+                                    g_mbar_expect_tx(ybar, 4096u);
+                                    g_tma_2d(ybuf, &L.map_y, ybar, (cb + 2) * 64, row0);
+                                }
+                                switch (L.act) {
+                                    case 1: f_epi_block_d<1>(taddr, yc, dst, lane); break;
+                                    case 2: f_epi_block_d<2>(taddr, yc, dst, lane); break;
+                                    case 3: f_epi_block_d<3>(taddr, yc, dst, lane); break;
+                                    default: f_epi_block_d<0>(taddr, yc, dst, lane); break;
+                                }
+                            }
+                            // generic-proxy writes -> visible to the async proxy (the next layer's
+                            // MMAs and the TMA store), then: k-block cb is ready in this quarter
+                            asm volatile("fence.proxy.async;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (l + 1 < ch.n_layers && cb < ch.L[l + 1].nkb)
+                                    f_arrive_leader_release(sfull0 + 8 * cb);
+                                g_tma_store_2d(&L.map_out, dst, cb * 64, row0);
+                            }
+                        } else {
+                            // the embeddings: fp32 rows, 16-byte stores
+                            const int row = row0 + lane;
+#pragma unroll
+                            for (int hseg = 0; hseg < 2; ++hseg) {
+                                float v[32];
+                                g_ld32(taddr + 32 * hseg, v);
+                                const float *b2 = bs + cb * 64 + 32 * hseg;
+                                switch (L.act) {
+                                    case 1: g_bias_act32<1>(v, b2); break;
+                                    case 2: g_bias_act32<2>(v, b2); break;
+                                    case 3: g_bias_act32<3>(v, b2); break;
+                                    default: g_bias_act32<0>(v, b2); break;
+                                }
+                                const int gcol0 = cb * 64 + 32 * hseg;
+                                if (row < ch.rows) {
+                                    float *op = L.out32 + (long long)row * L.ld32 + gcol0;
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        if (gcol0 + 4 * q + 4 <= L.n_out && (L.ld32 & 3) == 0)
+                                            *reinterpret_cast<float4 *>(op + 4 * q) =
+                                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                                        else
+#pragma unroll
+                                            for (int e2 = 0; e2 < 4; ++e2)
+                                                if (gcol0 + 4 * q + e2 < L.n_out) op[4 * q + e2] = v[4 * q + e2];
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    // this warp is done with accumulator a
+                    g_fence_before();
+                    __syncwarp();
+                    if (lane == 0) g_mbar_arrive_cta0(aempty0 + 8 * a);
+                }
+            }
+            // the block's output boxes have been read out of the slab (the next block's x may land)
+            if (lane == 0) {
+                g_store_wait_read0();
+                g_mbar_arrive(drained);
+            }
+        }
+    }
+    if (warp >= 2 && lane == 0) g_store_wait_all();
+    g_fence_before();
+    g_cluster_sync();
+    if (warp == 2) {
+        g_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512)
+                     : "memory");
+    }
+}
+
+}  // namespace abn
+
+using namespace abn;
+
+namespace {
+
+int f_sm_count() {
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sm_count;
+}
+
+template <int MODE>
+int f_launch(const FChain &ch, cudaStream_t st, const char *what) {
+    // slab + weight ring + barriers + (forward: staged biases | dgrad: y_below boxes) + alignment slack
+    constexpr unsigned smem = F_KB * F_SLAB_KB_BYTES + F_STAGES * F_B_BYTES + 1024 +
+                              (MODE == 0 ? 512 + 2 * 512 * 4 : 1024 + G_EPI_WARPS * 4096);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mlp_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return set_error(ABN_EIO, "%s: cannot reserve %u bytes of shared memory", what, smem);
+        configured = true;
+    }
+    const int sms = f_sm_count();
+    int grid = 2 * ch.tiles_m < sms ? 2 * ch.tiles_m : sms;
+    grid -= grid % 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, mlp_chain_kernel<MODE>, ch);
+    return check_launch(what);
+}
+
+}  // namespace
+
+extern "C" int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
+                                     const abn_mlp_layer *layers, int n_layers,
+                                     abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (rows == 0) return ABN_OK;
+    if (!x || !layers || rows < 0 || n_layers < 1 || n_layers > F_MAXL)
+        return set_error(ABN_EINVAL, "abn_mlp_forward_fused: 1..%d layers", F_MAXL);
+    FChain ch;
+    memset(&ch, 0, sizeof(ch));
+    ch.n_layers = n_layers;
+    ch.rows = (int)rows;
+    ch.tiles_m = (int)((rows + 2 * G_BM - 1) / (2 * G_BM));
+    int rc = g_make_map(&ch.map_x, x, rows, layers[0].n_in, ldx, G_BK, G_BM);
+    if (rc) return rc;
+    for (int l = 0; l < n_layers; ++l) {
+        const abn_mlp_layer &q = layers[l];
+        FLayer &L = ch.L[l];
+        const bool last = l == n_layers - 1;
+        if (!q.W || !q.out || q.n_in <= 0 || q.n_out <= 0 || q.act < 0 || q.act > 3 ||
+            q.n_in > F_KB * G_BK || q.n_out + (q.ones_col ? 1 : 0) > F_KB * G_BK ||
+            (l > 0 && q.n_in != layers[l - 1].n_out) || (!last && q.out_f32) ||
+            (q.out_f32 && q.ones_col))
+            return set_error(ABN_EINVAL, "abn_mlp_forward_fused: layer %d: widths up to %d, hidden "
+                             "outputs bf16, consecutive layers must fit", l, F_KB * G_BK);
+        L.bias = q.bias;
+        L.n_in = q.n_in; L.n_out = q.n_out; L.act = q.act;
+        L.ones_col = q.ones_col ? 1 : 0; L.out_f32 = q.out_f32 ? 1 : 0;
+        L.n_cap = q.n_out + L.ones_col;
+        L.nkb = (q.n_in + G_BK - 1) / G_BK;
+        L.tiles_n = (L.n_cap + 255) / 256;
+        rc = g_make_map(&L.map_w, q.W, q.n_out, q.n_in, q.ldw, G_BK, 128);
+        if (rc) return rc;
+        if (L.out_f32) {
+            L.out32 = static_cast<float *>(q.out);
+            L.ld32 = q.ldo;
+        } else {
+            if ((q.ldo & 7) || q.ldo < L.n_cap)
+                return set_error(ABN_EINVAL, "abn_mlp_forward_fused: layer %d: bf16 output rows must be "
+                                 "padded to a multiple of 8 elements covering n_out%s", l,
+                                 L.ones_col ? " + 1" : "");
+            rc = g_make_map(&L.map_out, q.out, rows, q.ldo, q.ldo, 64, 32);
+            if (rc) return rc;
+        }
+    }
+    return f_launch<0>(ch, (cudaStream_t)stream, "abn_mlp_forward_fused");
+}
+
+extern "C" int abn_mlp_dgrad_fused(const void *dz_top, int64_t ld_top, int64_t rows,
+                                   const abn_mlp_dlayer *layers, int n_layers,
+                                   abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (rows == 0 || n_layers == 0) return ABN_OK;
+    if (!dz_top || !layers || rows < 0 || n_layers < 0 || n_layers > F_MAXL)
+        return set_error(ABN_EINVAL, "abn_mlp_dgrad_fused: up to %d layers", F_MAXL);
+    FChain ch;
+    memset(&ch, 0, sizeof(ch));
+    ch.n_layers = n_layers;
+    ch.rows = (int)rows;
+    ch.tiles_m = (int)((rows + 2 * G_BM - 1) / (2 * G_BM));
+    // GEMM view of layer l: A = dz [rows, K = n_out], B = W [K = n_out, N = n_in] as stored
+    int rc = g_make_map(&ch.map_x, dz_top, rows, layers[0].n_out, ld_top, G_BK, G_BM);
+    if (rc) return rc;
+    for (int l = 0; l < n_layers; ++l) {
+        const abn_mlp_dlayer &q = layers[l];
+        FLayer &L = ch.L[l];
+        if (!q.W || !q.y_below || !q.dz_below || q.n_in <= 0 || q.n_out <= 0 || q.act_below < 0 ||
+            q.act_below > 3 || q.n_in > F_KB * G_BK || q.n_out > F_KB * G_BK ||
+            (l > 0 && q.n_out != layers[l - 1].n_in))
+            return set_error(ABN_EINVAL, "abn_mlp_dgrad_fused: layer %d: widths up to %d, consecutive "
+                             "layers must fit", l, F_KB * G_BK);
+        if ((q.ld_dz & 7) || q.ld_dz < q.n_in || (q.ld_y & 7) || q.ld_y < q.n_in)
+            return set_error(ABN_EINVAL, "abn_mlp_dgrad_fused: layer %d: bf16 rows must be padded to a "
+                             "multiple of 8 elements covering n_in", l);
+        L.n_in = q.n_in; L.n_out = q.n_out; L.act = q.act_below;
+        L.n_cap = q.n_in;
+        L.nkb = (q.n_out + G_BK - 1) / G_BK;
+        L.tiles_n = (L.n_cap + 255) / 256;
+        rc = g_make_map(&L.map_w, q.W, q.n_out, q.n_in, q.ldw, 64, 64);
+        if (rc) return rc;
+        rc = g_make_map(&L.map_out, q.dz_below, rows, q.ld_dz, q.ld_dz, 64, 32);
+        if (rc) return rc;
+        rc = g_make_map(&L.map_y, q.y_below, rows, q.ld_y, q.ld_y, 64, 32);
+        if (rc) return rc;
+    }
+    return f_launch<1>(ch, (cudaStream_t)stream, "abn_mlp_dgrad_fused");
+}

@@ -293,36 +293,87 @@ class SiameseTrainStep(object):
                 wait=self._dep[l - 1] if (l > 0 and l % G != 0) else None))
             wgrad.append((L, hb))
             hb = out
+        # Forward pass in ONE launch with the activations resident in shared memory
+        # (abn_mlp_forward_fused) when every layer fits its 512-feature slab; same bits as the
+        # chained launch, which serves everything else (ABN_FWD_FUSED=0 forces it).
+        self._fwd_fused = None
+        self._fwd_rows = rows
+        fits = all(L.n_in <= ops.MLP_MAX_WIDTH and L.n_out + 1 <= ops.MLP_MAX_WIDTH for L in self.chain)
+        if fits and len(self.chain) <= ops.MLP_MAX_LAYERS and os.environ.get("ABN_FWD_FUSED", "1") != "0":
+            self._fwd_fused = ops.mlp_layers(
+                [(L.wb, L.n_in, L.b, L.act, self.actb[l] if l < last else self.out_last, l < last)
+                 for l, L in enumerate(self.chain)])
+        # dz of the layer below = (dz W) * act'(its output); every dgrad problem signals its row
+        # blocks: the next dgrad problem AND the weight gradients of the layer below wait on them
         n_d = 0
-        for l in range(last, 0, -1):       # dz of the layer below = (dz W) * act'(its output)
+        base = len(self.chain)
+        dz_ready = {last: None}            # layer -> counters that say "dz of this layer is written"
+        for l in range(last, 0, -1):
             L = self.chain[l]
-            base = len(self.chain)
             self._dgrad_problems.append(ops.gemm_problem(
                 self.dzb[l], L.wb, rows, L.n_in, L.n_out, ops.GE_DACT, self.dzb[l - 1], b_mn=True,
                 act=self.chain[l - 1].act, yprev=self.actb[l - 1],
-                signal=self._dep[base + n_d] if (l > 1 and (n_d + 1) % G != 0) else None,
-                wait=self._dep[base + n_d - 1] if (n_d > 0 and n_d % G != 0) else None))
+                signal=self._dep[base + n_d], wait=dz_ready[l]))
+            dz_ready[l - 1] = self._dep[base + n_d]
             n_d += 1
-        # weight + bias gradients of ALL layers: one launch per group of 4 problems, split
-        # over the batch so that the group fills the machine about twice
-        tiles = sum(((L.n_out + 127) // 128) * ((L.n_in + 1 + 255) // 256) for L, _ in wgrad)
+        # dz chain in ONE launch with dz resident in shared memory (abn_mlp_dgrad_fused) when the
+        # layers fit its slab (ABN_BWD_FUSED=0: the grouped GEMM instead)
+        self._dgrad_fused = None
+        if fits and last >= 1 and last <= ops.MLP_MAX_LAYERS and os.environ.get("ABN_BWD_FUSED", "1") != "0":
+            self._dgrad_fused = ops.mlp_dlayers(
+                [(self.chain[l].wb, self.chain[l].n_in, self.chain[l - 1].act, self.actb[l - 1],
+                  self.dzb[l - 1]) for l in range(last, 0, -1)])
+        G = ops.GEMM_MAX_GROUP
+        merge = (self._dgrad_fused is None and 2 * len(self.chain) - 1 <= G and
+                 os.environ.get("ABN_BWD_MERGE", "1") != "0")
+        # weight + bias gradients of ALL layers, split over the batch: ~1.75 waves of CTA pairs
+        # when they have a launch of their own, ~3.5 inside the merged backward launch (measured;
+        # ABN_WGRAD_SPLIT overrides)
+        tiles = sum(((L.n_out + 255) // 256) * ((L.n_in + 1 + 255) // 256) for L, _ in wgrad)
+        waves4 = 14 if merge else 7
         split = max(1, min((rows + 63) // 64, int(os.environ.get("ABN_WGRAD_SPLIT", "0")) or
-                           max(1, (GEMM_CTAS // 2) // max(1, tiles // 2))))
-        self._wgrad_groups = []
-        probs = [ops.gemm_problem(self.dzb[l], xin, L.n_out, L.n_in, rows, ops.GE_ATOMIC, L.gW,
-                                  a_mn=True, b_mn=True, split_k=split, ones_out=L.gb)
-                 for l, (L, xin) in enumerate(wgrad)]
-        for i in range(0, len(probs), ops.GEMM_MAX_GROUP):
-            self._wgrad_groups.append(probs[i:i + ops.GEMM_MAX_GROUP])
+                           max(1, (waves4 * (GEMM_CTAS // 2) // 4) // max(1, tiles))))
+        self._wgrad_split = split
+
+        def wgrad_problem(l, wait):
+            L, xin = wgrad[l]
+            return ops.gemm_problem(self.dzb[l], xin, L.n_out, L.n_in, rows, ops.GE_ATOMIC, L.gW,
+                                    a_mn=True, b_mn=True, split_k=split, ones_out=L.gb, wait=wait)
+
+        # Grouped-GEMM launches of the backward pass.  Merged: dgrad(l), wgrad(l), dgrad(l-1), ...
+        # in ONE launch -- the weight-gradient tiles (whose dz is a layer older) fill the gaps the
+        # dgrad chain's dependencies leave.  Otherwise the dgrad chain(s) (unless the fused dgrad
+        # kernel runs), then the wgrad group(s).
+        self._backward_groups = []
+        if merge:
+            merged = []
+            for k, l in enumerate(range(last, 0, -1)):
+                merged.append(self._dgrad_problems[k])
+                merged.append(wgrad_problem(l, dz_ready[l]))
+            merged.append(wgrad_problem(0, dz_ready[0]))
+            self._backward_groups.append(merged)
+        else:
+            if self._dgrad_fused is None:
+                # a wait may only name a counter signalled inside the same group
+                for i in range(0, len(self._dgrad_problems), G):
+                    grp = self._dgrad_problems[i:i + G]
+                    grp[0].wait = None
+                    self._backward_groups.append(grp)
+            probs = [wgrad_problem(l, None) for l in range(len(wgrad))]
+            for i in range(0, len(probs), G):
+                self._backward_groups.append(probs[i:i + G])
 
     def _forward_bf16(self, x):
         if x is not None:       # fp32 batch -> bf16 A operand (the gather can also write it directly)
             ops.cast_bf16(x, self.xb, None)
         if not self._loss_cleared:          # (the gather kernel clears loss + counters together)
             self._dep.zero_()
-        G = ops.GEMM_MAX_GROUP
-        for i in range(0, len(self._fwd_problems), G):
-            ops.gemm_group(self._fwd_problems[i:i + G])
+        if self._fwd_fused is not None:
+            ops.mlp_forward_fused(self.xb, self._fwd_rows, self._fwd_fused)
+        else:
+            G = ops.GEMM_MAX_GROUP
+            for i in range(0, len(self._fwd_problems), G):
+                ops.gemm_group(self._fwd_problems[i:i + G])
         if self.heads:
             d = self.head_dim
             return [self.out_last[:, :d], self.out_last[:, d:]]
@@ -334,10 +385,9 @@ class SiameseTrainStep(object):
         elif not self._grads_clean:
             self.bucket.trained_grad.zero_()       # dW / db are accumulated with reds
         self._grads_clean = False
-        G = ops.GEMM_MAX_GROUP
-        for i in range(0, len(self._dgrad_problems), G):
-            ops.gemm_group(self._dgrad_problems[i:i + G])
-        for grp in self._wgrad_groups:
+        if self._dgrad_fused is not None:
+            ops.mlp_dgrad_fused(self.dzb[-1], self._fwd_rows, self._dgrad_fused)
+        for grp in self._backward_groups:
             ops.gemm_group(grp)
 
     # -------------------------------------------------------------- common ---

@@ -303,7 +303,7 @@ def cast_bf16(src, dst=None, dstT=None):
 
 # ------------------------------------- persistent grouped tcgen05 GEMM ---
 GE_BIAS_ACT, GE_DACT, GE_ATOMIC = 0, 1, 2
-GEMM_MAX_GROUP = 4
+GEMM_MAX_GROUP = 8
 
 
 def gemm_problem(A, B, M, N, K, epilogue, out, a_mn=False, b_mn=False, act=None, bias=None,
@@ -337,6 +337,53 @@ def gemm_group(problems):
     n = len(problems)
     arr = (_lib.GemmProblem * n)(*problems)
     check(_lib.lib().abn_gemm_bf16_group(arr, n, stream_ptr()))
+
+
+MLP_MAX_LAYERS = 8
+MLP_MAX_WIDTH = 512
+
+
+def mlp_layers(specs):
+    """specs: [(W bf16 [n_out, ld], n_in, bias fp32 or None, act, out tensor, ones_col)] ->
+    ctypes array of abn_mlp_layer (keeps the tensors alive)."""
+    arr = (_lib.MlpLayer * len(specs))()
+    keep = []
+    for a, (W, n_in, bias, act, out, ones_col) in zip(arr, specs):
+        a.W, a.ldw, a.bias = ptr(W), W.stride(0), ptr(bias)
+        a.n_in, a.n_out, a.act = int(n_in), int(W.shape[0]), ACT[act]
+        a.out, a.ldo, a.out_f32 = ptr(out), out.stride(0), int(out.dtype == torch.float32)
+        a.ones_col = int(bool(ones_col))
+        keep += [W, bias, out]
+    arr._keep = keep
+    return arr
+
+
+def mlp_forward_fused(x, rows, layers):
+    """Every layer of the forward pass in ONE launch, activations resident in shared memory
+    (abn_mlp_forward_fused); x: bf16 [rows, ld]."""
+    check(_lib.lib().abn_mlp_forward_fused(ptr(x), x.stride(0), int(rows), layers, len(layers),
+                                           stream_ptr()))
+
+
+def mlp_dlayers(specs):
+    """specs, top layer first: [(W bf16 [n_out, ld], n_in, act_below, y_below, dz_below)] ->
+    ctypes array of abn_mlp_dlayer."""
+    arr = (_lib.MlpDLayer * len(specs))()
+    keep = []
+    for a, (W, n_in, act_below, y_below, dz_below) in zip(arr, specs):
+        a.W, a.ldw, a.n_in, a.n_out = ptr(W), W.stride(0), int(n_in), int(W.shape[0])
+        a.act_below = ACT[act_below]
+        a.y_below, a.ld_y = ptr(y_below), y_below.stride(0)
+        a.dz_below, a.ld_dz = ptr(dz_below), dz_below.stride(0)
+        keep += [W, y_below, dz_below]
+    arr._keep = keep
+    return arr
+
+
+def mlp_dgrad_fused(dz_top, rows, layers):
+    """dz of every layer below the top one in ONE launch (abn_mlp_dgrad_fused)."""
+    check(_lib.lib().abn_mlp_dgrad_fused(ptr(dz_top), dz_top.stride(0), int(rows), layers,
+                                         len(layers), stream_ptr()))
 
 
 # ------------------------------- fused companions of the tensor-core step ---

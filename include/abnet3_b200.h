@@ -255,7 +255,7 @@ ABN_API int abn_linear_backward(const float *x, const float *W, const float *y,
  *   added to ones_out[M] instead of `out`.
  * Leading dimensions in elements; bf16 pointers 16-byte aligned, bf16 lds multiples of 8.
  * ---------------------------------------------------------------------- */
-#define ABN_GEMM_MAX_GROUP 4
+#define ABN_GEMM_MAX_GROUP 8
 typedef struct {
     const void *A; int64_t lda; int a_mn;
     const void *B; int64_t ldb; int b_mn;
@@ -271,13 +271,56 @@ typedef struct {
      * 256-row block once its output rows are in global memory.  wait / wait_count: the A
      * rows of a block are loaded only once wait[block] >= wait_count -- point `wait` at an
      * earlier problem's `signal` and leave wait_count 0 (= all of that problem's tiles over
-     * the block) to chain layers inside one launch (list the problems in dependency order). */
+     * the block) to chain layers inside one launch (list the problems in dependency order).
+     * A reduction problem (epilogue 2: its K dimension runs over the rows, e.g. dW = dz^T x)
+     * waits for every block its K range crosses, block by block as the k loop reaches them:
+     * the weight gradients of a layer can share the launch of the dgrad chain that produces
+     * their dz and fill the gaps its dependencies leave. */
     int32_t *signal;
     const int32_t *wait;
     int wait_count;
 } abn_gemm_problem;
 ABN_API int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_problems,
                                 abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (3b) the embedder's forward pass in ONE launch with the activations resident on chip:
+ * every layer y = act(x W^T + b) of SiameseNetwork.forward_once (abnet3/model.py:179-186)
+ * for a 256-row block per CTA pair.  The block's activations stay in shared memory as the
+ * next layer's A operand (written there by the epilogue), only the weights stream through
+ * TMA; hidden outputs also leave as bf16 rows (the backward pass reads them), the last layer
+ * may write fp32.  Same arithmetic, same k order and the same bits as the layers chained
+ * through abn_gemm_bf16_group.  Limits: n_in <= 512, n_out (+ ones_col) <= 512 per layer
+ * (ABN_EINVAL otherwise: use the grouped GEMM).
+ *   x [rows, n_in of layer 0] bf16, ldx elements; W [n_out, n_in] bf16, ldw; out: bf16
+ *   [rows, ldo] (ldo % 8 == 0, >= n_out + ones_col) or, last layer only, fp32 [rows, ldo].
+ * ---------------------------------------------------------------------- */
+#define ABN_MLP_MAX_LAYERS 8
+typedef struct {
+    const void *W; int64_t ldw;
+    const float *bias;          /* NULL: none */
+    int n_in, n_out, act;       /* act: ABN_ACT_* */
+    void *out; int64_t ldo; int out_f32;
+    int ones_col;               /* write 1.0 into column n_out of the bf16 output */
+} abn_mlp_layer;
+ABN_API int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
+                                  const abn_mlp_layer *layers, int n_layers, abn_stream_t stream);
+/* The input-gradient chain of the backward pass the same way (the autograd of those blocks,
+ * abnet3/trainer.py:238): layers listed from the top down, layer l computes
+ *   dz_below = (dz . W) * act'(y_below)      W [n_out, n_in] as stored, dz [rows, n_out]
+ * with dz of the first listed layer read from dz_top and every dz_below both written to
+ * global memory (bf16 rows: the weight-gradient GEMMs read them) and kept on chip as the next
+ * layer's A operand; y_below [rows, ld_y] is fetched per warp by TMA.  Limits: n_in, n_out
+ * <= 512. */
+typedef struct {
+    const void *W; int64_t ldw;
+    int n_in, n_out;
+    int act_below;              /* activation whose output y_below is */
+    const void *y_below; int64_t ld_y;
+    void *dz_below; int64_t ld_dz;
+} abn_mlp_dlayer;
+ABN_API int abn_mlp_dgrad_fused(const void *dz_top, int64_t ld_top, int64_t rows,
+                                const abn_mlp_dlayer *layers, int n_layers, abn_stream_t stream);
 
 /* fp32 [rows, cols] (ld_src) -> bf16 [rows, ld_dst] and/or transposed bf16
  * [cols, ld_T]: operand preparation for abn_gemm_bf16_group (the weights after

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../abnet3_b200"
 mkdir -p _obj_dbg
 FL="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -DABN_TC_DEBUG"
-for f in abn_capi abn_align abn_nn abn_tc abn_tc2 abn_fused; do
+for f in abn_capi abn_align abn_nn abn_tc abn_tc2 abn_tc3 abn_fused; do
   nvcc $FL -c csrc/$f.cu -o _obj_dbg/$f.o &
 done
 wait

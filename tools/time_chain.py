@@ -30,7 +30,7 @@ Ws = [bf(dims[i + 1], dims[i]) for i in range(4)]
 bias = [torch.zeros(dims[i + 1], device=DEV) for i in range(4)]
 out_last = torch.zeros(rows, 100, device=DEV)
 tiles_m = (rows + 255) // 256
-dep = torch.zeros((8, tiles_m), dtype=torch.int32, device=DEV)
+dep = torch.zeros((12, tiles_m), dtype=torch.int32, device=DEV)
 
 def chain(nodep):
     fw = []
@@ -65,7 +65,23 @@ def run_dg():
 gW = [torch.zeros(dims[i + 1], dims[i], device=DEV) for i in range(4)]
 gb = [torch.zeros(dims[i + 1], device=DEV) for i in range(4)]
 wg = [ops.gemm_problem(dzs[l + 1], acts[l], dims[l + 1], dims[l], rows, ops.GE_ATOMIC, gW[l], a_mn=True, b_mn=True,
-                       split_k=int(os.environ.get("WSPLIT", "18")), ones_out=gb[l]) for l in range(4)]
+                       split_k=int(os.environ.get("WSPLIT", "9")), ones_out=gb[l]) for l in range(4)]
+def merged(split):
+    """dgrad(l), wgrad(l), dgrad(l-1), ... in ONE launch; wgrad waits on the dz its layer needs."""
+    out, k, ready = [], 0, {3: None}
+    for l in range(3, 0, -1):
+        out.append(ops.gemm_problem(dzs[l + 1], Ws[l], rows, dims[l], dims[l + 1], ops.GE_DACT, dzs[l], b_mn=True,
+                                    act="sigmoid", yprev=acts[l], signal=dep[4 + k], wait=ready[l]))
+        out.append(ops.gemm_problem(dzs[l + 1], acts[l], dims[l + 1], dims[l], rows, ops.GE_ATOMIC, gW[l], a_mn=True,
+                                    b_mn=True, split_k=split, ones_out=gb[l], wait=ready[l]))
+        ready[l - 1] = dep[4 + k]
+        k += 1
+    out.append(ops.gemm_problem(dzs[1], acts[0], dims[1], dims[0], rows, ops.GE_ATOMIC, gW[0], a_mn=True,
+                                b_mn=True, split_k=split, ones_out=gb[0], wait=ready[0]))
+    return out
+mg = merged(int(os.environ.get("WSPLIT", "9")))
+def run_mg():
+    dep.zero_(); ops.gemm_group(mg)
 # each argument: comma-separated VAR=value settings applied for that measurement ("-" = none)
 for cfg in (sys.argv[1:] or ["-"]):
     sets = [kv.split("=") for kv in cfg.split(",") if "=" in kv]
@@ -78,6 +94,7 @@ for cfg in (sys.argv[1:] or ["-"]):
     t_dg = timeit(run_dg) if dbg == 0 else float("nan")
     t_dgn = timeit(lambda: ops.gemm_group(dg_nodep)) if dbg == 0 else float("nan")
     t_wg = timeit(lambda: ops.gemm_group(wg)) if dbg == 0 else float("nan")
-    print("%-40s fwd chain %5.1f nodep %5.1f | 4x500 %5.1f 1x500 %5.1f | dgrad chain %5.1f nodep %5.1f | wgrad %5.1f us" %
-          (cfg, t_dep, t_nodep, t_same, t_one, t_dg, t_dgn, t_wg), flush=True)
+    t_mg = timeit(run_mg) if dbg == 0 else float("nan")
+    print("%-40s fwd chain %5.1f nodep %5.1f | 4x500 %5.1f 1x500 %5.1f | dgrad chain %5.1f nodep %5.1f | wgrad %5.1f | bwd merged %5.1f us" %
+          (cfg, t_dep, t_nodep, t_same, t_one, t_dg, t_dgn, t_wg, t_mg), flush=True)
     for k_, v_ in sets: os.environ.pop(k_)
