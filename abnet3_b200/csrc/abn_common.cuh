@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <stdarg.h>
 #include <math.h>
@@ -37,6 +38,30 @@ __device__ __forceinline__ void cp_async_commit() {
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// Programmatic dependent launch for the small kernels of the training step: the kernel may be
+// scheduled while its predecessor drains; pdl_wait() (first statement of the kernel) blocks
+// until the predecessor's memory is visible, and lets the successor start its own prologue.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static int on = -1;                 // ABN_NO_PDL=1: plain stream order
+    if (on < 0) { const char *e = getenv("ABN_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    cfg.numAttrs = on ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -26,6 +26,7 @@ __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
                                    __nv_bfloat16 *__restrict__ xb, int64_t ldx,
                                    float *__restrict__ y_out, unsigned *__restrict__ zero_me,
                                    int zero_words) {
+    pdl_wait();
     if (zero_me && blockIdx.x == 0)
         for (int i = threadIdx.x; i < zero_words; i += blockDim.x) zero_me[i] = 0u;
     const int warps_per_block = blockDim.x >> 5;
@@ -64,6 +65,7 @@ pair_loss_dz_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
                     __nv_bfloat16 *__restrict__ dz1, __nv_bfloat16 *__restrict__ dz2,
                     int64_t ld_dz) {
     __shared__ float wsum[LZ_WARPS];
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float local = 0.f;
     for (int64_t row = (int64_t)blockIdx.x * LZ_WARPS + warp; row < n;
@@ -119,6 +121,7 @@ __global__ void optimizer_fused_kernel(float *__restrict__ p, float *__restrict_
                                        float *__restrict__ s0, float *__restrict__ s1, int kind,
                                        float lr, float momentum, float gscale, float bc1,
                                        float bc2_sqrt, int zero_grad, const SegTable tab) {
+    pdl_wait();
     const abn_param_segment sg = tab.s[blockIdx.y];
     __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < sg.count;
@@ -169,7 +172,7 @@ extern "C" int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *
         return set_error(ABN_EINVAL, "abn_gather_batch_bf16: bad argument");
     const int wpb = 8;
     const int64_t warps = 2 * n;
-    gather_bf16_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+    launch_pdl(gather_bf16_kernel, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), (cudaStream_t)stream,
         feat, dim, idx1, idx2, y_in, sel, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out,
         static_cast<unsigned *>(zero_me), zero_me ? zero_words : 0);
     return check_launch("abn_gather_batch_bf16");
@@ -187,7 +190,7 @@ extern "C" int abn_pair_loss_dz(const float *e1, const float *e2, const float *y
         return set_error(ABN_EINVAL, "abn_pair_loss_dz: bad argument");
     int64_t blocks = (n + LZ_WARPS - 1) / LZ_WARPS;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    pair_loss_dz_kernel<<<(unsigned)blocks, LZ_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_pdl(pair_loss_dz_kernel, dim3((unsigned)blocks), dim3(LZ_WARPS * 32), (cudaStream_t)stream,
         e1, e2, y, n, dim, ld, kind, margin, scale, act, loss, static_cast<__nv_bfloat16 *>(dz1),
         static_cast<__nv_bfloat16 *>(dz2), ld_dz);
     return check_launch("abn_pair_loss_dz");
@@ -219,7 +222,7 @@ extern "C" int abn_optimizer_step_fused(float *param, float *grad, float *state0
     if (bx > 148 * 4) bx = 148 * 4;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)n_segments);
-    optimizer_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(optimizer_fused_kernel, grid, dim3(256), (cudaStream_t)stream,
         param, grad, state0, state1, kind, lr, momentum, grad_scale, bc1, bc2s, zero_grad, tab);
     return check_launch("abn_optimizer_step_fused");
 }

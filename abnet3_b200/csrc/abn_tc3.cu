@@ -30,7 +30,7 @@ namespace abn {
 
 constexpr int F_MAXL = ABN_MLP_MAX_LAYERS;
 constexpr int F_KB = 8;                         // slab k-blocks (8 x 64 = 512 features)
-constexpr int F_STAGES = 4;                     // B ring
+constexpr int F_STAGES_FWD = 5, F_STAGES_DGRAD = 4;     // B ring (dgrad: the y_below boxes take the rest)
 constexpr unsigned F_SLAB_KB_BYTES = 128 * 64 * 2;      // 16 KB: this CTA's 128 rows of one k-block
 constexpr unsigned F_B_BYTES = 128 * 64 * 2;            // this CTA's half of a 256-column B tile
 
@@ -47,7 +47,17 @@ struct FChain {
     CUtensorMap map_x;              // x [rows, n_in0] bf16, box {64, 128}
     FLayer L[F_MAXL];
     int n_layers, rows, tiles_m;
+    long long *trace;               // debug: role timestamps per CTA and layer (NULL in production)
 };
+
+// debug timeline (tools/trace_fused.py): [cta][layer][slot]
+__device__ __forceinline__ void f_trace(const FChain &ch, int layer, int slot) {
+    if (ch.trace) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        ch.trace[((size_t)blockIdx.x * 8 + layer) * 16 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ void f_mbar_wait_cluster(unsigned bar, unsigned parity) {
     unsigned done = 0;
@@ -78,10 +88,11 @@ template <int ACT>
 __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, unsigned dst, int lane,
                                             int ones_at) {
     const unsigned swz = (unsigned)(lane & 7);
+    float v64[64];
+    g_ld64(taddr, v64);
 #pragma unroll
     for (int hseg = 0; hseg < 2; ++hseg) {
-        float v[32];
-        g_ld32(taddr + 32 * hseg, v);
+        float (&v)[32] = *reinterpret_cast<float (*)[32]>(&v64[32 * hseg]);
         unsigned pk[16];
         if (ACT == 1 || ACT == 2) {
             g_bias_act32_packed<ACT>(v, bs + 32 * hseg, pk);
@@ -111,10 +122,11 @@ __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, uns
 template <int ACT>
 __device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[8], unsigned dst, int lane) {
     const unsigned swz = (unsigned)(lane & 7);
+    float v64[64];
+    g_ld64(taddr, v64);
 #pragma unroll
     for (int hseg = 0; hseg < 2; ++hseg) {
-        float v[32];
-        g_ld32(taddr + 32 * hseg, v);
+        float (&v)[32] = *reinterpret_cast<float (*)[32]>(&v64[32 * hseg]);
         const uint4 yh[4] = {yc[4 * hseg], yc[4 * hseg + 1], yc[4 * hseg + 2], yc[4 * hseg + 3]};
         g_dact32<ACT>(v, yh);
 #pragma unroll
@@ -129,9 +141,12 @@ __device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[
 
 // MODE 0: forward (B = W K-major, bias + activation, last layer fp32)
 // MODE 1: dgrad   (B = W MN-major, x act'(y_below) with y_below fetched per warp by TMA)
+constexpr int F_EW_FWD = 16, F_EW_DGRAD = 8;        // epilogue warps: NQ = EW / 4 share a TMEM lane quarter
 template <int MODE>
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * (MODE == 0 ? F_EW_FWD : F_EW_DGRAD), 1)
 mlp_chain_kernel(const __grid_constant__ FChain ch) {
+    constexpr int EW = MODE == 0 ? F_EW_FWD : F_EW_DGRAD, NQ = EW / 4;
+    constexpr int F_STAGES = MODE == 0 ? F_STAGES_FWD : F_STAGES_DGRAD;
     extern __shared__ unsigned char smem_raw[];
     const unsigned raw = g_smem_u32(smem_raw);
     const unsigned base = (raw + 1023u) & ~1023u;
@@ -145,8 +160,8 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
     const unsigned afull0 = sfull0 + 8 * F_KB, aempty0 = afull0 + 16;   // [2] accumulators
     const unsigned slab_free = aempty0 + 16, drained = slab_free + 8;
     const unsigned tptr = drained + 8;
-    const unsigned ybar0 = tptr + 8;                                    // [G_EPI_WARPS] dgrad: y_below boxes
-    constexpr unsigned BAR_BYTES = 16 * F_STAGES + 16 * F_KB + 32 + 16 + 16 + 8 * G_EPI_WARPS;
+    const unsigned ybar0 = tptr + 8;                                    // [F_EW_DGRAD] dgrad: y_below boxes
+    constexpr unsigned BAR_BYTES = 16 * F_STAGES + 16 * F_KB + 32 + 16 + 16 + 8 * F_EW_DGRAD;
     volatile unsigned *tptr_gen = reinterpret_cast<volatile unsigned *>(
         gen + F_KB * F_SLAB_KB_BYTES + F_STAGES * F_B_BYTES + (tptr - bars));
     float *bias_s = reinterpret_cast<float *>(
@@ -165,11 +180,11 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
         }
         for (int a = 0; a < 2; ++a) {
             g_mbar_init(afull0 + 8 * a, 1);
-            g_mbar_init(aempty0 + 8 * a, 2 * G_EPI_WARPS);
+            g_mbar_init(aempty0 + 8 * a, 2 * EW);
         }
         g_mbar_init(slab_free, 1);
-        g_mbar_init(drained, G_EPI_WARPS);
-        for (int w = 0; w < G_EPI_WARPS; ++w) g_mbar_init(ybar0 + 8 * w, 1);
+        g_mbar_init(drained, EW);
+        for (int w = 0; w < F_EW_DGRAD; ++w) g_mbar_init(ybar0 + 8 * w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -231,8 +246,10 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                 for (int l = 0; l < ch.n_layers; ++l) {
                     const FLayer &L = ch.L[l];
                     for (int nt = 0; nt < L.tiles_n; ++nt) {
+                        f_trace(ch, l, 0 + 4 * nt);
                         g_mbar_wait(aempty0 + 8 * nt, ((aphase >> nt) & 1) ^ 1);     // epilogues drained it
                         aphase ^= 1u << nt;
+                        f_trace(ch, l, 1 + 4 * nt);
                         g_fence_after();
                         const unsigned idesc = g_idesc(2 * G_BM, f_n_eff(L, nt), 0, MODE);
                         const unsigned d_tmem = tmem + nt * 256;
@@ -258,6 +275,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                             g_commit_pair(bempty0 + 8 * s);
                         }
                         g_commit_pair(afull0 + 8 * nt);
+                        f_trace(ch, l, 2 + 4 * nt);
                     }
                 }
                 g_commit_pair(slab_free);
@@ -267,7 +285,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
         // ---------------------------------------------------------------------- epilogue
         const int ew = warp - 2;
         const int wq = warp & 3;                        // TMEM lane quarter of this warp
-        const int half = ew >> 2;                       // takes the 64-column blocks cb = half, half + 2, ..
+        const int half = ew >> 2;                       // takes the 64-column blocks cb = half, half + NQ, ..
         const int et = ew * 32 + lane;
         unsigned afphase = 0, lcount = 0, ycount = 0;
         for (int rb = pair; rb < ch.tiles_m; rb += npairs) {
@@ -279,7 +297,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                 const int nblk = (L.n_cap + 63) >> 6;
                 const unsigned ybuf = ybuf0 + ew * 4096u, ybar = ybar0 + 8 * ew;
                 if (MODE == 0) {
-                    for (int c = et; c < 512; c += 32 * G_EPI_WARPS)
+                    for (int c = et; c < 512; c += 32 * EW)
                         bs[c] = (L.bias && c < L.n_out) ? __ldg(L.bias + c) : 0.f;
                 }
                 // this warp's earlier output boxes have left the slab rows it is about to rewrite
@@ -290,17 +308,19 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                         g_tma_2d(ybuf, &L.map_y, ybar, half * 64, row0);
                     }
                 }
-                if (MODE == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");
+                if (MODE == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
                 else __syncwarp();
                 // the layer's MMAs read the whole slab: nothing may be written before the last
                 // accumulator is complete (tcgen05.commit covers every MMA issued before it)
+                if (et == 0) f_trace(ch, l, 8);
                 for (int a = 0; a < L.tiles_n; ++a) {
                     g_mbar_wait(afull0 + 8 * a, (afphase >> a) & 1);
                     afphase ^= 1u << a;
                 }
                 g_fence_after();
+                if (et == 0) f_trace(ch, l, 9);
                 for (int a = 0; a < L.tiles_n; ++a) {
-                    for (int cb = 4 * a + half; cb < 4 * a + 4 && cb < nblk; cb += 2) {
+                    for (int cb = 4 * a + half; cb < 4 * a + 4 && cb < nblk; cb += NQ) {
                         const unsigned taddr = tmem + ((unsigned)(wq * 32) << 16) + cb * 64;
                         if (MODE == 1 || !L.out_f32) {
                             const unsigned dst = slab + cb * F_SLAB_KB_BYTES + wq * 4096u;
@@ -323,9 +343,9 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                                  : "r"(ybuf + lane * 128 + (((unsigned)q ^ (unsigned)(lane & 7)) << 4))
                                                  : "memory");
                                 __syncwarp();               // every lane holds its y_below row: fetch the next box
-                                if (lane == 0 && cb + 2 < nblk) {
+                                if (lane == 0 && cb + NQ < nblk) {
                                     g_mbar_expect_tx(ybar, 4096u);
-                                    g_tma_2d(ybuf, &L.map_y, ybar, (cb + 2) * 64, row0);
+                                    g_tma_2d(ybuf, &L.map_y, ybar, (cb + NQ) * 64, row0);
                                 }
                                 switch (L.act) {
                                     case 1: f_epi_block_d<1>(taddr, yc, dst, lane); break;
@@ -336,7 +356,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                             }
                             // generic-proxy writes -> visible to the async proxy (the next layer's
                             // MMAs and the TMA store), then: k-block cb is ready in this quarter
-                            asm volatile("fence.proxy.async;" ::: "memory");
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) {
                                 if (l + 1 < ch.n_layers && cb < ch.L[l + 1].nkb)
@@ -378,6 +398,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                     g_fence_before();
                     __syncwarp();
                     if (lane == 0) g_mbar_arrive_cta0(aempty0 + 8 * a);
+                    if (et == 0) f_trace(ch, l, 10 + a);
                 }
             }
             // the block's output boxes have been read out of the slab (the next block's x may land)
@@ -401,6 +422,8 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
 
 using namespace abn;
 
+extern "C" void *abn_gemm_trace_buffer;      // debug hook (abn_tc2.cu)
+
 namespace {
 
 int f_sm_count() {
@@ -416,8 +439,9 @@ int f_sm_count() {
 template <int MODE>
 int f_launch(const FChain &ch, cudaStream_t st, const char *what) {
     // slab + weight ring + barriers + (forward: staged biases | dgrad: y_below boxes) + alignment slack
+    constexpr int F_STAGES = MODE == 0 ? F_STAGES_FWD : F_STAGES_DGRAD;
     constexpr unsigned smem = F_KB * F_SLAB_KB_BYTES + F_STAGES * F_B_BYTES + 1024 +
-                              (MODE == 0 ? 512 + 2 * 512 * 4 : 1024 + G_EPI_WARPS * 4096);
+                              (MODE == 0 ? 512 + 2 * 512 * 4 : 1024 + F_EW_DGRAD * 4096);
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(mlp_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -430,7 +454,7 @@ int f_launch(const FChain &ch, cudaStream_t st, const char *what) {
     grid -= grid % 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(G_THREADS);
+    cfg.blockDim = dim3(64 + 32 * (MODE == 0 ? F_EW_FWD : F_EW_DGRAD));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -492,6 +516,7 @@ extern "C" int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
             if (rc) return rc;
         }
     }
+    ch.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
     return f_launch<0>(ch, (cudaStream_t)stream, "abn_mlp_forward_fused");
 }
 
@@ -532,5 +557,6 @@ extern "C" int abn_mlp_dgrad_fused(const void *dz_top, int64_t ld_top, int64_t r
         rc = g_make_map(&L.map_y, q.y_below, rows, q.ld_y, q.ld_y, 64, 32);
         if (rc) return rc;
     }
+    ch.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
     return f_launch<1>(ch, (cudaStream_t)stream, "abn_mlp_dgrad_fused");
 }
