@@ -145,3 +145,35 @@ def test_step_agreement_and_gradient_allreduce_over_gloo():
         p.join(timeout=60)
     assert [r[1] for r in res] == [3, 3]                   # shortest shard decides
     assert [r[2] for r in res] == [9.0, 9.0]               # (1 + 2) summed over 3 steps
+
+
+def test_embedder_surface_and_feature_archives(tmp_path):
+    """abnet3/embedder.py:37-51 constructor contract, the .npz feature container round trip and the
+    loud failure without a GPU (no CPU path)."""
+    import numpy as np
+    import pytest
+    import torch
+    from abnet3_b200.embedder import (EmbedderBuilder, EmbedderSiamese, _load_features, _write_features)
+    from abnet3_b200.model import SiameseNetwork
+    with pytest.raises(ValueError):
+        EmbedderSiamese(network=None)
+    net = SiameseNetwork(input_dim=8, num_hidden_layers=1, hidden_dim=16, output_dim=4, p_dropout=0.0,
+                         activation_layer="sigmoid")
+    e = EmbedderSiamese(network=net, feature_path={"a": np.zeros((3, 8), np.float32)}, cuda=False)
+    assert e.batch_size == 5000 and e.output_path is None
+    with pytest.raises(NotImplementedError):
+        EmbedderBuilder(network=net).embed()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            e.embed()
+    items = ["s01_a", "s02_b"]
+    embs = [np.arange(12, dtype=np.float32).reshape(3, 4), np.ones((2, 4), np.float32)]
+    times = [0.0025 + 0.01 * np.arange(3), 0.0025 + 0.01 * np.arange(2)]
+    path = str(tmp_path / "out.npz")
+    _write_features(path, items, times, embs)
+    got_items, got_times, got_feats = _load_features(path)
+    assert got_items == items
+    for a, b in zip(got_feats, embs):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(got_times, times):
+        np.testing.assert_allclose(a, b)
