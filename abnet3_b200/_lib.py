@@ -58,7 +58,7 @@ class DpPeers(_c.Structure):
 class DpPush(_c.Structure):
     """abn_dp_push (include/abnet3_b200.h)."""
     _fields_ = [("param", _P * 8), ("recv", _P * 8), ("flags", _P * 8), ("rank", _I), ("world", _I),
-                ("n", _L), ("slice_cap", _L)]
+                ("n", _L), ("slice_cap", _L), ("one_shot", _I)]
 
 
 # name -> (restype, argtypes); mirrors include/abnet3_b200.h declaration order

@@ -524,26 +524,41 @@ struct DpPush {
     unsigned long long *flags[DP_MAX_WORLD];
     int rank, world;
     long long n, cap;
+    int one_shot;
 };
 
 __device__ __forceinline__ void dp_st4(float *p, float4 v) {
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
-// all blocks have passed: the last one to arrive raises `slot` = step on every rank
+// all blocks have passed: the last one to arrive raises `slot` = step on every rank -- one thread
+// per peer, so the W release stores (an NVLink round trip each) go out side by side
 __device__ __forceinline__ void dp_grid_raise(const DpPush &pp, int ticket, int slot,
                                               unsigned long long step) {
+    __shared__ int last_s;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long *mine = pp.flags[pp.rank];
         const unsigned long long t = atomicAdd(mine + ticket, 1ull);
-        if (t == (unsigned long long)gridDim.x - 1) {
-            mine[ticket] = 0;
-            __threadfence_system();
-            for (int q = 0; q < pp.world; ++q) dp_st_release(pp.flags[q] + slot + pp.rank, step);
-        }
+        last_s = t == (unsigned long long)gridDim.x - 1;
+        if (last_s) mine[ticket] = 0;
     }
+    __syncthreads();
+    if (last_s && threadIdx.x < pp.world) {
+        __threadfence_system();
+        dp_st_release(pp.flags[threadIdx.x] + slot + pp.rank, step);
+    }
+}
+// every rank has raised `slots[p] >= want`: one polling thread per peer
+__device__ __forceinline__ void dp_wait_all_par(const unsigned long long *slots, int world,
+                                                unsigned long long want) {
+    if (threadIdx.x < world) {
+        unsigned long long spins = 0;
+        while (dp_ld_acquire(slots + threadIdx.x) < want)
+            if (++spins > (1ull << 31)) __trap();
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(512)
@@ -559,19 +574,18 @@ dp_push_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restri
     const long long gstride = (long long)gridDim.x * blockDim.x;
     const int W = pp.world, R = pp.rank;
 
-    // phase 0: my slice j -> owner j's receive row R
-    for (int j = 0; j < W; ++j) {
+    // phase 0: slice j of my bucket -> owner j's receive row R (one pass over the bucket: every
+    // thread has stores in flight to several owners)
+    for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride) {
+        const int j = (int)(i / pp.cap);
         if (j == R) continue;
-        const long long lo = j * pp.cap, hi = min(pp.n, lo + pp.cap);
-        float *dst = pp.recv[j] + (long long)R * pp.cap;
-        for (long long i = lo + 4 * gtid; i < hi; i += 4 * gstride)
-            dp_st4(dst + (i - lo), *reinterpret_cast<const float4 *>(grad + i));
+        dp_st4(pp.recv[j] + (long long)R * pp.cap + (i - (long long)j * pp.cap),
+               *reinterpret_cast<const float4 *>(grad + i));
     }
     dp_grid_raise(pp, DPF_TICKET_A, DPF_PUSHED, step);
 
     // phase 1: reduce + update my slice, push the new parameters to everybody
-    if (threadIdx.x == 0) dp_wait_all(mine + DPF_PUSHED, W, step);
-    __syncthreads();
+    dp_wait_all_par(mine + DPF_PUSHED, W, step);
     {
         const long long lo = R * pp.cap, hi = min(pp.n, lo + pp.cap);
         const float *rv = pp.recv[R];
@@ -596,8 +610,7 @@ dp_push_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restri
     dp_grid_raise(pp, DPF_TICKET_B, DPF_UPDATED, step);
 
     // phase 2: all slices are in: bf16 operand copies, gradient bucket cleared
-    if (threadIdx.x == 0) dp_wait_all(mine + DPF_UPDATED, W, step);
-    __syncthreads();
+    dp_wait_all_par(mine + DPF_UPDATED, W, step);
     const float *pl = pp.param[R];
     for (int sidx = 0; sidx < tab.n; ++sidx) {
         const abn_param_segment sg = tab.s[sidx];
@@ -610,6 +623,93 @@ dp_push_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restri
     }
     for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride)
         *reinterpret_cast<float4 *>(grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the step counter advances once every block has read it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(mine + DPF_TICKET_C, 1ull);
+        if (t == (unsigned long long)gridDim.x - 1) {
+            mine[DPF_TICKET_C] = 0;
+            __threadfence();
+            mine[DPF_STEP] = step;
+        }
+    }
+}
+
+// One-shot variant: every rank pushes its WHOLE gradient bucket into every peer's receive row
+// (posted NVLink writes, (W - 1) x the bucket per rank), ONE all-to-all flag exchange, then each
+// rank sums the W copies in rank order and applies the optimizer to the whole bucket locally --
+// bf16 weight copies and the gradient reset in the same pass, no second hop.  The exchange is
+// latency bound (two-shot: two fence + flag + wait round trips, measured +24 us at 2 GPUs and
+// +62 us at 8), so one hop wins although it moves W/2 x the bytes.  Receive rows are double
+// buffered by step parity: a rank can only be one flag exchange ahead of its slowest peer.
+__global__ void __launch_bounds__(512)
+dp_push1_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restrict__ s1, int kind,
+                float lr, float momentum, float gscale, float bc1, float bc2_sqrt,
+                const SegTable tab, const DpPush pp) {
+    unsigned long long *mine = pp.flags[pp.rank];
+    __shared__ unsigned long long step_s;
+    if (threadIdx.x == 0) step_s = dp_ld_acquire(mine + DPF_STEP) + 1;
+    __syncthreads();
+    const unsigned long long step = step_s;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    const int W = pp.world, R = pp.rank;
+    const long long half = (long long)(step & 1ull) * W * pp.cap;       // this step's receive rows
+
+    for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride) {
+        const float4 v = *reinterpret_cast<const float4 *>(grad + i);
+        for (int q = 0; q < W; ++q)
+            if (q != R) dp_st4(pp.recv[q] + half + (long long)R * pp.cap + i, v);
+    }
+    dp_grid_raise(pp, DPF_TICKET_A, DPF_PUSHED, step);
+    dp_wait_all_par(mine + DPF_PUSHED, W, step);
+
+    const float *rv = pp.recv[R] + half;
+    float *pl = pp.param[R];
+    for (int sidx = 0; sidx < tab.n; ++sidx) {
+        const abn_param_segment sg = tab.s[sidx];
+        __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
+        const bool vec = ((sg.offset | sg.count) & 3) == 0 && (!wb || ((sg.n_in | sg.ld) & 3) == 0);
+        if (vec) {
+            for (long long j = 4 * gtid; j < sg.count; j += 4 * gstride) {
+                const long long i = sg.offset + j;
+                float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p = 0; p < W; ++p) {         // rank order: the same bits on every rank
+                    const float4 v = p == R ? *reinterpret_cast<const float4 *>(grad + i)
+                                            : dp_ld4(rv + (long long)p * pp.cap + i);
+                    gs.x += v.x; gs.y += v.y; gs.z += v.z; gs.w += v.w;
+                }
+                const float4 w4 = *reinterpret_cast<const float4 *>(pl + i);
+                float w[4] = {w4.x, w4.y, w4.z, w4.w};
+                const float g[4] = {gs.x * gscale, gs.y * gscale, gs.z * gscale, gs.w * gscale};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    w[e] = dp_update(w[e], g[e], s0, s1, i + e, kind, lr, momentum, bc1, bc2_sqrt);
+                *reinterpret_cast<float4 *>(pl + i) = make_float4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<float4 *>(grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (wb) {
+                    const long long r = j / sg.n_in;
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]), hi = __floats2bfloat162_rn(w[2], w[3]);
+                    *reinterpret_cast<uint2 *>(wb + r * sg.ld + (j - r * sg.n_in)) =
+                        make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+                }
+            }
+        } else {
+            for (long long j = gtid; j < sg.count; j += gstride) {
+                const long long i = sg.offset + j;
+                float gsum = 0.f;
+                for (int p = 0; p < W; ++p)
+                    gsum += p == R ? grad[i] : __ldcv(rv + (long long)p * pp.cap + i);
+                const float w = dp_update(pl[i], gsum * gscale, s0, s1, i, kind, lr, momentum, bc1, bc2_sqrt);
+                pl[i] = w;
+                grad[i] = 0.f;
+                if (wb) {
+                    const long long r = j / sg.n_in;
+                    wb[r * sg.ld + (j - r * sg.n_in)] = __float2bfloat16_rn(w);
+                }
+            }
+        }
+    }
     // the step counter advances once every block has read it
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -635,11 +735,12 @@ extern "C" int abn_dp_push_step(float *grad, float *state0, float *state1, int k
         return set_error(ABN_EINVAL, "abn_dp_push_step: bad argument");
     if (peers->world < 2 || peers->world > DP_MAX_WORLD || peers->rank < 0 ||
         peers->rank >= peers->world || peers->n <= 0 || (peers->n & 3) || (peers->slice_cap & 3) ||
-        peers->slice_cap * peers->world < peers->n)
+        peers->slice_cap * peers->world < peers->n || (peers->one_shot && peers->slice_cap < peers->n))
         return set_error(ABN_EINVAL, "abn_dp_push_step: world 2..%d, n and slice_cap multiples of 4, "
                          "world * slice_cap >= n", DP_MAX_WORLD);
     DpPush pp;
     pp.rank = peers->rank; pp.world = peers->world; pp.n = peers->n; pp.cap = peers->slice_cap;
+    pp.one_shot = peers->one_shot;
     for (int r = 0; r < peers->world; ++r) {
         if (!peers->param[r] || !peers->recv[r] || !peers->flags[r])
             return set_error(ABN_EINVAL, "abn_dp_push_step: rank %d is not mapped", r);
@@ -658,7 +759,11 @@ extern "C" int abn_dp_push_step(float *grad, float *state0, float *state1, int k
     }
     const float bc1 = 1.f - powf(0.9f, (float)step);
     const float bc2s = sqrtf(1.f - powf(0.999f, (float)step));
-    dp_push_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
-                                                          grad_scale, bc1, bc2s, tab, pp);
+    if (pp.one_shot)
+        dp_push1_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
+                                                               grad_scale, bc1, bc2s, tab, pp);
+    else
+        dp_push_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
+                                                              grad_scale, bc1, bc2s, tab, pp);
     return check_launch("abn_dp_push_step");
 }

@@ -139,14 +139,19 @@ class SiameseTrainStep(object):
         self._dp_push = None
         if self.precision == 1:
             self._build_chain()
-            # One-shot peer reads move (world - 1) x the bucket per rank: measured 203 us/step
-            # against 207 us with the captured NCCL all-reduce at 2 GPUs (177 us without any
-            # exchange); beyond 2 ranks NCCL's NVLS / tree all-reduce moves fewer bytes, so the
-            # peer-memory path is the default at world == 2 only (ABN_DP_P2P=1 forces, 0 disables).
+            # The gradient exchange is fused into the optimizer kernel over NVLink peer memory
+            # (CUDA IPC, device-side step flags, graph-replayable).  It is latency bound at this
+            # bucket size (2.8 MB), measured us/step over no exchange at all (tools/dp_check.py):
+            #   2 GPUs: one-shot push +19 | two-shot push +23 | one-shot reads +27 | NCCL +30
+            #   8 GPUs: one-shot push +53 | two-shot push +36 |                    | NCCL +62
+            # auto: one-shot push at world == 2, two-shot push beyond.  ABN_DP_P2P = push | push2 |
+            # 1 (reads) | 0 (NCCL all-reduce captured in the graph).
             p2p = os.environ.get("ABN_DP_P2P", "auto")
-            if self.world > 1 and p2p in ("push", "auto") and self.bucket.n_trained % 4 == 0:
-                try:        # two-shot, write-only exchange fused with the optimizer (any world size)
-                    self._dp_push = ops.dp_push_setup(self.bucket.param, self.bucket.n_trained, self.group)
+            if self.world > 1 and p2p in ("push", "push2", "auto") and self.bucket.n_trained % 4 == 0:
+                try:        # write-only exchange fused with the optimizer: one-shot ("push2": two-shot)
+                    one_shot = p2p == "push" or (p2p == "auto" and self.world <= 2)
+                    self._dp_push = ops.dp_push_setup(self.bucket.param, self.bucket.n_trained, self.group,
+                                                      one_shot=one_shot)
                 except Exception as exc:
                     import warnings
                     warnings.warn("peer-memory data parallelism unavailable (%s); using NCCL" % exc)

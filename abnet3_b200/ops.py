@@ -494,9 +494,11 @@ def dp_grad_reset(grad, peers):
     check(_lib.lib().abn_dp_grad_reset(ptr(grad), grad.numel(), ctypes.byref(peers), stream_ptr()))
 
 
-def dp_push_setup(param, n_trained, group=None):
-    """Two-shot, write-only exchange: share the parameter bucket, a receive buffer and a
-    flag block with every rank of ``group`` (CUDA IPC).  Collective."""
+def dp_push_setup(param, n_trained, group=None, one_shot=True):
+    """Write-only exchange over NVLink peer memory: share the parameter bucket, a receive buffer
+    and a flag block with every rank of ``group`` (CUDA IPC).  Collective.  one_shot: every rank
+    pushes its whole gradient bucket to every peer (one flag exchange); otherwise the two-shot
+    reduce-scatter / all-gather form."""
     import ctypes
     import torch.distributed as dist
     lib = _lib.lib()
@@ -505,8 +507,12 @@ def dp_push_setup(param, n_trained, group=None):
         raise RuntimeError("peer-memory data parallelism serves one box (world <= 8)")
     if n_trained % 4:
         raise RuntimeError("the trained parameter count must be a multiple of 4")
-    cap = ((n_trained + world - 1) // world + 3) // 4 * 4
-    recv = torch.zeros(world * cap, dtype=torch.float32, device=param.device)
+    if one_shot:
+        cap = (n_trained + 3) // 4 * 4
+        recv = torch.zeros(2 * world * cap, dtype=torch.float32, device=param.device)
+    else:
+        cap = ((n_trained + world - 1) // world + 3) // 4 * 4
+        recv = torch.zeros(world * cap, dtype=torch.float32, device=param.device)
     flags = torch.zeros(32, dtype=torch.int64, device=param.device)
     torch.cuda.synchronize()
 
@@ -516,15 +522,16 @@ def dp_push_setup(param, n_trained, group=None):
         check(lib.abn_ipc_export(ptr(t), h, ctypes.byref(off)))
         return bytes(h), int(off.value)
 
-    mine = {"param": export(param), "recv": export(recv), "flags": export(flags), "n": n_trained}
+    mine = {"param": export(param), "recv": export(recv), "flags": export(flags), "n": n_trained,
+            "one_shot": bool(one_shot)}
     everyone = [None] * world
     dist.all_gather_object(everyone, mine, group=group)
     pp = _lib.DpPush()
-    pp.rank, pp.world, pp.n, pp.slice_cap = rank, world, n_trained, cap
+    pp.rank, pp.world, pp.n, pp.slice_cap, pp.one_shot = rank, world, n_trained, cap, int(bool(one_shot))
     local = {"param": param, "recv": recv, "flags": flags}
     for r, info in enumerate(everyone):
-        if info["n"] != n_trained:
-            raise RuntimeError("rank %d trains a different number of parameters" % r)
+        if info["n"] != n_trained or info["one_shot"] != bool(one_shot):
+            raise RuntimeError("rank %d set the exchange up differently" % r)
         for key, arr in (("param", pp.param), ("recv", pp.recv), ("flags", pp.flags)):
             if r == rank:
                 arr[r] = ptr(local[key])

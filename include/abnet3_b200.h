@@ -421,6 +421,11 @@ typedef struct {
     void *flags[ABN_DP_MAX_WORLD];
     int rank, world;
     int64_t n, slice_cap;
+    /* one_shot != 0: every rank pushes its WHOLE bucket to every peer (receive buffer = 2 x world x
+     * slice_cap floats, slice_cap >= n, double buffered by step parity), one flag exchange, then a
+     * purely local rank-order sum + update: half the synchronisation latency of the two-shot form
+     * for world/2 x its bytes -- the exchange is latency bound at these bucket sizes. */
+    int one_shot;
 } abn_dp_push;
 ABN_API int abn_dp_push_step(float *grad, float *state0, float *state1, int kind, float lr,
                              float momentum, float grad_scale, int64_t step,

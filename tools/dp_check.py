@@ -58,7 +58,7 @@ def run(p2p, steps=12, graph=True, opt="adadelta", no_comm=False):
 l0, w0, dt0 = run(False, no_comm=True)
 if rank == 0:
     print("no communication at all: us/step %.1f" % (dt0 * 1e6), flush=True)
-for p2p in (("push", "0") if world > 2 else ("push", "1", "0")):
+for p2p in (("push", "push2", "0") if world > 2 else ("push", "push2", "1", "0")):
     losses, w, dt = run(p2p, opt="sgd")
     # every rank must hold the same weights
     ws = [torch.empty_like(w) for _ in range(world)]
