@@ -131,3 +131,61 @@ def test_bf16_multitask_step_tracks_fp32_step():
             assert float(upd16.norm()) == 0
         else:
             assert _rel(upd16, upd32) < 6e-2, k
+
+
+@pytest.mark.parametrize("env", [
+    {"ABN_FWD_FUSED": "0", "ABN_BWD_FUSED": "0"},                          # grouped GEMM, backward merged in one launch
+    {"ABN_FWD_FUSED": "0", "ABN_BWD_FUSED": "0", "ABN_BWD_MERGE": "0"},    # dgrad chain, then the wgrad group
+    {"ABN_FWD_FUSED": "1", "ABN_BWD_FUSED": "0"},
+    {"ABN_FWD_FUSED": "0", "ABN_BWD_FUSED": "1"},
+])
+def test_every_launch_plan_of_the_bf16_step_gives_the_same_update(env, monkeypatch):
+    """The step can run its GEMMs as the fused chain kernels (default), as one merged grouped
+    launch for the backward pass, or as separate grouped launches: same forward bits, and
+    weight updates equal up to the order of the fp32 wgrad reductions."""
+    cfg = dict(input_dim=280, num_hidden_layers=2, hidden_dim=500, output_dim=100, p_dropout=0.0,
+               activation_layer="sigmoid", precision="bf16")
+    torch.manual_seed(7)
+    ref_net = SiameseNetwork(**cfg).to(DEV)
+    alt_net = SiameseNetwork(**cfg).to(DEV)
+    alt_net.load_state_dict(ref_net.state_dict())
+    before = {k: v.clone() for k, v in ref_net.state_dict().items()}
+    for k in ("ABN_FWD_FUSED", "ABN_BWD_FUSED", "ABN_BWD_MERGE"):
+        monkeypatch.delenv(k, raising=False)
+    ref = SiameseTrainStep(ref_net, ("coscos2", 0.0, False), "sgd", lr=0.05, momentum=0.0)
+    n = 3000                                     # ragged last row block
+    x = torch.randn(2 * n, 280, device=DEV)
+    y = torch.where(torch.rand(n, device=DEV) < 0.5, 1.0, -1.0)
+    l_ref = float(ref.step(x, n, y).item())
+    assert ref._fwd_fused is not None and ref._dgrad_fused is not None
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = SiameseTrainStep(alt_net, ("coscos2", 0.0, False), "sgd", lr=0.05, momentum=0.0)
+    l_alt = float(alt.step(x, n, y).item())
+    assert (alt._fwd_fused is not None) == (env["ABN_FWD_FUSED"] == "1")
+    assert (alt._dgrad_fused is not None) == (env["ABN_BWD_FUSED"] == "1")
+    assert torch.equal(alt.acts[-1][:2 * n], ref.acts[-1][:2 * n])        # forward: identical bits
+    assert abs(l_alt - l_ref) <= 1e-5 * abs(l_ref)       # block partial sums are added atomically
+    for (k, a), (_, b) in zip(alt_net.state_dict().items(), ref_net.state_dict().items()):
+        assert _rel(a - before[k], b - before[k]) < 1e-4, k
+
+
+def test_network_wider_than_the_slab_trains_through_the_grouped_gemm():
+    cfg = dict(input_dim=280, num_hidden_layers=1, hidden_dim=640, output_dim=100, p_dropout=0.0,
+               activation_layer="sigmoid")
+    torch.manual_seed(8)
+    n32 = SiameseNetwork(**cfg).to(DEV)
+    n16 = SiameseNetwork(precision="bf16", **cfg).to(DEV)
+    n16.load_state_dict(n32.state_dict())
+    s32 = SiameseTrainStep(n32, ("coscos2", 0.0, False), "sgd", lr=0.05, momentum=0.0)
+    s16 = SiameseTrainStep(n16, ("coscos2", 0.0, False), "sgd", lr=0.05, momentum=0.0)
+    before = {k: v.clone() for k, v in n32.state_dict().items()}
+    n = 2048
+    x = torch.randn(2 * n, 280, device=DEV)
+    y = torch.where(torch.rand(n, device=DEV) < 0.5, 1.0, -1.0)
+    l32 = float(s32.step(x, n, y).item())
+    l16 = float(s16.step(x, n, y).item())
+    assert s16._fwd_fused is None and s16._dgrad_fused is None
+    assert abs(l16 - l32) <= 1e-2 * abs(l32)
+    for (k, a), (_, b) in zip(n16.state_dict().items(), n32.state_dict().items()):
+        assert _rel(a - before[k], b - before[k]) < 6e-2, k
