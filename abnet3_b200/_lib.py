@@ -76,6 +76,7 @@ SIGNATURES = {
                               _P]),
     "abn_diff_pairs": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "abn_compact_paths": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "abn_store_scalar64": (_I, [_P, _P, _P]),
     "abn_gather_batch": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
     "abn_pair_loss": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _P, _P, _P, _P]),
     "abn_linear_forward": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P, _P]),

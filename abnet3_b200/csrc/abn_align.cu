@@ -1520,6 +1520,18 @@ extern "C" int abn_compact_paths(const int32_t *src1, const int32_t *src2, const
     return check_launch("abn_compact_paths");
 }
 
+namespace abn {
+__global__ void store_scalar64_kernel(const long long *src, long long *dst) { *dst = *src; }
+}  // namespace abn
+
+extern "C" int abn_store_scalar64(const int64_t *src, int64_t *dst_host_mapped, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (!src || !dst_host_mapped) return set_error(ABN_EINVAL, "abn_store_scalar64: bad argument");
+    abn::store_scalar64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long *>(src), reinterpret_cast<long long *>(dst_host_mapped));
+    return check_launch("abn_store_scalar64");
+}
+
 extern "C" int abn_gather_batch(const float *feat, int dim, const int32_t *idx1,
                                 const int32_t *idx2, const int8_t *y_in, const int64_t *sel,
                                 int64_t n, float *x1, float *x2, float *y_out,

@@ -56,7 +56,18 @@ def _workspace(n_pairs, device, max_frames=1, budget=None):
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
-def align_pairs(feat, pair_tok, max_frames=None, stack=0):
+def read_scalar(src, host_scalar):
+    """int(src[0]) for a 1-element int64 device tensor WITHOUT a cudaMemcpy: a kernel stores it into
+    ``host_scalar`` (pinned 1-element int64 tensor) and the host waits on an event.  A small
+    device -> host memcpy would queue behind a bulk copy that is using the copy engine."""
+    check(_lib.lib().abn_store_scalar64(ptr(src), host_scalar.data_ptr(), stream_ptr()))
+    ev = torch.cuda.Event()
+    ev.record()
+    ev.synchronize()
+    return int(host_scalar[0])
+
+
+def align_pairs(feat, pair_tok, max_frames=None, stack=0, total_cap=None):
     """Fused cosine distance + DTW + traceback for every pair
     (abnet3/utils.py:147-153 per pair).  Returns an AlignResult whose idx1/idx2
     hold GLOBAL feature rows in per-pair slots of capacity n1+n2-1 starting at
@@ -70,7 +81,8 @@ def align_pairs(feat, pair_tok, max_frames=None, stack=0):
         max_frames = int(pair_tok[:, [1, 3]].max().item()) if P else 1
     cap = (pair_tok[:, 1] + pair_tok[:, 3] - 1).clamp_min(0)
     path_off = _excl_cumsum(cap)
-    total = int(path_off[-1].item()) if P else 0
+    # total_cap: sum(n1 + n2 - 1) when the caller already knows it from a host copy of the list
+    total = int(total_cap) if total_cap is not None else (int(path_off[-1].item()) if P else 0)
     idx1 = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     idx2 = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     path_len = torch.zeros(P, dtype=torch.int32, device=dev)
@@ -172,12 +184,18 @@ def diff_pairs(pair_tok, stretch=False):
     return idx1[:total], idx2[:total], out_off
 
 
-def compact_paths(res):
+def compact_paths(res, host_scalar=None):
     """Dense (idx1, idx2, dst_off) table from an AlignResult
-    (what FramesDataLoader.load_all_frames accumulates, dataloader.py:642-653)."""
+    (what FramesDataLoader.load_all_frames accumulates, dataloader.py:642-653).
+    host_scalar: pinned int64 [1] tensor through which the total is read (see read_scalar)."""
     P = res.path_len.numel()
     dst_off = _excl_cumsum(res.path_len)
-    total = int(dst_off[-1].item()) if P else 0
+    if P == 0:
+        total = 0
+    elif host_scalar is not None:
+        total = read_scalar(dst_off[-1:], host_scalar)
+    else:
+        total = int(dst_off[-1].item())
     d1 = torch.empty(max(total, 1), dtype=torch.int32, device=res.idx1.device)
     d2 = torch.empty(max(total, 1), dtype=torch.int32, device=res.idx1.device)
     check(_lib.lib().abn_compact_paths(ptr(res.idx1), ptr(res.idx2), ptr(res.path_off),

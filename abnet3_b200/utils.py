@@ -177,11 +177,12 @@ def align_pairs_host(feat_host, pair_tok_host, max_frames=None, stack=0, last_ro
     P = tok.shape[0]
     if max_frames is None:
         max_frames = int(pair_tok_host[:, [1, 3]].max().item()) if P else 1
-    # The pair list can be worked through in chunks so that the device -> host copy of a
-    # chunk's paths (side stream) overlaps the alignment of the next chunk.
-    # (measured at 1 M pairs: the extra launches, tails and host syncs of 4 chunks cost as
-    # much as the overlap gains -- one chunk is the default)
-    n_chunks = int(chunks) if chunks else 1
+    # The pair list is worked through in chunks so that the device -> host copy of a chunk's
+    # paths (side stream) overlaps the alignment of the next chunk.  Nothing in the loop may
+    # issue a small cudaMemcpy (a .item()): it would queue behind the bulk copy on the copy
+    # engine and hold back the next chunk's launches -- capacities come from the host copy of
+    # the list, the data-dependent total through a kernel store into pinned memory.
+    n_chunks = int(chunks) if chunks else (4 if P >= 200_000 else 1)
     n_chunks = max(1, min(n_chunks, max(P, 1)))
     bounds = [P * c // n_chunks for c in range(n_chunks + 1)]
     cap_total = int((pair_tok_host[:, 1].long() + pair_tok_host[:, 3].long() - 1).clamp_min(0).sum())
@@ -191,6 +192,7 @@ def align_pairs_host(feat_host, pair_tok_host, max_frames=None, stack=0, last_ro
     h_len = _pinned_buf("len", P, torch.int32)
     h_cost = _pinned_buf("cost", P, torch.float64)
     h_valid = _pinned_buf("valid", P, torch.uint8)
+    h_total = _pinned_buf("total", 1, torch.int64)
     main = torch.cuda.current_stream()
     side = _side_stream(dev)
     base = 0
@@ -199,8 +201,9 @@ def align_pairs_host(feat_host, pair_tok_host, max_frames=None, stack=0, last_ro
         lo, hi = bounds[c], bounds[c + 1]
         if hi == lo:
             continue
-        res = ops.align_pairs(feat, tok[lo:hi], max_frames=max_frames, stack=stack)
-        d1, d2, doff = ops.compact_paths(res)          # (host reads the chunk's total here)
+        cap_c = int((pair_tok_host[lo:hi, 1].long() + pair_tok_host[lo:hi, 3].long() - 1).clamp_min(0).sum())
+        res = ops.align_pairs(feat, tok[lo:hi], max_frames=max_frames, stack=stack, total_cap=cap_c)
+        d1, d2, doff = ops.compact_paths(res, host_scalar=h_total)    # (host learns the chunk's total here)
         n = d1.numel()
         goff = doff + base if base else doff
         done = torch.cuda.Event()

@@ -179,6 +179,12 @@ ABN_API int abn_compact_paths(const int32_t *src1, const int32_t *src2,
                       const int32_t *path_len, int n_pairs, int32_t *dst1,
                       int32_t *dst2, abn_stream_t stream);
 
+/* One int64 from device memory into PINNED (device-mapped) host memory by a kernel store, on
+ * `stream`: how a host-side pipeline learns a data-dependent size (the total path length of a
+ * chunk) while a bulk device -> host copy occupies the copy engine -- a cudaMemcpy of the scalar
+ * would queue behind it and stall the next chunk's launches. */
+ABN_API int abn_store_scalar64(const int64_t *src, int64_t *dst_host_mapped, abn_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Batch generation: gather feature rows for a batch of frame pairs.
  * Replaces the row gathers of abnet3/dataloader.py:204-205, :250-255 and
