@@ -331,11 +331,11 @@ class SiameseTrainStep(object):
         G = ops.GEMM_MAX_GROUP
         merge = (self._dgrad_fused is None and 2 * len(self.chain) - 1 <= G and
                  os.environ.get("ABN_BWD_MERGE", "1") != "0")
-        # weight + bias gradients of ALL layers, split over the batch: ~1.75 waves of CTA pairs
-        # when they have a launch of their own, ~3.5 inside the merged backward launch (measured;
-        # ABN_WGRAD_SPLIT overrides)
+        # weight + bias gradients of ALL layers, split over the batch: ONE wave of CTA pairs when
+        # they have a launch of their own (step: split 5 146.2 us | 9 149.8 | 10 147.9 | 6 159.1),
+        # ~3.5 waves inside the merged backward launch (measured; ABN_WGRAD_SPLIT overrides)
         tiles = sum(((L.n_out + 255) // 256) * ((L.n_in + 1 + 255) // 256) for L, _ in wgrad)
-        waves4 = 14 if merge else 7
+        waves4 = 14 if merge else 4
         split = max(1, min((rows + 63) // 64, int(os.environ.get("ABN_WGRAD_SPLIT", "0")) or
                            max(1, (waves4 * (GEMM_CTAS // 2) // 4) // max(1, tiles))))
         self._wgrad_split = split
