@@ -17,34 +17,61 @@
 
 namespace abn {
 
-// one warp per gathered row; 16-byte loads, 8-byte bf16x4 stores
+// one warp per gathered row; 16-byte loads, 8-byte bf16x4 stores.
+// cursor (nullable, int64[2] = {next table row, ticket}): without `sel` the batch is the table rows
+// cursor[0] .. cursor[0]+n-1 and the last block to finish advances cursor[0] by n -- an epoch of
+// fixed-size batches over a shuffled frame-pair table (abnet3/dataloader.py:686-739) replays as
+// ONE CUDA graph with no host-side bookkeeping per batch.  loss_acc (nullable, double[1]):
+// the previous step's loss (word 0 of zero_me) is added to it before it is cleared, i.e. the
+// `train_loss += loss.data[0]` of abnet3/trainer.py:242 without a host synchronisation per step.
 __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
                                    const int32_t *__restrict__ idx1,
                                    const int32_t *__restrict__ idx2,
                                    const int8_t *__restrict__ y_in,
-                                   const int64_t *__restrict__ sel, int64_t n,
+                                   const int8_t *__restrict__ y2_in,
+                                   const int64_t *__restrict__ sel, int64_t *cursor, int64_t n,
                                    __nv_bfloat16 *__restrict__ xb, int64_t ldx,
-                                   float *__restrict__ y_out, unsigned *__restrict__ zero_me,
-                                   int zero_words) {
+                                   float *__restrict__ y_out, float *__restrict__ y2_out,
+                                   unsigned *__restrict__ zero_me, int zero_words,
+                                   double *__restrict__ loss_acc) {
     pdl_wait();
-    if (zero_me && blockIdx.x == 0)
+    if (zero_me && blockIdx.x == 0) {
+        if (loss_acc && threadIdx.x == 0) loss_acc[0] += (double)__uint_as_float(zero_me[0]);
+        __syncthreads();
         for (int i = threadIdx.x; i < zero_words; i += blockDim.x) zero_me[i] = 0u;
+    }
     const int warps_per_block = blockDim.x >> 5;
     const int64_t w = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (w >= 2 * n) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t k = w >> 1;
-    const int side = (int)(w & 1);
-    const int64_t pos = sel ? sel[k] : k;
-    const int32_t row = side ? idx2[pos] : idx1[pos];
-    const float4 *src = reinterpret_cast<const float4 *>(feat + (size_t)row * dim);
-    uint2 *dst = reinterpret_cast<uint2 *>(xb + (size_t)(side ? n + k : k) * ldx);
-    for (int c = lane; c < dim / 4; c += 32) {
-        const float4 v = __ldg(src + c);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-        dst[c] = make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+    const int64_t base = (cursor && !sel) ? *reinterpret_cast<volatile int64_t *>(cursor) : 0;
+    if (w < 2 * n) {
+        const int lane = threadIdx.x & 31;
+        const int64_t k = w >> 1;
+        const int side = (int)(w & 1);
+        const int64_t pos = sel ? sel[k] : base + k;
+        const int32_t row = side ? idx2[pos] : idx1[pos];
+        const float4 *src = reinterpret_cast<const float4 *>(feat + (size_t)row * dim);
+        uint2 *dst = reinterpret_cast<uint2 *>(xb + (size_t)(side ? n + k : k) * ldx);
+        for (int c = lane; c < dim / 4; c += 32) {
+            const float4 v = __ldg(src + c);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            dst[c] = make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+        }
+        if (side == 0 && lane == 0) {
+            if (y_out) y_out[k] = y_in ? (float)y_in[pos] : 1.f;
+            if (y2_out) y2_out[k] = y2_in ? (float)y2_in[pos] : 1.f;
+        }
     }
-    if (side == 0 && lane == 0 && y_out) y_out[k] = y_in ? (float)y_in[pos] : 1.f;
+    if (cursor && !sel) {          // every block has read cursor[0] before it takes its ticket
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long *>(cursor + 1), 1ull);
+            if (t == (unsigned long long)gridDim.x - 1) {
+                cursor[1] = 0;
+                cursor[0] = base + n;
+                __threadfence();
+            }
+        }
+    }
 }
 
 constexpr int LZ_WARPS = 8;
@@ -162,20 +189,30 @@ __global__ void optimizer_fused_kernel(float *__restrict__ p, float *__restrict_
 
 using namespace abn;
 
+extern "C" int abn_gather_step_bf16(const float *feat, int dim, const int32_t *idx1,
+                                    const int32_t *idx2, const int8_t *y_in, const int8_t *y2_in,
+                                    const int64_t *sel, int64_t *cursor, int64_t n, void *xb,
+                                    int64_t ldx, float *y_out, float *y2_out, void *zero_me,
+                                    int zero_words, double *loss_acc, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (n == 0) return ABN_OK;
+    if (!feat || !idx1 || !idx2 || !xb || n < 0 || dim <= 0 || (dim & 3) || ldx < dim || (ldx & 3) ||
+        (loss_acc && (!zero_me || zero_words < 1)))
+        return set_error(ABN_EINVAL, "abn_gather_step_bf16: bad argument");
+    const int wpb = 8;
+    const int64_t warps = 2 * n;
+    launch_pdl(gather_bf16_kernel, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), (cudaStream_t)stream,
+        feat, dim, idx1, idx2, y_in, y2_in, sel, cursor, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out,
+        y2_out, static_cast<unsigned *>(zero_me), zero_me ? zero_words : 0, loss_acc);
+    return check_launch("abn_gather_step_bf16");
+}
+
 extern "C" int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *idx1,
                                      const int32_t *idx2, const int8_t *y_in, const int64_t *sel,
                                      int64_t n, void *xb, int64_t ldx, float *y_out,
                                      void *zero_me, int zero_words, abn_stream_t stream) {
-    if (int rc = require_sm100()) return rc;
-    if (n == 0) return ABN_OK;
-    if (!feat || !idx1 || !idx2 || !xb || n < 0 || dim <= 0 || (dim & 3) || ldx < dim || (ldx & 3))
-        return set_error(ABN_EINVAL, "abn_gather_batch_bf16: bad argument");
-    const int wpb = 8;
-    const int64_t warps = 2 * n;
-    launch_pdl(gather_bf16_kernel, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), (cudaStream_t)stream,
-        feat, dim, idx1, idx2, y_in, sel, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out,
-        static_cast<unsigned *>(zero_me), zero_me ? zero_words : 0);
-    return check_launch("abn_gather_batch_bf16");
+    return abn_gather_step_bf16(feat, dim, idx1, idx2, y_in, nullptr, sel, nullptr, n, xb, ldx, y_out,
+                                nullptr, zero_me, zero_words, nullptr, stream);
 }
 
 extern "C" int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,

@@ -8,6 +8,7 @@ Same class names, constructor arguments, ``load_data`` / ``batch_iterator`` /
 * ``PairsDataLoader``      (:355-546)  frame-indexed knn pair file
 * ``FramesDataLoader``     (:580-739)  all pairs aligned once, frame batches
 * ``MultiTaskDataLoader``  (:742-792)  adds speaker labels
+* ``MultiTaskFramesDataLoader``        (new) frame batches with speaker labels
 
 What changed underneath: the corpus lives on the GPU as one [n_rows, dim] table
 (utils.FeatureTable); every 'same' pair of a pair list is aligned in ONE batched
@@ -108,6 +109,20 @@ class OriginalDataLoader(DataLoader):
         self.train_files = None
         self.pairs = {'train': None, 'dev': None}
         self._cache = {}
+        self._shard = None
+
+    def shard(self, rank, world_size):
+        """Data parallelism (new): this process keeps every ``world_size``-th pair of the
+        train and dev lists, starting at ``rank`` (pairs are independent: DTW alignment needs
+        no communication).  Call before ``load_data``; the trainer does so under torchrun."""
+        if self.pairs['train'] is not None and self._shard != (rank, world_size):
+            raise RuntimeError("shard() must be called before the pairs are loaded")
+        self._shard = (int(rank), int(world_size))
+
+    def _sharded(self, pairs):
+        if self._shard is None or self._shard[1] <= 1:
+            return pairs
+        return pairs[self._shard[0]::self._shard[1]]
 
     # pickling without the features (dataloader.py:86-117)
     def __getstate__(self):
@@ -128,6 +143,7 @@ class OriginalDataLoader(DataLoader):
         self.train_files = None
         self.pairs = {'train': None, 'dev': None}
         self._cache = {}
+        self._shard = None
         self.load_data()
 
     def whoami(self):
@@ -144,11 +160,11 @@ class OriginalDataLoader(DataLoader):
             self.features = features
         if self.pairs['train'] is None:
             print("Loading word pairs")
-            self.pairs['train'] = read_dataset(
-                os.path.join(self.pairs_path, 'train_pairs/dataset'))
+            self.pairs['train'] = self._sharded(read_dataset(
+                os.path.join(self.pairs_path, 'train_pairs/dataset')))
         if self.pairs['dev'] is None:
-            self.pairs['dev'] = read_dataset(
-                os.path.join(self.pairs_path, 'dev_pairs/dataset'))
+            self.pairs['dev'] = self._sharded(read_dataset(
+                os.path.join(self.pairs_path, 'dev_pairs/dataset')))
         self.train_files = list({pair[0] for pair in self.pairs['train']} |
                                 {pair[3] for pair in self.pairs['train']})
 
@@ -339,6 +355,7 @@ class PairsDataLoader(OriginalDataLoader):
         self.files = set()
         self.seed = 0
         self._cache = {}
+        self._shard = None
 
     def __getstate__(self):
         return (self.pairs_path,
@@ -386,6 +403,7 @@ class PairsDataLoader(OriginalDataLoader):
         elif self.split_method == self.SPLIT_EACH_FILE:
             self.pairs['train'], self.pairs['test'] = self.split_train_test_each_file(pairs)
         for mode in ('train', 'test'):
+            self.pairs[mode] = self._sharded(self.pairs[mode])
             toks = set()
             for file1, begin1, end1, file2, begin2, end2 in self.pairs[mode]:
                 toks.add((file1, begin1, end1))
@@ -463,6 +481,11 @@ class FramesDataLoader(OriginalDataLoader):
     ``exact_numpy_shuffle``: shuffle with the host numpy RNG exactly like
     ``np.random.shuffle(frames)`` (:670, :717); when False (default for tables
     above ``EXACT_SHUFFLE_LIMIT`` rows) a device permutation is used instead.
+
+    New: ``epoch_table(train_mode)`` hands the trainer the shuffled device table and the
+    batch range of the epoch instead of materialised batches, so the fused training step
+    gathers its rows itself (abnet3_b200.engine.SiameseTrainStep.sweep_table);
+    ``from_tokens`` builds a loader from token row ranges already on the device.
     """
     EXACT_SHUFFLE_LIMIT = 4_000_000
 
@@ -476,95 +499,160 @@ class FramesDataLoader(OriginalDataLoader):
         self.frame_pairs = {'train': None, 'dev': None}
         self.max_batches_per_epoch = max_batches_per_epoch
         self.exact_numpy_shuffle = exact_numpy_shuffle
+        self._tokens_given = None
         if self.max_batches_per_epoch is not None:
             self.batch_position = 0
 
+    @classmethod
+    def from_tokens(cls, table, tokens, batch_size=100, randomize_dataset=True,
+                    max_batches_per_epoch=None, **kwargs):
+        """A loader over a device-resident ``utils.FeatureTable`` and token row ranges
+        instead of files: ``tokens = {'train': (same_tok, diff_tok), 'dev': (...)}`` with
+        int32 [P, 4] CUDA tensors (row1, n1, row2, n2) -- what ``load_data`` derives from
+        the pair files and the frame times."""
+        self = cls(None, None, batch_size=batch_size, randomize_dataset=randomize_dataset,
+                   max_batches_per_epoch=max_batches_per_epoch, **kwargs)
+        self.features = _TableOnly(table)
+        self.pairs = {'train': [], 'dev': []}
+        self._tokens_given = tokens
+        return self
+
     def load_data(self):
-        super(FramesDataLoader, self).load_data()
+        if self._tokens_given is None:
+            super(FramesDataLoader, self).load_data()
         for mode in ('train', 'dev'):
             if self.frame_pairs[mode] is None:
                 if mode == 'train':
                     print("Loading all frames..", end='', flush=True)
                 self.token_features[mode], self.frame_pairs[mode] = \
-                    self.load_all_frames(self.pairs[mode])
+                    self.load_all_frames(self.pairs[mode], mode)
                 if mode == 'train':
                     print("Done. %s frame pairs in total." % self.frame_pairs[mode][0].numel())
 
+    def realign(self, mode='train'):
+        """Drop and recompute the frame-pair table of ``mode`` (alignment of every same pair +
+        diff pairs + shuffle): what the reference does once per run (:642-671)."""
+        self.frame_pairs[mode] = None
+        self.token_features[mode], self.frame_pairs[mode] = \
+            self.load_all_frames(self.pairs[mode], mode)
+        return self.frame_pairs[mode]
+
     def _shuffle(self, table):
-        idx1, idx2, y = table
-        n = idx1.numel()
+        """np.random.shuffle of the frame-pair list (:670, :717), in place (the table's device
+        addresses stay valid for CUDA graphs built on them)."""
+        n = table[0].numel()
+        if n == 0:
+            return table
         exact = self.exact_numpy_shuffle
         if exact is None:
             exact = n <= self.EXACT_SHUFFLE_LIMIT
         if exact:
             perm = np.arange(n)
             np.random.shuffle(perm)             # same draws as shuffling the list of n tuples
-            perm = torch.from_numpy(perm).to(idx1.device)
+            perm = torch.from_numpy(perm).to(table[0].device)
         else:
-            perm = torch.randperm(n, device=idx1.device)
-        return idx1[perm].contiguous(), idx2[perm].contiguous(), y[perm].contiguous()
+            perm = torch.randperm(n, device=table[0].device)
+        for t in table:
+            t.copy_(t[perm])
+        return table
 
-    def load_all_frames(self, pairs):
-        """dataloader.py:617-671: -> (token table, (idx1, idx2, y)) on the device;
-        same pairs in list order (each a DTW path), then diff pairs truncated to
-        min(n1, n2) leading frames, then one global shuffle."""
-        grouped = group_pairs(pairs)
+    def _pair_labels(self, plist_same, plist_diff, mode):
+        """Extra per-PAIR label columns (none here; see MultiTaskFramesDataLoader)."""
+        return []
+
+    def _frames_from_tokens(self, same_tok, diff_tok, pair_labels=()):
+        """Device side of load_all_frames: same_tok / diff_tok int32 [P, 4] (host arrays or
+        CUDA tensors); pair_labels: [(same int8 [Ps], diff int8 [Pd]), ...] extra label
+        columns, expanded to frames.  -> (idx1, idx2, y[, extra...]) before the shuffle."""
         dev = self.table.feat.device
-        same_tok = self._tokens(grouped['same'])
-        diff_tok = self._tokens(grouped['diff'])
+
+        def on_dev(tok):
+            return tok if isinstance(tok, torch.Tensor) else torch.from_numpy(tok).to(dev)
+
         parts1, parts2, labels = [], [], []
+        extra = [[] for _ in pair_labels]
         if len(same_tok):
-            al = self._align(same_tok)
-            d1, d2, _, valid = al.dev
+            tok_d = on_dev(same_tok)
+            longest = int(tok_d[:, [1, 3]].max().item())
+            res = ops.align_pairs(self.table.feat, tok_d, max_frames=max(longest, 1),
+                                  stack=self.table.stack)
+            d1, d2, doff = ops.compact_paths(res)
             parts1.append(d1)
             parts2.append(d2)
             labels.append(torch.ones(d1.numel(), dtype=torch.int8, device=dev))
-            self.statistics_training['SameType'] += int(valid.sum().item())
+            for k, (ls, _) in enumerate(pair_labels):
+                extra[k].append(torch.repeat_interleave(on_dev(ls), res.path_len.long()))
+            self.statistics_training['SameType'] += int(res.valid.sum().item())
         if len(diff_tok):
-            i1, i2, off = ops.diff_pairs(torch.from_numpy(diff_tok).to(dev), stretch=False)
+            tok_d = on_dev(diff_tok)
+            i1, i2, off = ops.diff_pairs(tok_d, stretch=False)
             parts1.append(i1)
             parts2.append(i2)
             labels.append(-torch.ones(i1.numel(), dtype=torch.int8, device=dev))
-            self.statistics_training['DiffType'] += int(((diff_tok[:, 1] > 0) &
-                                                         (diff_tok[:, 3] > 0)).sum())
+            for k, (_, ld) in enumerate(pair_labels):
+                extra[k].append(torch.repeat_interleave(on_dev(ld), off[1:] - off[:-1]))
+            self.statistics_training['DiffType'] += int(((tok_d[:, 1] > 0) &
+                                                         (tok_d[:, 3] > 0)).sum().item())
         if not parts1:
             empty = torch.zeros(0, dtype=torch.int32, device=dev)
-            return (same_tok, diff_tok), (empty, empty, torch.zeros(0, dtype=torch.int8,
-                                                                    device=dev))
-        table = (torch.cat(parts1).contiguous(), torch.cat(parts2).contiguous(),
-                 torch.cat(labels).contiguous())
+            e8 = torch.zeros(0, dtype=torch.int8, device=dev)
+            return (empty, empty.clone()) + tuple(e8.clone() for _ in range(1 + len(extra)))
+        y = torch.cat(labels).contiguous()
+        cols = [torch.cat(e).contiguous() for e in extra]
+        # label column order of the table: extra columns (y_spk) first, y_phn last
+        return (torch.cat(parts1).contiguous(), torch.cat(parts2).contiguous()) + \
+            tuple(cols) + (y,)
+
+    def load_all_frames(self, pairs, mode='train'):
+        """dataloader.py:617-671: -> (token table, (idx1, idx2, y)) on the device;
+        same pairs in list order (each a DTW path), then diff pairs truncated to
+        min(n1, n2) leading frames, then one global shuffle."""
+        if self._tokens_given is not None:
+            same_tok, diff_tok = self._tokens_given[mode][:2]
+            plabels = self._tokens_given[mode][2] if len(self._tokens_given[mode]) > 2 else ()
+        else:
+            grouped = group_pairs(pairs)
+            same_tok = self._tokens(grouped['same'])
+            diff_tok = self._tokens(grouped['diff'])
+            plabels = self._pair_labels(grouped['same'], grouped['diff'], mode)
+        table = self._frames_from_tokens(same_tok, diff_tok, plabels)
         return (same_tok, diff_tok), self._shuffle(table)
 
     def load_batch(self, frames, token_feats=None):
         """dataloader.py:673-684.  ``frames`` = (lo, hi) slice of the frame-pair
         table (or an int64 index tensor); returns device (X1, X2, y)."""
-        idx1, idx2, y = self._active_table
+        table = self._active_table
+        idx1, idx2, y = table[0], table[1], table[-1]
         dev = idx1.device
         if isinstance(frames, tuple):
             lo, hi = frames
             n = hi - lo
-            buf = torch.empty((2 * n, self.table.dim), dtype=torch.float32, device=dev)
-            yo = torch.empty(n, dtype=torch.float32, device=dev)
-            ops.gather_batch(self.table.feat, idx1[lo:hi], idx2[lo:hi], y[lo:hi], None, n,
-                             out=(buf[:n], buf[n:], yo))
+            sel = None
+            idx1, idx2, cols = idx1[lo:hi], idx2[lo:hi], [c[lo:hi] for c in table[2:]]
         else:
             n = frames.numel()
-            buf = torch.empty((2 * n, self.table.dim), dtype=torch.float32, device=dev)
+            sel, cols = frames, list(table[2:])
+        buf = torch.empty((2 * n, self.table.dim), dtype=torch.float32, device=dev)
+        outs = []
+        for k, col in enumerate(cols):
             yo = torch.empty(n, dtype=torch.float32, device=dev)
-            ops.gather_batch(self.table.feat, idx1, idx2, y, frames, n,
-                             out=(buf[:n], buf[n:], yo))
-        return buf[:n], buf[n:], yo
+            if k == 0:
+                ops.gather_batch(self.table.feat, idx1, idx2, col, sel, n, out=(buf[:n], buf[n:], yo))
+            else:
+                yo.copy_((col if sel is None else col[sel]).float())
+            outs.append(yo)
+        return (buf[:n], buf[n:]) + tuple(outs)
 
-    def batch_iterator(self, train_mode=True):
-        """dataloader.py:686-739"""
+    def _epoch_plan(self, mode):
+        """The batch schedule of one epoch (dataloader.py:686-739): reshuffles as the
+        reference does and returns (table, first_batch, n_batches, num_pairs)."""
         self.load_data()
-        mode = 'train' if train_mode else 'dev'
         num_pairs = self.frame_pairs[mode][0].numel()
         num_batches = num_pairs // self.batch_size
         if num_batches == 0:
             num_batches = 1
         if mode == 'dev' or self.max_batches_per_epoch is None:
-            batch_ids = range(num_batches)
+            first, count = 0, num_batches
             if self.randomize_dataset:
                 self.frame_pairs[mode] = self._shuffle(self.frame_pairs[mode])
         else:
@@ -573,15 +661,65 @@ class FramesDataLoader(OriginalDataLoader):
                 if self.randomize_dataset:
                     self.frame_pairs[mode] = self._shuffle(self.frame_pairs[mode])
                 self.batch_position = 0
-            batch_ids = range(self.batch_position,
-                              min(self.batch_position + self.max_batches_per_epoch,
-                                  num_batches))
+            first = self.batch_position
+            count = min(self.batch_position + self.max_batches_per_epoch, num_batches) - first
             self.batch_position += self.max_batches_per_epoch
         self._active_table = self.frame_pairs[mode]
-        for i in batch_ids:
+        return self._active_table, first, count, num_pairs
+
+    def epoch_table(self, train_mode=True):
+        """-> (feat, table, batch_size, first_row, n_batches): the epoch's batches are the
+        consecutive ``batch_size``-row slices of ``table`` from ``first_row`` on (the single
+        batch of a table smaller than ``batch_size`` is the whole table)."""
+        table, first, count, num_pairs = self._epoch_plan('train' if train_mode else 'dev')
+        bs = min(self.batch_size, num_pairs)
+        if num_pairs == 0:
+            count = 0
+        return self.table.feat, table, bs, first * self.batch_size, count
+
+    def batch_iterator(self, train_mode=True):
+        """dataloader.py:686-739"""
+        table, first, count, num_pairs = self._epoch_plan('train' if train_mode else 'dev')
+        for i in range(first, first + count):
             lo = i * self.batch_size
             hi = min(lo + self.batch_size, num_pairs)
             yield self.load_batch((lo, hi))
+
+
+class _TableOnly(object):
+    """Stand-in for a Features_Accessor when only the device table exists."""
+
+    def __init__(self, table):
+        self.table = table
+
+
+class MultiTaskFramesDataLoader(FramesDataLoader):
+    """Frame batches with speaker labels (new): FramesDataLoader's one-time alignment and
+    fixed-size frame batches (dataloader.py:580-739) with MultiTaskDataLoader's labels
+    (:742-792; load_frames_from_pairs :195-202, :235-242).  Yields (X1, X2, y_spk, y_phn);
+    the table is (idx1, idx2, y_spk, y_phn).  ``y_spk`` follows the reference's rule
+    ``spk1 is spk2`` on the values of ``fid2spk`` (quirk q2: object identity)."""
+
+    def __init__(self, pairs_path, features_path, fid2spk_file=None, **kwargs):
+        super().__init__(pairs_path, features_path, **kwargs)
+        self.fid2spk_file = fid2spk_file
+        self._fid2spk = None
+
+    def _pair_labels(self, plist_same, plist_diff, mode):
+        if self._fid2spk is None:
+            self._fid2spk = read_spkid_file(self.fid2spk_file)
+        spk = self._fid2spk
+
+        def col(plist, same_key, diff_key):
+            out = np.empty(len(plist), dtype=np.int8)
+            for k, p in enumerate(plist):
+                same = spk[p[0]] is spk[p[3]]
+                out[k] = 1 if same else -1
+                self.statistics_training[same_key if same else diff_key] += 1
+            return out
+
+        return [(col(plist_same, 'SameTypeSameSpk', 'SameTypeDiffSpk'),
+                 col(plist_diff, 'DiffTypeSameSpk', 'DiffTypeDiffSpk'))]
 
 
 class MultiTaskDataLoader(OriginalDataLoader):

@@ -18,11 +18,12 @@ buffer (and their ``.grad`` at views of one flat gradient buffer), so
 Two kernel paths, selected by ``network.precision``:
 
 ``fp32``  SIMT GEMMs (abn_linear_forward / backward): the 1e-4 parity path.
-``bf16``  tcgen05 tensor cores (abn_gemm_bf16_tn): activations live in bf16 (plus
-          a transposed bf16 copy written by the same epilogue for the weight-
-          gradient GEMM), the dgrad epilogue applies act'(y) of the layer below
+``bf16``  tcgen05 tensor cores (abn_mlp_forward_fused / abn_mlp_dgrad_fused /
+          abn_gemm_bf16_group): activations and dz live in bf16 in their natural
+          row-major layout, the dgrad epilogue applies act'(y) of the layer below
           and emits that layer's dz directly, the two multitask heads run as one
           200-wide layer; master weights, loss, embeddings and gradients stay fp32.
+          This is the default on CUDA (``network.precision``).
 
 ``state_dict`` / ``.pth`` interchange is unaffected: the module tree and the
 parameter shapes are those of the reference.
@@ -108,7 +109,7 @@ class SiameseTrainStep(object):
                  process_group=None):
         if optimizer_type not in OPTIMIZERS:
             raise ValueError("fused step supports %s, got %r" % (OPTIMIZERS, optimizer_type))
-        network._check_supported()
+        network._check_supported(training=True)     # whatever the mode at construction time
         self.network = network
         self.loss_spec = loss_spec
         self.kind, self.lr, self.momentum = optimizer_type, float(lr), float(momentum or 0.0)
@@ -120,6 +121,14 @@ class SiameseTrainStep(object):
             trained += [h[0][0] for h in self.heads] + [h[0][1] for h in self.heads]
         self.bucket = FlatBucket(network, trained)
         dev = self.bucket.param.device
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and \
+            dist.is_initialized() else 1
+        if self.world > 1:
+            # every rank starts from rank 0's initialisation (each process draws its own
+            # xavier weights unless the caller seeded them identically)
+            dist.broadcast(self.bucket.param, src=dist.get_global_rank(process_group, 0)
+                           if process_group is not None else 0, group=process_group)
         n = self.bucket.n_trained
         self.state0 = torch.zeros(n, dtype=torch.float32, device=dev)
         self.state1 = torch.zeros(n, dtype=torch.float32, device=dev) \
@@ -128,11 +137,12 @@ class SiameseTrainStep(object):
         self.loss_buf = self._zbuf[:1].view(torch.float32)
         self.step_count = 0
         self.precision = PRECISIONS[network.precision]
-        self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and \
-            dist.is_initialized() else 1
         self._rows = -1
-        self._static_n = None
+        self._plans = {}
+        self._graphs = {}
+        self._warm = {}
+        self._cursor = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
         self._loss_cleared = False
         self._grads_clean = False
         self._dp = None
@@ -165,15 +175,44 @@ class SiameseTrainStep(object):
                     self._dp = None
 
     # ------------------------------------------------------------ fp32 path ---
+    # Buffers, GEMM problem lists and CUDA graphs of one batch size form a "plan"; plans are
+    # cached per row count (LRU), so alternating batch sizes (train / dev sweeps, the ragged
+    # token batches of OriginalDataLoader) do not rebuild or invalidate each other.
+    _PLAN_ATTRS = ("acts", "dacts", "head_acts", "head_dacts", "xb", "actb", "dzb", "out_last",
+                   "_zbuf", "loss_buf", "_dep", "_fwd_problems", "_dgrad_problems", "_fwd_fused",
+                   "_fwd_rows", "_dgrad_fused", "_wgrad_split", "_backward_groups", "_gy",
+                   "_graphs", "_warm", "_gsel", "_sx", "_sy", "_static_n", "_graph_fb",
+                   "_graph_opt", "_eager_warm")
+    MAX_PLANS = 6
+
     def _reserve(self, rows):
         if rows == self._rows:
             return
+        if self._rows >= 0:                       # park the active plan
+            self._plans[self._rows] = {k: getattr(self, k) for k in self._PLAN_ATTRS
+                                       if hasattr(self, k)}
+        plan = self._plans.pop(rows, None)
+        if plan is not None:
+            for k, v in plan.items():
+                setattr(self, k, v)
+            self._rows = rows
+            return
+        while len(self._plans) >= self.MAX_PLANS:
+            self._plans.pop(next(iter(self._plans)))
         dev = self.bucket.param.device
+        self._graphs, self._warm = {}, {}
+        self._gsel = self._sx = self._sy = self._static_n = None
+        self._graph_fb = self._graph_opt = None
+        self._eager_warm = 0
+        self._gy = [torch.empty(max(rows // 2, 1), dtype=torch.float32, device=dev)
+                    for _ in range(2 if self.heads else 1)]
 
         def buf(width):
             return torch.empty((rows, width), dtype=torch.float32, device=dev)
 
         if self.precision == 0:
+            zb = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._zbuf, self.loss_buf = zb, zb[:1].view(torch.float32)
             self.acts = [buf(W.shape[0]) for W, _, _ in self.trunk]
             self.dacts = [buf(W.shape[0]) for W, _, _ in self.trunk]
             self.head_acts = [[buf(W.shape[0]) for W, _, _ in h] for h in self.heads]
@@ -251,6 +290,17 @@ class SiameseTrainStep(object):
         self._segments = ops.param_segments(entries)
         self._grads_clean = False
         self.refresh_bf16_weights()
+        # load_state_dict / load_network copy into the fp32 masters in place: redo the bf16
+        # operand copies (the fused optimizer only keeps them current during training)
+        import weakref
+        me = weakref.ref(self)
+
+        def _after_load(module, incompatible_keys):
+            eng = me()
+            if eng is not None and eng.network is module:
+                eng.refresh_bf16_weights()
+
+        self._load_hook = self.network.register_load_state_dict_post_hook(_after_load)
 
     def refresh_bf16_weights(self):
         """bf16 operand copies of the fp32 master weights (after load_state_dict; the
@@ -282,7 +332,6 @@ class SiameseTrainStep(object):
         tiles_m = (rows + 255) // 256
         n_dep = 2 * len(self.chain) + 2
         zbuf = torch.zeros(1 + n_dep * tiles_m, dtype=torch.int32, device=dev)
-        zbuf[:1].copy_(self._zbuf[:1])
         self._zbuf = zbuf                  # one contiguous block: the gather kernel clears it
         self.loss_buf = zbuf[:1].view(torch.float32)
         self._dep = zbuf[1:].view(n_dep, tiles_m)
@@ -446,7 +495,15 @@ class SiameseTrainStep(object):
                              w * (1.0 / n if avg else 1.0), act, loss_out=self.loss_buf)
 
     def _grad_scale(self):
-        avg = self.loss_spec[2] if not self.heads else self.loss_spec[0][2]
+        """Ranks SUM their gradients; a loss averaged over the batch (``avg=True``) is averaged
+        over the global batch by scaling the sum with 1 / world."""
+        if not self.heads:
+            avg = self.loss_spec[2]
+        else:
+            avg = self.loss_spec[0][2]
+            if self.world > 1 and bool(self.loss_spec[1][2]) != bool(avg):
+                raise ValueError("data-parallel multitask training needs the same `avg` flag "
+                                 "on both head losses")
         return 1.0 / self.world if (self.world > 1 and avg) else 1.0
 
     def _allreduce(self):
@@ -478,14 +535,13 @@ class SiameseTrainStep(object):
                            self.state1, self.kind, self.lr, self.momentum, scale, step)
 
     # ---- CUDA graphs ----------------------------------------------------------
-    # The step is a few dozen small launches on fixed buffers; replaying them as two
-    # graphs (forward+loss+backward | optimizer) removes the launch latency that
-    # otherwise dominates a sub-millisecond step.  The NCCL all-reduce stays between
-    # the two graphs.
+    # The step is a handful of small launches on fixed buffers; replaying them as one
+    # graph removes the launch latency that otherwise dominates a sub-millisecond step.
     def input_buffers(self, n):
         """Static (x [2n, D], labels...) buffers of the graphed step: producers
         (abn_gather_batch) may write straight into them."""
-        if self._static_n != n:
+        self._reserve(2 * n)
+        if getattr(self, "_static_n", None) != n or self._sx is None:
             dev = self.bucket.param.device
             d_in = self.trunk[0][0].shape[1]
             self._sx = torch.empty((2 * n, d_in), dtype=torch.float32, device=dev)
@@ -503,6 +559,7 @@ class SiameseTrainStep(object):
 
     def step_graphed(self, x, n, *labels):
         """Same as step(do_training=True) through CUDA graphs (SGD / Adadelta)."""
+        self._check_trainable()
         bufs = self.input_buffers(n)
         for dst, src in zip(bufs, (x,) + tuple(labels)):
             if dst.data_ptr() != src.data_ptr():
@@ -530,81 +587,135 @@ class SiameseTrainStep(object):
         self.step_count += 1
         return self.loss_buf
 
-    # ---- batch generation fused in front (tensor-core path, single-label networks) ----
+    # ---- batch generation fused in front (tensor-core path) --------------------------
+    # A frame-pair table is (idx1, idx2 int32 global rows, y int8) or, for the multitask
+    # network, (idx1, idx2, y_spk, y_phn): what FramesDataLoader keeps on the device.
     def gather_buffers(self, n):
         """Static ``sel`` [n] int64 buffer of step_gather: write the batch's positions
         in the frame-pair table into it (e.g. ``sel.copy_(perm[lo:lo + n])``)."""
-        if getattr(self, "_gsel_n", None) != n:
-            dev = self.bucket.param.device
-            self._gsel = torch.zeros(n, dtype=torch.int64, device=dev)
-            self._gy = torch.empty(n, dtype=torch.float32, device=dev)
-            self._gsel_n = n
-            self._graph_g = None
-            self._g_warm = 0
+        self._reserve(2 * n)
+        if getattr(self, "_gsel", None) is None or self._gsel.numel() != n:
+            self._gsel = torch.zeros(n, dtype=torch.int64, device=self.bucket.param.device)
         return self._gsel
 
-    def _gather_fwd_loss_bwd(self, feat, idx1, idx2, y, n):
+    def _check_table(self, table):
+        want = 4 if self.heads else 3
+        if len(table) != want:
+            raise ValueError("frame-pair table of %d arrays expected (idx1, idx2, %s)"
+                             % (want, "y_spk, y_phn" if self.heads else "y"))
+
+    def _check_trainable(self):
+        """Training-mode restrictions of the kernels, re-checked at every training step (the
+        network may have been built or put in eval() before the engine was)."""
+        self.network._check_supported(training=True)
+
+    def _table_fwd_loss(self, feat, table, n, sel, train):
+        """gather -> forward -> loss [-> backward] of one batch of the table."""
         self._reserve(2 * n)
-        # abn_gather_batch_bf16 writes the first layer's bf16 operand and clears the loss
-        ops.gather_batch_bf16(feat, idx1, idx2, y, self._gsel, n, self.xb, y_out=self._gy,
-                              zero=self._zbuf)
+        ys = table[2:]
+        two = len(ys) > 1
+        # the gather kernel writes the first layer's bf16 operand, adds the previous step's loss
+        # to the sweep accumulator and clears loss + dependency counters
+        ops.gather_batch_bf16(feat, table[0], table[1], ys[0], sel, n, self.xb, y_out=self._gy[0],
+                              zero=self._zbuf, y2=ys[1] if two else None,
+                              y2_out=self._gy[1] if two else None,
+                              cursor=None if sel is not None else self._cursor,
+                              loss_acc=self._loss_acc)
         self._loss_cleared = True
         out = self._forward_bf16(None)
-        self._loss_and_seed(out, n, [self._gy])
-        self.backward(None)
+        self._loss_and_seed(out, n, self._gy)
+        if train:
+            self.backward(None)
 
-    def step_gather(self, feat, idx1, idx2, y, n, graph=True):
-        """One training step on the batch ``sel`` (gather_buffers) of the device-resident
-        frame-pair table (idx1, idx2, y int8) over ``feat``: gather -> forward -> loss ->
-        backward [-> all-reduce] -> optimizer, replayed as CUDA graphs after two eager
-        steps.  What FramesDataLoader.load_batch + TrainerSiamese.optimize_model do per
-        batch (abnet3/dataloader.py:673-684, abnet3/trainer.py:226-243)."""
-        if self.precision != 1 or self.heads:
-            raise ValueError("step_gather serves the bf16 path of SiameseNetwork")
-        self.gather_buffers(n)
+    def _table_step(self, feat, table, n, sel=None, train=True, graph=True):
+        if self.precision != 1:
+            raise ValueError("the gather-fused step serves the bf16 tensor-core path "
+                             "(network.precision == 'bf16')")
+        self._check_table(table)
+        if train:
+            self._check_trainable()
+        self._reserve(2 * n)
         scale = self._grad_scale()
-        key = (feat.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), y.data_ptr())
-        use_graph = graph and self.kind != "adam"
-        if use_graph and self._graph_g is not None and self._graph_g[0] == key:
-            self._graph_g[1].replay()
-            if self._graph_g[2] is not None:        # all-reduce outside the graphs
+        key = (feat.data_ptr(),) + tuple(t.data_ptr() for t in table) + \
+            (None if sel is None else sel.data_ptr(), bool(train))
+        use_graph = graph and (self.kind != "adam" or not train)
+        g = self._graphs.get(key) if use_graph else None
+        if g is not None:
+            g[0].replay()
+            if g[1] is not None:                    # NCCL all-reduce between two graphs
                 self._allreduce()
-                self._graph_g[2].replay()
-            self.step_count += 1
+                g[1].replay()
+            self.step_count += int(train)
             return self.loss_buf
-        if use_graph and self._g_warm >= 2:
+        if use_graph and self._warm.get(key, 0) >= 2:
             torch.cuda.synchronize()
             fused_ar = self.world > 1 and os.environ.get("ABN_GRAPH_ALLREDUCE", "1") == "1"
-            g_fb = torch.cuda.CUDAGraph()
-            if self.world == 1 or fused_ar:
-                # ONE graph: gather .. backward, the NCCL all-reduce (captured), optimizer
-                with torch.cuda.graph(g_fb):
-                    self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)
-                    if self.world > 1:
-                        self._allreduce()
-                    self._optimizer(scale, 1)
-                self._graph_g = (key, g_fb, None)
+            g_main, g_opt = torch.cuda.CUDAGraph(), None
+            if not train or self.world == 1 or fused_ar:
+                # ONE graph: gather .. backward, the all-reduce (NCCL capture, or fused into
+                # the optimizer kernel over peer memory), optimizer
+                with torch.cuda.graph(g_main):
+                    self._table_fwd_loss(feat, table, n, sel, train)
+                    if train:
+                        if self.world > 1:
+                            self._allreduce()
+                        self._optimizer(scale, 1)
             else:
                 g_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_fb):
-                    self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)
+                with torch.cuda.graph(g_main):
+                    self._table_fwd_loss(feat, table, n, sel, train)
                 with torch.cuda.graph(g_opt):
                     self._optimizer(scale, 1)
-                self._graph_g = (key, g_fb, g_opt)
-            return self.step_gather(feat, idx1, idx2, y, n, graph=True)
-        self._g_warm += 1
-        self._gather_fwd_loss_bwd(feat, idx1, idx2, y, n)
-        if self.world > 1:
-            self._allreduce()
-        self.step_count += 1
-        self._optimizer(scale, self.step_count)
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = (g_main, g_opt)
+            return self._table_step(feat, table, n, sel, train, graph)
+        self._warm[key] = self._warm.get(key, 0) + 1
+        self._table_fwd_loss(feat, table, n, sel, train)
+        if train:
+            if self.world > 1:
+                self._allreduce()
+            self.step_count += 1
+            self._optimizer(scale, self.step_count)
         return self.loss_buf
+
+    def step_gather(self, feat, idx1, idx2, y, n, graph=True, y2=None, do_training=True):
+        """One training step on the batch ``sel`` (gather_buffers) of the device-resident
+        frame-pair table (idx1, idx2, y int8 [, y2 = y_phn when y = y_spk]) over ``feat``:
+        gather -> forward -> loss -> backward [-> all-reduce] -> optimizer, replayed as a
+        CUDA graph after two eager steps.  What FramesDataLoader.load_batch +
+        TrainerSiamese.optimize_model do per batch (abnet3/dataloader.py:673-684,
+        abnet3/trainer.py:226-243)."""
+        sel = self.gather_buffers(n)
+        table = (idx1, idx2, y) if y2 is None else (idx1, idx2, y, y2)
+        return self._table_step(feat, table, n, sel, do_training, graph)
+
+    def sweep_table(self, feat, table, n, n_batches, start=0, do_training=True, graph=True):
+        """One sweep of abnet3/trainer.py:229-243 over ``n_batches`` consecutive batches of
+        ``n`` rows of an (already shuffled) device-resident frame-pair table, starting at
+        row ``start``.  The batch position lives on the device (the gather kernel advances
+        it), so after two eager steps the sweep is ``n_batches`` replays of one CUDA graph
+        with no other per-batch work.  Returns the summed loss as a float64 device tensor
+        [1] (read it once per sweep; the reference synchronises on every step, :242)."""
+        if n_batches <= 0:
+            return torch.zeros(1, dtype=torch.float64, device=self.bucket.param.device)
+        if start + n * n_batches > table[0].numel():
+            raise ValueError("the sweep runs past the end of the frame-pair table")
+        self._reserve(2 * n)
+        self._cursor.copy_(torch.tensor([start, 0], dtype=torch.int64), non_blocking=True)
+        self.loss_buf.zero_()
+        self._loss_acc.zero_()
+        for _ in range(n_batches):
+            self._table_step(feat, table, n, None, do_training, graph)
+        return self._loss_acc + self.loss_buf.double()
 
     def step(self, x, n, *labels, do_training=True, graph=False):
         """x = [X1; X2] as one [2n, D] batch; labels float32 [n] (y) or
         (y_spk, y_phn).  Returns the loss as a 1-element device tensor that is
         overwritten by the next step.  graph=True replays CUDA graphs (not for Adam,
         whose bias correction changes every step)."""
+        if do_training:
+            self._check_trainable()
         if graph and do_training and self.kind != "adam":
             return self.step_graphed(x, n, *labels)
         out = self.forward(x)

@@ -107,11 +107,12 @@ class NetworkBuilder(nn.Module):
             layer.bias.data.fill_(0.0)
 
     # -- kernel path helpers ------------------------------------------------
-    def _check_supported(self):
+    def _check_supported(self, training=None):
+        training = self.training if training is None else training
         if self.batch_norm:
             raise NotImplementedError(
                 "batch_norm=True is not implemented by the sm_100a kernels (no fallback)")
-        if self.training and self.p_dropout > 0:
+        if training and self.p_dropout > 0:
             raise NotImplementedError(
                 "dropout with p > 0 in training mode is not implemented by the sm_100a "
                 "kernels (use p_dropout=0 as in test/data/buckeye.yaml, or eval mode)")
@@ -144,13 +145,14 @@ def _layer(n_in, n_out, p_dropout, batch_norm, act_cls):
 
 
 class SiameseNetwork(NetworkBuilder):
-    """abnet3/model.py:82-208.  Same parameters; ``precision`` ('fp32' | 'bf16')
-    selects the kernel path of the layers."""
+    """abnet3/model.py:82-208.  Same parameters; ``precision`` selects the kernel path of
+    the layers: 'bf16' (default) = tcgen05 tensor cores with fp32 accumulation and fp32
+    master weights, 'fp32' = the SIMT kernels (the 1e-4 parity path)."""
 
     def __init__(self, input_dim=None, num_hidden_layers=None, hidden_dim=None,
                  output_dim=None, p_dropout=0.1, batch_norm=False,
                  type_init='xavier_uni', activation_layer=None,
-                 output_path=None, last_non_linearity="default", precision="fp32"):
+                 output_path=None, last_non_linearity="default", precision="bf16"):
         super(SiameseNetwork, self).__init__()
         assert activation_layer in ('relu', 'sigmoid', 'tanh')
         assert type_init in ('xavier_uni', 'xavier_normal', 'orthogonal')
@@ -239,7 +241,7 @@ class SiameseMultitaskNetwork(NetworkBuilder):
                  hidden_dim=None,
                  output_dim=None, p_dropout=0.1, batch_norm=False,
                  type_init='xavier_uni', activation_layer=None,
-                 output_path=None, precision="fp32"):
+                 output_path=None, precision="bf16"):
         super(SiameseMultitaskNetwork, self).__init__()
         assert activation_layer in ('relu', 'sigmoid', 'tanh')
         assert type_init in ('xavier_uni', 'xavier_normal', 'orthogonal')

@@ -7,10 +7,16 @@ pass, per-epoch train sweep + dev sweep, early stopping on the SUMMED dev loss
 run every step through the fused kernels (abnet3_b200.engine).
 
 New: data parallelism.  Under ``torchrun`` (one process per GPU,
-``torch.distributed`` initialised with NCCL) every rank trains on its own shard
-of the pair list and the flat gradient bucket is all-reduced once per step;
-ranks agree on the number of steps per epoch (the minimum over ranks) so the
-collective never deadlocks.  ``shard_pairs`` cuts a pair list for a rank.
+``torch.distributed`` initialised with NCCL) every rank starts from rank 0's
+weights, aligns and trains on its own shard of the pair lists
+(``dataloader.shard(rank, world)``, applied by the trainer) and the flat gradient
+bucket is exchanged once per step; ranks agree ONCE per epoch on the number of
+steps (the minimum over ranks) so the exchange never deadlocks.
+
+With a ``FramesDataLoader`` and the bf16 engine (the default) a sweep is
+``engine.sweep_table``: the batch position lives on the device and every step is
+one replay of a CUDA graph (gather -> forward -> loss -> backward -> exchange ->
+optimizer); nothing is copied or synchronised per batch.
 
 The loss is accumulated on the device and read back once per sweep (the
 reference synchronises on ``loss.data[0]`` every step, :242).
@@ -77,6 +83,8 @@ class TrainerBuilder:
         self.seed = seed
         self.cuda = cuda
         self.statistics_training = {}
+        self.train_losses = []
+        self.dev_losses = []
         self.dataloader = dataloader
         self.feature_generator = feature_generator
         self.checkpoints = checkpoints
@@ -106,6 +114,13 @@ class TrainerBuilder:
             if optimizer_type == 'sgd':
                 kw['momentum'] = self.momentum or 0.0
             self.optimizer = cls(self.network.parameters(), **kw)
+            if self.world > 1:          # same starting point on every rank
+                for p in self.network.parameters():
+                    dist.broadcast(p.data, src=0)
+        if self.world > 1 and self.dataloader is not None and hasattr(self.dataloader, 'shard'):
+            # every rank aligns and trains on its own part of the pair lists
+            if getattr(self.dataloader, '_shard', None) is None:
+                self.dataloader.shard(self.rank, self.world)
 
     def params(self):
         params = copy.copy(self.__dict__)
@@ -213,27 +228,74 @@ class TrainerSiamese(TrainerBuilder):
         labels = [t.cuda().float().contiguous() for t in batch[2:]]
         return _joint(x1.float(), x2.float()), x1.shape[0], labels
 
+    def _reduce_grads(self):
+        """torch.optim fallback under data parallelism: sum the gradients over the ranks
+        (mean for an averaged loss), as the fused engine does inside its step."""
+        if self.world <= 1:
+            return
+        avg = bool(getattr(self.loss, 'avg', False))
+        for p in self.network.parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad)
+                if avg:
+                    p.grad.div_(self.world)
+
+    def _agreed_batches(self, n_batches):
+        """Ranks must run the same number of training steps (one gradient exchange each):
+        ONE min-reduction per epoch; the reference already drops the tail
+        (abnet3/dataloader.py:708)."""
+        if self.world <= 1:
+            return n_batches
+        t = torch.tensor([n_batches], dtype=torch.int64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
+
+    def _sweep_table(self, train_mode, do_training):
+        """Sweep over a device-resident frame-pair table (FramesDataLoader.epoch_table):
+        the engine gathers every batch itself and replays one CUDA graph per step."""
+        feat, table, bs, first_row, n_batches = self.dataloader.epoch_table(train_mode=train_mode)
+        training = train_mode and do_training
+        if training:
+            n_batches = self._agreed_batches(n_batches)
+        total = self.engine.sweep_table(feat, table, bs, n_batches, start=first_row,
+                                        do_training=training)
+        return float(total.item()), n_batches
+
     def _sweep(self, train_mode, do_training):
         """One pass over the dataloader; returns (summed loss, number of batches)."""
+        if (self.engine is not None and self.engine.precision == 1
+                and hasattr(self.dataloader, 'epoch_table')):
+            return self._sweep_table(train_mode, do_training)
         total = torch.zeros(1, dtype=torch.float32, device='cuda')
         n_batches = 0
+        training = train_mode and do_training
         it = self.dataloader.batch_iterator(train_mode=train_mode)
         while True:
             batch = next(it, None)
-            if self.world > 1 and (train_mode and do_training):
+            if self.world > 1 and training:
+                # generator loaders do not know their length in advance
                 if not all_ranks_have_batch(batch is not None, 'cuda', self.world):
                     break
             if batch is None:
                 break
             if self.engine is not None:
                 x, n, labels = self._joint_batch(batch)
-                loss = self.engine.step(x, n, *labels, do_training=train_mode and do_training)
+                loss = self.engine.step(x, n, *labels, do_training=training)
                 total += loss
+            elif training and self.optimizer_type == 'LBFGS':
+                def closure():
+                    self.optimizer.zero_grad()
+                    out = self.give_batch_to_network(batch)
+                    out.backward()
+                    self._reduce_grads()
+                    return out
+                total += self.optimizer.step(closure).detach()
             else:
                 loss = self.give_batch_to_network(batch)
                 self.optimizer.zero_grad()
-                if train_mode and do_training:
+                if training:
                     loss.backward()
+                    self._reduce_grads()
                     self.optimizer.step()
                 total += loss.detach()
             n_batches += 1
@@ -245,6 +307,7 @@ class TrainerSiamese(TrainerBuilder):
         train_loss, num_batches_train = self._sweep(True, do_training)
         self.network.eval()
         dev_loss, num_batches_dev = self._sweep(False, False)
+        self.last_sweep = {'train_batches': num_batches_train, 'dev_batches': num_batches_dev}
         if self.world > 1:
             t = torch.tensor([train_loss, num_batches_train, dev_loss, num_batches_dev],
                              dtype=torch.float64, device='cuda')

@@ -263,6 +263,31 @@ class FeatureTable(object):
         if self.feat.is_cuda:
             self.stack = self._detect_stack()
 
+    @classmethod
+    def from_device(cls, feat, file_off, files=None):
+        """Wrap a table that is already on the GPU: ``feat`` [n_rows, dim] float32 CUDA
+        tensor, ``file_off`` [n_files + 1] row offsets (any integer sequence).  No host copy
+        is kept (``host`` is None); frame times default to 0.0025 + 0.01 k."""
+        self = cls.__new__(cls)
+        off = [int(v) for v in (file_off.tolist() if hasattr(file_off, "tolist") else file_off)]
+        self.files = list(files) if files is not None else ["file%d" % i for i in range(len(off) - 1)]
+        self.row0 = {f: off[i] for i, f in enumerate(self.files)}
+        self.nrows = {f: off[i + 1] - off[i] for i, f in enumerate(self.files)}
+        self.times = {f: 0.0025 + 0.01 * np.arange(self.nrows[f]) for f in self.files}
+        self.dim = int(feat.shape[1])
+        self.host = None
+        self.device = feat.device
+        self.feat = feat
+        self.stack = self._detect_stack() if feat.is_cuda else 0
+        return self
+
+    @classmethod
+    def from_host(cls, feat_host, file_off, files=None, device=None):
+        """Upload a host table ([n_rows, dim] float32 CPU tensor, ideally pinned) in ONE
+        asynchronous copy and wrap it (see from_device)."""
+        dev = device if device is not None else _device()
+        return cls.from_device(feat_host.to(dev, non_blocking=True), file_off, files)
+
     def _detect_stack(self, stack=7):
         """7 when every file is a 7-frame stack of dim/7-wide frames
         (abnet3/features.py:135-159), checked row by row on the device; the

@@ -369,6 +369,20 @@ ABN_API int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *idx
                                   const int32_t *idx2, const int8_t *y_in, const int64_t *sel,
                                   int64_t n, void *xb, int64_t ldx, float *y_out, void *zero_me,
                                   int zero_words, abn_stream_t stream);
+/* abn_gather_step_bf16: abn_gather_batch_bf16 for an EPOCH of fixed-size frame batches over a
+ *   device-resident, already shuffled frame-pair table (FramesDataLoader.batch_iterator,
+ *   abnet3/dataloader.py:686-739, feeding abnet3/trainer.py:231-243), so that a training step
+ *   replays as one CUDA graph with no per-batch host work:
+ *   - y2_in / y2_out (nullable): a second label column (y_spk beside y_phn, dataloader.py:753-792);
+ *   - cursor (nullable, device int64[2] = {next row, 0}): when sel == NULL the batch is the table
+ *     rows cursor[0] .. cursor[0]+n-1 and the kernel advances cursor[0] by n;
+ *   - loss_acc (nullable, device double[1]): before zero_me is cleared its word 0 (the previous
+ *     step's float loss) is added to loss_acc -- `train_loss += loss.data[0]`, trainer.py:242. */
+ABN_API int abn_gather_step_bf16(const float *feat, int dim, const int32_t *idx1,
+                                 const int32_t *idx2, const int8_t *y_in, const int8_t *y2_in,
+                                 const int64_t *sel, int64_t *cursor, int64_t n, void *xb,
+                                 int64_t ldx, float *y_out, float *y2_out, void *zero_me,
+                                 int zero_words, double *loss_acc, abn_stream_t stream);
 ABN_API int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,
                              int64_t ld, int kind, float margin, float scale, int act, float *loss,
                              void *dz1, void *dz2, int64_t ld_dz, abn_stream_t stream);

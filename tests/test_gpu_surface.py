@@ -55,7 +55,7 @@ CFGS = {
 
 @pytest.mark.parametrize("name", sorted(CFGS))
 def test_siamese_network_matches_reference_golden(gold, name):
-    net = SiameseNetwork(**CFGS[name]).to(DEV)
+    net = SiameseNetwork(precision="fp32", **CFGS[name]).to(DEV)
     _load_sd(net, gold, name)
     net.train()
     x1 = torch.from_numpy(gold[name + "/x1"]).to(DEV)
@@ -81,7 +81,7 @@ def test_multitask_network_matches_reference_golden(gold):
     cfg = dict(input_dim=40, num_hidden_layers_shared=2, num_hidden_layers_spk=1,
                num_hidden_layers_phn=1, hidden_dim=48, output_dim=20, p_dropout=0.0,
                activation_layer="sigmoid")
-    net = SiameseMultitaskNetwork(**cfg).to(DEV)
+    net = SiameseMultitaskNetwork(precision="fp32", **cfg).to(DEV)
     _load_sd(net, gold, "multi")
     net.train()
     x1, x2 = torch.from_numpy(gold["multi/x1"]).to(DEV), torch.from_numpy(gold["multi/x2"]).to(DEV)
@@ -124,7 +124,7 @@ def test_fused_train_step_matches_autograd_and_torch_optim(opt, lr):
     """trainer.py:237-240 on the canonical 280-500-500-500-100 network."""
     torch.manual_seed(0)
     net = SiameseNetwork(input_dim=280, num_hidden_layers=2, hidden_dim=500, output_dim=100,
-                         p_dropout=0.0, activation_layer="sigmoid").to(DEV)
+                         p_dropout=0.0, activation_layer="sigmoid", precision="fp32").to(DEV)
     sd0 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
     step = SiameseTrainStep(net, ("coscos2", 0.0, False), opt, lr=lr, momentum=0.9)
     ref = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
@@ -159,7 +159,7 @@ def test_graphed_step_equals_eager_step():
     torch.manual_seed(3)
     cfg = dict(input_dim=280, num_hidden_layers=2, hidden_dim=500, output_dim=100, p_dropout=0.0,
                activation_layer="sigmoid")
-    a, b = SiameseNetwork(**cfg).to(DEV), SiameseNetwork(**cfg).to(DEV)
+    a, b = SiameseNetwork(precision="fp32", **cfg).to(DEV), SiameseNetwork(precision="fp32", **cfg).to(DEV)
     b.load_state_dict(a.state_dict())
     sa = SiameseTrainStep(a, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
     sb = SiameseTrainStep(b, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
@@ -179,7 +179,7 @@ def test_fused_multitask_step_matches_autograd():
     net = SiameseMultitaskNetwork(input_dim=280, num_hidden_layers_shared=2,
                                   num_hidden_layers_spk=1, num_hidden_layers_phn=1,
                                   hidden_dim=500, output_dim=100, p_dropout=0.0,
-                                  activation_layer="sigmoid").to(DEV)
+                                  activation_layer="sigmoid", precision="fp32").to(DEV)
     sd0 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
     spec = (("coscos2", 0.0, False), ("coscos2", 0.0, False), 0.3)
     step = SiameseTrainStep(net, spec, "sgd", lr=0.05, momentum=0.0)

@@ -88,7 +88,7 @@ def test_bf16_training_step_tracks_fp32_step():
     torch.manual_seed(0)
     cfg = dict(input_dim=280, num_hidden_layers=2, hidden_dim=500, output_dim=100, p_dropout=0.0,
                activation_layer="sigmoid")
-    n32 = SiameseNetwork(**cfg).to(DEV)
+    n32 = SiameseNetwork(precision="fp32", **cfg).to(DEV)
     n16 = SiameseNetwork(precision="bf16", **cfg).to(DEV)
     n16.load_state_dict(n32.state_dict())
     s32 = SiameseTrainStep(n32, ("coscos2", 0.0, False), "sgd", lr=0.05, momentum=0.0)
@@ -111,7 +111,7 @@ def test_bf16_multitask_step_tracks_fp32_step():
     cfg = dict(input_dim=280, num_hidden_layers_shared=2, num_hidden_layers_spk=1,
                num_hidden_layers_phn=1, hidden_dim=500, output_dim=100, p_dropout=0.0,
                activation_layer="sigmoid")
-    n32 = SiameseMultitaskNetwork(**cfg).to(DEV)
+    n32 = SiameseMultitaskNetwork(precision="fp32", **cfg).to(DEV)
     n16 = SiameseMultitaskNetwork(precision="bf16", **cfg).to(DEV)
     n16.load_state_dict(n32.state_dict())
     spec = (("coscos2", 0.0, False), ("coscos2", 0.0, False), 0.3)
@@ -174,7 +174,7 @@ def test_network_wider_than_the_slab_trains_through_the_grouped_gemm():
     cfg = dict(input_dim=280, num_hidden_layers=1, hidden_dim=640, output_dim=100, p_dropout=0.0,
                activation_layer="sigmoid")
     torch.manual_seed(8)
-    n32 = SiameseNetwork(**cfg).to(DEV)
+    n32 = SiameseNetwork(precision="fp32", **cfg).to(DEV)
     n16 = SiameseNetwork(precision="bf16", **cfg).to(DEV)
     n16.load_state_dict(n32.state_dict())
     s32 = SiameseTrainStep(n32, ("coscos2", 0.0, False), "sgd", lr=0.05, momentum=0.0)
