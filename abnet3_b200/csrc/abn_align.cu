@@ -591,7 +591,7 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity) 
 template <bool TO_GMEM, typename L>
 __device__ __forceinline__ int stack_epilogue(const float *Gs, const float *norms, const int *tb,
                                               unsigned dsk_addr, float *dist_gmem, int n1, int n2,
-                                              int tid) {
+                                              int tid, int ld_gmem) {
     constexpr int RUN = 8;
     int bad = 0;
     const int W = n2 + RUN - 1;
@@ -614,7 +614,7 @@ __device__ __forceinline__ int stack_epilogue(const float *Gs, const float *norm
             const float dd = cell_distance(tot, norms[i], norms[L::ROWS_A + j]);
             if (k >= klo && k < khi) {
                 if (!(dd >= 0.f)) bad = 1;
-                if (TO_GMEM) dist_gmem[(size_t)i * n2 + j] = dd;
+                if (TO_GMEM) dist_gmem[(size_t)i * ld_gmem + j] = dd;
                 else asm volatile("st.shared.f32 [%0], %1;" ::"r"(dsk_addr + 4u * (unsigned)(tb[i + j] + i)),
                                   "f"(dd) : "memory");
             }
@@ -731,9 +731,9 @@ align_stack_kernel(const AlignArgs a) {
         if (!a.dist_out) skew_guards(Ds, tb, n1, tid);
         if (a.dist_out)
             bad = stack_epilogue<true, L>(Gs, norms, tb, sbase, a.dist_out + a.dist_off[p], n1, n2,
-                                          tid);
+                                          tid, n2);
         else
-            bad = stack_epilogue<false, L>(Gs, norms, tb, sbase, nullptr, n1, n2, tid);
+            bad = stack_epilogue<false, L>(Gs, norms, tb, sbase, nullptr, n1, n2, tid, n2);
         bad = __syncthreads_or(bad);
         if (tid == 0) {
             a.valid[p] = bad ? 0 : 1;
@@ -848,6 +848,7 @@ class_scatter_kernel(const AlignArgs a, const int *__restrict__ class_off,
         if (p < a.n_pairs) {
             cls[u] = pair_class(reinterpret_cast<const int4 *>(a.pair_tok)[p], a.n_rows, a.stack);
             rank[u] = atomicAdd(&hist[cls[u]], 1);
+            if (cls[u] == CLS_LONG && a.dist_out) a.valid[p] = 1;     // tiles clear it on a NaN
         }
     }
     __syncthreads();
@@ -863,180 +864,337 @@ class_scatter_kernel(const AlignArgs a, const int *__restrict__ class_off,
 }
 
 
-// ------------------------------------------------- long tokens (> 96 frames)
-// One CTA walks the n1 x n2 matrix in 96 x 96 tiles, band by band: the tile's
-// distances are computed into smem exactly like a (6,6) class pair, then warp 0
-// sweeps the tile with the accumulated costs of the row above (`top`) and of
-// the column to the left (`left`) as boundary conditions, so the recurrence is
-// the same cell-by-cell sequence of float64 operations as the un-tiled sweep.
-// Directions are packed 2 bits per cell for the whole matrix in smem.
-constexpr int LT = NM_SHORT;     // tile side
+// ------------------------------------------- long tokens, two-kernel path
+// Long pairs follow the same two-stage scheme as the fused classes, with the matrix cut in
+// tiles for the distance stage and in 128-row bands for the DTW stage:
+//   long_tile_kernel<STACKED>  one CTA per (pair, tile): the tile's distances exactly like a
+//       (6,6) class pair -- stacked tables through the 40-deep Gram + 7-tap diagonal sums
+//       (90 x 90 tiles: 96 extended frames per side), generic tables through the 280-deep
+//       register tile (96 x 96) -- written to the pair's skew-layout slot in the hand-over
+//       workspace (anti-diagonal segments of a tile are contiguous there).  Tiles are
+//       independent: the whole device works on the distance stage of a window of pairs.
+//   dtw_band_kernel            one warp per pair.  Lane l owns rows 128 b + 4 l .. + 3 of band
+//       b and sweeps the band's anti-diagonals over ALL columns (n2 + 127 steps, coalesced
+//       skew-layout loads, same float64 recurrence and tie order as dtw_skew_kernel); the
+//       band's last row is the next band's boundary (shared memory).  Directions go to a
+//       per-warp scratch area in global memory (one coalesced 128-byte store per 4 steps),
+//       lane 0 walks them back.
+constexpr int LT_GEN = NM_SHORT;          // 96
+constexpr int LT_STK = STACK_MAXN;        // 90
+constexpr int BAND_G = 4, BAND_ROWS = 32 * BAND_G;
+constexpr int LONG_SLACK = 2 * BAND_ROWS + 16;     // floats a band sweep may read past the matrix
+constexpr int LONG_DTW_WARPS = 4;
+constexpr int LONG_DTW_MAX_CTAS = 1024;
 
-struct LongLayout {
-    int ldp;                     // bytes per row of the packed direction matrix
-    unsigned top0_off, top1_off, left_off, dirs_off, path_off, misc_off, total;
+struct LongArgs {
+    float *dws;             // hand-over slots of the window's long pairs
+    unsigned *bad;          // one flag per slot: a NaN / negative distance was seen
+    uint8_t *dirs;          // per-warp direction scratch of dtw_band_kernel
+    size_t slot_cells;      // floats per slot
+    size_t dirs_bytes;      // bytes per warp
+    int lw0, lw1;           // window inside the CLS_LONG class (positions relative to its start)
+    int tcap;               // tiles per side of the largest matrix
 };
-__host__ __device__ inline LongLayout long_layout(int nmax) {
-    using L = ClassLayout<NCLS_SIDE, NCLS_SIDE>;
-    LongLayout o;
-    o.ldp = (nmax + 3) / 4;
-    o.top0_off = a16(L::PATH_OFF);                       // the class layout's path / misc area is unused
-    o.top1_off = o.top0_off + 8u * (nmax + 1);
-    o.left_off = o.top1_off + 8u * (nmax + 1);
-    o.dirs_off = a16(o.left_off + 8u * LT);
-    o.path_off = a16(o.dirs_off + (unsigned)nmax * o.ldp);
-    o.misc_off = a16(o.path_off + 4u * 2u * nmax);       // two uint16 arrays of 2 nmax entries
-    o.total = o.misc_off + 32u;
-    return o;
+
+__host__ __device__ inline size_t long_dirs_bytes(int nmax) {
+    const size_t bands = (size_t)(nmax + BAND_ROWS - 1) / BAND_ROWS;
+    return bands * (size_t)((nmax + BAND_ROWS + 3) / 4 + 1) * BAND_ROWS;
 }
 
-// top[1 + j] = C[i0 - 1][j] (top[0] unused pad so that top[j0] is the corner of column j0)
-template <int G>
-__device__ __forceinline__ double tile_wavefront(const float *D, int ldd, int h, int w, int i0g,
-                                                 int j0g, const double *top, double *top_next,
-                                                 double *left, uint8_t *dirs, int ldp, int lane) {
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    double cur[G], prev[G];
-    unsigned bits[G];
-    const int r0 = lane * G;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        cur[g] = prev[g] = (r0 + g < h) ? left[r0 + g] : INF;
-        bits[g] = 0;
-    }
-    // value "two steps ago" of the row above this lane's first row: its left boundary
-    double nbprev = lane == 0 ? top[j0g] : ((r0 - 1 < h) ? left[r0 - 1] : INF);
-    const int T = h + w - 1;
-    for (int t = 0; t < T; ++t) {
-        double up0 = __shfl_up_sync(0xffffffffu, cur[G - 1], 1);
-        if (lane == 0) up0 = top[1 + j0g + min(t, w - 1)];
-        const double dg0 = nbprev;
-        nbprev = up0;
-        double nw[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int r = r0 + g, j = t - r;
-            const bool ok = (r < h) & ((unsigned)j < (unsigned)w);
-            const int cell = ok ? r * ldd + j : 0;
-            const double d = (double)D[cell];
-            const double up = g == 0 ? up0 : cur[g - 1];
-            const double dg = g == 0 ? dg0 : prev[g - 1];
-            const double lf = cur[g];
-            const bool up_le = up <= lf;
-            const double m1 = up_le ? up : lf;
-            const bool use_dg = dg <= m1;
-            double m = use_dg ? dg : m1;
-            const unsigned dir = use_dg ? DIR_DIAG : (up_le ? DIR_UP : DIR_LEFT);
-            m = ((i0g + r) | (j0g + j)) == 0 ? 0.0 : m;
-            const double v = d + m;
-            nw[g] = ok ? v : lf;
-            if (ok) {
-                bits[g] |= dir << (2 * (j & 3));
-                if ((j & 3) == 3 || j == w - 1) {
-                    dirs[(i0g + r) * ldp + ((j0g + j) >> 2)] = (uint8_t)bits[g];
-                    bits[g] = 0;
-                }
-                if (r == h - 1) top_next[1 + j0g + j] = v;
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) { prev[g] = cur[g]; cur[g] = nw[g]; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-        if (r0 + g < h) left[r0 + g] = cur[g];          // right column -> next tile's left
-    double c = 0.0;
-#pragma unroll
-    for (int g = 0; g < G; ++g) c = ((h - 1) % G == g) ? cur[g] : c;
-    return __shfl_sync(0xffffffffu, c, (h - 1) / G);
-}
-
+template <bool STACKED, int R>
 __global__ void __launch_bounds__(AL_THREADS)
-align_long_kernel(const AlignArgs a, int nmax) {
-    using L = ClassLayout<NCLS_SIDE, NCLS_SIDE>;
+long_tile_kernel(const AlignArgs a, const LongArgs la) {
+    using LS = StackLayout<R, R>;
+    using LG = DistLayout<R, R>;
+    constexpr int LTS = STACKED ? 16 * R - 2 * STACK_H : 16 * R;
+    constexpr unsigned TBG_OFF = STACKED ? LS::TOTAL : LG::TOTAL;     // int[32 R]: global bases per tile diagonal
     extern __shared__ __align__(16) unsigned char smem[];
-    const LongLayout LL = long_layout(nmax);
     const int tid = threadIdx.x;
-    const int beg = a.class_off[CLS_LONG], end = a.class_off[CLS_LONG + 1];
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const unsigned sbase = smem_u32(smem);
     float *Ds = reinterpret_cast<float *>(smem);
-    double *topbuf[2] = {reinterpret_cast<double *>(smem + LL.top0_off),
-                         reinterpret_cast<double *>(smem + LL.top1_off)};
-    double *left = reinterpret_cast<double *>(smem + LL.left_off);
-    uint8_t *dirs = smem + LL.dirs_off;
-    uint16_t *pb_i = reinterpret_cast<uint16_t *>(smem + LL.path_off);
-    uint16_t *pb_j = pb_i + 2 * nmax;
-    int *misc = reinterpret_cast<int *>(smem + LL.misc_off);
-
-    for (int it = beg + blockIdx.x; it < end; it += gridDim.x) {
-        const int p = a.order[it];
+    int *tb = reinterpret_cast<int *>(smem + (STACKED ? LS::TB_OFF : LG::TB_OFF));
+    int *tbg = reinterpret_cast<int *>(smem + TBG_OFF);
+    const int cbeg = a.class_off[CLS_LONG], cend = a.class_off[CLS_LONG + 1];
+    const int lo = cbeg + la.lw0, hi = min(cend, cbeg + la.lw1);
+    const int t2 = la.tcap * la.tcap;
+    unsigned phase = 0;
+    const unsigned bar = sbase + LS::BAR_OFF;
+    if (STACKED) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    const long long n_work = (long long)max(hi - lo, 0) * t2;
+    for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int k = (int)(w / t2), tile = (int)(w - (long long)k * t2);
+        const int bi = tile / la.tcap, bj = tile - bi * la.tcap;
+        const int p = a.order[lo + k];
         const int4 tk = reinterpret_cast<const int4 *>(a.pair_tok)[p];
         const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
-        if (n1 > nmax || n2 > nmax) {      // max_frames promised by the caller was too small
-            if (tid == 0) {
-                a.valid[p] = 0;
-                if (!a.dist_out) { a.path_len[p] = 0; a.cost[p] = nan(""); }
+        const int i0 = bi * LTS, j0 = bj * LTS;
+        if (i0 >= n1 || j0 >= n2) continue;                 // CTA-uniform
+        const int h = min(LTS, n1 - i0), wd = min(LTS, n2 - j0);
+        const int slot = k;
+        float *dst = la.dws ? la.dws + (size_t)slot * la.slot_cells : nullptr;
+        const float *g1 = a.feat + (size_t)s1 * a.dim, *g2 = a.feat + (size_t)s2 * a.dim;
+        int bad = 0;
+        if (!a.dist_out) {
+            skew_table(tb, h, wd, tid);                                       // tile-local layout
+            for (int t = tid; t < h + wd - 1; t += AL_THREADS)                // where diagonal t of the tile starts
+                tbg[t] = skew_base(i0 + j0 + t, n1, n2) + i0;                 // in the pair's slot (row i0)
+        }
+        if (STACKED) {
+            const int he = h + 2 * STACK_H, we = wd + 2 * STACK_H;
+            float *Gs = reinterpret_cast<float *>(smem + LS::G_OFF);
+            float *n40 = reinterpret_cast<float *>(smem + LS::N40_OFF);
+            float *norms = reinterpret_cast<float *>(smem + LS::NORMS_OFF);
+            const int warp = tid >> 5, lane = tid & 31;
+            const int ti = (warp >> 1) * 8 + (lane >> 2);
+            const int tj = (warp & 1) * 4 + (lane & 3);
+            if (tid == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                             "r"((unsigned)(he + we) * (STACK_F * 4u)) : "memory");
+            for (int e = tid; e < he + we; e += AL_THREADS) {
+                const bool first = e < he;
+                const int ee = first ? e : e - he;
+                const float *src = first ? ext_frame(g1, n1, a.dim, i0 + ee) : ext_frame(g2, n2, a.dim, j0 + ee);
+                bulk_g2s(sbase + ((first ? 0 : LS::ROWS_A) + ee) * (KCP * 4), src, STACK_F * 4u, bar);
             }
-            continue;
-        }
-        for (int j = tid; j <= n2; j += AL_THREADS) topbuf[0][j] = INF;
-        int any_bad = 0;
-        double cost = 0.0;
-        int band = 0;
-        for (int i0 = 0; i0 < n1 && !any_bad; i0 += LT, ++band) {
-            const int h = min(LT, n1 - i0);
-            const double *top = topbuf[band & 1];
-            double *top_next = topbuf[(band + 1) & 1];
-            for (int r = tid; r < LT; r += AL_THREADS) left[r] = INF;
-            if (tid == 0) top_next[0] = INF;
-            for (int j0 = 0; j0 < n2; j0 += LT) {
-                const int w = min(LT, n2 - j0);
-                int bad = 0;
-                pair_distance<NCLS_SIDE, NCLS_SIDE, L>(
-                    smem, a.feat + (size_t)(s1 + i0) * a.dim, a.feat + (size_t)(s2 + j0) * a.dim, h,
-                    w, a.dim,
-                    a.dist_out ? a.dist_out + a.dist_off[p] + (size_t)i0 * n2 + j0 : nullptr, n2,
-                    nullptr, bad);
-                bad = __syncthreads_or(bad);
-                if (bad) { any_bad = 1; break; }
-                if (!a.dist_out && tid < 32)
-                    cost = tile_wavefront<3>(Ds, L::LDD, h, w, i0, j0, top, top_next, left, dirs,
-                                             LL.ldp, tid);
-                __syncthreads();
+            mbar_wait_parity(bar, phase);
+            phase ^= 1u;
+            for (int q = tid; q < he + we; q += AL_THREADS) {
+                const int row = q < he ? q : LS::ROWS_A + (q - he);
+                n40[row] = row_sumsq(sbase + row * (KCP * 4), STACK_F / 4);
             }
-        }
-        if (a.dist_out) {
-            if (tid == 0) a.valid[p] = any_bad ? 0 : 1;
-            continue;
-        }
-        if (any_bad) {
-            if (tid == 0) { a.path_len[p] = 0; a.cost[p] = nan(""); a.valid[p] = 0; }
+            float acc[R][2 * R];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < 2 * R; ++c) acc[r][c] = 0.f;
+            {
+                const unsigned a_addr = sbase + ti * (KCP * 4);
+                const unsigned b_addr = sbase + (LS::ROWS_A + tj) * (KCP * 4);
+#pragma unroll 2
+                for (int k4 = 0; k4 < STACK_F / 4; ++k4) {
+                    float4 av[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) av[r] = lds128(a_addr + (16 * r) * (KCP * 4) + k4 * 16);
+#pragma unroll
+                    for (int cg = 0; cg < R; ++cg) {
+                        float4 bv[2];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            bv[c] = lds128(b_addr + (8 * (2 * cg + c)) * (KCP * 4) + k4 * 16);
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                float t = acc[r][2 * cg + c];
+                                t = fmaf(av[r].x, bv[c].x, t);
+                                t = fmaf(av[r].y, bv[c].y, t);
+                                t = fmaf(av[r].z, bv[c].z, t);
+                                t = fmaf(av[r].w, bv[c].w, t);
+                                acc[r][2 * cg + c] = t;
+                            }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < 2 * R; ++c) Gs[(ti + 16 * r) * LS::LDG + tj + 8 * c] = acc[r][c];
             __syncthreads();
+            for (int q = tid; q < h + wd; q += AL_THREADS) {
+                const int r0 = q < h ? q : LS::ROWS_A + (q - h);
+                float ss = 0.f;
+#pragma unroll
+                for (int c = 0; c < STACK_S; ++c) ss += n40[r0 + c];
+                norms[r0] = recip_norm(ss);
+            }
+            __syncthreads();
+            if (a.dist_out)
+                bad = stack_epilogue<true, LS>(Gs, norms, tb, sbase,
+                                               a.dist_out + a.dist_off[p] + (size_t)i0 * n2 + j0, h, wd, tid, n2);
+            else
+                bad = stack_epilogue<false, LS>(Gs, norms, tb, sbase, nullptr, h, wd, tid, wd);
+        } else {
+            pair_distance<R, R, LG>(
+                smem, g1 + (size_t)i0 * a.dim, g2 + (size_t)j0 * a.dim, h, wd, a.dim,
+                a.dist_out ? a.dist_out + a.dist_off[p] + (size_t)i0 * n2 + j0 : nullptr, n2,
+                a.dist_out ? nullptr : tb, bad);
+        }
+        bad = __syncthreads_or(bad);
+        if (bad && tid == 0) {
+            if (a.dist_out) a.valid[p] = 0;
+            else la.bad[slot] = 1u;
+        }
+        if (!a.dist_out) {
+            // tile-local skew -> the pair's slot: diagonal t of the tile is one contiguous run of
+            // rows rlo .. rhi in both layouts; one warp per diagonal
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int t = warp; t < h + wd - 1; t += AL_THREADS / 32) {
+                const int rlo = max(0, t - wd + 1), rhi = min(h - 1, t);
+                const float *src = Ds + tb[t];
+                float *d = dst + tbg[t];
+                for (int r = rlo + lane; r <= rhi; r += 32) d[r] = src[r];
+            }
+            // the +inf guard after diagonal i - 1 of the pair (the cell left of row i)
+            if (bj == 0)
+                for (int r = tid; r < h; r += AL_THREADS) {
+                    const int i = i0 + r;
+                    if (i >= 1) dst[skew_base(i - 1, n1, n2) + i] = __int_as_float(0x7f800000);
+                }
+        }
+        if (STACKED) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(LONG_DTW_WARPS * 32)
+dtw_band_kernel(const AlignArgs a, const LongArgs la, int nmax) {
+    constexpr int G = BAND_G;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned per_warp = 2u * 8u * (unsigned)(nmax + 2) + 4u * 2u * (unsigned)nmax;
+    unsigned char *mine = smem + warp * per_warp;
+    double *topbuf0 = reinterpret_cast<double *>(mine);
+    uint16_t *pb_i = reinterpret_cast<uint16_t *>(mine + 2u * 8u * (unsigned)(nmax + 2));
+    uint16_t *pb_j = pb_i + 2 * nmax;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int cbeg = a.class_off[CLS_LONG], cend = a.class_off[CLS_LONG + 1];
+    const int lo = cbeg + la.lw0, hi = min(cend, cbeg + la.lw1);
+    const int gw = blockIdx.x * LONG_DTW_WARPS + warp;
+    uint8_t *dirs = la.dirs + (size_t)gw * la.dirs_bytes;
+    const unsigned band_bytes = (unsigned)((nmax + BAND_ROWS + 3) / 4 + 1) * BAND_ROWS;
+    const int r0 = lane * G;
+
+    for (int k = gw; lo + k < hi; k += gridDim.x * LONG_DTW_WARPS) {
+        const int p = a.order[lo + k];
+        const int4 tk = reinterpret_cast<const int4 *>(a.pair_tok)[p];
+        const int s1 = tk.x, n1 = tk.y, s2 = tk.z, n2 = tk.w;
+        if (la.bad[k] || n1 > nmax || n2 > nmax) {    // NaN in the matrix (utils.py:59), or max_frames was too small
+            if (lane == 0) { a.valid[p] = 0; a.path_len[p] = 0; a.cost[p] = nan(""); }
             continue;
         }
-        if (tid == 0) {
-            int i = n1 - 1, j = n2 - 1, len = 1;
+        const float *__restrict__ D = la.dws + (size_t)k * la.slot_cells;
+        const int T = n1 + n2 - 1;
+        const int n_bands = (n1 + BAND_ROWS - 1) / BAND_ROWS;
+        for (int j = lane; j <= n2; j += 32) topbuf0[j] = j == 0 ? 0.0 : INF;     // C[-1][-1] = 0 feeds (0, 0)
+        __syncwarp();
+        double cost = 0.0;
+        for (int b = 0; b < n_bands; ++b) {
+            const int ib = b * BAND_ROWS;
+            const int rows = min(BAND_ROWS, n1 - ib);
+            const int S = n2 + rows - 1;                       // band steps: cell (ib + r, s - r)
+            const double *top = topbuf0 + (b & 1) * (nmax + 2);
+            double *top_next = topbuf0 + ((b + 1) & 1) * (nmax + 2);
+            if (lane == 0) top_next[0] = INF;                  // C[last row][-1]
+            uint32_t *dirs32 = reinterpret_cast<uint32_t *>(dirs + (size_t)b * band_bytes);
+            const int r_last = rows - 1;                       // the row whose values are the next band's top
+            double cur[G], prev[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) cur[g] = prev[g] = INF;
+            double nbprev = lane == 0 ? top[0] : INF;
+            const float *Dl = D + ib + r0;
+            asm volatile("" : "+l"(Dl));
+            int bases = 0;
+#define ABN_BAND_LOAD(dst, s_first)                                                         \
+            {                                                                               \
+                if (((s_first) & 31) == 0)                                                  \
+                    bases = skew_base(min(ib + (s_first) + lane, T - 1), n1, n2);           \
+                _Pragma("unroll") for (int u = 0; u < 4; ++u) {                             \
+                    const int bs = __shfl_sync(FULL, bases, ((s_first) + u) & 31);          \
+                    _Pragma("unroll") for (int g = 0; g < G; ++g) dst[u][g] = __ldg(Dl + bs + g); \
+                }                                                                           \
+            }
+#define ABN_BAND_STEP(dc, u, s)                                                             \
+            {                                                                               \
+                double up0 = __shfl_up_sync(FULL, cur[G - 1], 1);                           \
+                if (lane == 0) up0 = top[1 + min((s), n2 - 1)];                             \
+                const double dg0 = nbprev;                                                  \
+                nbprev = up0;                                                               \
+                double nw[G];                                                               \
+                _Pragma("unroll") for (int g = 0; g < G; ++g) {                             \
+                    const double d = (double)dc[u][g];                                      \
+                    const double up = g == 0 ? up0 : cur[g > 0 ? g - 1 : 0];                \
+                    const double dg = g == 0 ? dg0 : prev[g > 0 ? g - 1 : 0];               \
+                    const double lf = cur[g];                                               \
+                    const bool up_le = up <= lf;                                            \
+                    const double m1 = up_le ? up : lf;                                      \
+                    const bool use_dg = dg <= m1;                                           \
+                    const double mm = use_dg ? dg : m1;                                     \
+                    const unsigned dir = use_dg ? DIR_DIAG : (up_le ? DIR_UP : DIR_LEFT);   \
+                    nw[g] = d + mm;                                                         \
+                    bits |= dir << (8 * g + 2 * (u));                                       \
+                    const int jj = (s) - (r0 + g);                                          \
+                    if (r0 + g == r_last && (unsigned)jj < (unsigned)n2) top_next[1 + jj] = nw[g]; \
+                }                                                                           \
+                _Pragma("unroll") for (int g = 0; g < G; ++g) { prev[g] = cur[g]; cur[g] = nw[g]; } \
+            }
+#define ABN_BAND_BLOCK(dc, dnext, s0)                                                       \
+            {                                                                               \
+                ABN_BAND_LOAD(dnext, (s0) + 4)                                              \
+                unsigned bits = 0;                                                          \
+                if ((s0) + 4 <= S) {                                                        \
+                    ABN_BAND_STEP(dc, 0, (s0)) ABN_BAND_STEP(dc, 1, (s0) + 1)               \
+                    ABN_BAND_STEP(dc, 2, (s0) + 2) ABN_BAND_STEP(dc, 3, (s0) + 3)           \
+                } else {                                                                    \
+                    ABN_BAND_STEP(dc, 0, (s0))                                              \
+                    if ((s0) + 1 < S) ABN_BAND_STEP(dc, 1, (s0) + 1)                        \
+                    if ((s0) + 2 < S) ABN_BAND_STEP(dc, 2, (s0) + 2)                        \
+                }                                                                           \
+                dirs32[((s0) >> 2) * 32 + lane] = bits;                                     \
+            }
+            float da[4][G], db[4][G];
+            ABN_BAND_LOAD(da, 0)
+            for (int s0 = 0; s0 < S; s0 += 8) {
+                ABN_BAND_BLOCK(da, db, s0)
+                if (s0 + 4 < S) ABN_BAND_BLOCK(db, da, s0 + 4)
+            }
+#undef ABN_BAND_BLOCK
+#undef ABN_BAND_STEP
+#undef ABN_BAND_LOAD
+            if (b == n_bands - 1) {
+                const int gl = r_last % G;
+                double c = cur[0];
+                c = gl == 1 ? cur[1] : c;
+                c = gl == 2 ? cur[2] : c;
+                c = gl == 3 ? cur[3] : c;
+                cost = __shfl_sync(FULL, c, r_last / G);
+            }
+            __syncwarp();
+        }
+        __threadfence_block();
+        __syncwarp();
+        int len = 0;
+        if (lane == 0) {
+            int i = n1 - 1, j = n2 - 1;
+            len = 1;
             pb_i[0] = (uint16_t)i; pb_j[0] = (uint16_t)j;
-            while ((i | j) != 0) {
-                const unsigned d = (dirs[i * LL.ldp + (j >> 2)] >> (2 * (j & 3))) & 3u;
+            while ((i | j) != 0 && len < T) {
+                const int b = i >> 7, r = i & (BAND_ROWS - 1), s = j + r;
+                const unsigned byte = *reinterpret_cast<volatile uint8_t *>(
+                    dirs + (size_t)b * band_bytes + (size_t)(s >> 2) * BAND_ROWS + r);
+                const unsigned d = (byte >> (2 * (s & 3))) & 3u;
                 i -= (d != DIR_LEFT);
                 j -= (d != DIR_UP);
                 pb_i[len] = (uint16_t)i; pb_j[len] = (uint16_t)j; ++len;
             }
-            misc[0] = len;
             a.path_len[p] = len;
             a.cost[p] = cost;
             a.valid[p] = 1;
         }
-        __syncthreads();
-        const int len = misc[0];
+        len = __shfl_sync(FULL, len, 0);
+        __syncwarp();
         const int64_t off = a.path_off[p];
-        for (int k = tid; k < len; k += AL_THREADS) {
-            a.idx1[off + k] = s1 + (int)pb_i[len - 1 - k];
-            a.idx2[off + k] = s2 + (int)pb_j[len - 1 - k];
+        for (int q = lane; q < len; q += 32) {
+            a.idx1[off + q] = s1 + (int)pb_i[len - 1 - q];
+            a.idx2[off + q] = s2 + (int)pb_j[len - 1 - q];
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -1251,13 +1409,34 @@ static int class_table(const ClassLaunch **generic, const ClassLaunch **stacked)
     return ABN_OK;
 }
 
-// hand-over slot of one pair (floats): the largest matrix of the fused classes
+// hand-over slot of one pair (floats): the largest matrix of the fused classes, or -- when the
+// pair list may hold long tokens (above STACK_MAXN frames: the stacked kernels route those to
+// the long path) -- the largest matrix overall
+static bool may_be_long(int max_frames) { return max_frames > STACK_MAXN; }
 static size_t slot_cells_for(int max_frames) {
-    const size_t ns = (size_t)(max_frames < NM_SHORT ? max_frames : NM_SHORT);
+    if (may_be_long(max_frames)) {
+        const size_t n = (size_t)(max_frames < NM_SHORT ? NM_SHORT : max_frames);
+        return (n * n + n + LONG_SLACK + 3) & ~(size_t)3;
+    }
+    const size_t ns = (size_t)max_frames;
     return (ns * ns + ns + SKEW_SLACK + 3) & ~(size_t)3;
 }
-static size_t ws_dist_off(int n_pairs) {
-    return (WS_ORDER + sizeof(int32_t) * (size_t)(n_pairs > 0 ? n_pairs : 0) + 255) & ~(size_t)255;
+static int long_dtw_warps(int n_pairs) {
+    const int want = ((n_pairs > 0 ? n_pairs : 1) + LONG_DTW_WARPS - 1) / LONG_DTW_WARPS * LONG_DTW_WARPS;
+    const int cap = LONG_DTW_MAX_CTAS * LONG_DTW_WARPS;
+    return want < cap ? want : cap;
+}
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+// workspace: header | order | [long path: bad flags | direction scratch] | hand-over slots
+static size_t ws_bad_off(int n_pairs) {
+    return a256(WS_ORDER + sizeof(int32_t) * (size_t)(n_pairs > 0 ? n_pairs : 0));
+}
+static size_t ws_dirs_off(int n_pairs) {
+    return a256(ws_bad_off(n_pairs) + sizeof(unsigned) * (size_t)(n_pairs > 0 ? n_pairs : 0));
+}
+static size_t ws_dist_off(int n_pairs, int max_frames) {
+    if (!may_be_long(max_frames)) return ws_bad_off(n_pairs);
+    return a256(ws_dirs_off(n_pairs) + (size_t)long_dtw_warps(n_pairs) * long_dirs_bytes(max_frames));
 }
 
 struct DtwLaunch { int grid; unsigned smem; int t4_cap; };
@@ -1297,7 +1476,7 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
         return set_error(ABN_ERANGE, "%s: token of %d frames exceeds %d", who, max_frames, NM_LIMIT);
     const bool dist_only = a.dist_out != nullptr;
     const size_t slot = slot_cells_for(max_frames);
-    const size_t d_off = ws_dist_off(a.n_pairs);
+    const size_t d_off = ws_dist_off(a.n_pairs, max_frames);
     const size_t need = dist_only ? WS_ORDER + sizeof(int32_t) * (size_t)a.n_pairs
                                   : d_off + slot * sizeof(float);
     if (!workspace || workspace_bytes < need)
@@ -1328,30 +1507,94 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
     class_count_kernel<<<blocks, BK_THREADS, 0, st>>>(a, counts);
     class_scan_kernel<<<1, 32, 0, st>>>(counts, class_off);
     class_scatter_kernel<<<blocks, BK_THREADS, 0, st>>>(a, class_off, cursor, order);
+    size_t chunk = dist_only ? (size_t)a.n_pairs : (workspace_bytes - d_off) / (slot * sizeof(float));
+    if (chunk > (size_t)a.n_pairs) chunk = (size_t)a.n_pairs;
     if (max_frames + ext > NM_SHORT) {
-        const int nmax = max_frames;
-        const LongLayout LL = long_layout(nmax);
-        if (cudaFuncSetAttribute(align_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)LL.total) != cudaSuccess)
-            return set_error(ABN_EIO, "%s: cannot reserve %u bytes of shared memory", who, LL.total);
-        int per_sm = 0, dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_long_kernel, AL_THREADS,
-                                                      LL.total);
-        const int long_grid = (per_sm > 0 ? per_sm : 1) * sms;
-        const int grid = long_grid < a.n_pairs ? long_grid : a.n_pairs;
-        align_long_kernel<<<grid, AL_THREADS, LL.total, st>>>(a, nmax);
-        if (cudaError_t e = cudaGetLastError())
-            return set_error(ABN_EIO, "%s: long-token kernel launch (smem %u): %s", who, LL.total,
-                             cudaGetErrorString(e));
+        // long pairs: tile distance kernel -> skew slots -> band DTW kernel, in windows of
+        // `chunk` pairs of the long class (its size is only known on the device: windows past
+        // its end find nothing to do)
+        // tiles: the side that cuts the longest token evenly, on the smallest class that holds it
+        // (a 100-frame token is 2 x 2 tiles of 50 on the (4,4) class, not 4 tiles of the (6,6) one)
+        static int tile_grid[2][3] = {{0, 0, 0}, {0, 0, 0}}, band_grid = 0, sms = 0;
+        const int which = a.stack ? 1 : 0;
+        const int lt_max = a.stack ? LT_STK : LT_GEN;
+        const int nt = (max_frames + lt_max - 1) / lt_max;
+        int R = ((max_frames + nt - 1) / nt + ext + 15) / 16;
+        if (R < 4) R = 4;
+        const int lt = 16 * R - ext;
+        typedef void (*TileKernel)(const AlignArgs, const LongArgs);
+        static const TileKernel kernels[2][3] = {
+            {long_tile_kernel<false, 4>, long_tile_kernel<false, 5>, long_tile_kernel<false, 6>},
+            {long_tile_kernel<true, 4>, long_tile_kernel<true, 5>, long_tile_kernel<true, 6>}};
+        static const unsigned smem_of[2][3] = {
+            {DistLayout<4, 4>::TOTAL, DistLayout<5, 5>::TOTAL, DistLayout<6, 6>::TOTAL},
+            {StackLayout<4, 4>::TOTAL, StackLayout<5, 5>::TOTAL, StackLayout<6, 6>::TOTAL}};
+        const TileKernel tile_kernel = kernels[which][R - 4];
+        const unsigned tile_smem = smem_of[which][R - 4] + 32u * R * 4u;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        if (!tile_grid[which][R - 4]) {
+            if (cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tile_smem) != cudaSuccess)
+                return set_error(ABN_EIO, "%s: cannot reserve %u bytes of shared memory", who, tile_smem);
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel, AL_THREADS, tile_smem);
+            tile_grid[which][R - 4] = (per_sm > 0 ? per_sm : 1) * sms;
+        }
+        const unsigned band_smem = LONG_DTW_WARPS * (24u * (unsigned)max_frames + 32u);
+        {
+            static unsigned band_smem_set = 0;
+            if (band_smem > band_smem_set) {
+                if (cudaFuncSetAttribute(dtw_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)band_smem) != cudaSuccess)
+                    return set_error(ABN_EIO, "%s: cannot reserve %u bytes of shared memory", who, band_smem);
+                band_smem_set = band_smem;
+                band_grid = 0;
+            }
+            if (!band_grid) {
+                int per_sm = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_band_kernel,
+                                                              LONG_DTW_WARPS * 32, band_smem_set);
+                band_grid = (per_sm > 0 ? per_sm : 1) * sms;
+                if (band_grid > LONG_DTW_MAX_CTAS) band_grid = LONG_DTW_MAX_CTAS;
+            }
+        }
+        LongArgs la{};
+        la.tcap = (max_frames + lt - 1) / lt;
+        la.slot_cells = slot;
+        la.dirs_bytes = long_dirs_bytes(max_frames);
+        la.bad = reinterpret_cast<unsigned *>(ws + ws_bad_off(a.n_pairs));
+        la.dirs = ws + ws_dirs_off(a.n_pairs);
+        la.dws = dist_only ? nullptr : reinterpret_cast<float *>(ws + d_off);
+        const int max_warps = long_dtw_warps(a.n_pairs);
+        for (size_t w0 = 0; w0 < (size_t)a.n_pairs; w0 += chunk) {
+            la.lw0 = (int)w0;
+            la.lw1 = (int)(w0 + chunk < (size_t)a.n_pairs ? w0 + chunk : (size_t)a.n_pairs);
+            const int span = la.lw1 - la.lw0;
+            if (!dist_only) cudaMemsetAsync(la.bad, 0, sizeof(unsigned) * (size_t)span, st);
+            const long long work = (long long)span * la.tcap * la.tcap;
+            const int tg = (long long)tile_grid[which][R - 4] < work ? tile_grid[which][R - 4] : (int)work;
+            tile_kernel<<<tg, AL_THREADS, tile_smem, st>>>(a, la);
+            if (cudaError_t e = cudaGetLastError())
+                return set_error(ABN_EIO, "%s: long-token tile kernel launch (smem %u): %s", who,
+                                 tile_smem, cudaGetErrorString(e));
+            if (dist_only) continue;
+            int bg = (span + LONG_DTW_WARPS - 1) / LONG_DTW_WARPS;
+            if (bg > band_grid) bg = band_grid;
+            if (bg * LONG_DTW_WARPS > max_warps) bg = max_warps / LONG_DTW_WARPS;
+            dtw_band_kernel<<<bg, LONG_DTW_WARPS * 32, band_smem, st>>>(a, la, max_frames);
+            if (cudaError_t e = cudaGetLastError())
+                return set_error(ABN_EIO, "%s: long-token DTW kernel launch (smem %u): %s", who,
+                                 band_smem, cudaGetErrorString(e));
+        }
     }
     // The fused classes run in rounds over windows of the class-sorted pair order, as many
     // pairs per round as the workspace has hand-over slots for.  Per round and class row:
     // the row's distance kernels (large classes first), then ONE DTW launch over the row.
     const int side = ((max_frames + ext < NM_SHORT ? max_frames + ext : NM_SHORT) + 15) / 16;
-    size_t chunk = dist_only ? (size_t)a.n_pairs : (workspace_bytes - d_off) / (slot * sizeof(float));
-    if (chunk > (size_t)a.n_pairs) chunk = (size_t)a.n_pairs;
     if (!dist_only) a.dws = reinterpret_cast<float *>(ws + d_off);
     for (size_t w0 = 0; w0 < (size_t)a.n_pairs; w0 += chunk) {
         a.w0 = (int)w0;
@@ -1388,20 +1631,22 @@ extern "C" size_t abn_align_workspace_bytes(int n_pairs, int max_frames, int rou
     if (rounds < 1) rounds = 1;
     size_t per_round = ((size_t)n_pairs + rounds - 1) / rounds;
     if (per_round < 1) per_round = 1;
-    return ws_dist_off(n_pairs) + per_round * slot_cells_for(max_frames) * sizeof(float);
+    if (max_frames > NM_LIMIT) max_frames = NM_LIMIT;
+    return ws_dist_off(n_pairs, max_frames) + per_round * slot_cells_for(max_frames) * sizeof(float);
 }
 
 // kernels one abn_align_pairs call enqueues (for launch accounting in benchmarks)
 extern "C" int abn_align_launches(int n_pairs, int max_frames, int stack, size_t workspace_bytes) {
     if (n_pairs <= 0 || max_frames <= 0) return 0;
     const int ext = stack ? 2 * STACK_H : 0;
-    const size_t slot = slot_cells_for(max_frames) * sizeof(float), d_off = ws_dist_off(n_pairs);
+    if (max_frames > NM_LIMIT) max_frames = NM_LIMIT;
+    const size_t slot = slot_cells_for(max_frames) * sizeof(float), d_off = ws_dist_off(n_pairs, max_frames);
     size_t chunk = workspace_bytes > d_off ? (workspace_bytes - d_off) / slot : 0;
     if (chunk < 1) return 0;
     if (chunk > (size_t)n_pairs) chunk = (size_t)n_pairs;
     const int rounds = (int)(((size_t)n_pairs + chunk - 1) / chunk);
     const int side = ((max_frames + ext < NM_SHORT ? max_frames + ext : NM_SHORT) + 15) / 16;
-    return 3 + (max_frames + ext > NM_SHORT ? 1 : 0) + rounds * (side * side + side);
+    return 3 + (max_frames + ext > NM_SHORT ? 2 * rounds : 0) + rounds * (side * side + side);
 }
 
 extern "C" int abn_align_pairs(const float *feat, int64_t n_rows, int dim,

@@ -514,6 +514,7 @@ class FramesDataLoader(OriginalDataLoader):
                    max_batches_per_epoch=max_batches_per_epoch, **kwargs)
         self.features = _TableOnly(table)
         self.pairs = {'train': [], 'dev': []}
+        self._shard = (0, 1)            # the caller hands every rank its own token arrays
         self._tokens_given = tokens
         return self
 

@@ -1010,12 +1010,12 @@ def run_sweep(args, rank, world, local_rank, dev):
         for n in lengths:
             c = synth.make_corpus(max(400, 40_000 // n), seed=n, device="cpu", len_range=(n, n),
                                   tokens_per_file=200)
-            ps = synth.make_same_pairs(c, max(cores * 8, int(2.0e8 / (n * n))), seed=1).numpy()
+            ps = synth.make_same_pairs(c, max(cores * 8, int(3.0e9 / (n * n))), seed=1).numpy()
             r, dt, _, _ = cpu_align_rate(c.feat.numpy(), ps, cores)
             cpu_l.append({"frames_per_token": n, "pairs_per_s": r, "sample_pairs": len(ps), "seconds": dt})
         hm = len(cpu_l) / sum(1.0 / x["pairs_per_s"] for x in cpu_l)
         cpu = {"value": hm, "unit": "pairs/s", "cores": cores, "kind": "port", "per_length": cpu_l,
-               "sample": "per length a sample of about 2e8 / n^2 pairs on %d processes; value = pairs/s "
+               "sample": "per length a sample of about 3e9 / n^2 pairs on %d processes; value = pairs/s "
                          "of equal pair counts at the four lengths (harmonic mean)" % cores}
     if rank == 0:
         worst = min(per_len, key=lambda r: r["roofline_frac"])

