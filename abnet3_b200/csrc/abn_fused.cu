@@ -51,10 +51,24 @@ __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
         const int32_t row = side ? idx2[pos] : idx1[pos];
         const float4 *src = reinterpret_cast<const float4 *>(feat + (size_t)row * dim);
         uint2 *dst = reinterpret_cast<uint2 *>(xb + (size_t)(side ? n + k : k) * ldx);
-        for (int c = lane; c < dim / 4; c += 32) {
-            const float4 v = __ldg(src + c);
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            dst[c] = make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+        const int nv = dim >> 2;
+        if (nv <= 96) {            // (280-wide rows: 70 float4) every load in flight before the first store
+            float4 v[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (lane + 32 * u < nv) v[u] = __ldg(src + lane + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (lane + 32 * u < nv) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                    dst[lane + 32 * u] = make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+                }
+        } else {
+            for (int c = lane; c < nv; c += 32) {
+                const float4 v = __ldg(src + c);
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                dst[c] = make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+            }
         }
         if (side == 0 && lane == 0) {
             if (y_out) y_out[k] = y_in ? (float)y_in[pos] : 1.f;
@@ -141,6 +155,104 @@ pair_loss_dz_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
     }
 }
 
+// Vector form for dim <= 128, dim % 4 == 0, 16-byte aligned rows: EIGHT lanes per frame pair (four
+// pairs per warp at a time), float4 loads kept in registers between the reduction and the
+// gradient pass, 8-byte bf16x4 stores.  Same arithmetic per element as the kernel above; the
+// three sums of a pair are reduced over 8 lanes instead of 32 (a different fp32 summation
+// order: the parity tests bound both against the oracle).
+__global__ void __launch_bounds__(LZ_WARPS * 32)
+pair_loss_dz_vec_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
+                        const float *__restrict__ y, int64_t n, int dim, int64_t ld, int kind,
+                        float margin, float scale, int act, float *__restrict__ loss,
+                        __nv_bfloat16 *__restrict__ dz1, __nv_bfloat16 *__restrict__ dz2,
+                        int64_t ld_dz) {
+    __shared__ float wsum[LZ_WARPS];
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 7, slot = lane >> 3;
+    const int nv = dim >> 2;
+    float local = 0.f;
+    for (int64_t row0 = ((int64_t)blockIdx.x * LZ_WARPS + warp) * 4; row0 < n;
+         row0 += (int64_t)gridDim.x * LZ_WARPS * 4) {
+        const int64_t row = row0 + slot;
+        const bool live = row < n;
+        const float4 *a4 = reinterpret_cast<const float4 *>(e1 + (live ? row : 0) * ld);
+        const float4 *b4 = reinterpret_cast<const float4 *>(e2 + (live ? row : 0) * ld);
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = sub + 8 * u;
+            av[u] = (live && c < nv) ? a4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            bv[u] = (live && c < nv) ? b4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float dot = 0.f, na = 0.f, nb = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dot = fmaf(av[u].x, bv[u].x, dot); na = fmaf(av[u].x, av[u].x, na); nb = fmaf(bv[u].x, bv[u].x, nb);
+            dot = fmaf(av[u].y, bv[u].y, dot); na = fmaf(av[u].y, av[u].y, na); nb = fmaf(bv[u].y, bv[u].y, nb);
+            dot = fmaf(av[u].z, bv[u].z, dot); na = fmaf(av[u].z, av[u].z, na); nb = fmaf(bv[u].z, bv[u].z, nb);
+            dot = fmaf(av[u].w, bv[u].w, dot); na = fmaf(av[u].w, av[u].w, na); nb = fmaf(bv[u].w, bv[u].w, nb);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            na += __shfl_xor_sync(0xffffffffu, na, o);
+            nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        }
+        const float ra = sqrtf(na), rb = sqrtf(nb);
+        const float an = fmaxf(ra, LZ_EPS), bn = fmaxf(rb, LZ_EPS);
+        const float inv = 1.f / (an * bn);
+        const float c = dot * inv;
+        const float lab = live ? y[row] : 0.f;
+        float term, dldc;
+        if (kind == 0) {          // coscos2, loss.py:59-62
+            if (lab == 1.f)       { term = 0.5f * (1.f - c); dldc = -0.5f; }
+            else if (lab == -1.f) { term = c * c;            dldc = 2.f * c; }
+            else                  { term = c;                dldc = 1.f; }
+        } else {                  // cosmargin, loss.py:98-101
+            if (lab == 1.f)       { term = 1.f - c;          dldc = -1.f; }
+            else if (lab == -1.f) { const float h = c - margin;
+                                    term = fmaxf(h, 0.f);    dldc = h > 0.f ? 1.f : 0.f; }
+            else                  { term = c;                dldc = 1.f; }
+        }
+        if (live && sub == 0) local += term;
+        const float g = dldc * scale;
+        const float ka = ra > LZ_EPS ? c / (an * an) : 0.f;
+        const float kb = rb > LZ_EPS ? c / (bn * bn) : 0.f;
+        if (live) {
+            uint2 *ga = reinterpret_cast<uint2 *>(dz1 + row * ld_dz);
+            uint2 *gb = reinterpret_cast<uint2 *>(dz2 + row * ld_dz);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int cc = sub + 8 * u;
+                if (cc < nv) {
+                    const float4 x = av[u], z = bv[u];
+                    __nv_bfloat162 a0 = __floats2bfloat162_rn(g * (z.x * inv - ka * x.x) * dact_of(x.x, act),
+                                                              g * (z.y * inv - ka * x.y) * dact_of(x.y, act));
+                    __nv_bfloat162 a1 = __floats2bfloat162_rn(g * (z.z * inv - ka * x.z) * dact_of(x.z, act),
+                                                              g * (z.w * inv - ka * x.w) * dact_of(x.w, act));
+                    __nv_bfloat162 b0 = __floats2bfloat162_rn(g * (x.x * inv - kb * z.x) * dact_of(z.x, act),
+                                                              g * (x.y * inv - kb * z.y) * dact_of(z.y, act));
+                    __nv_bfloat162 b1 = __floats2bfloat162_rn(g * (x.z * inv - kb * z.z) * dact_of(z.z, act),
+                                                              g * (x.w * inv - kb * z.w) * dact_of(z.w, act));
+                    ga[cc] = make_uint2(*reinterpret_cast<unsigned *>(&a0), *reinterpret_cast<unsigned *>(&a1));
+                    gb[cc] = make_uint2(*reinterpret_cast<unsigned *>(&b0), *reinterpret_cast<unsigned *>(&b1));
+                }
+            }
+        }
+    }
+    local += __shfl_xor_sync(0xffffffffu, local, 8);
+    local += __shfl_xor_sync(0xffffffffu, local, 16);
+    if (lane == 0) wsum[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LZ_WARPS; ++w) s += wsum[w];
+        if (s != 0.f) atomicAdd(loss, s * scale);
+    }
+}
+
 struct SegTable { abn_param_segment s[ABN_MAX_PARAM_SEGMENTS]; int n; };
 
 // grid.y = segment; same update rules as optimizer_kernel (abn_nn.cu)
@@ -151,6 +263,63 @@ __global__ void optimizer_fused_kernel(float *__restrict__ p, float *__restrict_
     pdl_wait();
     const abn_param_segment sg = tab.s[blockIdx.y];
     __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
+    if (((sg.offset | sg.count) & 3) == 0 && (!wb || ((sg.n_in | sg.ld) & 3) == 0)) {
+        // 4 consecutive elements per thread: 16-byte accesses on every array
+        for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j < sg.count;
+             j += (int64_t)gridDim.x * blockDim.x * 4) {
+            const int64_t i = sg.offset + j;
+            const float4 g4 = *reinterpret_cast<const float4 *>(g + i);
+            const float4 w4 = *reinterpret_cast<const float4 *>(p + i);
+            float w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float gr[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+            if (kind == 0) {
+                if (momentum != 0.f) {
+                    const float4 m4 = *reinterpret_cast<const float4 *>(s0 + i);
+                    float b[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { b[e] = momentum * b[e] + gr[e]; w[e] -= lr * b[e]; }
+                    *reinterpret_cast<float4 *>(s0 + i) = make_float4(b[0], b[1], b[2], b[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) w[e] -= lr * gr[e];
+                }
+            } else {
+                const float4 a4 = *reinterpret_cast<const float4 *>(s0 + i);
+                const float4 b4 = *reinterpret_cast<const float4 *>(s1 + i);
+                float sa[4] = {a4.x, a4.y, a4.z, a4.w}, sb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (kind == 1) {        // torch.optim.Adadelta(rho=0.9, eps=1e-6)
+                        const float rho = 0.9f, eps = 1e-6f;
+                        const float sq = rho * sa[e] + (1.f - rho) * gr[e] * gr[e];
+                        const float stdv = sqrtf(sq + eps);
+                        const float delta = sqrtf(sb[e] + eps) / stdv * gr[e];
+                        sa[e] = sq;
+                        sb[e] = rho * sb[e] + (1.f - rho) * delta * delta;
+                        w[e] -= lr * delta;
+                    } else {                // torch.optim.Adam(betas=(0.9, 0.999), eps=1e-8)
+                        const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+                        const float m = b1 * sa[e] + (1.f - b1) * gr[e];
+                        const float v = b2 * sb[e] + (1.f - b2) * gr[e] * gr[e];
+                        sa[e] = m; sb[e] = v;
+                        const float denom = sqrtf(v) / bc2_sqrt + eps;
+                        w[e] -= (lr / bc1) * (m / denom);
+                    }
+                }
+                *reinterpret_cast<float4 *>(s0 + i) = make_float4(sa[0], sa[1], sa[2], sa[3]);
+                *reinterpret_cast<float4 *>(s1 + i) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+            }
+            *reinterpret_cast<float4 *>(p + i) = make_float4(w[0], w[1], w[2], w[3]);
+            if (zero_grad) *reinterpret_cast<float4 *>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wb) {
+                const int64_t r = j / sg.n_in;
+                __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]), hi = __floats2bfloat162_rn(w[2], w[3]);
+                *reinterpret_cast<uint2 *>(wb + r * sg.ld + (j - r * sg.n_in)) =
+                    make_uint2(*reinterpret_cast<unsigned *>(&lo), *reinterpret_cast<unsigned *>(&hi));
+            }
+        }
+        return;
+    }
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < sg.count;
          j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = sg.offset + j;
@@ -225,6 +394,16 @@ extern "C" int abn_pair_loss_dz(const float *e1, const float *e2, const float *y
     if (!e1 || !e2 || !y || !loss || !dz1 || !dz2 || n < 0 || dim <= 0 || ld < dim ||
         ld_dz < dim || (kind != 0 && kind != 1) || act < 0 || act > 3)
         return set_error(ABN_EINVAL, "abn_pair_loss_dz: bad argument");
+    const bool vec = dim <= 128 && !(dim & 3) && !(ld & 3) && !(ld_dz & 3) &&
+                     !(((uintptr_t)e1 | (uintptr_t)e2) & 15) && !(((uintptr_t)dz1 | (uintptr_t)dz2) & 7);
+    if (vec) {
+        int64_t blocks = (n + 4 * LZ_WARPS - 1) / (4 * LZ_WARPS);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        launch_pdl(pair_loss_dz_vec_kernel, dim3((unsigned)blocks), dim3(LZ_WARPS * 32), (cudaStream_t)stream,
+            e1, e2, y, n, dim, ld, kind, margin, scale, act, loss, static_cast<__nv_bfloat16 *>(dz1),
+            static_cast<__nv_bfloat16 *>(dz2), ld_dz);
+        return check_launch("abn_pair_loss_dz");
+    }
     int64_t blocks = (n + LZ_WARPS - 1) / LZ_WARPS;
     if (blocks > 148 * 8) blocks = 148 * 8;
     launch_pdl(pair_loss_dz_kernel, dim3((unsigned)blocks), dim3(LZ_WARPS * 32), (cudaStream_t)stream,
@@ -255,7 +434,7 @@ extern "C" int abn_optimizer_step_fused(float *param, float *grad, float *state0
     }
     const float bc1 = 1.f - powf(0.9f, (float)step);
     const float bc2s = sqrtf(1.f - powf(0.999f, (float)step));
-    int64_t bx = (longest + 255) / 256;
+    int64_t bx = (longest / 4 + 255) / 256;
     if (bx > 148 * 4) bx = 148 * 4;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)n_segments);

@@ -253,13 +253,27 @@ class TrainerSiamese(TrainerBuilder):
     def _sweep_table(self, train_mode, do_training):
         """Sweep over a device-resident frame-pair table (FramesDataLoader.epoch_table):
         the engine gathers every batch itself and replays one CUDA graph per step."""
+        import os
+        trace = os.environ.get("ABN_TRACE_SWEEP") == "1"
+        if trace:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
         feat, table, bs, first_row, n_batches = self.dataloader.epoch_table(train_mode=train_mode)
         training = train_mode and do_training
         if training:
             n_batches = self._agreed_batches(n_batches)
+        if trace:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
         total = self.engine.sweep_table(feat, table, bs, n_batches, start=first_row,
                                         do_training=training)
-        return float(total.item()), n_batches
+        out = float(total.item())
+        if trace:
+            import sys
+            t2 = time.perf_counter()
+            sys.stderr.write("[sweep train=%d] epoch_table %.1f ms | %d batches %.1f ms\n"
+                             % (train_mode, 1e3 * (t1 - t0), n_batches, 1e3 * (t2 - t1)))
+        return out, n_batches
 
     def _sweep(self, train_mode, do_training):
         """One pass over the dataloader; returns (summed loss, number of batches)."""

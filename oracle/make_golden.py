@@ -18,6 +18,8 @@ cosine.npz   abnet3.utils.cosine_distance on seeded float32 inputs incl. the
 nets.npz     abnet3.model.SiameseNetwork / SiameseMultitaskNetwork forward,
              abnet3.loss.coscos2 / cosmargin / weighted_loss_multi values and
              autograd gradients, for fixed state_dicts and inputs.
+trajectory.npz  the losses of 300 training steps of the live reference (network + coscos2 +
+             torch.optim.Adadelta) on the seeded inputs of oracle/trajectory.py.
 dtw.npz      OUR oracle's DTW (oracle/dtw_oracle.c) on seeded matrices, kept
              as a regression fixture.  Not a reference output: PARITY UNPINNED.
 """
@@ -232,12 +234,52 @@ def make_dtw():
     print("dtw.npz:", len(cases), "+ 4 tie cases (oracle regression, unpinned)")
 
 
+def make_trajectory(ref_model, ref_loss):
+    """300 training steps of the LIVE reference (abnet3.model.SiameseNetwork 280-500-500-500-100
+    sigmoid + abnet3.loss.coscos2(avg=False) + torch.optim.Adadelta(lr=0.1), the loop of
+    abnet3/trainer.py:231-243) on the deterministic inputs of oracle/trajectory.py, fp32 on the
+    CPU.  Only the losses are stored."""
+    import torch
+    from oracle import trajectory as tj
+    torch.set_num_threads(os.cpu_count() or 1)
+    feat = torch.from_numpy(tj.features())
+    batches = tj.batches()
+
+    def run(perturb):
+        net = ref_model.SiameseNetwork(input_dim=280, num_hidden_layers=2, hidden_dim=500,
+                                       output_dim=100, p_dropout=0.0, activation_layer="sigmoid",
+                                       batch_norm=False, output_path=None)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in tj.state_dict(perturb=perturb).items()})
+        net.train()
+        loss_fn = ref_loss.coscos2(avg=False)
+        opt = torch.optim.Adadelta(net.parameters(), lr=0.1)
+        losses = []
+        for i1, i2, y in batches:
+            e1, e2 = net(feat[torch.from_numpy(i1).long()], feat[torch.from_numpy(i2).long()])
+            loss = loss_fn(e1, e2, torch.from_numpy(y))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        return np.asarray(losses, dtype=np.float64), net
+
+    losses, net = run(0.0)
+    perturbed, _ = run(1e-6)          # how well conditioned the trajectory is, in the reference itself
+    norms = {k.replace(".", "_"): float(v.detach().double().norm()) for k, v in net.state_dict().items()}
+    np.savez(os.path.join(GOLD, "trajectory.npz"), losses=losses, losses_perturbed=perturbed,
+             **{"norm_" + k: np.float64(v) for k, v in norms.items()})
+    print("trajectory.npz: loss %.3f -> %.3f over %d steps; 1e-6 perturbation moves a loss by at "
+          "most %.2e relative" % (losses[0], losses[-1], len(losses),
+                                  float(np.max(np.abs(perturbed - losses) / losses))))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref_utils, ref_model, ref_loss = import_reference()
     make_cosine(ref_utils)
     make_nets(ref_model, ref_loss)
     make_dtw()
+    make_trajectory(ref_model, ref_loss)
 
 
 if __name__ == "__main__":

@@ -71,7 +71,8 @@ def test_fused_optimizer_matches_plain_step_and_refreshes_bf16_weights():
         for step in (1, 2):
             ops.optimizer_step(pa, ga, sa[0], sa[1], kind, 0.1, 0.9, 0.5, step)
             ops.optimizer_step_fused(pb, gb, sb[0], sb[1], kind, 0.1, 0.9, 0.5, step, seg, zero_grad=True)
-            assert torch.equal(pa, pb)
+            # same update rule; the 4-wide kernel may contract its multiply-adds differently
+            assert torch.allclose(pa, pb, rtol=2e-6, atol=1e-7)
             assert torch.equal(wb[:, :n_in], pb[:nw].view(n_out, n_in).bfloat16())
             assert float(gb.abs().max()) == 0.0
             gb.copy_(g0)

@@ -92,6 +92,38 @@ def test_dtw_matches_bruteforce_recurrence():
         np.testing.assert_array_equal(p2, q2)
 
 
+def test_dtw_c_oracle_agrees_with_the_independent_numpy_dtw_on_10k_matrices():
+    """The unpinned DTW oracle's second opinion: oracle/dtw_numpy.py (inf-bordered matrix,
+    argmin traceback, batched numpy) against oracle/dtw_oracle.c -- costs bit for bit, paths
+    step for step -- on 10 000 matrices: continuous random ones, float32-valued ones (what the
+    GPU hands over), and coarse grids where a large share of the traceback steps are exact
+    ties."""
+    from oracle.dtw_numpy import dtw_batch
+    rng = np.random.default_rng(2024)
+    total, tie_steps = 0, 0
+    cases = []
+    for shape, n, kind in [((12, 12), 2500, "uniform"), ((7, 19), 1500, "uniform"),
+                           ((23, 9), 1500, "f32"), ((16, 16), 2500, "grid4"),
+                           ((9, 14), 1500, "grid2"), ((1, 11), 250, "grid2"), ((13, 1), 250, "uniform")]:
+        if kind == "uniform":
+            D = rng.random((n,) + shape)
+        elif kind == "f32":
+            D = rng.random((n,) + shape).astype(np.float32).astype(np.float64)
+        else:
+            D = rng.integers(0, int(kind[4:]), (n,) + shape).astype(np.float64) / 4.0
+        cases.append(D)
+    for D in cases:
+        cost, paths = dtw_batch(D)
+        for b in range(D.shape[0]):
+            c, p1, p2, ties = dtw(D[b], return_ties=True)
+            assert c == cost[b]
+            np.testing.assert_array_equal(p1, paths[b][0])
+            np.testing.assert_array_equal(p2, paths[b][1])
+            tie_steps += ties
+            total += 1
+    assert total == 10000 and tie_steps > 15000        # the tie rule was exercised, a lot
+
+
 def test_dtw_tie_rule_is_diag_then_up_then_left(dtw_gold):
     for k in range(int(dtw_gold["n_tie_cases"])):
         d = dtw_gold["tie_d%d" % k]
@@ -191,3 +223,24 @@ def test_multitask_restatement_matches_reference(nets_gold):
             assert v.grad is None
         else:
             np.testing.assert_allclose(v.grad.numpy(), ref, rtol=2e-5, atol=1e-7)
+
+
+def test_training_loop_restatement_reproduces_the_reference_trajectory(golden_dir):
+    """oracle/nets.py + torch.optim.Adadelta (what bench.py's CPU arm times) against the first
+    40 losses of the live reference's trajectory fixture, and the fixture's own conditioning."""
+    from oracle import trajectory as tj
+    gold = np.load(os.path.join(golden_dir, "trajectory.npz"))
+    ref, pert = gold["losses"], gold["losses_perturbed"]
+    assert len(ref) == tj.STEPS and ref[-1] < 0.1 * ref[0]
+    assert np.max(np.abs(pert - ref) / ref) < 1e-4          # well conditioned in the reference itself
+    feat = torch.from_numpy(tj.features())
+    sd = {k: torch.from_numpy(v).requires_grad_() for k, v in tj.state_dict().items()}
+    opt = torch.optim.Adadelta(list(sd.values()), lr=0.1)
+    for k, (i1, i2, y) in enumerate(tj.batches()[:40]):
+        x = torch.cat([feat[torch.from_numpy(i1).long()], feat[torch.from_numpy(i2).long()]])
+        e = onets.siamese_forward_once(sd, x)
+        loss = onets.coscos2(e[:tj.BATCH], e[tj.BATCH:], torch.from_numpy(y), avg=False)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(float(loss.detach()) - ref[k]) <= 1e-4 * ref[k], k
