@@ -68,7 +68,7 @@ def test_sweep_table_equals_batches_stepped_one_by_one(multitask):
     assert abs(total - ref_total) <= 1e-5 * abs(ref_total), (total, ref_total)
     assert int(ea._cursor[0].item()) == start + nb * B        # the device-side batch position
     for (k, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
-        assert _rel(a, b) < 5e-4, k
+        assert _rel(a, b) < 2e-3, k
     # evaluation sweep: no weight changes, same loss as eager forward + loss
     before = ea.bucket.param.clone()
     ev = float(ea.sweep_table(feat, table, B, 3, start=0, do_training=False).item())
@@ -121,7 +121,7 @@ def test_trainer_epoch_over_frames_dataloader(multitask):
     ref_total = float(ref.sweep_table(c.feat, tab, 2048, nb, start=0, graph=False).item())
     assert abs(tr.train_losses[-1] * nb - ref_total) <= 1e-4 * abs(ref_total)
     for (k, a), (_, b) in zip(net.state_dict().items(), ref_net.state_dict().items()):
-        assert _rel(a, b) < 5e-4, k
+        assert _rel(a, b) < 2e-3, k
     dtab = dl.frame_pairs["dev"]
     ndb = max(dtab[0].numel() // 2048, 1)
     ref_dev = float(ref.sweep_table(c.feat, dtab, min(2048, dtab[0].numel()), ndb, do_training=False,

@@ -386,3 +386,80 @@ def test_pairs_dataloader_on_reference_pair_file(golden_dir):
         ref = load_frames_from_pairs(acc, group_pairs(pairs[i * 4:(i + 1) * 4]), frames=True,
                                      align_different_words=True)
         _compare_batches(batch, ref)
+
+
+def test_c1_one_epoch_on_the_reference_pair_file_gpu_vs_oracle(golden_dir):
+    """Config C1 (BASELINE.json configs[0]): the reference's own pair set
+    (test/data/dataloader/pairs_knn.txt) over synthetic 280-dim files, SiameseNetwork
+    280-500-500-100 sigmoid, coscos2, ONE epoch (train sweep + test sweep) through
+    PairsDataLoader + TrainerSiamese on the GPU (fp32 path) against the same epoch replayed on
+    the CPU: the oracle's batches (abnet3/dataloader.py:510-546, :166-261), the oracle network
+    and loss under torch autograd, torch.optim.SGD(lr, momentum) as abnet3/trainer.py:70-72."""
+    import random
+    from oracle.make_golden import smooth_tokens
+    from abnet3_b200.trainer import TrainerSiamese
+    rng = np.random.default_rng(1)
+    feats = {"file%d" % i: smooth_tokens(rng, 80000, 280, rho=0.95) for i in range(5)}
+    kw = dict(ratio_split_train_test=1.0, batch_size=4, train_iterations=4, test_iterations=2)
+    dl = PairsDataLoader(os.path.join(golden_dir, "pairs_knn.txt"), feats,
+                         os.path.join(golden_dir, "id_to_file.txt"), **kw)
+    # the fixture's 30 pairs all train (its 70 % split leaves one pair, SURVEY 8d "bypass the stale
+    # split"); the test sweep runs over the same pairs
+    dl.load_pairs()
+    assert len(dl.pairs['train']) == 30
+    dl.pairs['test'], dl.tokens['test'] = dl.pairs['train'], dl.tokens['train']
+    torch.manual_seed(11)
+    net = SiameseNetwork(input_dim=280, num_hidden_layers=1, hidden_dim=500, output_dim=100,
+                         p_dropout=0.0, activation_layer="sigmoid", precision="fp32").to(DEV)
+    sd0 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    tr = TrainerSiamese(network=net, loss=coscos2(avg=True), optimizer_type="sgd", lr=0.05,
+                        momentum=0.9, cuda=True, dataloader=dl, log_dir="/tmp/abn_test_runs")
+    random.seed(21)
+    dev_loss = tr.optimize_model(do_training=True)
+
+    # ---- the same epoch on the CPU
+    acc = FeaturesAccessor({k: None for k in feats}, feats)
+    sd = {k: v.clone().requires_grad_() for k, v in sd0.items()}
+    opt = torch.optim.SGD(list(sd.values()), lr=0.05, momentum=0.9)
+    random.seed(21)
+
+    def epoch_batches(mode, iterations):
+        allpos, tokens = dl.pairs[mode], dl.tokens[mode]
+        n_pairs = iterations * 4
+        n_pos = min(int(n_pairs * 0.5), len(allpos))
+        pos = [p + ['same'] for p in random.sample(allpos, n_pos)]
+        toks = random.choices(tokens, k=2 * (n_pairs - n_pos))
+        neg = [list(toks[i]) + list(toks[i + 1]) + ["diff"] for i in range(0, len(toks), 2)]
+        pairs = pos + neg
+        random.shuffle(pairs)
+        for i in range(iterations):
+            batch = pairs[i * 4:(i + 1) * 4]
+            if batch:
+                yield load_frames_from_pairs(acc, group_pairs(batch), frames=True,
+                                             align_different_words=True)
+
+    def loss_of(batch):
+        X1, X2, y = (torch.from_numpy(np.ascontiguousarray(a)) for a in batch)
+        n = X1.shape[0]
+        e = onets.siamese_forward_once(sd, torch.cat([X1, X2]).float())
+        return onets.coscos2(e[:n], e[n:], y.float(), avg=True)
+
+    train_total, nb = 0.0, 0
+    for batch in epoch_batches('train', 4):
+        loss = loss_of(batch)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        train_total += float(loss.detach())
+        nb += 1
+    dev_total, ndb = 0.0, 0
+    with torch.no_grad():
+        for batch in epoch_batches('test', 2):
+            dev_total += float(loss_of(batch))
+            ndb += 1
+    assert nb == 4 and tr.last_sweep == {'train_batches': nb, 'dev_batches': ndb}
+    assert abs(tr.train_losses[-1] - train_total / nb) <= 1e-4 * abs(train_total / nb)
+    assert abs(dev_loss - dev_total) <= 1e-4 * abs(dev_total)
+    for k, v in net.state_dict().items():
+        upd_gpu, upd_cpu = v.detach().cpu() - sd0[k], sd[k].detach() - sd0[k]
+        assert float((upd_gpu - upd_cpu).norm()) <= 1e-3 * float(upd_cpu.norm()), k
