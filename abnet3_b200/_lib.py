@@ -87,7 +87,7 @@ SIGNATURES = {
     "abn_cast_bf16": (_I, [_P, _L, _I, _L, _P, _L, _P, _L, _P]),
     "abn_optimizer_step": (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _F, _L, _P]),
     "abn_gather_batch_bf16": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _I, _P]),
-    "abn_gather_step_bf16": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P, _I, _P, _P]),
+    "abn_gather_step_bf16": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P, _P, _I, _P, _P]),
     "abn_pair_loss_dz": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _I, _P, _P, _P, _L, _P]),
     "abn_optimizer_step_fused": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _I, _P]),
     "abn_ipc_export": (_I, [_P, _P, _P]),

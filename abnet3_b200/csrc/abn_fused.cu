@@ -21,7 +21,9 @@ namespace abn {
 // cursor (nullable, int64[2] = {next table row, ticket}): without `sel` the batch is the table rows
 // cursor[0] .. cursor[0]+n-1 and the last block to finish advances cursor[0] by n -- an epoch of
 // fixed-size batches over a shuffled frame-pair table (abnet3/dataloader.py:686-739) replays as
-// ONE CUDA graph with no host-side bookkeeping per batch.  loss_acc (nullable, double[1]):
+// ONE CUDA graph with no host-side bookkeeping per batch.  table_rows > 0: a batch that would run
+// past the table is skipped (the cursor still advances): the gather of batch k + 1 is issued as a
+// prefetch beside the training step of batch k.  loss_acc (nullable, double[1]):
 // the previous step's loss (word 0 of zero_me) is added to it before it is cleared, i.e. the
 // `train_loss += loss.data[0]` of abnet3/trainer.py:242 without a host synchronisation per step.
 __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
@@ -29,7 +31,8 @@ __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
                                    const int32_t *__restrict__ idx2,
                                    const int8_t *__restrict__ y_in,
                                    const int8_t *__restrict__ y2_in,
-                                   const int64_t *__restrict__ sel, int64_t *cursor, int64_t n,
+                                   const int64_t *__restrict__ sel, int64_t *cursor, int64_t table_rows,
+                                   int64_t n,
                                    __nv_bfloat16 *__restrict__ xb, int64_t ldx,
                                    float *__restrict__ y_out, float *__restrict__ y2_out,
                                    unsigned *__restrict__ zero_me, int zero_words,
@@ -43,7 +46,9 @@ __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
     const int warps_per_block = blockDim.x >> 5;
     const int64_t w = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     const int64_t base = (cursor && !sel) ? *reinterpret_cast<volatile int64_t *>(cursor) : 0;
-    if (w < 2 * n) {
+    // a PREFETCH past the end of the table (the sweep's last step) gathers nothing
+    const bool in_table = !(cursor && !sel && table_rows > 0 && base + n > table_rows);
+    if (w < 2 * n && in_table) {
         const int lane = threadIdx.x & 31;
         const int64_t k = w >> 1;
         const int side = (int)(w & 1);
@@ -360,7 +365,8 @@ using namespace abn;
 
 extern "C" int abn_gather_step_bf16(const float *feat, int dim, const int32_t *idx1,
                                     const int32_t *idx2, const int8_t *y_in, const int8_t *y2_in,
-                                    const int64_t *sel, int64_t *cursor, int64_t n, void *xb,
+                                    const int64_t *sel, int64_t *cursor, int64_t table_rows,
+                                    int64_t n, void *xb,
                                     int64_t ldx, float *y_out, float *y2_out, void *zero_me,
                                     int zero_words, double *loss_acc, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
@@ -371,7 +377,7 @@ extern "C" int abn_gather_step_bf16(const float *feat, int dim, const int32_t *i
     const int wpb = 8;
     const int64_t warps = 2 * n;
     launch_pdl(gather_bf16_kernel, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), (cudaStream_t)stream,
-        feat, dim, idx1, idx2, y_in, y2_in, sel, cursor, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out,
+        feat, dim, idx1, idx2, y_in, y2_in, sel, cursor, table_rows, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out,
         y2_out, static_cast<unsigned *>(zero_me), zero_me ? zero_words : 0, loss_acc);
     return check_launch("abn_gather_step_bf16");
 }
@@ -380,7 +386,7 @@ extern "C" int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *
                                      const int32_t *idx2, const int8_t *y_in, const int64_t *sel,
                                      int64_t n, void *xb, int64_t ldx, float *y_out,
                                      void *zero_me, int zero_words, abn_stream_t stream) {
-    return abn_gather_step_bf16(feat, dim, idx1, idx2, y_in, nullptr, sel, nullptr, n, xb, ldx, y_out,
+    return abn_gather_step_bf16(feat, dim, idx1, idx2, y_in, nullptr, sel, nullptr, 0, n, xb, ldx, y_out,
                                 nullptr, zero_me, zero_words, nullptr, stream);
 }
 

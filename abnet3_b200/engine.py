@@ -182,7 +182,7 @@ class SiameseTrainStep(object):
                    "_zbuf", "loss_buf", "_dep", "_fwd_problems", "_dgrad_problems", "_fwd_fused",
                    "_fwd_rows", "_dgrad_fused", "_wgrad_split", "_backward_groups", "_gy",
                    "_graphs", "_warm", "_gsel", "_sx", "_sy", "_static_n", "_graph_fb",
-                   "_graph_opt", "_eager_warm")
+                   "_graph_opt", "_eager_warm", "_pipe")
     MAX_PLANS = 6
 
     def _reserve(self, rows):
@@ -203,6 +203,7 @@ class SiameseTrainStep(object):
         self._graphs, self._warm = {}, {}
         self._gsel = self._sx = self._sy = self._static_n = None
         self._graph_fb = self._graph_opt = None
+        self._pipe = None
         self._eager_warm = 0
         self._gy = [torch.empty(max(rows // 2, 1), dtype=torch.float32, device=dev)
                     for _ in range(2 if self.heads else 1)]
@@ -416,6 +417,23 @@ class SiameseTrainStep(object):
             probs = [wgrad_problem(l, None) for l in range(len(wgrad))]
             for i in range(0, len(probs), G):
                 self._backward_groups.append(probs[i:i + G])
+        # Pipelined sweeps (sweep_table): the gather of batch k + 1 runs beside the step of batch
+        # k, so the input operand, its labels and the [loss | counters] block exist twice.  Only
+        # the layer-0 weight-gradient problem reads x: the second set of backward groups differs
+        # from the first in that operand alone.
+        self._pipe = None
+        if self._fwd_fused is not None and self._dgrad_fused is not None and not merge:
+            xb2 = b16(rows, ops.pad_row(d_in + 1), d_in)
+            zbuf2 = torch.zeros_like(self._zbuf)
+            gy2 = [torch.empty_like(t) for t in self._gy]
+            xb1 = self.xb
+            wgrad[0] = (wgrad[0][0], xb2)
+            probs2 = [wgrad_problem(l, None) for l in range(len(wgrad))]
+            wgrad[0] = (wgrad[0][0], xb1)
+            groups2 = [probs2[i:i + G] for i in range(0, len(probs2), G)]
+            self._pipe = [dict(xb=self.xb, _zbuf=self._zbuf, _gy=self._gy,
+                               _backward_groups=self._backward_groups),
+                          dict(xb=xb2, _zbuf=zbuf2, _gy=gy2, _backward_groups=groups2)]
 
     def _forward_bf16(self, x):
         if x is not None:       # fp32 batch -> bf16 A operand (the gather can also write it directly)
@@ -703,11 +721,118 @@ class SiameseTrainStep(object):
             raise ValueError("the sweep runs past the end of the frame-pair table")
         self._reserve(2 * n)
         self._cursor.copy_(torch.tensor([start, 0], dtype=torch.int64), non_blocking=True)
-        self.loss_buf.zero_()
         self._loss_acc.zero_()
+        if self._can_pipeline(do_training):
+            return self._sweep_pipelined(feat, table, n, n_batches, do_training, graph)
+        self.loss_buf.zero_()
         for _ in range(n_batches):
             self._table_step(feat, table, n, None, do_training, graph)
         return self._loss_acc + self.loss_buf.double()
+
+    # ---- pipelined sweep: the next batch is gathered beside the current step ------------
+    # The gather (16 384 random 1 120-byte rows: HBM latency bound, ~12 us) depends on nothing
+    # the step computes, and the forward / dgrad chain kernels leave 20 of the 148 SMs idle
+    # (64 row blocks on 74 CTA pairs): batch k + 1 is gathered on a side stream, into the second
+    # operand buffer, while batch k trains.  Inside the CUDA graph that is a fork / join.
+    def _can_pipeline(self, train):
+        if os.environ.get("ABN_PIPELINE", "1") == "0" or self.precision != 1:
+            return False
+        if getattr(self, "_pipe", None) is None:
+            return False
+        if train and self.kind == "adam":
+            return False
+        # the NCCL all-reduce between two graphs keeps the plain sequence
+        if train and self.world > 1 and self._dp is None and self._dp_push is None and \
+                os.environ.get("ABN_GRAPH_ALLREDUCE", "1") != "1":
+            return False
+        return True
+
+    def _use_parity(self, p):
+        for k, v in self._pipe[p].items():
+            setattr(self, k, v)
+        self.loss_buf = self._zbuf[:1].view(torch.float32)
+
+    def _pipe_gather(self, feat, table, n, p):
+        """Gather the batch at the device cursor into operand set p (adds that set's previous
+        loss to the sweep accumulator and clears it)."""
+        q = self._pipe[p]
+        ys = table[2:]
+        two = len(ys) > 1
+        ops.gather_batch_bf16(feat, table[0], table[1], ys[0], None, n, q["xb"], y_out=q["_gy"][0],
+                              zero=q["_zbuf"], y2=ys[1] if two else None,
+                              y2_out=q["_gy"][1] if two else None, cursor=self._cursor,
+                              loss_acc=self._loss_acc, table_rows=table[0].numel())
+
+    def _pipe_step(self, feat, table, n, p, train, scale, step):
+        """Step on operand set p; the gather of the NEXT batch into set 1 - p runs on the side
+        stream meanwhile."""
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+        at = int(os.environ.get("ABN_PREFETCH_AT", "0"))      # 0: beside forward .. 3: beside wgrad
+
+        def fork(stage):
+            if stage == (at if train else min(at, 1)):
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self._pipe_gather(feat, table, n, 1 - p)
+
+        fork(0)
+        self._use_parity(p)
+        self._loss_cleared = True
+        out = self._forward_bf16(None)
+        fork(1)
+        self._loss_and_seed(out, n, self._gy)
+        if train:
+            fork(2)
+            if not self._grads_clean:
+                self.bucket.trained_grad.zero_()
+            self._grads_clean = False
+            if self._dgrad_fused is not None:
+                ops.mlp_dgrad_fused(self.dzb[-1], self._fwd_rows, self._dgrad_fused)
+            fork(3)
+            for grp in self._backward_groups:
+                ops.gemm_group(grp)
+            if self.world > 1:
+                self._allreduce()
+            self._optimizer(scale, step)
+        main.wait_stream(side)
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.bucket.param.device)
+        return self._side
+
+    def _sweep_pipelined(self, feat, table, n, n_batches, train, graph):
+        self._check_table(table)
+        if train:
+            self._check_trainable()
+        scale = self._grad_scale()
+        for q in self._pipe:
+            q["_zbuf"][:1].zero_()
+        key = ("pipe", feat.data_ptr()) + tuple(t.data_ptr() for t in table) + (bool(train),)
+        self._pipe_gather(feat, table, n, 0)                  # batch 0 -> set 0
+        for b in range(n_batches):
+            p = b & 1
+            g = self._graphs.get(key + (p,)) if graph else None
+            if g is not None:
+                g[0].replay()
+            elif graph and self._warm.get(key + (p,), 0) >= 1:
+                torch.cuda.synchronize()
+                g_main = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_main):
+                    self._pipe_step(feat, table, n, p, train, scale, 1)
+                if len(self._graphs) >= 12:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key + (p,)] = (g_main, None)
+                g_main.replay()
+            else:
+                self._warm[key + (p,)] = self._warm.get(key + (p,), 0) + 1
+                self._pipe_step(feat, table, n, p, train, scale, self.step_count + 1)
+            self.step_count += int(train)
+        total = self._loss_acc + self._pipe[0]["_zbuf"][:1].view(torch.float32).double() + \
+            self._pipe[1]["_zbuf"][:1].view(torch.float32).double()
+        self._use_parity(0)
+        return total
 
     def step(self, x, n, *labels, do_training=True, graph=False):
         """x = [X1; X2] as one [2n, D] batch; labels float32 [n] (y) or

@@ -406,12 +406,13 @@ def mlp_dgrad_fused(dz_top, rows, layers):
 
 # ------------------------------- fused companions of the tensor-core step ---
 def gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=None, zero=None, y2=None, y2_out=None,
-                      cursor=None, loss_acc=None):
+                      cursor=None, loss_acc=None, table_rows=0):
     """xb[:n] = bf16(feat[idx1[pos]]), xb[n:2n] = bf16(feat[idx2[pos]]), y_out = float(y[pos]) (and
     y2_out = float(y2[pos])) with pos = sel[k], or cursor[0] + k when ``sel`` is None and a
     ``cursor`` (device int64 [2]) is given -- the kernel then advances cursor[0] by n.  ``zero``
     (contiguous 4-byte-element tensor) is cleared by the same kernel, after its word 0 (the
-    previous step's loss) has been added to ``loss_acc`` (device float64 [1]) when given."""
+    previous step's loss) has been added to ``loss_acc`` (device float64 [1]) when given.
+    ``table_rows`` > 0: in cursor mode a batch past the end of the table is not gathered."""
     _req(feat, torch.float32, "feat")
     _req(idx1, torch.int32, "idx1")
     _req(idx2, torch.int32, "idx2")
@@ -427,7 +428,8 @@ def gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=None, zero=None, y2
     if not (xb.is_cuda and xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and xb.shape[0] >= 2 * n):
         raise TypeError("xb must be a CUDA bf16 [>= 2n, ld] tensor")
     check(_lib.lib().abn_gather_step_bf16(ptr(feat), feat.shape[1], ptr(idx1), ptr(idx2), ptr(y), ptr(y2),
-                                          ptr(sel), ptr(cursor), n, ptr(xb), xb.stride(0), ptr(y_out),
+                                          ptr(sel), ptr(cursor), int(table_rows), n, ptr(xb),
+                                          xb.stride(0), ptr(y_out),
                                           ptr(y2_out), ptr(zero),
                                           zero.numel() if zero is not None else 0, ptr(loss_acc),
                                           stream_ptr()))

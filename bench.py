@@ -689,7 +689,7 @@ def run_path(args, rank, world, local_rank, dev):
 
     def build(table):
         loader = LoaderCls.from_tokens(table, tokens, batch_size=B, randomize_dataset=True,
-                                       max_batches_per_epoch=None)
+                                       max_batches_per_epoch=None, exact_numpy_shuffle=False)
         return loader
 
     loader = build(ftable)
@@ -828,7 +828,8 @@ def run_path(args, rank, world, local_rank, dev):
                     tk = {"train": (dt[0], dt[1], [tuple(dl[0])]), "dev": (dt[2], dt[3], [tuple(dl[1])])}
                 else:
                     tk = {"train": (dt[0], dt[1]), "dev": (dt[2], dt[3])}
-                ld = LoaderCls.from_tokens(tab, tk, batch_size=B, randomize_dataset=True)
+                ld = LoaderCls.from_tokens(tab, tk, batch_size=B, randomize_dataset=True,
+                                           exact_numpy_shuffle=False)
                 if cap:
                     o2 = ld.epoch_table
                     ld.epoch_table = lambda train_mode=True: (lambda r: r[:4] + (min(r[4], cap),))(o2(train_mode))

@@ -375,12 +375,15 @@ ABN_API int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *idx
  *   replays as one CUDA graph with no per-batch host work:
  *   - y2_in / y2_out (nullable): a second label column (y_spk beside y_phn, dataloader.py:753-792);
  *   - cursor (nullable, device int64[2] = {next row, 0}): when sel == NULL the batch is the table
- *     rows cursor[0] .. cursor[0]+n-1 and the kernel advances cursor[0] by n;
+ *     rows cursor[0] .. cursor[0]+n-1 and the kernel advances cursor[0] by n; table_rows > 0:
+ *     a batch that would run past row table_rows is not gathered (prefetch of the batch after
+ *     the sweep's last one);
  *   - loss_acc (nullable, device double[1]): before zero_me is cleared its word 0 (the previous
  *     step's float loss) is added to loss_acc -- `train_loss += loss.data[0]`, trainer.py:242. */
 ABN_API int abn_gather_step_bf16(const float *feat, int dim, const int32_t *idx1,
                                  const int32_t *idx2, const int8_t *y_in, const int8_t *y2_in,
-                                 const int64_t *sel, int64_t *cursor, int64_t n, void *xb,
+                                 const int64_t *sel, int64_t *cursor, int64_t table_rows,
+                                 int64_t n, void *xb,
                                  int64_t ldx, float *y_out, float *y2_out, void *zero_me,
                                  int zero_words, double *loss_acc, abn_stream_t stream);
 ABN_API int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,

@@ -49,8 +49,12 @@ def _table(n_fp, n_rows, multitask, seed=3):
     return feat, (idx1, idx2) + tuple(cols)
 
 
+@pytest.mark.parametrize("pipeline", ["1", "0"])
 @pytest.mark.parametrize("multitask", [False, True])
-def test_sweep_table_equals_batches_stepped_one_by_one(multitask):
+def test_sweep_table_equals_batches_stepped_one_by_one(multitask, pipeline, monkeypatch):
+    """pipeline=1 (default): the next batch is gathered on a side stream beside the current step
+    (second operand set, fork / join inside the CUDA graph); 0: one stream, one operand set."""
+    monkeypatch.setenv("ABN_PIPELINE", pipeline)
     B, nb, start = 1000, 7, 3000
     feat, table = _table(12000, 5000, multitask)
     net_a, loss = _net(multitask)
@@ -66,9 +70,19 @@ def test_sweep_table_equals_batches_stepped_one_by_one(multitask):
         labels = [c[sl].float() for c in table[2:]]
         ref_total += float(eb.step(x, B, *labels).item())
     assert abs(total - ref_total) <= 1e-5 * abs(ref_total), (total, ref_total)
-    assert int(ea._cursor[0].item()) == start + nb * B        # the device-side batch position
+    # the device-side batch position (a pipelined sweep has prefetched one batch more)
+    assert int(ea._cursor[0].item()) == start + (nb + (pipeline == "1")) * B
+    assert (ea._pipe is not None) and ea._can_pipeline(True) == (pipeline == "1")
     for (k, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
         assert _rel(a, b) < 2e-3, k
+    # a sweep that ends exactly at the end of the table (the prefetch past it gathers nothing)
+    last = float(ea.sweep_table(feat, table, B, 2, start=table[0].numel() - 2 * B).item())
+    ref_last = 0.0
+    for k in range(2):
+        sl = slice(table[0].numel() - (2 - k) * B, table[0].numel() - (1 - k) * B)
+        x = torch.cat([feat[table[0][sl].long()], feat[table[1][sl].long()]])
+        ref_last += float(eb.step(x, B, *[c[sl].float() for c in table[2:]]).item())
+    assert abs(last - ref_last) <= 1e-4 * abs(ref_last), (last, ref_last)
     # evaluation sweep: no weight changes, same loss as eager forward + loss
     before = ea.bucket.param.clone()
     ev = float(ea.sweep_table(feat, table, B, 3, start=0, do_training=False).item())
