@@ -33,16 +33,22 @@ class GemmProblem(_c.Structure):
                 ("signal", _P), ("wait", _P), ("wait_count", _I)]
 
 
+class Dropout(_c.Structure):
+    """abn_dropout (include/abnet3_b200.h): device {seed, step} state, p, layer id."""
+    _fields_ = [("state", _P), ("p", _F), ("layer", _I)]
+
+
 class MlpLayer(_c.Structure):
     """abn_mlp_layer (include/abnet3_b200.h)."""
     _fields_ = [("W", _P), ("ldw", _L), ("bias", _P), ("n_in", _I), ("n_out", _I), ("act", _I),
-                ("out", _P), ("ldo", _L), ("out_f32", _I), ("ones_col", _I)]
+                ("out", _P), ("ldo", _L), ("out_f32", _I), ("ones_col", _I), ("drop", Dropout)]
 
 
 class MlpDLayer(_c.Structure):
     """abn_mlp_dlayer (include/abnet3_b200.h)."""
     _fields_ = [("W", _P), ("ldw", _L), ("n_in", _I), ("n_out", _I), ("act_below", _I),
-                ("y_below", _P), ("ld_y", _L), ("dz_below", _P), ("ld_dz", _L)]
+                ("y_below", _P), ("ld_y", _L), ("dz_below", _P), ("ld_dz", _L),
+                ("drop_below", Dropout)]
 
 
 class ParamSegment(_c.Structure):
@@ -81,6 +87,9 @@ SIGNATURES = {
     "abn_pair_loss": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _P, _P, _P, _P]),
     "abn_linear_forward": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P, _P]),
     "abn_linear_backward": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "abn_dropout_mask": (_I, [_P, _L, _I, _P, _P]),
+    "abn_linear_forward_drop": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P, _P, _L, _P]),
+    "abn_linear_backward_drop": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _L, _P]),
     "abn_gemm_bf16_group": (_I, [_P, _I, _P]),
     "abn_mlp_forward_fused": (_I, [_P, _L, _L, _P, _I, _P]),
     "abn_mlp_dgrad_fused": (_I, [_P, _L, _L, _P, _I, _P]),
@@ -89,6 +98,7 @@ SIGNATURES = {
     "abn_gather_batch_bf16": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _I, _P]),
     "abn_gather_step_bf16": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P, _P, _I, _P, _P]),
     "abn_pair_loss_dz": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _I, _P, _P, _P, _L, _P]),
+    "abn_pair_loss_dz_drop": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _I, _P, _P, _P, _L, _P, _L, _I, _P]),
     "abn_optimizer_step_fused": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _I, _P]),
     "abn_ipc_export": (_I, [_P, _P, _P]),
     "abn_ipc_import": (_I, [_P, _L, _P]),

@@ -36,10 +36,11 @@ int require_sm100() {
 }
 
 int simt_linear_forward(const float *x, const float *W, const float *b, int64_t m, int n_in,
-                        int n_out, int act, float *y, cudaStream_t st);
+                        int n_out, int act, float *y, const abn_dropout *drop, int64_t row_offset,
+                        cudaStream_t st);
 int simt_linear_backward(const float *x, const float *W, const float *y, float *dy, int64_t m,
                          int n_in, int n_out, int act, int accumulate, float *dx, float *dW,
-                         float *db, cudaStream_t st);
+                         float *db, const abn_dropout *drop, int64_t row_offset, cudaStream_t st);
 
 }  // namespace abn
 
@@ -66,29 +67,47 @@ extern "C" int abn_device_info(int *sm_count, int *cc_major, int *cc_minor,
     return ABN_OK;
 }
 
+extern "C" int abn_linear_forward_drop(const float *x, const float *W, const float *b, int64_t m,
+                                       int n_in, int n_out, int act, int precision, float *y,
+                                       const abn_dropout *drop, int64_t row_offset,
+                                       abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (m == 0) return ABN_OK;
+    if (!x || !W || !y || m < 0 || m > 0x7fffffff || n_in <= 0 || n_out <= 0 || act < 0 || act > 3 ||
+        (drop && (drop->p < 0.f || drop->p >= 1.f)))
+        return set_error(ABN_EINVAL, "abn_linear_forward: bad argument");
+    if (precision == 0)
+        return simt_linear_forward(x, W, b, m, n_in, n_out, act, y, drop, row_offset,
+                                   (cudaStream_t)stream);
+    return set_error(ABN_EINVAL, "abn_linear_forward: unknown precision %d", precision);
+}
+
 extern "C" int abn_linear_forward(const float *x, const float *W, const float *b, int64_t m,
                                   int n_in, int n_out, int act, int precision, float *y,
                                   abn_stream_t stream) {
+    return abn_linear_forward_drop(x, W, b, m, n_in, n_out, act, precision, y, nullptr, 0, stream);
+}
+
+extern "C" int abn_linear_backward_drop(const float *x, const float *W, const float *y, float *dy,
+                                        int64_t m, int n_in, int n_out, int act, int precision,
+                                        int accumulate, float *dx, float *dW, float *db,
+                                        const abn_dropout *drop, int64_t row_offset,
+                                        abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (m == 0) return ABN_OK;
-    if (!x || !W || !y || m < 0 || m > 0x7fffffff || n_in <= 0 || n_out <= 0 || act < 0 || act > 3)
-        return set_error(ABN_EINVAL, "abn_linear_forward: bad argument");
+    if (!x || !W || !y || !dy || m < 0 || m > 0x7fffffff || n_in <= 0 || n_out <= 0 || act < 0 ||
+        act > 3 || (drop && (drop->p < 0.f || drop->p >= 1.f)))
+        return set_error(ABN_EINVAL, "abn_linear_backward: bad argument");
     if (precision == 0)
-        return simt_linear_forward(x, W, b, m, n_in, n_out, act, y, (cudaStream_t)stream);
-    return set_error(ABN_EINVAL, "abn_linear_forward: unknown precision %d", precision);
+        return simt_linear_backward(x, W, y, dy, m, n_in, n_out, act, accumulate, dx, dW, db, drop,
+                                    row_offset, (cudaStream_t)stream);
+    return set_error(ABN_EINVAL, "abn_linear_backward: unknown precision %d", precision);
 }
 
 extern "C" int abn_linear_backward(const float *x, const float *W, const float *y, float *dy,
                                    int64_t m, int n_in, int n_out, int act, int precision,
                                    int accumulate, float *dx, float *dW, float *db,
                                    abn_stream_t stream) {
-    if (int rc = require_sm100()) return rc;
-    if (m == 0) return ABN_OK;
-    if (!x || !W || !y || !dy || m < 0 || m > 0x7fffffff || n_in <= 0 || n_out <= 0 || act < 0 ||
-        act > 3)
-        return set_error(ABN_EINVAL, "abn_linear_backward: bad argument");
-    if (precision == 0)
-        return simt_linear_backward(x, W, y, dy, m, n_in, n_out, act, accumulate, dx, dW, db,
-                                    (cudaStream_t)stream);
-    return set_error(ABN_EINVAL, "abn_linear_backward: unknown precision %d", precision);
+    return abn_linear_backward_drop(x, W, y, dy, m, n_in, n_out, act, precision, accumulate, dx, dW,
+                                    db, nullptr, 0, stream);
 }

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include "abn_common.cuh"
+#include "abn_drop.cuh"
 
 namespace abn {
 
@@ -109,10 +110,11 @@ pair_loss_dz_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
                     const float *__restrict__ y, int64_t n, int dim, int64_t ld, int kind,
                     float margin, float scale, int act, float *__restrict__ loss,
                     __nv_bfloat16 *__restrict__ dz1, __nv_bfloat16 *__restrict__ dz2,
-                    int64_t ld_dz) {
+                    int64_t ld_dz, const DropArgs drop, long long row2_off, int col_off) {
     __shared__ float wsum[LZ_WARPS];
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long dkey = drop.state ? drop_key(drop) : 0ull;
     float local = 0.f;
     for (int64_t row = (int64_t)blockIdx.x * LZ_WARPS + warp; row < n;
          row += (int64_t)gridDim.x * LZ_WARPS) {
@@ -146,8 +148,14 @@ pair_loss_dz_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
         __nv_bfloat16 *ga = dz1 + row * ld_dz, *gb = dz2 + row * ld_dz;
         for (int k = lane; k < dim; k += 32) {
             const float x = a[k], z = b[k];      // L1 hits: read a moment ago
-            ga[k] = __float2bfloat16_rn(g * (z * inv - ka * x) * dact_of(x, act));
-            gb[k] = __float2bfloat16_rn(g * (x * inv - kb * z) * dact_of(z, act));
+            float da = g * (z * inv - ka * x) * dact_of(x, act);
+            float db = g * (x * inv - kb * z) * dact_of(z, act);
+            if (drop.state) {       // the output layer's dropout (abnet3/model.py:136-141)
+                da = drop_keep(dkey, row, col_off + k, drop.thresh) ? da * drop.inv_keep : 0.f;
+                db = drop_keep(dkey, row2_off + row, col_off + k, drop.thresh) ? db * drop.inv_keep : 0.f;
+            }
+            ga[k] = __float2bfloat16_rn(da);
+            gb[k] = __float2bfloat16_rn(db);
         }
     }
     if (lane == 0) wsum[warp] = local;
@@ -170,11 +178,12 @@ pair_loss_dz_vec_kernel(const float *__restrict__ e1, const float *__restrict__ 
                         const float *__restrict__ y, int64_t n, int dim, int64_t ld, int kind,
                         float margin, float scale, int act, float *__restrict__ loss,
                         __nv_bfloat16 *__restrict__ dz1, __nv_bfloat16 *__restrict__ dz2,
-                        int64_t ld_dz) {
+                        int64_t ld_dz, const DropArgs drop, long long row2_off, int col_off) {
     __shared__ float wsum[LZ_WARPS];
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, slot = lane >> 3;
+    const unsigned long long dkey = drop.state ? drop_key(drop) : 0ull;
     const int nv = dim >> 2;
     float local = 0.f;
     for (int64_t row0 = ((int64_t)blockIdx.x * LZ_WARPS + warp) * 4; row0 < n;
@@ -232,14 +241,26 @@ pair_loss_dz_vec_kernel(const float *__restrict__ e1, const float *__restrict__ 
                 const int cc = sub + 8 * u;
                 if (cc < nv) {
                     const float4 x = av[u], z = bv[u];
-                    __nv_bfloat162 a0 = __floats2bfloat162_rn(g * (z.x * inv - ka * x.x) * dact_of(x.x, act),
-                                                              g * (z.y * inv - ka * x.y) * dact_of(x.y, act));
-                    __nv_bfloat162 a1 = __floats2bfloat162_rn(g * (z.z * inv - ka * x.z) * dact_of(x.z, act),
-                                                              g * (z.w * inv - ka * x.w) * dact_of(x.w, act));
-                    __nv_bfloat162 b0 = __floats2bfloat162_rn(g * (x.x * inv - kb * z.x) * dact_of(z.x, act),
-                                                              g * (x.y * inv - kb * z.y) * dact_of(z.y, act));
-                    __nv_bfloat162 b1 = __floats2bfloat162_rn(g * (x.z * inv - kb * z.z) * dact_of(z.z, act),
-                                                              g * (x.w * inv - kb * z.w) * dact_of(z.w, act));
+                    float da[4] = {g * (z.x * inv - ka * x.x) * dact_of(x.x, act),
+                                   g * (z.y * inv - ka * x.y) * dact_of(x.y, act),
+                                   g * (z.z * inv - ka * x.z) * dact_of(x.z, act),
+                                   g * (z.w * inv - ka * x.w) * dact_of(x.w, act)};
+                    float db[4] = {g * (x.x * inv - kb * z.x) * dact_of(z.x, act),
+                                   g * (x.y * inv - kb * z.y) * dact_of(z.y, act),
+                                   g * (x.z * inv - kb * z.z) * dact_of(z.z, act),
+                                   g * (x.w * inv - kb * z.w) * dact_of(z.w, act)};
+                    if (drop.state) {       // the output layer's dropout (abnet3/model.py:136-141)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = col_off + 4 * cc + e;
+                            da[e] = drop_keep(dkey, row, col, drop.thresh) ? da[e] * drop.inv_keep : 0.f;
+                            db[e] = drop_keep(dkey, row2_off + row, col, drop.thresh) ? db[e] * drop.inv_keep : 0.f;
+                        }
+                    }
+                    __nv_bfloat162 a0 = __floats2bfloat162_rn(da[0], da[1]);
+                    __nv_bfloat162 a1 = __floats2bfloat162_rn(da[2], da[3]);
+                    __nv_bfloat162 b0 = __floats2bfloat162_rn(db[0], db[1]);
+                    __nv_bfloat162 b1 = __floats2bfloat162_rn(db[2], db[3]);
                     ga[cc] = make_uint2(*reinterpret_cast<unsigned *>(&a0), *reinterpret_cast<unsigned *>(&a1));
                     gb[cc] = make_uint2(*reinterpret_cast<unsigned *>(&b0), *reinterpret_cast<unsigned *>(&b1));
                 }
@@ -394,7 +415,18 @@ extern "C" int abn_pair_loss_dz(const float *e1, const float *e2, const float *y
                                 int64_t ld, int kind, float margin, float scale, int act,
                                 float *loss, void *dz1, void *dz2, int64_t ld_dz,
                                 abn_stream_t stream) {
+    return abn_pair_loss_dz_drop(e1, e2, y, n, dim, ld, kind, margin, scale, act, loss, dz1, dz2, ld_dz,
+                                 nullptr, 0, 0, stream);
+}
+
+extern "C" int abn_pair_loss_dz_drop(const float *e1, const float *e2, const float *y, int64_t n, int dim,
+                                     int64_t ld, int kind, float margin, float scale, int act,
+                                     float *loss, void *dz1, void *dz2, int64_t ld_dz,
+                                     const abn_dropout *drop, int64_t row2_offset, int col_offset,
+                                     abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
+    const DropArgs da = drop_args(drop);
+    const long long r2 = (long long)row2_offset;
     if (n == 0) return ABN_OK;
     if (ld == 0) ld = dim;
     if (!e1 || !e2 || !y || !loss || !dz1 || !dz2 || n < 0 || dim <= 0 || ld < dim ||
@@ -407,14 +439,14 @@ extern "C" int abn_pair_loss_dz(const float *e1, const float *e2, const float *y
         if (blocks > 148 * 8) blocks = 148 * 8;
         launch_pdl(pair_loss_dz_vec_kernel, dim3((unsigned)blocks), dim3(LZ_WARPS * 32), (cudaStream_t)stream,
             e1, e2, y, n, dim, ld, kind, margin, scale, act, loss, static_cast<__nv_bfloat16 *>(dz1),
-            static_cast<__nv_bfloat16 *>(dz2), ld_dz);
+            static_cast<__nv_bfloat16 *>(dz2), ld_dz, da, r2, col_offset);
         return check_launch("abn_pair_loss_dz");
     }
     int64_t blocks = (n + LZ_WARPS - 1) / LZ_WARPS;
     if (blocks > 148 * 8) blocks = 148 * 8;
     launch_pdl(pair_loss_dz_kernel, dim3((unsigned)blocks), dim3(LZ_WARPS * 32), (cudaStream_t)stream,
         e1, e2, y, n, dim, ld, kind, margin, scale, act, loss, static_cast<__nv_bfloat16 *>(dz1),
-        static_cast<__nv_bfloat16 *>(dz2), ld_dz);
+        static_cast<__nv_bfloat16 *>(dz2), ld_dz, da, r2, col_offset);
     return check_launch("abn_pair_loss_dz");
 }
 

@@ -6,6 +6,7 @@
 //   Linear -> act blocks     abnet3/model.py:133-170, forward :179-186
 //   optimizer.step()         abnet3/trainer.py:68-87, :240 (torch.optim semantics)
 #include "abn_common.cuh"
+#include "abn_drop.cuh"
 
 namespace abn {
 
@@ -131,7 +132,8 @@ template <bool AK, bool BK>
 __global__ void __launch_bounds__(GT)
 sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C,
              int M, int N, int K, int lda, int ldb, int ldc, int epi,
-             const float *__restrict__ bias, int act, int ksplit_len) {
+             const float *__restrict__ bias, int act, int ksplit_len,
+             const DropArgs drop = DropArgs{nullptr, 0u, 1.f, 0}, long long drop_row0 = 0) {
     __shared__ float As[2][GK][GM + 4];
     __shared__ float Bs[2][GK][GN + 4];
     const int tid = threadIdx.x;
@@ -208,17 +210,25 @@ sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__
         __syncthreads();
     }
 
+    const bool dropping = epi == EPI_BIAS_ACT && drop.state != nullptr;
+    const unsigned long long dkey = dropping ? drop_key(drop) : 0ull;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (gm >= M) continue;
+        // this thread's four columns n0 + 4 tx .. + 3 share one draw (abn_drop.cuh)
+        const unsigned long long dbits = dropping ? drop_bits4(dkey, drop_row0 + gm, (n0 >> 2) + tx) : 0ull;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
             float v = acc[i][j];
             float *dst = C + (size_t)gm * ldc + gn;
-            if (epi == EPI_BIAS_ACT) *dst = act_fwd(v + (bias ? bias[gn] : 0.f), act);
+            if (epi == EPI_BIAS_ACT) {
+                float z = v + (bias ? bias[gn] : 0.f);
+                if (dropping) z = drop_keep_of(dbits, j, drop.thresh) ? z * drop.inv_keep : 0.f;
+                *dst = act_fwd(z, act);
+            }
             else if (epi == EPI_STORE) *dst = v;
             else if (epi == EPI_ADD) *dst += v;
             else atomicAdd(dst, v);
@@ -228,11 +238,13 @@ sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__
 
 // dz = dy * act'(y) in place, and db (+)= column sums of dz.
 __global__ void act_backward_kernel(const float *__restrict__ y, float *__restrict__ dy, int64_t m,
-                                    int n, int act, float *__restrict__ db, int rows_per_block) {
+                                    int n, int act, float *__restrict__ db, int rows_per_block,
+                                    const DropArgs drop, long long drop_row0) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= n) return;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
     const int64_t r1 = min(m, r0 + rows_per_block);
+    const unsigned long long dkey = drop.state ? drop_key(drop) : 0ull;
     float s = 0.f;
     for (int64_t r = r0; r < r1; ++r) {
         const size_t o = (size_t)r * n + col;
@@ -244,6 +256,7 @@ __global__ void act_backward_kernel(const float *__restrict__ y, float *__restri
             case 3: g = yy > 0.f ? g : 0.f; break;
             default: break;
         }
+        if (drop.state) g = drop_keep(dkey, drop_row0 + r, col, drop.thresh) ? g * drop.inv_keep : 0.f;
         dy[o] = g;
         s += g;
     }
@@ -306,31 +319,42 @@ extern "C" int abn_pair_loss(const float *e1, const float *e2, const float *y, i
 namespace abn {
 // y = act(x W^T + b) on the fp32 SIMT path
 int simt_linear_forward(const float *x, const float *W, const float *b, int64_t m, int n_in,
-                        int n_out, int act, float *y, cudaStream_t st) {
+                        int n_out, int act, float *y, const abn_dropout *drop, int64_t row_offset,
+                        cudaStream_t st) {
     dim3 grid((n_out + GN - 1) / GN, (unsigned)((m + GM - 1) / GM), 1);
     sgemm_kernel<true, true><<<grid, GT, 0, st>>>(x, W, y, (int)m, n_out, n_in, n_in, n_in, n_out,
-                                                  EPI_BIAS_ACT, b, act, n_in);
+                                                  EPI_BIAS_ACT, b, act, n_in, drop_args(drop),
+                                                  (long long)row_offset);
     return check_launch("abn_linear_forward(simt)");
 }
 
 int launch_act_backward(const float *y, float *dy, int64_t m, int n_out, int act, float *db,
-                        cudaStream_t st) {
+                        const abn_dropout *drop, int64_t row_offset, cudaStream_t st) {
     const int rows_per_block = 128;
     dim3 grid((n_out + 127) / 128, (unsigned)((m + rows_per_block - 1) / rows_per_block));
-    act_backward_kernel<<<grid, 128, 0, st>>>(y, dy, m, n_out, act, db, rows_per_block);
+    act_backward_kernel<<<grid, 128, 0, st>>>(y, dy, m, n_out, act, db, rows_per_block,
+                                              drop_args(drop), (long long)row_offset);
     return check_launch("abn_linear_backward(act)");
+}
+
+// the keep mask of one layer, 1 byte per element (tests: mask replay in the oracle)
+__global__ void dropout_mask_kernel(const DropArgs drop, int64_t rows, int cols, uint8_t *__restrict__ mask) {
+    const unsigned long long key = drop_key(drop);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols;
+         e += (int64_t)gridDim.x * blockDim.x)
+        mask[e] = drop_keep(key, e / cols, (int)(e % cols), drop.thresh) ? 1 : 0;
 }
 
 int simt_linear_backward(const float *x, const float *W, const float *y, float *dy, int64_t m,
                          int n_in, int n_out, int act, int accumulate, float *dx, float *dW,
-                         float *db, cudaStream_t st) {
+                         float *db, const abn_dropout *drop, int64_t row_offset, cudaStream_t st) {
     const int acc_dx = accumulate & 2;
     accumulate &= 1;
     if (!accumulate) {
         if (db) cudaMemsetAsync(db, 0, sizeof(float) * n_out, st);
         if (dW) cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)n_out * n_in, st);
     }
-    if (int rc = launch_act_backward(y, dy, m, n_out, act, db, st)) return rc;
+    if (int rc = launch_act_backward(y, dy, m, n_out, act, db, drop, row_offset, st)) return rc;
     if (dx) {   // dx[m, n_in] = dz[m, n_out] @ W[n_out, n_in]
         dim3 grid((n_in + GN - 1) / GN, (unsigned)((m + GM - 1) / GM), 1);
         sgemm_kernel<true, false><<<grid, GT, 0, st>>>(dy, W, dx, (int)m, n_in, n_out, n_out, n_in,
@@ -371,4 +395,17 @@ extern "C" int abn_optimizer_step(float *param, const float *grad, float *state0
     optimizer_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         param, grad, state0, state1, n, kind, lr, momentum, grad_scale, bc1, bc2s);
     return check_launch("abn_optimizer_step");
+}
+
+extern "C" int abn_dropout_mask(const abn_dropout *drop, int64_t rows, int cols, uint8_t *mask,
+                                abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (!drop || !drop->state || !mask || rows < 0 || cols <= 0 || drop->p <= 0.f || drop->p >= 1.f)
+        return set_error(ABN_EINVAL, "abn_dropout_mask: bad argument (0 < p < 1, state on the device)");
+    if (rows == 0) return ABN_OK;
+    int64_t blocks = (rows * cols + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    abn::dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(abn::drop_args(drop), rows,
+                                                                                 cols, mask);
+    return check_launch("abn_dropout_mask");
 }

@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include "abn_tc_ptx.cuh"
+#include "abn_drop.cuh"
 
 namespace abn {
 
@@ -42,6 +43,7 @@ struct FLayer {
     float *out32; long long ld32;   // last layer: fp32 rows
     int n_in, n_out, act, ones_col, out_f32;
     int nkb, tiles_n, n_cap;        // GEMM view: K = 64 nkb, N = n_cap (forward: n_out + ones_col; dgrad: n_in)
+    DropArgs drop;                  // forward: this layer's dropout; dgrad: the dropout of the layer below
 };
 struct FChain {
     CUtensorMap map_x;              // x [rows, n_in0] bf16, box {64, 128}
@@ -84,9 +86,22 @@ __device__ __forceinline__ int f_n_eff(const FLayer &L, int nt) {
 
 // One 64-column block of a hidden layer: TMEM -> bias + activation -> bf16 -> this warp's 32
 // rows of slab k-block cb (the next layer's A operand), then a TMA store of the same box.
-template <int ACT>
+// z -> keep ? z / (1 - p) : 0 on 32 consecutive columns starting at col0 (a multiple of 4)
+__device__ __forceinline__ void f_drop32(float (&v)[32], const DropArgs &dr, unsigned long long dkey,
+                                         long long row, int col0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const unsigned long long bits = drop_bits4(dkey, row, (col0 >> 2) + q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            v[4 * q + e] = drop_keep_of(bits, e, dr.thresh) ? v[4 * q + e] * dr.inv_keep : 0.f;
+    }
+}
+
+template <int ACT, bool DROP>
 __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, unsigned dst, int lane,
-                                            int ones_at) {
+                                            int ones_at, const DropArgs &dr, unsigned long long dkey,
+                                            long long row, int col0) {
     const unsigned swz = (unsigned)(lane & 7);
     float v64[64];
     g_ld64(taddr, v64);
@@ -94,7 +109,15 @@ __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, uns
     for (int hseg = 0; hseg < 2; ++hseg) {
         float (&v)[32] = *reinterpret_cast<float (*)[32]>(&v64[32 * hseg]);
         unsigned pk[16];
-        if (ACT == 1 || ACT == 2) {
+        if (DROP && dr.state) {     // Linear -> Dropout -> act (abnet3/model.py:136-141)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += bs[32 * hseg + j];
+            f_drop32(v, dr, dkey, row, col0 + 32 * hseg);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = g_act<ACT>(v[j]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
+        } else if (ACT == 1 || ACT == 2) {
             g_bias_act32_packed<ACT>(v, bs + 32 * hseg, pk);
         } else {
             g_bias_act32<ACT>(v, bs + 32 * hseg);
@@ -119,8 +142,10 @@ __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, uns
 }
 
 // dgrad: TMEM -> x act'(y_below) -> bf16 -> slab rows (y_below's box sits in `ybuf`)
-template <int ACT>
-__device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[8], unsigned dst, int lane) {
+template <int ACT, bool DROP>
+__device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[8], unsigned dst, int lane,
+                                              const DropArgs &dr, unsigned long long dkey, long long row,
+                                              int col0) {
     const unsigned swz = (unsigned)(lane & 7);
     float v64[64];
     g_ld64(taddr, v64);
@@ -129,6 +154,7 @@ __device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[
         float (&v)[32] = *reinterpret_cast<float (*)[32]>(&v64[32 * hseg]);
         const uint4 yh[4] = {yc[4 * hseg], yc[4 * hseg + 1], yc[4 * hseg + 2], yc[4 * hseg + 3]};
         g_dact32<ACT>(v, yh);
+        if (DROP && dr.state) f_drop32(v, dr, dkey, row, col0 + 32 * hseg);     // dz * keep / (1 - p)
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
@@ -142,7 +168,7 @@ __device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[
 // MODE 0: forward (B = W K-major, bias + activation, last layer fp32)
 // MODE 1: dgrad   (B = W MN-major, x act'(y_below) with y_below fetched per warp by TMA)
 constexpr int F_EW_FWD = 16, F_EW_DGRAD = 8;        // epilogue warps: NQ = EW / 4 share a TMEM lane quarter
-template <int MODE>
+template <int MODE, bool DROP>
 __global__ void __launch_bounds__(64 + 32 * (MODE == 0 ? F_EW_FWD : F_EW_DGRAD), 1)
 mlp_chain_kernel(const __grid_constant__ FChain ch) {
     constexpr int EW = MODE == 0 ? F_EW_FWD : F_EW_DGRAD, NQ = EW / 4;
@@ -296,9 +322,12 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                 float *bs = bias_s + (lcount & 1u) * 512;
                 const int nblk = (L.n_cap + 63) >> 6;
                 const unsigned ybuf = ybuf0 + ew * 4096u, ybar = ybar0 + 8 * ew;
+                const unsigned long long dkey = (DROP && L.drop.state) ? drop_key(L.drop) : 0ull;
+                const long long drow = row0 + lane;
                 if (MODE == 0) {
                     for (int c = et; c < 512; c += 32 * EW)
                         bs[c] = (L.bias && c < L.n_out) ? __ldg(L.bias + c) : 0.f;
+                    if (et < 32) bias_s[1024 + et] = 0.f;
                 }
                 // this warp's earlier output boxes have left the slab rows it is about to rewrite
                 if (lane == 0) {
@@ -327,10 +356,10 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                             if (MODE == 0) {
                                 const int ones_at = L.ones_col ? L.n_out - cb * 64 : -1;
                                 switch (L.act) {
-                                    case 1: f_epi_block<1>(taddr, bs + cb * 64, dst, lane, ones_at); break;
-                                    case 2: f_epi_block<2>(taddr, bs + cb * 64, dst, lane, ones_at); break;
-                                    case 3: f_epi_block<3>(taddr, bs + cb * 64, dst, lane, ones_at); break;
-                                    default: f_epi_block<0>(taddr, bs + cb * 64, dst, lane, ones_at); break;
+                                    case 1: f_epi_block<1, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64); break;
+                                    case 2: f_epi_block<2, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64); break;
+                                    case 3: f_epi_block<3, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64); break;
+                                    default: f_epi_block<0, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64); break;
                                 }
                             } else {
                                 g_mbar_wait(ybar, ycount & 1u);
@@ -348,10 +377,10 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                     g_tma_2d(ybuf, &L.map_y, ybar, (cb + NQ) * 64, row0);
                                 }
                                 switch (L.act) {
-                                    case 1: f_epi_block_d<1>(taddr, yc, dst, lane); break;
-                                    case 2: f_epi_block_d<2>(taddr, yc, dst, lane); break;
-                                    case 3: f_epi_block_d<3>(taddr, yc, dst, lane); break;
-                                    default: f_epi_block_d<0>(taddr, yc, dst, lane); break;
+                                    case 1: f_epi_block_d<1, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64); break;
+                                    case 2: f_epi_block_d<2, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64); break;
+                                    case 3: f_epi_block_d<3, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64); break;
+                                    default: f_epi_block_d<0, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64); break;
                                 }
                             }
                             // generic-proxy writes -> visible to the async proxy (the next layer's
@@ -371,6 +400,12 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                 float v[32];
                                 g_ld32(taddr + 32 * hseg, v);
                                 const float *b2 = bs + cb * 64 + 32 * hseg;
+                                if (DROP && L.drop.state) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] += b2[j];
+                                    f_drop32(v, L.drop, dkey, drow, cb * 64 + 32 * hseg);
+                                    b2 = bias_s + 1024;              // 32 zeros: the bias is in already
+                                }
                                 switch (L.act) {
                                     case 1: g_bias_act32<1>(v, b2); break;
                                     case 2: g_bias_act32<2>(v, b2); break;
@@ -436,15 +471,15 @@ int f_sm_count() {
     return sm_count;
 }
 
-template <int MODE>
+template <int MODE, bool DROP>
 int f_launch(const FChain &ch, cudaStream_t st, const char *what) {
     // slab + weight ring + barriers + (forward: staged biases | dgrad: y_below boxes) + alignment slack
     constexpr int F_STAGES = MODE == 0 ? F_STAGES_FWD : F_STAGES_DGRAD;
     constexpr unsigned smem = F_KB * F_SLAB_KB_BYTES + F_STAGES * F_B_BYTES + 1024 +
-                              (MODE == 0 ? 512 + 2 * 512 * 4 : 1024 + F_EW_DGRAD * 4096);
+                              (MODE == 0 ? 512 + 2 * 512 * 4 + 128 : 1024 + F_EW_DGRAD * 4096);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(mlp_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(mlp_chain_kernel<MODE, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return set_error(ABN_EIO, "%s: cannot reserve %u bytes of shared memory", what, smem);
         configured = true;
@@ -466,7 +501,7 @@ int f_launch(const FChain &ch, cudaStream_t st, const char *what) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl() ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, mlp_chain_kernel<MODE>, ch);
+    cudaLaunchKernelEx(&cfg, mlp_chain_kernel<MODE, DROP>, ch);
     return check_launch(what);
 }
 
@@ -499,6 +534,7 @@ extern "C" int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
         L.bias = q.bias;
         L.n_in = q.n_in; L.n_out = q.n_out; L.act = q.act;
         L.ones_col = q.ones_col ? 1 : 0; L.out_f32 = q.out_f32 ? 1 : 0;
+        L.drop = drop_args(&q.drop);
         L.n_cap = q.n_out + L.ones_col;
         L.nkb = (q.n_in + G_BK - 1) / G_BK;
         L.tiles_n = (L.n_cap + 255) / 256;
@@ -517,7 +553,10 @@ extern "C" int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
         }
     }
     ch.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
-    return f_launch<0>(ch, (cudaStream_t)stream, "abn_mlp_forward_fused");
+    bool any_drop = false;
+    for (int l = 0; l < n_layers; ++l) any_drop |= ch.L[l].drop.state != nullptr;
+    return any_drop ? f_launch<0, true>(ch, (cudaStream_t)stream, "abn_mlp_forward_fused")
+                    : f_launch<0, false>(ch, (cudaStream_t)stream, "abn_mlp_forward_fused");
 }
 
 extern "C" int abn_mlp_dgrad_fused(const void *dz_top, int64_t ld_top, int64_t rows,
@@ -547,6 +586,7 @@ extern "C" int abn_mlp_dgrad_fused(const void *dz_top, int64_t ld_top, int64_t r
             return set_error(ABN_EINVAL, "abn_mlp_dgrad_fused: layer %d: bf16 rows must be padded to a "
                              "multiple of 8 elements covering n_in", l);
         L.n_in = q.n_in; L.n_out = q.n_out; L.act = q.act_below;
+        L.drop = drop_args(&q.drop_below);
         L.n_cap = q.n_in;
         L.nkb = (q.n_out + G_BK - 1) / G_BK;
         L.tiles_n = (L.n_cap + 255) / 256;
@@ -558,5 +598,8 @@ extern "C" int abn_mlp_dgrad_fused(const void *dz_top, int64_t ld_top, int64_t r
         if (rc) return rc;
     }
     ch.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
-    return f_launch<1>(ch, (cudaStream_t)stream, "abn_mlp_dgrad_fused");
+    bool any_drop = false;
+    for (int l = 0; l < n_layers; ++l) any_drop |= ch.L[l].drop.state != nullptr;
+    return any_drop ? f_launch<1, true>(ch, (cudaStream_t)stream, "abn_mlp_dgrad_fused")
+                    : f_launch<1, false>(ch, (cudaStream_t)stream, "abn_mlp_dgrad_fused");
 }

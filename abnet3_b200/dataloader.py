@@ -25,8 +25,9 @@ permutation seed for every batch, speaker labels by object identity
 ``align_different_words=True``.  Labels are yielded as float32 (+1 / -1); the
 reference yields float64 / int64 with the same values.
 
-Out of scope: temporal-coherence batches (``tcl > 0``,
-``TemporalCoherenceDataLoader``) and ``MultimodalDataLoader``.
+Temporal-coherence batches (``tcl > 0``, dataloader.py:314-352) are built in index
+space with the reference's ``random`` draws.  Out of scope:
+``MultimodalDataLoader``.
 """
 import os
 import random
@@ -88,14 +89,14 @@ def _diff_rows(tok, stretch):
 class OriginalDataLoader(DataLoader):
     """abnet3/dataloader.py:43-352."""
 
+    TCL_DISTANCE_SAME = [1]  # abnet3/dataloader.py:51-52 (Synnaeve & Dupoux temporal coherence loss)
+    TCL_DISTANCES_DIFF = [15, 20, 25, 30]
+
     def __init__(self, pairs_path, features_path, num_max_minibatches=1000,
                  seed=None, batch_size=8, shuffle_between_epochs=False,
                  align_different_words=False,
                  tcl=0.0):
         assert 0 <= tcl < 1
-        if tcl > 0:
-            raise NotImplementedError("temporal-coherence batches (tcl > 0) are out of scope "
-                                      "of this package (SURVEY.md section 2)")
         self.pairs_path = pairs_path
         self.features_path = features_path
         self.statistics_training = defaultdict(int)
@@ -301,6 +302,52 @@ class OriginalDataLoader(DataLoader):
         return self._assemble(grouped['same'], same_tok, al, same_ids, grouped['diff'], diff_tok,
                               0, fid2spk)
 
+    def add_tcl_to_batch(self, batch):
+        """dataloader.py:314-322: append tcl / (1 - tcl) x the batch's frame pairs of
+        temporal-coherence pairs (after the batch's own, un-shuffled, like the reference)."""
+        X1, X2, Y = batch
+        num_pairs = Y.shape[0]
+        num_pairs_to_add = int((self.tcl * num_pairs) / (1 - self.tcl))
+        X1_tcl, X2_tcl, Y_tcl = self.temporal_coherence_loss(num_pairs_to_add)
+        if Y_tcl.shape[0] == 0:
+            return batch
+        n = num_pairs + Y_tcl.shape[0]
+        buf = torch.empty((2 * n, X1.shape[1]), dtype=X1.dtype, device=X1.device)
+        buf[:num_pairs].copy_(X1)
+        buf[num_pairs:n].copy_(X1_tcl)
+        buf[n:n + num_pairs].copy_(X2)
+        buf[n + num_pairs:].copy_(X2_tcl)
+        return buf[:n], buf[n:], torch.cat((Y, Y_tcl))
+
+    def temporal_coherence_loss(self, num_pairs):
+        """dataloader.py:324-352 in index space: per iteration one random (file, t), the frame
+        pair (t, t + 1) as 'same' and (t, t + 15 / 20 / 25 / 30) as 'different'; same draws from
+        ``random`` as the reference; the rows are gathered on the device."""
+        rows1, rows2, Y = [], [], []
+        pairs_per_iteration = len(self.TCL_DISTANCES_DIFF) + len(self.TCL_DISTANCE_SAME)
+        tab = self.table
+        for _ in range(round(num_pairs / pairs_per_iteration)):
+            files = list(tab.files)
+            if self.train_files is not None:
+                files = self.train_files
+            f = random.choice(files)
+            key = tab._key(f)
+            t = random.choice(range(tab.nrows[key] - max(self.TCL_DISTANCES_DIFF)))
+            for delta, lab in [(d, 1) for d in self.TCL_DISTANCE_SAME] + \
+                              [(d, -1) for d in self.TCL_DISTANCES_DIFF]:
+                rows1.append(tab.row0[key] + t)
+                rows2.append(tab.row0[key] + t + delta)
+                Y.append(lab)
+        dev = tab.feat.device
+        n = len(Y)
+        if n == 0:
+            e = torch.empty((0, tab.dim), dtype=torch.float32, device=dev)
+            return e, e.clone(), torch.empty(0, dtype=torch.float32, device=dev)
+        i1 = torch.tensor(rows1, dtype=torch.int32, device=dev)
+        i2 = torch.tensor(rows2, dtype=torch.int32, device=dev)
+        x1, x2, _ = ops.gather_batch(tab.feat, i1, i2, None, None, n)
+        return x1, x2, torch.tensor(Y, dtype=torch.float32, device=dev)
+
     def batch_iterator(self, train_mode=True):
         """dataloader.py:263-312: batches of `batch_size` token pairs, at most
         `num_max_minibatches` random batches per epoch.  Yields (X1, X2, y)."""
@@ -321,7 +368,10 @@ class OriginalDataLoader(DataLoader):
             selected = np.random.permutation(range(num_batches))
         for batch_id in selected:
             lo = starts[batch_id]
-            yield self._batch_from_slice(mode, pairs, pairs[lo:lo + self.batch_size], lo)
+            batch = self._batch_from_slice(mode, pairs, pairs[lo:lo + self.batch_size], lo)
+            if self.tcl > 0:                    # dataloader.py:303-305
+                batch = self.add_tcl_to_batch(batch)
+            yield batch
 
 
 class PairsDataLoader(OriginalDataLoader):

@@ -75,7 +75,7 @@ class _ForwardChain(object):
     chunk buffers reused, one abn_mlp_forward_fused launch per chunk."""
 
     def __init__(self, network, max_rows):
-        trunk, heads = _trained_layers(network)
+        trunk, heads = network.inference_layers()         # (eval-mode BatchNorm folded in)
         layers = [(W.data, b.data, act) for W, b, act in trunk]
         self.head_dim = 0
         if heads:       # the two heads side by side: one [2d, hidden] layer

@@ -109,7 +109,7 @@ class SiameseTrainStep(object):
                  process_group=None):
         if optimizer_type not in OPTIMIZERS:
             raise ValueError("fused step supports %s, got %r" % (OPTIMIZERS, optimizer_type))
-        network._check_supported(training=True)     # whatever the mode at construction time
+        network._check_supported(training=True, fused=True)     # whatever the mode at construction
         self.network = network
         self.loss_spec = loss_spec
         self.kind, self.lr, self.momentum = optimizer_type, float(lr), float(momentum or 0.0)
@@ -137,6 +137,11 @@ class SiameseTrainStep(object):
         self.loss_buf = self._zbuf[:1].view(torch.float32)
         self.step_count = 0
         self.precision = PRECISIONS[network.precision]
+        # Dropout (abnet3/model.py:111, :136-141; the reference's default is p = 0.1): active while
+        # the network is in train() mode, as in the reference; the keep masks are a function of a
+        # device-side {seed, step} the kernels re-evaluate (include/abnet3_b200.h, abn_dropout)
+        self.p_drop = float(getattr(network, "p_dropout", 0.0) or 0.0)
+        self._drop_state = ops.dropout_state(dev) if self.p_drop > 0 else None
         self._rows = -1
         self._plans = {}
         self._graphs = {}
@@ -174,6 +179,31 @@ class SiameseTrainStep(object):
                     warnings.warn("peer-memory data parallelism unavailable (%s); using NCCL" % exc)
                     self._dp = None
 
+    # -------------------------------------------------------------- dropout ---
+    def _drop_on(self):
+        return self.p_drop > 0 and self.network.training
+
+    def _drop(self, layer):
+        """ctypes abn_dropout of one layer for the current pass (None when inactive)."""
+        if not self._drop_on():
+            return None
+        return ops.dropout_spec(self._drop_state, self.p_drop, layer)
+
+    def _drop_advance(self):
+        """Next step, next masks (after the last kernel that evaluates this step's)."""
+        if self._drop_on():
+            self._drop_state[1:].add_(1)
+
+    def dropout_masks(self, rows):
+        """Keep masks of every layer at the CURRENT step, in forward order (tests: replayed in
+        the oracle).  bf16 path: the two multitask heads are one 2d-wide layer."""
+        if self.precision == 1:
+            widths = [L.n_out for L in self.chain]
+        else:
+            widths = [W.shape[0] for W, _, _ in self.trunk] + [h[0][0].shape[0] for h in self.heads]
+        return [ops.dropout_mask(self._drop_state, self.p_drop, l, rows, w)
+                for l, w in enumerate(widths)]
+
     # ------------------------------------------------------------ fp32 path ---
     # Buffers, GEMM problem lists and CUDA graphs of one batch size form a "plan"; plans are
     # cached per row count (LRU), so alternating batch sizes (train / dev sweeps, the ragged
@@ -182,7 +212,7 @@ class SiameseTrainStep(object):
                    "_zbuf", "loss_buf", "_dep", "_fwd_problems", "_dgrad_problems", "_fwd_fused",
                    "_fwd_rows", "_dgrad_fused", "_wgrad_split", "_backward_groups", "_gy",
                    "_graphs", "_warm", "_gsel", "_sx", "_sy", "_static_n", "_graph_fb",
-                   "_graph_opt", "_eager_warm", "_pipe")
+                   "_graph_opt", "_eager_warm", "_pipe", "_fwd_fused_drop", "_dgrad_fused_drop")
     MAX_PLANS = 6
 
     def _reserve(self, rows):
@@ -224,13 +254,15 @@ class SiameseTrainStep(object):
 
     def _forward_fp32(self, x):
         h = x
+        nt = len(self.trunk)
         for l, (W, b, act) in enumerate(self.trunk):
-            h = ops.linear_forward(h, W.data, b.data, act, 0, out=self.acts[l])
+            h = ops.linear_forward(h, W.data, b.data, act, 0, out=self.acts[l], drop=self._drop(l))
         outs = []
         for hi, head in enumerate(self.heads):
             g = h
             for l, (W, b, act) in enumerate(head):
-                g = ops.linear_forward(g, W.data, b.data, act, 0, out=self.head_acts[hi][l])
+                g = ops.linear_forward(g, W.data, b.data, act, 0, out=self.head_acts[hi][l],
+                                       drop=self._drop(nt + hi))
             outs.append(g)
         return outs if self.heads else h
 
@@ -245,14 +277,16 @@ class SiameseTrainStep(object):
                     dx = self.head_dacts[hi][l - 1] if l > 0 else self.dacts[-1]
                     ops.linear_backward(xin, W.data, self.head_acts[hi][l], self.head_dacts[hi][l],
                                         act, 0, dW=W.grad, db=b.grad, accumulate=False,
-                                        dx=dx, accumulate_dx=(l == 0 and not first))
+                                        dx=dx, accumulate_dx=(l == 0 and not first),
+                                        drop=self._drop(len(trunk) + hi))
                 first = False
         for l in reversed(range(len(trunk))):
             W, b, act = trunk[l]
             xin = self.acts[l - 1] if l > 0 else x
             ops.linear_backward(xin, W.data, self.acts[l], self.dacts[l], act, 0,
                                 need_dx=(l > 0), dW=W.grad, db=b.grad, accumulate=False,
-                                dx=self.dacts[l - 1] if l > 0 else None)
+                                dx=self.dacts[l - 1] if l > 0 else None, drop=self._drop(l))
+        self._drop_advance()
 
     # ------------------------------------------------- bf16 tensor-core path ---
     # Every contraction is one problem of the persistent grouped tcgen05 GEMM
@@ -354,10 +388,15 @@ class SiameseTrainStep(object):
         self._fwd_fused = None
         self._fwd_rows = rows
         fits = all(L.n_in <= ops.MLP_MAX_WIDTH and L.n_out + 1 <= ops.MLP_MAX_WIDTH for L in self.chain)
+        self._fwd_fused_drop = None
         if fits and len(self.chain) <= ops.MLP_MAX_LAYERS and os.environ.get("ABN_FWD_FUSED", "1") != "0":
             self._fwd_fused = ops.mlp_layers(
                 [(L.wb, L.n_in, L.b, L.act, self.actb[l] if l < last else self.out_last, l < last)
                  for l, L in enumerate(self.chain)])
+            if self.p_drop > 0:
+                self._fwd_fused_drop = ops.mlp_layers(
+                    [(L.wb, L.n_in, L.b, L.act, self.actb[l] if l < last else self.out_last, l < last,
+                      (self._drop_state, self.p_drop, l)) for l, L in enumerate(self.chain)])
         # dz of the layer below = (dz W) * act'(its output); every dgrad problem signals its row
         # blocks: the next dgrad problem AND the weight gradients of the layer below wait on them
         n_d = 0
@@ -374,10 +413,21 @@ class SiameseTrainStep(object):
         # dz chain in ONE launch with dz resident in shared memory (abn_mlp_dgrad_fused) when the
         # layers fit its slab (ABN_BWD_FUSED=0: the grouped GEMM instead)
         self._dgrad_fused = None
+        self._dgrad_fused_drop = None
         if fits and last >= 1 and last <= ops.MLP_MAX_LAYERS and os.environ.get("ABN_BWD_FUSED", "1") != "0":
             self._dgrad_fused = ops.mlp_dlayers(
                 [(self.chain[l].wb, self.chain[l].n_in, self.chain[l - 1].act, self.actb[l - 1],
                   self.dzb[l - 1]) for l in range(last, 0, -1)])
+            if self.p_drop > 0:
+                self._dgrad_fused_drop = ops.mlp_dlayers(
+                    [(self.chain[l].wb, self.chain[l].n_in, self.chain[l - 1].act, self.actb[l - 1],
+                      self.dzb[l - 1], (self._drop_state, self.p_drop, l - 1))
+                     for l in range(last, 0, -1)])
+        if self.p_drop > 0 and (self._fwd_fused is None or (last >= 1 and self._dgrad_fused is None)):
+            raise NotImplementedError(
+                "dropout with p > 0 on the bf16 path is implemented by the fused chain kernels only "
+                "(layer widths <= %d, at most %d layers); use precision='fp32' for this network"
+                % (ops.MLP_MAX_WIDTH, ops.MLP_MAX_LAYERS))
         G = ops.GEMM_MAX_GROUP
         merge = (self._dgrad_fused is None and 2 * len(self.chain) - 1 <= G and
                  os.environ.get("ABN_BWD_MERGE", "1") != "0")
@@ -441,7 +491,8 @@ class SiameseTrainStep(object):
         if not self._loss_cleared:          # (the gather kernel clears loss + counters together)
             self._dep.zero_()
         if self._fwd_fused is not None:
-            ops.mlp_forward_fused(self.xb, self._fwd_rows, self._fwd_fused)
+            ops.mlp_forward_fused(self.xb, self._fwd_rows,
+                                  self._fwd_fused_drop if self._drop_on() else self._fwd_fused)
         else:
             G = ops.GEMM_MAX_GROUP
             for i in range(0, len(self._fwd_problems), G):
@@ -458,7 +509,9 @@ class SiameseTrainStep(object):
             self.bucket.trained_grad.zero_()       # dW / db are accumulated with reds
         self._grads_clean = False
         if self._dgrad_fused is not None:
-            ops.mlp_dgrad_fused(self.dzb[-1], self._fwd_rows, self._dgrad_fused)
+            ops.mlp_dgrad_fused(self.dzb[-1], self._fwd_rows,
+                                self._dgrad_fused_drop if self._drop_on() else self._dgrad_fused)
+        self._drop_advance()
         for grp in self._backward_groups:
             ops.gemm_group(grp)
 
@@ -498,10 +551,12 @@ class SiameseTrainStep(object):
         """Tensor-core path: the loss kernel writes the output layer's dz (bf16) directly."""
         dz = self.dzb[-1]
         act = self.chain[-1].act
+        drop = self._drop(len(self.chain) - 1)
         if not self.heads:
             kind, margin, avg = self.loss_spec
             ops.pair_loss_dz(out[:n], out[n:], labels[0], dz[:n], dz[n:], kind, margin,
-                             1.0 / n if avg else 1.0, act, loss_out=self.loss_buf)
+                             1.0 / n if avg else 1.0, act, loss_out=self.loss_buf, drop=drop,
+                             row2_offset=n)
             return
         spec_spk, spec_phn, weight = self.loss_spec
         d = self.head_dim
@@ -510,7 +565,8 @@ class SiameseTrainStep(object):
             kind, margin, avg = spec
             dzh = dz[:, hi * d:(hi + 1) * d]
             ops.pair_loss_dz(out[hi][:n], out[hi][n:], y, dzh[:n], dzh[n:], kind, margin,
-                             w * (1.0 / n if avg else 1.0), act, loss_out=self.loss_buf)
+                             w * (1.0 / n if avg else 1.0), act, loss_out=self.loss_buf, drop=drop,
+                             row2_offset=n, col_offset=hi * d)
 
     def _grad_scale(self):
         """Ranks SUM their gradients; a loss averaged over the batch (``avg=True``) is averaged
@@ -644,6 +700,8 @@ class SiameseTrainStep(object):
         self._loss_and_seed(out, n, self._gy)
         if train:
             self.backward(None)
+        else:
+            self._drop_advance()
 
     def _table_step(self, feat, table, n, sel=None, train=True, graph=True):
         if self.precision != 1:
@@ -655,7 +713,7 @@ class SiameseTrainStep(object):
         self._reserve(2 * n)
         scale = self._grad_scale()
         key = (feat.data_ptr(),) + tuple(t.data_ptr() for t in table) + \
-            (None if sel is None else sel.data_ptr(), bool(train))
+            (None if sel is None else sel.data_ptr(), bool(train), self._drop_on())
         use_graph = graph and (self.kind != "adam" or not train)
         g = self._graphs.get(key) if use_graph else None
         if g is not None:
@@ -768,33 +826,23 @@ class SiameseTrainStep(object):
         stream meanwhile."""
         main = torch.cuda.current_stream()
         side = self._side_stream()
-        at = int(os.environ.get("ABN_PREFETCH_AT", "0"))      # 0: beside forward .. 3: beside wgrad
-
-        def fork(stage):
-            if stage == (at if train else min(at, 1)):
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    self._pipe_gather(feat, table, n, 1 - p)
-
-        fork(0)
+        # fork at the very start of the step: the gather then runs beside the forward chain (a
+        # fork later in the sequence cuts the programmatic-dependent-launch chain of the main
+        # stream and gains nothing: 134.5 us/step here against 141-143, tools/time_sweep.py)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._pipe_gather(feat, table, n, 1 - p)
         self._use_parity(p)
         self._loss_cleared = True
         out = self._forward_bf16(None)
-        fork(1)
         self._loss_and_seed(out, n, self._gy)
         if train:
-            fork(2)
-            if not self._grads_clean:
-                self.bucket.trained_grad.zero_()
-            self._grads_clean = False
-            if self._dgrad_fused is not None:
-                ops.mlp_dgrad_fused(self.dzb[-1], self._fwd_rows, self._dgrad_fused)
-            fork(3)
-            for grp in self._backward_groups:
-                ops.gemm_group(grp)
+            self.backward(None)
             if self.world > 1:
                 self._allreduce()
             self._optimizer(scale, step)
+        else:
+            self._drop_advance()
         main.wait_stream(side)
 
     def _side_stream(self):
@@ -809,7 +857,8 @@ class SiameseTrainStep(object):
         scale = self._grad_scale()
         for q in self._pipe:
             q["_zbuf"][:1].zero_()
-        key = ("pipe", feat.data_ptr()) + tuple(t.data_ptr() for t in table) + (bool(train),)
+        key = ("pipe", feat.data_ptr()) + tuple(t.data_ptr() for t in table) + \
+            (bool(train), self._drop_on())
         self._pipe_gather(feat, table, n, 0)                  # batch 0 -> set 0
         for b in range(n_batches):
             p = b & 1
@@ -846,6 +895,7 @@ class SiameseTrainStep(object):
         out = self.forward(x)
         self._loss_and_seed(out, n, labels)
         if not do_training:
+            self._drop_advance()
             return self.loss_buf
         self.backward(x)
         if self.world > 1:

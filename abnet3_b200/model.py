@@ -11,8 +11,11 @@ ONE kernel (abn_linear_forward: GEMM + bias + activation) and its backward as
 abn_linear_backward; both branches of the siamese pair go through the layers
 as a single 2B-row batch.
 
-Not supported by the kernels (they raise instead of silently falling back):
-``batch_norm=True`` and dropout with p > 0 in training mode.
+Dropout (the reference's default is p = 0.1) runs inside the kernels' epilogues in train()
+mode: the keep mask is a counter-based hash of (seed, step, layer, row, col), re-evaluated by
+the backward kernels (include/abnet3_b200.h, abn_dropout).  ``batch_norm=True`` works in eval
+mode (embedding a trained network: the running statistics are folded into W and b); BatchNorm
+with batch statistics (training mode) raises instead of silently falling back.
 """
 import torch
 import torch.nn as nn
@@ -36,9 +39,14 @@ class _LinearActFn(torch.autograd.Function):
     """y = act(x W^T + b) with the fused backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, precision):
+    def forward(ctx, x, weight, bias, act, precision, drop=None):
         x = x.contiguous()
-        if precision == 1:
+        ctx.drop = drop
+        if drop is not None:
+            # dropout between the GEMM and the activation: the fp32 kernels evaluate the mask in
+            # their epilogues (the tensor-core version lives in the fused training engine)
+            y = ops.linear_forward(x, weight, bias, act, 0, drop=drop)
+        elif precision == 1:
             # tensor-core forward (tcgen05): bf16 operand copies made on the fly; the
             # training engine keeps them resident instead (abnet3_b200.engine)
             m, n_in = x.shape
@@ -63,8 +71,8 @@ class _LinearActFn(torch.autograd.Function):
         # autograd backward always takes the fp32 kernels (the fused engine has the
         # tensor-core backward)
         dx, dW, db = ops.linear_backward(x, weight, y, dz, ctx.act, 0,
-                                         need_dx=ctx.needs_input_grad[0])
-        return dx, dW, db, None, None
+                                         need_dx=ctx.needs_input_grad[0], drop=ctx.drop)
+        return dx, dW, db, None, None, None
 
 
 def _joint(input1, input2):
@@ -107,25 +115,77 @@ class NetworkBuilder(nn.Module):
             layer.bias.data.fill_(0.0)
 
     # -- kernel path helpers ------------------------------------------------
-    def _check_supported(self, training=None):
+    def _check_supported(self, training=None, fused=False):
         training = self.training if training is None else training
-        if self.batch_norm:
+        if self.batch_norm and training:
             raise NotImplementedError(
-                "batch_norm=True is not implemented by the sm_100a kernels (no fallback)")
-        if training and self.p_dropout > 0:
-            raise NotImplementedError(
-                "dropout with p > 0 in training mode is not implemented by the sm_100a "
-                "kernels (use p_dropout=0 as in test/data/buckeye.yaml, or eval mode)")
+                "batch_norm=True in training mode (batch statistics) is not implemented by the "
+                "sm_100a kernels; in eval mode the running statistics are folded into the layer")
 
-    def _block(self, x, seq, act):
-        """Run one `Linear -> Dropout -> [act]` Sequential through the kernel."""
-        lin = seq[0]
-        return _LinearActFn.apply(x, lin.weight, lin.bias, act, PRECISIONS[self.precision])
+    # -- dropout (abnet3/model.py:136-141: Linear -> Dropout(p) -> act) -------------
+    def _drop_for_call(self, device):
+        """One forward pass in train() mode = one set of masks: a SNAPSHOT of the {seed, step}
+        state that the forward and the (later) backward kernels of this pass both read; the
+        network's own counter moves on."""
+        if not (self.training and self.p_dropout > 0):
+            return None
+        st = self.__dict__.get("_drop_state")
+        if st is None or st.device != device:
+            st = ops.dropout_state(device)
+            self.__dict__["_drop_state"] = st
+        snap = st.clone()
+        st[1:].add_(1)
+        return snap
 
-    def _stack(self, x, seq, act):
-        for m in seq:
+    def _drop_spec(self, snap, layer):
+        return None if snap is None else ops.dropout_spec(snap, float(self.p_dropout), layer)
+
+    @staticmethod
+    def _blocks(seq):
+        """[(Linear, BatchNorm1d or None)] of a Sequential of `Linear -> Dropout -> [BatchNorm1d]
+        -> [act]` groups (abnet3/model.py:132-141)."""
+        mods = list(seq)
+        out = []
+        for k, m in enumerate(mods):
             if isinstance(m, nn.Linear):
-                x = _LinearActFn.apply(x, m.weight, m.bias, act, PRECISIONS[self.precision])
+                bn = None
+                for nxt in mods[k + 1:]:
+                    if isinstance(nxt, nn.Linear):
+                        break
+                    if isinstance(nxt, nn.BatchNorm1d):
+                        bn = nxt
+                        break
+                out.append((m, bn))
+        return out
+
+    @staticmethod
+    def _effective(lin, bn):
+        """(weight, bias) of the layer as the kernels see it.  Eval-mode BatchNorm1d is the
+        affine map (z - mean) / sqrt(var + eps) * gamma + beta on the layer's pre-activation
+        (the Dropout between them is the identity in eval mode): folded into W and b."""
+        if bn is None:
+            return lin.weight, lin.bias
+        s = torch.rsqrt(bn.running_var + bn.eps)
+        if bn.weight is not None:
+            s = s * bn.weight
+        W = (lin.weight * s.unsqueeze(1)).contiguous()
+        b = (lin.bias - bn.running_mean) * s
+        if bn.bias is not None:
+            b = b + bn.bias
+        return W.detach(), b.detach().contiguous()
+
+    def _block(self, x, seq, act, snap=None, layer=0):
+        """Run one `Linear -> Dropout -> [BatchNorm1d] -> [act]` Sequential through the kernel."""
+        lin, bn = self._blocks(seq)[0]
+        W, b = self._effective(lin, bn)
+        return _LinearActFn.apply(x, W, b, act, PRECISIONS[self.precision],
+                                  self._drop_spec(snap, layer))
+
+    def _stack(self, x, seq, act, snap=None, layer0=0):
+        for k, (lin, bn) in enumerate(self._blocks(seq)):
+            W, b = self._effective(lin, bn)
+            x = _LinearActFn.apply(x, W, b, act, PRECISIONS[self.precision],
+                                   self._drop_spec(snap, layer0 + k))
         return x
 
     def _as_input(self, x):
@@ -204,15 +264,27 @@ class SiameseNetwork(NetworkBuilder):
         """abnet3/model.py:179-186"""
         self._check_supported()
         h = self._as_input(x)
-        h = self._block(h, self.input_emb, self.activation_layer)
-        h = self._stack(h, self.hidden_layers, self.activation_layer)
-        return self._block(h, self.output_layer, self._last_act())
+        snap = self._drop_for_call(h.device)
+        h = self._block(h, self.input_emb, self.activation_layer, snap, 0)
+        h = self._stack(h, self.hidden_layers, self.activation_layer, snap, 1)
+        return self._block(h, self.output_layer, self._last_act(), snap, 1 + self.num_hidden_layers)
 
     def forward(self, input1, input2):
         """abnet3/model.py:188-196: shared weights on both inputs (one 2B batch)."""
         n = input1.shape[0]
         out = self.forward_once(_joint(self._as_input(input1), self._as_input(input2)))
         return out[:n], out[n:]
+
+    def inference_layers(self):
+        """-> (trunk [(W, b, act)], heads []) with eval-mode BatchNorm folded in."""
+        out = []
+        for seq, act in ((self.input_emb, self.activation_layer),
+                         (self.hidden_layers, self.activation_layer),
+                         (self.output_layer, self._last_act())):
+            for lin, bn in self._blocks(seq):
+                W, b = self._effective(lin, bn)
+                out.append((W.detach(), b.detach(), act))
+        return out, []
 
     def layer_specs(self):
         """[(weight, bias, act)] in forward order, for the fused training engine."""
@@ -289,11 +361,29 @@ class SiameseMultitaskNetwork(NetworkBuilder):
         """abnet3/model.py:346-354"""
         self._check_supported()
         h = self._as_input(x)
-        h = self._block(h, self.input_emb, self.activation_layer)
-        h = self._stack(h, self.hidden_layers_shared, self.activation_layer)
-        output_spk = self._block(h, self.output_layer_spk, self.activation_layer)
-        output_phn = self._block(h, self.output_layer_phn, self.activation_layer)
+        snap = self._drop_for_call(h.device)
+        nt = 1 + self.num_hidden_layers_shared
+        h = self._block(h, self.input_emb, self.activation_layer, snap, 0)
+        h = self._stack(h, self.hidden_layers_shared, self.activation_layer, snap, 1)
+        output_spk = self._block(h, self.output_layer_spk, self.activation_layer, snap, nt)
+        output_phn = self._block(h, self.output_layer_phn, self.activation_layer, snap, nt + 1)
         return output_spk, output_phn
+
+    def inference_layers(self):
+        """-> (trunk [(W, b, act)], heads [[(W, b, act)], [(W, b, act)]]) with eval-mode
+        BatchNorm folded in."""
+        act = self.activation_layer
+        trunk = []
+        for seq in (self.input_emb, self.hidden_layers_shared):
+            for lin, bn in self._blocks(seq):
+                W, b = self._effective(lin, bn)
+                trunk.append((W.detach(), b.detach(), act))
+        heads = []
+        for seq in (self.output_layer_spk, self.output_layer_phn):
+            lin, bn = self._blocks(seq)[0]
+            W, b = self._effective(lin, bn)
+            heads.append([(W.detach(), b.detach(), act)])
+        return trunk, heads
 
     def forward(self, input1, input2):
         """abnet3/model.py:356-364: returns (spk1, phn1, spk2, phn2)."""

@@ -255,19 +255,57 @@ def pair_loss(e1, e2, y, kind="coscos2", margin=0.5, scale=1.0, loss_out=None,
     return loss, de1, de2
 
 
-def linear_forward(x, W, b, act, precision=0, out=None):
+# ------------------------------------------------------------------ dropout ---
+def dropout_state(device, seed=None):
+    """Device {seed, step} of the dropout masks (abn_dropout): an int64 [2] tensor.  ``seed``
+    None: drawn from torch's CPU generator (so ``torch.manual_seed`` controls it).  Advance the
+    step with ``state[1] += 1`` (stream ordered; CUDA-graph capturable)."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return torch.tensor([seed, 0], dtype=torch.int64, device=device)
+
+
+def dropout_spec(state, p, layer):
+    """ctypes abn_dropout for one layer (state None or p == 0: no dropout)."""
+    d = _lib.Dropout()
+    if state is not None and p > 0:
+        _req(state, torch.int64, "dropout state")
+        d.state, d.p, d.layer = ptr(state), float(p), int(layer)
+        d._keep = state
+    else:
+        d.state, d.p, d.layer = None, 0.0, 0
+    return d
+
+
+def _drop_ref(drop):
+    import ctypes
+    return ctypes.byref(drop) if drop is not None and drop.state else None
+
+
+def dropout_mask(state, p, layer, rows, cols):
+    """The keep mask (uint8 [rows, cols], 1 = kept) of ``layer`` at the state's CURRENT step:
+    what the kernels evaluate in their epilogues (tests replay it in the oracle)."""
+    import ctypes
+    mask = torch.empty((rows, cols), dtype=torch.uint8, device=state.device)
+    d = dropout_spec(state, p, layer)
+    check(_lib.lib().abn_dropout_mask(ctypes.byref(d), rows, cols, ptr(mask), stream_ptr()))
+    return mask
+
+
+def linear_forward(x, W, b, act, precision=0, out=None, drop=None, row_offset=0):
     _req(x, torch.float32, "x")
     _req(W, torch.float32, "W")
     m, n_in = x.shape
     n_out = W.shape[0]
     y = out if out is not None else torch.empty((m, n_out), dtype=torch.float32, device=x.device)
-    check(_lib.lib().abn_linear_forward(ptr(x), ptr(W), ptr(b), m, n_in, n_out, ACT[act],
-                                        precision, ptr(y), stream_ptr()))
+    check(_lib.lib().abn_linear_forward_drop(ptr(x), ptr(W), ptr(b), m, n_in, n_out, ACT[act],
+                                             precision, ptr(y), _drop_ref(drop), int(row_offset),
+                                             stream_ptr()))
     return y
 
 
 def linear_backward(x, W, y, dy, act, precision=0, need_dx=True, dW=None, db=None,
-                    accumulate=False, dx=None, accumulate_dx=False):
+                    accumulate=False, dx=None, accumulate_dx=False, drop=None, row_offset=0):
     """dy is overwritten with dz = dy * act'(y).  Returns (dx, dW, db)."""
     _req(dy, torch.float32, "dy")
     m, n_in = x.shape
@@ -279,11 +317,11 @@ def linear_backward(x, W, y, dy, act, precision=0, need_dx=True, dW=None, db=Non
         dW = torch.empty_like(W)
         db = torch.empty(n_out, dtype=torch.float32, device=x.device)
         accumulate = False
-    check(_lib.lib().abn_linear_backward(ptr(x), ptr(W), ptr(y), ptr(dy), m, n_in, n_out,
-                                         ACT[act], precision,
-                                         int(bool(accumulate)) | (2 if accumulate_dx else 0),
-                                         ptr(dx), ptr(dW),
-                                         ptr(db), stream_ptr()))
+    check(_lib.lib().abn_linear_backward_drop(ptr(x), ptr(W), ptr(y), ptr(dy), m, n_in, n_out,
+                                              ACT[act], precision,
+                                              int(bool(accumulate)) | (2 if accumulate_dx else 0),
+                                              ptr(dx), ptr(dW), ptr(db), _drop_ref(drop),
+                                              int(row_offset), stream_ptr()))
     return dx, dW, db
 
 
@@ -362,15 +400,20 @@ MLP_MAX_WIDTH = 512
 
 
 def mlp_layers(specs):
-    """specs: [(W bf16 [n_out, ld], n_in, bias fp32 or None, act, out tensor, ones_col)] ->
-    ctypes array of abn_mlp_layer (keeps the tensors alive)."""
+    """specs: [(W bf16 [n_out, ld], n_in, bias fp32 or None, act, out tensor, ones_col
+    [, (dropout state, p, layer) or None])] -> ctypes array of abn_mlp_layer (keeps the tensors
+    alive)."""
     arr = (_lib.MlpLayer * len(specs))()
     keep = []
-    for a, (W, n_in, bias, act, out, ones_col) in zip(arr, specs):
+    for a, spec in zip(arr, specs):
+        W, n_in, bias, act, out, ones_col = spec[:6]
         a.W, a.ldw, a.bias = ptr(W), W.stride(0), ptr(bias)
         a.n_in, a.n_out, a.act = int(n_in), int(W.shape[0]), ACT[act]
         a.out, a.ldo, a.out_f32 = ptr(out), out.stride(0), int(out.dtype == torch.float32)
         a.ones_col = int(bool(ones_col))
+        if len(spec) > 6 and spec[6] is not None:          # (state, p, layer): dropout
+            a.drop = dropout_spec(*spec[6])
+            keep.append(spec[6][0])
         keep += [W, bias, out]
     arr._keep = keep
     return arr
@@ -388,11 +431,15 @@ def mlp_dlayers(specs):
     ctypes array of abn_mlp_dlayer."""
     arr = (_lib.MlpDLayer * len(specs))()
     keep = []
-    for a, (W, n_in, act_below, y_below, dz_below) in zip(arr, specs):
+    for a, spec in zip(arr, specs):
+        W, n_in, act_below, y_below, dz_below = spec[:5]
         a.W, a.ldw, a.n_in, a.n_out = ptr(W), W.stride(0), int(n_in), int(W.shape[0])
         a.act_below = ACT[act_below]
         a.y_below, a.ld_y = ptr(y_below), y_below.stride(0)
         a.dz_below, a.ld_dz = ptr(dz_below), dz_below.stride(0)
+        if len(spec) > 5 and spec[5] is not None:          # dropout of the layer below
+            a.drop_below = dropout_spec(*spec[5])
+            keep.append(spec[5][0])
         keep += [W, y_below, dz_below]
     arr._keep = keep
     return arr
@@ -436,7 +483,7 @@ def gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=None, zero=None, y2
 
 
 def pair_loss_dz(e1, e2, y, dz1, dz2, kind="coscos2", margin=0.5, scale=1.0, act=None,
-                 loss_out=None):
+                 loss_out=None, drop=None, row2_offset=0, col_offset=0):
     """Loss value (accumulated into loss_out) and dz = dL/de * act'(e) as bf16 rows."""
     _req(y, torch.float32, "y")
     n, dim = e1.shape
@@ -444,9 +491,10 @@ def pair_loss_dz(e1, e2, y, dz1, dz2, kind="coscos2", margin=0.5, scale=1.0, act
     if e2.stride(0) != ld or dz1.stride(0) != dz2.stride(0):
         raise ValueError("e1/e2 and dz1/dz2 must share their row strides")
     loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=e1.device)
-    check(_lib.lib().abn_pair_loss_dz(ptr(e1), ptr(e2), ptr(y), n, dim, ld, LOSS_KIND[kind],
-                                      float(margin), float(scale), ACT[act], ptr(loss), ptr(dz1),
-                                      ptr(dz2), dz1.stride(0), stream_ptr()))
+    check(_lib.lib().abn_pair_loss_dz_drop(ptr(e1), ptr(e2), ptr(y), n, dim, ld, LOSS_KIND[kind],
+                                           float(margin), float(scale), ACT[act], ptr(loss), ptr(dz1),
+                                           ptr(dz2), dz1.stride(0), _drop_ref(drop), int(row2_offset),
+                                           int(col_offset), stream_ptr()))
     return loss
 
 

@@ -217,6 +217,25 @@ ABN_API int abn_pair_loss(const float *e1, const float *e2, const float *y, int6
                   float *de1, float *de2, abn_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Dropout between Linear and activation in TRAINING mode (abnet3/model.py:136-141:
+ * `Linear -> Dropout(p) -> [BatchNorm] -> act`, default p = 0.1 at :111): the layer computes
+ *   y = act(keep * z / (1 - p)),   z = x W^T + b,   dz = dy * act'(y) * keep / (1 - p).
+ * The keep mask is a pure function of (seed, step, layer, row, col) -- a counter-based hash
+ * (splitmix64 of the key and the position, 16 bits per element: p is resolved to 1 / 65536) --
+ * that every kernel re-evaluates in its epilogue: no mask is stored, and the backward pass
+ * sees exactly the forward pass's mask.  `state` is a DEVICE array {seed, step}: kernels read
+ * it at run time, so a CUDA-graph replay sees the step the host (or a captured kernel) has
+ * advanced.  p == 0 or state == NULL: no dropout (eval mode).
+ * abn_dropout_mask writes the mask (1 = kept) of one layer for inspection / replay in tests. */
+typedef struct {
+    const unsigned long long *state;    /* device {seed, step} */
+    float p;                            /* drop probability */
+    int layer;                          /* which layer's mask */
+} abn_dropout;
+ABN_API int abn_dropout_mask(const abn_dropout *drop, int64_t rows, int cols, uint8_t *mask,
+                             abn_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * (3) Embedder MLP layers.
  * Replace one `Linear -> Dropout(p=0) -> activation` block of
  * abnet3/model.py:133-170 (forward) and its autograd backward.
@@ -238,6 +257,16 @@ ABN_API int abn_linear_backward(const float *x, const float *W, const float *y,
                         int n_in, int n_out, int act, int precision,
                         int accumulate, float *dx, float *dW, float *db,
                         abn_stream_t stream);
+/* The same two calls with dropout on the layer's pre-activation (drop == NULL or p == 0: as
+ * above).  Mask rows are row_offset + the row index inside the call. */
+ABN_API int abn_linear_forward_drop(const float *x, const float *W, const float *b,
+                       int64_t m, int n_in, int n_out, int act, int precision,
+                       float *y, const abn_dropout *drop, int64_t row_offset, abn_stream_t stream);
+ABN_API int abn_linear_backward_drop(const float *x, const float *W, const float *y,
+                        float *dy /* overwritten with dz */, int64_t m,
+                        int n_in, int n_out, int act, int precision,
+                        int accumulate, float *dx, float *dW, float *db,
+                        const abn_dropout *drop, int64_t row_offset, abn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * (3) tensor-core path, persistent grouped GEMM: up to ABN_GEMM_MAX_GROUP problems
@@ -308,6 +337,7 @@ typedef struct {
     int n_in, n_out, act;       /* act: ABN_ACT_* */
     void *out; int64_t ldo; int out_f32;
     int ones_col;               /* write 1.0 into column n_out of the bf16 output */
+    abn_dropout drop;           /* dropout on this layer's pre-activation (p = 0: none) */
 } abn_mlp_layer;
 ABN_API int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
                                   const abn_mlp_layer *layers, int n_layers, abn_stream_t stream);
@@ -324,6 +354,7 @@ typedef struct {
     int act_below;              /* activation whose output y_below is */
     const void *y_below; int64_t ld_y;
     void *dz_below; int64_t ld_dz;
+    abn_dropout drop_below;     /* the dropout of the layer whose output y_below is */
 } abn_mlp_dlayer;
 ABN_API int abn_mlp_dgrad_fused(const void *dz_top, int64_t ld_top, int64_t rows,
                                 const abn_mlp_dlayer *layers, int n_layers, abn_stream_t stream);
@@ -389,6 +420,12 @@ ABN_API int abn_gather_step_bf16(const float *feat, int dim, const int32_t *idx1
 ABN_API int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,
                              int64_t ld, int kind, float margin, float scale, int act, float *loss,
                              void *dz1, void *dz2, int64_t ld_dz, abn_stream_t stream);
+/* ... with the output layer's dropout folded into dz (mask rows: row for dz1, row2_offset + row
+ * for dz2; mask columns: col_offset + column -- the two multitask heads are one 2d-wide layer) */
+ABN_API int abn_pair_loss_dz_drop(const float *e1, const float *e2, const float *y, int64_t n, int dim,
+                                  int64_t ld, int kind, float margin, float scale, int act, float *loss,
+                                  void *dz1, void *dz2, int64_t ld_dz, const abn_dropout *drop,
+                                  int64_t row2_offset, int col_offset, abn_stream_t stream);
 #define ABN_MAX_PARAM_SEGMENTS 24
 typedef struct {
     int64_t offset, count;      /* range of the flat bucket */

@@ -214,3 +214,40 @@ def load_all_frames(features, pairs, shuffle=False):
     if shuffle:
         np.random.shuffle(frames)
     return token_feats, frames
+
+
+TCL_DISTANCE_SAME = [1]                                  # abnet3/dataloader.py:51-52
+TCL_DISTANCES_DIFF = [15, 20, 25, 30]
+
+
+def temporal_coherence_loss(features, num_pairs, train_files=None):
+    """abnet3/dataloader.py:324-352, verbatim control flow (the ``random`` module's state
+    decides the draws): -> (X1, X2, Y)."""
+    import random
+    X1, X2, Y = [], [], []
+    pairs_per_iteration = len(TCL_DISTANCES_DIFF) + len(TCL_DISTANCE_SAME)
+    for _ in range(round(num_pairs / pairs_per_iteration)):
+        files = list(features.features.keys())
+        if train_files is not None:
+            files = train_files
+        f = random.choice(files)
+        file_features = features.features[f]
+        t = random.choice(range(len(file_features) - max(TCL_DISTANCES_DIFF)))
+        for delta in TCL_DISTANCE_SAME:
+            X1.append(file_features[t])
+            X2.append(file_features[t + delta])
+            Y.append(1)
+        for delta in TCL_DISTANCES_DIFF:
+            X1.append(file_features[t])
+            X2.append(file_features[t + delta])
+            Y.append(-1)
+    return np.vstack(X1), np.vstack(X2), np.array(Y)
+
+
+def add_tcl_to_batch(features, batch, tcl, train_files=None):
+    """abnet3/dataloader.py:314-322."""
+    X1, X2, Y = batch
+    num_pairs = len(Y)
+    num_pairs_to_add = int((tcl * num_pairs) / (1 - tcl))
+    X1_tcl, X2_tcl, Y_tcl = temporal_coherence_loss(features, num_pairs_to_add, train_files)
+    return np.vstack((X1, X1_tcl)), np.vstack((X2, X2_tcl)), np.concatenate((Y, Y_tcl))

@@ -163,11 +163,3 @@ def test_engine_refreshes_bf16_weights_after_load_state_dict():
     net.load_state_dict(other.state_dict())              # copies into the fp32 masters in place
     got = float(eng.sweep_table(feat, table, 1000, 2, do_training=False).item())
     assert abs(got - want) <= 1e-6 * abs(want)     # (block partial sums are added atomically)
-
-
-def test_training_with_dropout_is_rejected_whatever_the_mode_at_construction():
-    net = SiameseNetwork(input_dim=280, num_hidden_layers=1, hidden_dim=64, output_dim=16,
-                         p_dropout=0.1, activation_layer="sigmoid").to(DEV)
-    net.eval()
-    with pytest.raises(NotImplementedError):
-        SiameseTrainStep(net, ("coscos2", 0.0, False), "sgd", lr=0.01, momentum=0.0)

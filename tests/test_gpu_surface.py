@@ -106,17 +106,41 @@ def test_unsupported_configurations_fail_loudly():
     net = SiameseNetwork(input_dim=8, num_hidden_layers=1, hidden_dim=8, output_dim=4,
                          p_dropout=0.1, activation_layer="relu").to(DEV)
     x = torch.randn(4, 8, device=DEV)
-    net.train()
-    with pytest.raises(NotImplementedError):
-        net(x, x)
     net.eval()
     net(x, x)                                    # dropout is the identity in eval mode
     bn = SiameseNetwork(input_dim=8, num_hidden_layers=1, hidden_dim=8, output_dim=4,
                         p_dropout=0.0, batch_norm=True, activation_layer="relu").to(DEV)
+    bn.train()
     with pytest.raises(NotImplementedError):
-        bn(x, x)
+        bn(x, x)                                 # batch statistics: not implemented
     with pytest.raises(RuntimeError):
         net(x.cpu(), x.cpu())                    # no CPU path
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_batch_norm_network_in_eval_mode_matches_torch_modules(precision, tol):
+    """batch_norm=True (abnet3/model.py:136-141: Linear -> Dropout -> BatchNorm1d -> act) in eval
+    mode: the running statistics are folded into W and b; checked against torch's own modules
+    of the same tree (which is what the reference executes), also through the embedder."""
+    from abnet3_b200.embedder import EmbedderSiamese
+    torch.manual_seed(3)
+    net = SiameseNetwork(input_dim=280, num_hidden_layers=2, hidden_dim=500, output_dim=100,
+                         p_dropout=0.1, batch_norm=True, activation_layer="sigmoid",
+                         precision=precision).to(DEV)
+    for m in net.modules():                      # non-trivial statistics and affine parameters
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(0, 0.3)
+            m.running_var.uniform_(0.5, 2.0)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    net.eval()
+    x = torch.randn(700, 280, device=DEV)
+    with torch.no_grad():
+        want = net.output_layer(net.hidden_layers(net.input_emb(x)))      # plain torch modules
+        got = net.forward_once(x)
+    assert float((got - want).abs().max()) < tol
+    emb = EmbedderSiamese(network=net, feature_path={"a": x.cpu().numpy()}, output_path=None).embed()
+    assert float(np.abs(emb["a"] - want.cpu().numpy()).max()) < tol
 
 
 @pytest.mark.parametrize("opt,lr", [("sgd", 0.05), ("adadelta", 0.1), ("adam", 0.002)])
@@ -307,6 +331,32 @@ def test_original_dataloader_align_different_words_quirk(corpus_files):
     for batch, b in zip(got, sel):
         ref = load_frames_from_pairs(acc, group_pairs(pairs[starts[b]:starts[b] + 8]),
                                      align_different_words=True)
+        _compare_batches(batch, ref)
+
+
+def test_temporal_coherence_batches_match_reference_semantics(corpus_files):
+    """tcl > 0 (abnet3/dataloader.py:303-352): every batch gets tcl / (1 - tcl) x its frame
+    pairs of (t, t+1) 'same' and (t, t+15..30) 'different' pairs of random files, appended
+    after the shuffled batch, with the reference's own ``random`` draws."""
+    import random
+    from oracle.align import add_tcl_to_batch
+    root, acc = corpus_files
+    dl = OriginalDataLoader(str(root), str(root / "features.npz"), num_max_minibatches=3,
+                            batch_size=8, tcl=0.3)
+    np.random.seed(31)
+    random.seed(32)
+    got = list(dl.batch_iterator(train_mode=True))
+    np.random.seed(31)
+    random.seed(32)
+    pairs = dl.pairs['train']
+    starts = list(range(0, len(pairs), 8))
+    sel = np.random.choice(range(len(starts)), 3, replace=False)
+    assert len(got) == 3
+    for batch, b in zip(got, sel):
+        ref = load_frames_from_pairs(acc, group_pairs(pairs[starts[b]:starts[b] + 8]))
+        n0 = len(ref[2])
+        ref = add_tcl_to_batch(acc, ref, 0.3, dl.train_files)
+        assert len(ref[2]) > n0                       # pairs were added
         _compare_batches(batch, ref)
 
 
