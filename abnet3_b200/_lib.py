@@ -75,6 +75,8 @@ SIGNATURES = {
     "abn_align_workspace_bytes": (_c.c_size_t, [_I, _I, _I]),
     "abn_align_launches": (_I, [_I, _I, _I, _c.c_size_t]),
     "abn_stack_upload": (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    "abn_stack_from_frames": (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    "abn_pack_directions": (_I, [_P, _P, _P, _P, _I, _P, _P, _P]),
     "abn_stack_violations": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "abn_cosine_distance": (_I, [_P, _L, _I, _P, _I, _I, _I, _P, _P, _P, _P, _c.c_size_t, _P]),
     "abn_dtw_from_dist": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -1702,6 +1702,68 @@ extern "C" int abn_stack_upload(float *feat_dev, const float *feat_host, int64_t
     return check_launch("abn_stack_upload");
 }
 
+extern "C" int abn_stack_from_frames(float *feat_dev, const float *frames, int64_t n_rows, int f,
+                                     int stack, const uint8_t *last_row_of_file, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (!feat_dev || !frames || n_rows < 0 || f <= 0 || (f & 3) || stack < 3 || !(stack & 1))
+        return set_error(ABN_EINVAL, "abn_stack_from_frames: bad argument (odd stack >= 3, f %% 4 == 0)");
+    if (n_rows == 0) return ABN_OK;
+    const int dim = f * stack, h = stack / 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the frames become the middle block of every row, the kernel fills in the rest
+    cudaError_t e = cudaMemcpy2DAsync(feat_dev + h * f, (size_t)dim * 4, frames, (size_t)f * 4,
+                                      (size_t)f * 4, (size_t)n_rows, cudaMemcpyDefault, st);
+    if (e != cudaSuccess)
+        return set_error(ABN_EIO, "abn_stack_from_frames: cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+    const int wpb = 8;
+    restack_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(feat_dev, n_rows, dim,
+                                                                              stack, last_row_of_file);
+    return check_launch("abn_stack_from_frames");
+}
+
+namespace abn {
+// one warp per pair: direction of step k = (idx1[k] - idx1[k-1], idx2[k] - idx2[k-1])
+__global__ void pack_directions_kernel(const int32_t *__restrict__ idx1, const int32_t *__restrict__ idx2,
+                                       const int64_t *__restrict__ dst_off,
+                                       const int32_t *__restrict__ path_len, int n_pairs,
+                                       const int64_t *__restrict__ dir_off, uint8_t *__restrict__ dirs) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (p >= n_pairs) return;
+    const int lane = threadIdx.x & 31;
+    const int nd = path_len[p] - 1;
+    if (nd <= 0) return;
+    const int32_t *a = idx1 + dst_off[p], *b = idx2 + dst_off[p];
+    uint8_t *out = dirs + dir_off[p];
+    for (int byte = lane; byte < (nd + 3) / 4; byte += 32) {
+        unsigned v = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = 4 * byte + u + 1;
+            if (k <= nd) {
+                const int di = a[k] - a[k - 1], dj = b[k] - b[k - 1];
+                const unsigned d = (di && dj) ? DIR_DIAG : (di ? DIR_UP : DIR_LEFT);
+                v |= d << (2 * u);
+            }
+        }
+        out[byte] = (uint8_t)v;
+    }
+}
+}  // namespace abn
+
+extern "C" int abn_pack_directions(const int32_t *idx1, const int32_t *idx2, const int64_t *dst_off,
+                                   const int32_t *path_len, int n_pairs, const int64_t *dir_off,
+                                   uint8_t *dirs, abn_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    if (n_pairs == 0) return ABN_OK;
+    if (!idx1 || !idx2 || !dst_off || !path_len || !dir_off || !dirs || n_pairs < 0)
+        return set_error(ABN_EINVAL, "abn_pack_directions: bad argument");
+    const int wpb = 8;
+    abn::pack_directions_kernel<<<(n_pairs + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+        idx1, idx2, dst_off, path_len, n_pairs, dir_off, dirs);
+    return check_launch("abn_pack_directions");
+}
+
 extern "C" int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int stack,
                                     const uint8_t *last_row_of_file, unsigned long long *count,
                                     abn_stream_t stream) {

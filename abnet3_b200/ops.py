@@ -143,6 +143,38 @@ def stack_upload(feat_host, stack=7, last_row_of_file=None, out=None):
     return feat
 
 
+def stack_from_frames(frames, stack=7, last_row_of_file=None, out=None):
+    """Stacked device table [n_rows, stack * f] from the UN-STACKED frames [n_rows, f] (a CPU
+    tensor, ideally pinned, or a CUDA tensor): abnet3/features.py:135-159 on the device.  The
+    frames are all that crosses PCIe."""
+    if frames.dtype != torch.float32 or not frames.is_contiguous() or frames.dim() != 2:
+        raise TypeError("frames must be a contiguous float32 [n_rows, f] tensor")
+    dev = frames.device if frames.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    if last_row_of_file is not None:
+        _req(last_row_of_file, torch.uint8, "last_row_of_file")
+    n, f = frames.shape
+    feat = out if out is not None else torch.empty((n, stack * f), dtype=torch.float32, device=dev)
+    check(_lib.lib().abn_stack_from_frames(ptr(feat), frames.data_ptr(), n, f, int(stack),
+                                           ptr(last_row_of_file), stream_ptr()))
+    return feat
+
+
+def pack_directions(d1, d2, dst_off, path_len, n_total):
+    """The dense paths (compact_paths: ``n_total`` index pairs) as 2-bit step directions, four
+    per byte (abn_pack_directions).  Returns (dirs uint8 [(n_total + 2 P) // 4 + 1], dir_off int64
+    [P + 1]); pair p's path_len[p] - 1 directions start at byte dir_off[p]."""
+    _req(d1, torch.int32, "idx1")
+    _req(d2, torch.int32, "idx2")
+    _req(path_len, torch.int32, "path_len")
+    P = path_len.numel()
+    nbytes = ((path_len.to(torch.int64) - 1).clamp_min(0) + 3) // 4
+    dir_off = _excl_cumsum(nbytes)
+    dirs = torch.empty((int(n_total) + 2 * P) // 4 + 1, dtype=torch.uint8, device=d1.device)
+    check(_lib.lib().abn_pack_directions(ptr(d1), ptr(d2), ptr(dst_off), ptr(path_len), P,
+                                         ptr(dir_off), ptr(dirs), stream_ptr()))
+    return dirs, dir_off
+
+
 def dtw_from_dist(dist, dist_off, shape, max_frames=None):
     """Batched DTW on given float64 matrices (the call at abnet3/utils.py:149-151).
     Returns (path1, path2, path_off, path_len, cost, valid) with LOCAL indices."""

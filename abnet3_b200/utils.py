@@ -19,7 +19,7 @@ import torch
 from . import ops
 
 __all__ = ["cosine_distance", "DTW", "get_dtw_alignment", "Features_Accessor",
-           "FeatureTable", "BatchAligner", "align_pairs_host", "read_dataset",
+           "FeatureTable", "BatchAligner", "align_pairs_host", "decode_directions", "read_dataset",
            "group_pairs", "read_pairs", "read_spkid_file", "read_spk_list", "read_feats"]
 
 
@@ -154,25 +154,49 @@ def _pinned_buf(name, numel, dtype):
 
 
 def align_pairs_host(feat_host, pair_tok_host, max_frames=None, stack=0, last_row_of_file=None,
-                     chunks=None):
+                     chunks=None, frames_host=None, paths="indices"):
     """Host buffers in, host results out -- the call a user of the reference's
     dataloader would make for a whole pair list.
 
-    ``feat_host`` [n_rows, dim] float32 and ``pair_tok_host`` [P, 4] int32 are
-    (ideally pinned) CPU tensors; ``stack=7`` when the table is a verified 7x40
-    stack (FeatureTable.stack); with ``last_row_of_file`` ([n_rows] uint8 CPU tensor
-    marking the last row of every file) the upload then carries only the 40-wide middle
-    block of every row and the stack is rebuilt on the device (7x fewer PCIe bytes, same
-    table).  Copies both to the GPU, aligns every pair,
-    compacts the paths and copies them back.  Returns CPU tensors
-    ``(idx1, idx2, pair_off, path_len, cost, valid)``: pair p's aligned global
-    rows are ``idx1[pair_off[p]:pair_off[p+1]]`` / ``idx2[...]``."""
+    Input, one of:
+
+    * ``feat_host`` [n_rows, dim] float32 -- the stacked table the reference keeps in RAM
+      (abnet3/utils.py:211-217).  The whole table is uploaded; with ``last_row_of_file`` the
+      device then checks whether it is a 7 x 40 stack and, if so, aligns on the stacked fast path
+      (same bits).  (``stack=7`` + ``last_row_of_file``: the caller vouches for the structure and
+      only the middle blocks are uploaded; kept for compatibility -- prefer ``frames_host``,
+      which needs no promise.)
+    * ``frames_host`` [n_rows, f] float32 -- the UN-STACKED frames (what abnet3/features.py:135-159
+      stacks) with ``last_row_of_file`` ([n_rows] uint8 CPU tensor marking the last row of every
+      file): uploaded as they are (7 x fewer bytes) and stacked on the device; the alignment then
+      takes the stacked fast path.  Token rows in ``pair_tok_host`` index frames = table rows.
+
+    ``pair_tok_host`` [P, 4] int32 (row1, n1, row2, n2); CPU tensors, ideally pinned.
+
+    Output, ``paths``:
+
+    * ``"indices"``: ``(idx1, idx2, pair_off, path_len, cost, valid)``: pair p's aligned global
+      rows are ``idx1[pair_off[p]:pair_off[p+1]]`` / ``idx2[...]`` (two int32 per path step);
+    * ``"directions"``: ``(dirs, dir_off, path_len, cost, valid)``: the paths as 2-bit step
+      directions (abn_pack_directions; 32 x fewer bytes over PCIe); ``decode_directions``
+      restores the index pairs on the host when they are wanted there."""
     dev = _device()
-    if stack and last_row_of_file is not None:
+    if paths not in ("indices", "directions"):
+        raise ValueError("paths must be 'indices' or 'directions'")
+    if frames_host is not None:
+        last = last_row_of_file.to(dev, non_blocking=True) if last_row_of_file is not None else None
+        stack = stack or 7
+        feat = ops.stack_from_frames(frames_host, stack, last)
+    elif stack and last_row_of_file is not None:
         last = last_row_of_file.to(dev, non_blocking=True)
         feat = ops.stack_upload(feat_host, stack, last)
     else:
         feat = feat_host.to(dev, non_blocking=True)
+        if last_row_of_file is not None and feat.shape[1] == 280 and feat.shape[0] > 1:
+            # the whole table was uploaded; whether it is a 7 x 40 stack is CHECKED on the device
+            # (1 ms), not promised: if so the alignment takes the stacked fast path (same bits)
+            last = last_row_of_file.to(dev, non_blocking=True)
+            stack = 7 if ops.stack_violations(feat, 7, last) == 0 else 0
     tok = pair_tok_host.to(dev, non_blocking=True)
     P = tok.shape[0]
     if max_frames is None:
@@ -186,8 +210,12 @@ def align_pairs_host(feat_host, pair_tok_host, max_frames=None, stack=0, last_ro
     n_chunks = max(1, min(n_chunks, max(P, 1)))
     bounds = [P * c // n_chunks for c in range(n_chunks + 1)]
     cap_total = int((pair_tok_host[:, 1].long() + pair_tok_host[:, 3].long() - 1).clamp_min(0).sum())
-    h_idx1 = _pinned_buf("idx1", max(cap_total, 1), torch.int32)
-    h_idx2 = _pinned_buf("idx2", max(cap_total, 1), torch.int32)
+    as_dirs = paths == "directions"
+    if as_dirs:
+        h_dirs = _pinned_buf("dirs", (cap_total + 2 * P) // 4 + n_chunks + 1, torch.uint8)
+    else:
+        h_idx1 = _pinned_buf("idx1", max(cap_total, 1), torch.int32)
+        h_idx2 = _pinned_buf("idx2", max(cap_total, 1), torch.int32)
     h_off = _pinned_buf("off", P + 1, torch.int64)
     h_len = _pinned_buf("len", P, torch.int32)
     h_cost = _pinned_buf("cost", P, torch.float64)
@@ -205,24 +233,68 @@ def align_pairs_host(feat_host, pair_tok_host, max_frames=None, stack=0, last_ro
         res = ops.align_pairs(feat, tok[lo:hi], max_frames=max_frames, stack=stack, total_cap=cap_c)
         d1, d2, doff = ops.compact_paths(res, host_scalar=h_total)    # (host learns the chunk's total here)
         n = d1.numel()
-        goff = doff + base if base else doff
+        if as_dirs:
+            dirs, dir_off = ops.pack_directions(d1, d2, doff, res.path_len, n)
+            nb = dirs.numel()
+            goff = dir_off + base if base else dir_off
+        else:
+            goff = doff + base if base else doff
         done = torch.cuda.Event()
         done.record(main)
         side.wait_event(done)
         with torch.cuda.stream(side):
-            h_idx1[base:base + n].copy_(d1, non_blocking=True)
-            h_idx2[base:base + n].copy_(d2, non_blocking=True)
+            if as_dirs:
+                h_dirs[base:base + nb].copy_(dirs, non_blocking=True)
+            else:
+                h_idx1[base:base + n].copy_(d1, non_blocking=True)
+                h_idx2[base:base + n].copy_(d2, non_blocking=True)
             h_off[lo:hi + 1].copy_(goff, non_blocking=True)
             h_len[lo:hi].copy_(res.path_len, non_blocking=True)
             h_cost[lo:hi].copy_(res.cost, non_blocking=True)
             h_valid[lo:hi].copy_(res.valid, non_blocking=True)
-        keep.append((res, d1, d2, goff))           # alive until the side stream has read them
-        base += n
+        keep.append((res, d1, d2, goff, dirs if as_dirs else None))   # alive until the side stream has read them
+        base += nb if as_dirs else n
     if P == 0:
         h_off.zero_()
     side.synchronize()
     main.synchronize()
+    if as_dirs:
+        return h_dirs[:base], h_off, h_len, h_cost, h_valid
     return h_idx1[:base], h_idx2[:base], h_off, h_len, h_cost, h_valid
+
+
+def decode_directions(dirs, dir_off, path_len, pair_tok):
+    """Host decoder of the ``paths="directions"`` result: -> (idx1, idx2, pair_off) as int32 /
+    int64 numpy arrays, identical to what ``paths="indices"`` returns.  Every path starts at the
+    pair's first rows; direction 0 advances both tokens, 1 the first, 2 the second."""
+    dirs = np.asarray(dirs, dtype=np.uint8)
+    dir_off = np.asarray(dir_off, dtype=np.int64)
+    L = np.asarray(path_len, dtype=np.int64)
+    tok = np.asarray(pair_tok, dtype=np.int64)
+    P = L.shape[0]
+    pair_off = np.zeros(P + 1, dtype=np.int64)
+    np.cumsum(L, out=pair_off[1:])
+    total = int(pair_off[-1])
+    idx1 = np.zeros(total, dtype=np.int64)
+    idx2 = np.zeros(total, dtype=np.int64)
+    if total == 0:
+        return idx1.astype(np.int32), idx2.astype(np.int32), pair_off
+    # step k >= 1 of pair p sits at bit pair (k - 1) of the pair's byte run
+    pid = np.repeat(np.arange(P), L)
+    k = np.arange(total) - pair_off[pid]
+    km1 = np.maximum(k - 1, 0)
+    byte = dirs[np.minimum(dir_off[pid] + (km1 >> 2), max(dirs.shape[0] - 1, 0))]
+    d = (byte >> (2 * (km1 & 3)).astype(np.uint8)) & 3
+    first = k == 0
+    di = np.where(first, 0, (d != 2).astype(np.int64))
+    dj = np.where(first, 0, (d != 1).astype(np.int64))
+    c1, c2 = np.cumsum(di), np.cumsum(dj)
+    start = pair_off[:-1][L > 0]
+    base1 = np.repeat(c1[start], L[L > 0])
+    base2 = np.repeat(c2[start], L[L > 0])
+    idx1 = tok[pid, 0] + c1 - base1
+    idx2 = tok[pid, 2] + c2 - base2
+    return idx1.astype(np.int32), idx2.astype(np.int32), pair_off
 
 
 _side = {}
@@ -279,6 +351,21 @@ class FeatureTable(object):
         self.device = feat.device
         self.feat = feat
         self.stack = self._detect_stack() if feat.is_cuda else 0
+        return self
+
+    @classmethod
+    def from_frames(cls, frames, file_off, files=None, stack=7, device=None):
+        """First-class UN-STACKED input: ``frames`` [n_rows, f] float32 (CPU, ideally pinned, or
+        CUDA) are the f-wide frames of every file back to back; the 7-frame stack of
+        abnet3/features.py:135-159 is built on the device (only the frames cross PCIe: 7 x fewer
+        bytes than the stacked table) and the alignment takes the stacked fast path."""
+        dev = device if device is not None else (frames.device if frames.is_cuda else _device())
+        off = [int(v) for v in (file_off.tolist() if hasattr(file_off, "tolist") else file_off)]
+        last = torch.zeros(frames.shape[0], dtype=torch.uint8)
+        ends = [o - 1 for o in off[1:] if o > 0]
+        last[torch.tensor(ends, dtype=torch.int64)] = 1
+        feat = ops.stack_from_frames(frames, stack, last.to(dev, non_blocking=True))
+        self = cls.from_device(feat, off, files)
         return self
 
     @classmethod

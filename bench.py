@@ -512,12 +512,50 @@ def align_leg(args, corpus, pairs, world, rank, local_rank, dev, steps, sample_c
             dt = max_over_ranks(time.perf_counter() - tt0, dev, world)
             return world * P * e_steps / dt, int(d2h)
 
-        v_full, d2h = run_e2e(stack=0)
+        host_last0 = torch.empty(last.shape, dtype=last.dtype, pin_memory=True)
+        host_last0.copy_(last)
+        v_full, d2h = run_e2e(stack=0, last_row_of_file=host_last0)
         rec["e2e"] = {"value": v_full, "unit": "pairs/s",
                       "h2d_bytes_per_step": int(host_feat.numel() * 4 + host_pairs.numel() * 4),
                       "d2h_bytes_per_step": d2h, "steps": e_steps,
-                      "call": "abnet3_b200.utils.align_pairs_host(feat_host [N,280], pair_tok_host): "
-                              "the whole table it is handed is uploaded, every pass"}
+                      "call": "abnet3_b200.utils.align_pairs_host(feat_host [N,280], pair_tok_host, "
+                              "last_row_of_file): the whole table it is handed is uploaded, every pass "
+                              "(its stack structure is checked on the device); paths come back as two "
+                              "int32 per step"}
+        if stack:
+            # first-class un-stacked input: the [N, 40] frames + file-edge flags are all there is
+            # to upload (nothing vouched for); paths come back as 2-bit directions
+            f = FEAT_DIM // 7
+            host_frames = torch.empty((feat.shape[0], f), dtype=feat.dtype, pin_memory=True)
+            host_frames.copy_(feat[:, 3 * f:4 * f])
+            host_last = torch.empty(last.shape, dtype=last.dtype, pin_memory=True)
+            host_last.copy_(last)
+            host_feat = None
+            torch.cuda.synchronize()
+
+            def run_e2e_frames():
+                kw = dict(max_frames=max_frames, frames_host=host_frames, last_row_of_file=host_last,
+                          paths="directions")
+                hres = utils.align_pairs_host(None, host_pairs, **kw)
+                d2h_b = sum(t.numel() * t.element_size() for t in hres)
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                tt0 = time.perf_counter()
+                for _ in range(e_steps):
+                    hres = utils.align_pairs_host(None, host_pairs, **kw)
+                torch.cuda.synchronize()
+                dt = max_over_ranks(time.perf_counter() - tt0, dev, world)
+                return world * P * e_steps / dt, int(d2h_b)
+
+            v_un, d2h_un = run_e2e_frames()
+            rec["e2e_unstacked"] = {
+                "value": v_un, "unit": "pairs/s",
+                "h2d_bytes_per_step": int(host_frames.numel() * 4 + host_last.numel() + host_pairs.numel() * 4),
+                "d2h_bytes_per_step": d2h_un, "steps": e_steps,
+                "call": "abnet3_b200.utils.align_pairs_host(frames_host=[N,40] frames, last_row_of_file, "
+                        "pair_tok_host, paths='directions'): un-stacked input stacked on the device, paths "
+                        "back as 2-bit step directions (utils.decode_directions restores the indices)"}
         del host_feat
     return rec, res
 
@@ -962,7 +1000,8 @@ def run_align_only(args, rank, world, local_rank, dev):
                        "corpus_frames": int(corpus.feat.shape[0]),
                        "l2": "inputs larger than L2 (feature table %.1f GB, every step re-reads it)"
                              % (corpus.feat.numel() * 4 / 1e9)},
-            "roofline": rec["roofline"], "e2e": rec.get("e2e"), "cpu_baseline": cpu,
+            "roofline": rec["roofline"], "e2e": rec.get("e2e"),
+            "e2e_unstacked": rec.get("e2e_unstacked"), "cpu_baseline": cpu,
             "gpu_launches": args.steps * rec["launches_per_pass"], "clocks": rec["clocks"],
             "align": {k: rec[k] for k in ("valid_pairs", "mean_path_len", "aligned_frame_pairs_per_s")},
         }

@@ -84,6 +84,25 @@ ABN_API int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int
  * [n_rows] uint8, NULL = one file).  feat_dev [n_rows, dim] ends up identical to feat_host. */
 ABN_API int abn_stack_upload(float *feat_dev, const float *feat_host, int64_t n_rows, int dim,
                              int stack, const uint8_t *last_row_of_file, abn_stream_t stream);
+/* First-class UN-STACKED input: `frames` [n_rows, f] float32 (host, ideally
+ * pinned, or device) holds the f-wide frames themselves -- what abnet3/features.py:135-159
+ * stacks -- and last_row_of_file (device, [n_rows] uint8, NULL = one file) marks the file edges.
+ * Builds feat_dev [n_rows, stack * f]: row t = [x[t - stack/2] .. x[t + stack/2]], zeros outside
+ * the file, exactly the reference's stack_fbanks.  Every byte the caller hands over is copied
+ * (stack x fewer than the stacked table), nothing has to be vouched for. */
+ABN_API int abn_stack_from_frames(float *feat_dev, const float *frames, int64_t n_rows, int f,
+                                  int stack, const uint8_t *last_row_of_file, abn_stream_t stream);
+
+/* Compact form of the alignment result for the trip back to the host: the path of pair p
+ * (dense table idx1 / idx2 [dst_off[p] .. dst_off[p] + path_len[p]) from abn_compact_paths)
+ * as its step DIRECTIONS, 2 bits each (0 = diagonal (+1, +1), 1 = up (+1, +0), 2 = left
+ * (+0, +1)), four per byte, path_len[p] - 1 of them starting at byte dir_off[p] of `dirs`
+ * (dir_off[p + 1] - dir_off[p] = ceil((path_len[p] - 1) / 4), caller-computed prefix sums).
+ * Every path starts at (row1, row2) of the pair, so directions + pair_tok restore the index
+ * pairs (abnet3_b200.utils.decode_directions): 32 x fewer bytes than two int32 per step. */
+ABN_API int abn_pack_directions(const int32_t *idx1, const int32_t *idx2, const int64_t *dst_off,
+                                const int32_t *path_len, int n_pairs, const int64_t *dir_off,
+                                uint8_t *dirs, abn_stream_t stream);
 
 /* Device workspace for abn_align_pairs / abn_cosine_distance over n_pairs pairs.
  * Both bucket the pairs into token-length classes on the device and keep the

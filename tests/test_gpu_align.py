@@ -469,3 +469,33 @@ def test_alignment_invariants_at_scale():
         for v in dist[doff[p] + i * b + j]:
             acc += v
         assert acc == cost[p], (p, acc, cost[p])
+
+
+def test_unstacked_input_and_direction_stream_through_the_host_call():
+    """align_pairs_host(frames_host=[N, 40] frames, last_row_of_file, paths='directions'): the
+    un-stacked frames are stacked on the device exactly like abnet3/features.py:135-159 (the
+    table equals the stacked one bit for bit), and the 2-bit direction stream decodes to the
+    index pairs of the plain call."""
+    from abnet3_b200 import utils
+    c = synth.make_corpus(300, cluster_size=8, tokens_per_file=40, seed=23)
+    last = torch.zeros(c.feat.shape[0], dtype=torch.uint8)
+    last[(c.file_off[1:] - 1).long()] = 1
+    frames = c.feat[:, 120:160].contiguous()
+    built = ops.stack_from_frames(frames, 7, last.to(DEV))
+    assert torch.equal(built.cpu(), c.feat)
+    tab = utils.FeatureTable.from_frames(frames.pin_memory(), c.file_off)
+    assert tab.stack == 7 and torch.equal(tab.feat.cpu(), c.feat)
+    pairs = synth.make_same_pairs(c, 500, seed=24)
+    pairs[7, 1] = 0                                            # a skipped pair (s > e)
+    ref = utils.align_pairs_host(c.feat, pairs, chunks=3)
+    ref = [t.clone() for t in ref]
+    got = utils.align_pairs_host(None, pairs, frames_host=frames, last_row_of_file=last,
+                                 paths="directions", chunks=3)
+    dirs, dir_off, plen, cost, valid = got
+    assert torch.equal(plen, ref[3]) and torch.equal(valid, ref[5])
+    assert torch.equal(cost[valid.bool()], ref[4][valid.bool()])
+    assert dirs.numel() * 16 < ref[0].numel() * 8 + 16 * 500      # 2 bits instead of 64 per step
+    i1, i2, off = utils.decode_directions(dirs.numpy(), dir_off.numpy(), plen.numpy(), pairs.numpy())
+    np.testing.assert_array_equal(off, ref[2].numpy())
+    np.testing.assert_array_equal(i1, ref[0].numpy())
+    np.testing.assert_array_equal(i2, ref[1].numpy())

@@ -177,3 +177,42 @@ def test_embedder_surface_and_feature_archives(tmp_path):
         np.testing.assert_array_equal(a, b)
     for a, b in zip(got_times, times):
         np.testing.assert_allclose(a, b)
+
+
+def test_direction_stream_decoder_restores_index_pairs():
+    """utils.decode_directions: the host side of align_pairs_host(paths='directions')."""
+    from abnet3_b200.utils import decode_directions
+    rng = np.random.default_rng(0)
+    P = 60
+    tok = np.zeros((P, 4), np.int64)
+    paths, dirs, dir_off, L = [], [], [0], []
+    for p in range(P):
+        n1, n2 = rng.integers(1, 30, 2)
+        tok[p] = [rng.integers(0, 1000), n1, rng.integers(0, 1000), n2]
+        if p % 7 == 3:                               # a dropped pair: empty path
+            L.append(0)
+            dir_off.append(dir_off[-1])
+            paths.append((np.zeros(0, int), np.zeros(0, int)))
+            continue
+        i = j = 0
+        pi, pj, ds = [0], [0], []
+        while (i, j) != (n1 - 1, n2 - 1):
+            opts = ([0] if i < n1 - 1 and j < n2 - 1 else []) + ([1] if i < n1 - 1 else []) + \
+                   ([2] if j < n2 - 1 else [])
+            d = rng.choice(opts)
+            ds.append(d)
+            i += d != 2
+            j += d != 1
+            pi.append(i)
+            pj.append(j)
+        L.append(len(pi))
+        paths.append((np.array(pi) + tok[p, 0], np.array(pj) + tok[p, 2]))
+        b = np.zeros((len(ds) + 3) // 4, np.uint8)
+        for k, d in enumerate(ds):
+            b[k // 4] |= d << (2 * (k % 4))
+        dirs.append(b)
+        dir_off.append(dir_off[-1] + len(b))
+    i1, i2, off = decode_directions(np.concatenate(dirs), np.array(dir_off), np.array(L), tok)
+    for p in range(P):
+        np.testing.assert_array_equal(i1[off[p]:off[p + 1]], paths[p][0])
+        np.testing.assert_array_equal(i2[off[p]:off[p + 1]], paths[p][1])
