@@ -173,6 +173,7 @@ pair_loss_dz_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
 // gradient pass, 8-byte bf16x4 stores.  Same arithmetic per element as the kernel above; the
 // three sums of a pair are reduced over 8 lanes instead of 32 (a different fp32 summation
 // order: the parity tests bound both against the oracle).
+template <bool DROP>
 __global__ void __launch_bounds__(LZ_WARPS * 32)
 pair_loss_dz_vec_kernel(const float *__restrict__ e1, const float *__restrict__ e2,
                         const float *__restrict__ y, int64_t n, int dim, int64_t ld, int kind,
@@ -183,7 +184,7 @@ pair_loss_dz_vec_kernel(const float *__restrict__ e1, const float *__restrict__ 
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, slot = lane >> 3;
-    const unsigned long long dkey = drop.state ? drop_key(drop) : 0ull;
+    const unsigned long long dkey = (DROP && drop.state) ? drop_key(drop) : 0ull;
     const int nv = dim >> 2;
     float local = 0.f;
     for (int64_t row0 = ((int64_t)blockIdx.x * LZ_WARPS + warp) * 4; row0 < n;
@@ -249,7 +250,7 @@ pair_loss_dz_vec_kernel(const float *__restrict__ e1, const float *__restrict__ 
                                    g * (x.y * inv - kb * z.y) * dact_of(z.y, act),
                                    g * (x.z * inv - kb * z.z) * dact_of(z.z, act),
                                    g * (x.w * inv - kb * z.w) * dact_of(z.w, act)};
-                    if (drop.state) {       // the output layer's dropout (abnet3/model.py:136-141)
+                    if (DROP && drop.state) {       // the output layer's dropout (abnet3/model.py:136-141)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int col = col_off + 4 * cc + e;
@@ -437,9 +438,14 @@ extern "C" int abn_pair_loss_dz_drop(const float *e1, const float *e2, const flo
     if (vec) {
         int64_t blocks = (n + 4 * LZ_WARPS - 1) / (4 * LZ_WARPS);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        launch_pdl(pair_loss_dz_vec_kernel, dim3((unsigned)blocks), dim3(LZ_WARPS * 32), (cudaStream_t)stream,
-            e1, e2, y, n, dim, ld, kind, margin, scale, act, loss, static_cast<__nv_bfloat16 *>(dz1),
-            static_cast<__nv_bfloat16 *>(dz2), ld_dz, da, r2, col_offset);
+        if (da.state)
+            launch_pdl(pair_loss_dz_vec_kernel<true>, dim3((unsigned)blocks), dim3(LZ_WARPS * 32),
+                (cudaStream_t)stream, e1, e2, y, n, dim, ld, kind, margin, scale, act, loss,
+                static_cast<__nv_bfloat16 *>(dz1), static_cast<__nv_bfloat16 *>(dz2), ld_dz, da, r2, col_offset);
+        else
+            launch_pdl(pair_loss_dz_vec_kernel<false>, dim3((unsigned)blocks), dim3(LZ_WARPS * 32),
+                (cudaStream_t)stream, e1, e2, y, n, dim, ld, kind, margin, scale, act, loss,
+                static_cast<__nv_bfloat16 *>(dz1), static_cast<__nv_bfloat16 *>(dz2), ld_dz, da, r2, col_offset);
         return check_launch("abn_pair_loss_dz");
     }
     int64_t blocks = (n + LZ_WARPS - 1) / LZ_WARPS;

@@ -98,17 +98,22 @@ __device__ __forceinline__ void f_drop32(float (&v)[32], const DropArgs &dr, uns
     }
 }
 
+// `gate` (0 = none): an mbarrier (with `gate_parity`) that must have completed before the slab is
+// written -- the commit of the layer's LAST accumulator: the tensor core reads the slab until
+// then.  The TMEM load and the math of the first accumulator's blocks run while the second
+// accumulator's MMAs are still in flight; only the stores wait.
 template <int ACT, bool DROP>
 __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, unsigned dst, int lane,
                                             int ones_at, const DropArgs &dr, unsigned long long dkey,
-                                            long long row, int col0) {
+                                            long long row, int col0, unsigned gate, unsigned gate_parity) {
     const unsigned swz = (unsigned)(lane & 7);
     float v64[64];
     g_ld64(taddr, v64);
+    unsigned pk[32];
 #pragma unroll
     for (int hseg = 0; hseg < 2; ++hseg) {
         float (&v)[32] = *reinterpret_cast<float (*)[32]>(&v64[32 * hseg]);
-        unsigned pk[16];
+        unsigned (&pkh)[16] = *reinterpret_cast<unsigned (*)[16]>(&pk[16 * hseg]);
         if (DROP && dr.state) {     // Linear -> Dropout -> act (abnet3/model.py:136-141)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += bs[32 * hseg + j];
@@ -116,39 +121,44 @@ __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, uns
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = g_act<ACT>(v[j]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 16; ++j) pkh[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
         } else if (ACT == 1 || ACT == 2) {
-            g_bias_act32_packed<ACT>(v, bs + 32 * hseg, pk);
+            g_bias_act32_packed<ACT>(v, bs + 32 * hseg, pkh);
         } else {
             g_bias_act32<ACT>(v, bs + 32 * hseg);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 16; ++j) pkh[j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
         }
         const int jo = ones_at - 32 * hseg;             // the column of ones, if it is in this half
         if (jo >= 0 && jo < 32) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (2 * j == jo) pk[j] = (pk[j] & 0xffff0000u) | 0x3f80u;
-                if (2 * j + 1 == jo) pk[j] = (pk[j] & 0x0000ffffu) | 0x3f800000u;
+                if (2 * j == jo) pkh[j] = (pkh[j] & 0xffff0000u) | 0x3f80u;
+                if (2 * j + 1 == jo) pkh[j] = (pkh[j] & 0x0000ffffu) | 0x3f800000u;
             }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                         ::"r"(dst + lane * 128 + (((unsigned)(4 * hseg + q) ^ swz) << 4)),
-                           "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                         : "memory");
     }
+    if (gate) {
+        g_mbar_wait(gate, gate_parity);
+        g_fence_after();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(dst + lane * 128 + (((unsigned)q ^ swz) << 4)),
+                       "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                     : "memory");
 }
 
 // dgrad: TMEM -> x act'(y_below) -> bf16 -> slab rows (y_below's box sits in `ybuf`)
 template <int ACT, bool DROP>
 __device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[8], unsigned dst, int lane,
                                               const DropArgs &dr, unsigned long long dkey, long long row,
-                                              int col0) {
+                                              int col0, unsigned gate, unsigned gate_parity) {
     const unsigned swz = (unsigned)(lane & 7);
     float v64[64];
     g_ld64(taddr, v64);
+    unsigned pk[32];
 #pragma unroll
     for (int hseg = 0; hseg < 2; ++hseg) {
         float (&v)[32] = *reinterpret_cast<float (*)[32]>(&v64[32 * hseg]);
@@ -156,13 +166,18 @@ __device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[
         g_dact32<ACT>(v, yh);
         if (DROP && dr.state) f_drop32(v, dr, dkey, row, col0 + 32 * hseg);     // dz * keep / (1 - p)
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                         ::"r"(dst + lane * 128 + (((unsigned)(4 * hseg + q) ^ swz) << 4)),
-                           "r"(g_pack_bf16(v[8 * q], v[8 * q + 1])), "r"(g_pack_bf16(v[8 * q + 2], v[8 * q + 3])),
-                           "r"(g_pack_bf16(v[8 * q + 4], v[8 * q + 5])), "r"(g_pack_bf16(v[8 * q + 6], v[8 * q + 7]))
-                         : "memory");
+        for (int j = 0; j < 16; ++j) pk[16 * hseg + j] = g_pack_bf16(v[2 * j], v[2 * j + 1]);
     }
+    if (gate) {
+        g_mbar_wait(gate, gate_parity);
+        g_fence_after();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(dst + lane * 128 + (((unsigned)q ^ swz) << 4)),
+                       "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                     : "memory");
 }
 
 // MODE 0: forward (B = W K-major, bias + activation, last layer fp32)
@@ -339,27 +354,39 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                 }
                 if (MODE == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
                 else __syncwarp();
-                // the layer's MMAs read the whole slab: nothing may be written before the last
-                // accumulator is complete (tcgen05.commit covers every MMA issued before it)
                 if (et == 0) f_trace(ch, l, 8);
+                // accumulator a is read as soon as ITS MMAs are complete; the slab (which the
+                // layer's remaining MMAs still read) is written only after the last accumulator's
+                // commit (tcgen05.commit covers every MMA issued before it) -- the `gate` of the
+                // first blocks
+                unsigned waited = 0;
+                const int a_last = L.tiles_n - 1;
                 for (int a = 0; a < L.tiles_n; ++a) {
-                    g_mbar_wait(afull0 + 8 * a, (afphase >> a) & 1);
-                    afphase ^= 1u << a;
-                }
-                g_fence_after();
-                if (et == 0) f_trace(ch, l, 9);
-                for (int a = 0; a < L.tiles_n; ++a) {
+                    if (!((waited >> a) & 1u)) {
+                        g_mbar_wait(afull0 + 8 * a, (afphase >> a) & 1);
+                        afphase ^= 1u << a;
+                        waited |= 1u << a;
+                    }
+                    g_fence_after();
+                    if (et == 0) f_trace(ch, l, 9);
                     for (int cb = 4 * a + half; cb < 4 * a + 4 && cb < nblk; cb += NQ) {
+                        unsigned gate = 0, gate_parity = 0;
+                        if ((MODE == 1 || !L.out_f32) && !((waited >> a_last) & 1u)) {
+                            gate = afull0 + 8 * a_last;
+                            gate_parity = (afphase >> a_last) & 1;
+                            afphase ^= 1u << a_last;            // (waited on inside the block function)
+                            waited |= 1u << a_last;
+                        }
                         const unsigned taddr = tmem + ((unsigned)(wq * 32) << 16) + cb * 64;
                         if (MODE == 1 || !L.out_f32) {
                             const unsigned dst = slab + cb * F_SLAB_KB_BYTES + wq * 4096u;
                             if (MODE == 0) {
                                 const int ones_at = L.ones_col ? L.n_out - cb * 64 : -1;
                                 switch (L.act) {
-                                    case 1: f_epi_block<1, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64); break;
-                                    case 2: f_epi_block<2, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64); break;
-                                    case 3: f_epi_block<3, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64); break;
-                                    default: f_epi_block<0, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64); break;
+                                    case 1: f_epi_block<1, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
+                                    case 2: f_epi_block<2, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
+                                    case 3: f_epi_block<3, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
+                                    default: f_epi_block<0, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
                                 }
                             } else {
                                 g_mbar_wait(ybar, ycount & 1u);
@@ -377,10 +404,10 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                     g_tma_2d(ybuf, &L.map_y, ybar, (cb + NQ) * 64, row0);
                                 }
                                 switch (L.act) {
-                                    case 1: f_epi_block_d<1, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64); break;
-                                    case 2: f_epi_block_d<2, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64); break;
-                                    case 3: f_epi_block_d<3, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64); break;
-                                    default: f_epi_block_d<0, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64); break;
+                                    case 1: f_epi_block_d<1, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
+                                    case 2: f_epi_block_d<2, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
+                                    case 3: f_epi_block_d<3, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
+                                    default: f_epi_block_d<0, DROP>(taddr, yc, dst, lane, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
                                 }
                             }
                             // generic-proxy writes -> visible to the async proxy (the next layer's
