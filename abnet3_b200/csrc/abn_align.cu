@@ -1513,14 +1513,21 @@ static int run_align(AlignArgs a, int max_frames, void *workspace, size_t worksp
         // long pairs: tile distance kernel -> skew slots -> band DTW kernel, in windows of
         // `chunk` pairs of the long class (its size is only known on the device: windows past
         // its end find nothing to do)
-        // tiles: the side that cuts the longest token evenly, on the smallest class that holds it
-        // (a 100-frame token is 2 x 2 tiles of 50 on the (4,4) class, not 4 tiles of the (6,6) one)
+        // tiles: the (4,4) class (58 x 58 on a stacked table, 64 x 64 otherwise) -- five resident
+        // CTAs per SM instead of two for the (6,6) class, and 7 x 58 covers 400 frames with less
+        // padding than 5 x 90: 595 k pairs/s against 466 k at 400 frames (tools/time_long.py;
+        // ABN_LONG_R = 5 | 6 selects the larger classes)
         static int tile_grid[2][3] = {{0, 0, 0}, {0, 0, 0}}, band_grid = 0, sms = 0;
         const int which = a.stack ? 1 : 0;
         const int lt_max = a.stack ? LT_STK : LT_GEN;
         const int nt = (max_frames + lt_max - 1) / lt_max;
-        int R = ((max_frames + nt - 1) / nt + ext + 15) / 16;
-        if (R < 4) R = 4;
+        int R = 4;
+        (void)nt;
+        {   // experiment knob: ABN_LONG_R = 4 | 5 | 6 forces the tile class
+            static int forced = -1;
+            if (forced < 0) { const char *e = getenv("ABN_LONG_R"); forced = e ? atoi(e) : 0; }
+            if (forced >= 4 && forced <= 6) R = forced;
+        }
         const int lt = 16 * R - ext;
         typedef void (*TileKernel)(const AlignArgs, const LongArgs);
         static const TileKernel kernels[2][3] = {
@@ -1702,22 +1709,38 @@ extern "C" int abn_stack_upload(float *feat_dev, const float *feat_host, int64_t
     return check_launch("abn_stack_upload");
 }
 
+namespace abn {
+// row t of the stacked table from the un-stacked frames: block c = frames[t + c - h] inside the
+// file, zeros outside (abnet3/features.py:135-159); one warp per row, 16-byte accesses
+__global__ void stack_build_kernel(float *__restrict__ feat, const float *__restrict__ frames,
+                                   int64_t n_rows, int f, int stack,
+                                   const uint8_t *__restrict__ last_row_of_file) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (t >= n_rows) return;
+    const int lane = threadIdx.x & 31, h = stack / 2, f4 = f >> 2;
+    int back = 0, fwd = 0;
+    while (back < h && t - back - 1 >= 0 && !(last_row_of_file && last_row_of_file[t - back - 1])) ++back;
+    while (fwd < h && t + fwd + 1 < n_rows && !(last_row_of_file && last_row_of_file[t + fwd])) ++fwd;
+    float4 *row = reinterpret_cast<float4 *>(feat + (size_t)t * f * stack);
+    for (int e = lane; e < stack * f4; e += 32) {
+        const int c = e / f4, k = e - c * f4, d = c - h;
+        const bool inside = d < 0 ? -d <= back : d <= fwd;
+        row[e] = inside ? __ldg(reinterpret_cast<const float4 *>(frames + (size_t)(t + d) * f) + k)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+}  // namespace abn
+
 extern "C" int abn_stack_from_frames(float *feat_dev, const float *frames, int64_t n_rows, int f,
                                      int stack, const uint8_t *last_row_of_file, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (!feat_dev || !frames || n_rows < 0 || f <= 0 || (f & 3) || stack < 3 || !(stack & 1))
         return set_error(ABN_EINVAL, "abn_stack_from_frames: bad argument (odd stack >= 3, f %% 4 == 0)");
     if (n_rows == 0) return ABN_OK;
-    const int dim = f * stack, h = stack / 2;
-    cudaStream_t st = (cudaStream_t)stream;
-    // the frames become the middle block of every row, the kernel fills in the rest
-    cudaError_t e = cudaMemcpy2DAsync(feat_dev + h * f, (size_t)dim * 4, frames, (size_t)f * 4,
-                                      (size_t)f * 4, (size_t)n_rows, cudaMemcpyDefault, st);
-    if (e != cudaSuccess)
-        return set_error(ABN_EIO, "abn_stack_from_frames: cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
     const int wpb = 8;
-    restack_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(feat_dev, n_rows, dim,
-                                                                              stack, last_row_of_file);
+    stack_build_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        feat_dev, frames, n_rows, f, stack, last_row_of_file);
     return check_launch("abn_stack_from_frames");
 }
 

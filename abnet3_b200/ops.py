@@ -153,8 +153,9 @@ def stack_from_frames(frames, stack=7, last_row_of_file=None, out=None):
     if last_row_of_file is not None:
         _req(last_row_of_file, torch.uint8, "last_row_of_file")
     n, f = frames.shape
+    frames_d = frames if frames.is_cuda else frames.to(dev, non_blocking=True)   # ONE contiguous upload
     feat = out if out is not None else torch.empty((n, stack * f), dtype=torch.float32, device=dev)
-    check(_lib.lib().abn_stack_from_frames(ptr(feat), frames.data_ptr(), n, f, int(stack),
+    check(_lib.lib().abn_stack_from_frames(ptr(feat), ptr(frames_d), n, f, int(stack),
                                            ptr(last_row_of_file), stream_ptr()))
     return feat
 

@@ -84,12 +84,12 @@ ABN_API int abn_stack_violations(const float *feat, int64_t n_rows, int dim, int
  * [n_rows] uint8, NULL = one file).  feat_dev [n_rows, dim] ends up identical to feat_host. */
 ABN_API int abn_stack_upload(float *feat_dev, const float *feat_host, int64_t n_rows, int dim,
                              int stack, const uint8_t *last_row_of_file, abn_stream_t stream);
-/* First-class UN-STACKED input: `frames` [n_rows, f] float32 (host, ideally
- * pinned, or device) holds the f-wide frames themselves -- what abnet3/features.py:135-159
- * stacks -- and last_row_of_file (device, [n_rows] uint8, NULL = one file) marks the file edges.
- * Builds feat_dev [n_rows, stack * f]: row t = [x[t - stack/2] .. x[t + stack/2]], zeros outside
- * the file, exactly the reference's stack_fbanks.  Every byte the caller hands over is copied
- * (stack x fewer than the stacked table), nothing has to be vouched for. */
+/* First-class UN-STACKED input: `frames` [n_rows, f] float32 (DEVICE: the caller
+ * uploads the frames as they are, one contiguous copy, stack x fewer bytes than the stacked
+ * table) holds the f-wide frames themselves -- what abnet3/features.py:135-159 stacks -- and
+ * last_row_of_file (device, [n_rows] uint8, NULL = one file) marks the file edges.  Builds
+ * feat_dev [n_rows, stack * f]: row t = [x[t - stack/2] .. x[t + stack/2]], zeros outside the
+ * file, exactly the reference's stack_fbanks.  Nothing has to be vouched for. */
 ABN_API int abn_stack_from_frames(float *feat_dev, const float *frames, int64_t n_rows, int f,
                                   int stack, const uint8_t *last_row_of_file, abn_stream_t stream);
 

@@ -14,8 +14,8 @@ WANT = {
     "align_class_kernel_4_4": r"align_class_kernelILi4ELi4E",
     "align_stack_kernel_4_4": r"align_stack_kernelILi4ELi4E",
     "dtw_skew_kernel_2": r"dtw_skew_kernelILi2E",
-    "long_tile_kernel_stacked_6": r"long_tile_kernelILb1ELi6E",
-    "long_tile_kernel_generic_6": r"long_tile_kernelILb0ELi6E",
+    "long_tile_kernel_stacked_4": r"long_tile_kernelILb1ELi4E",
+    "long_tile_kernel_generic_4": r"long_tile_kernelILb0ELi4E",
     "dtw_band_kernel": r"dtw_band_kernel",
     "mlp_chain_kernel_0_forward": r"mlp_chain_kernelILi0ELb0E",
     "mlp_chain_kernel_1_dgrad": r"mlp_chain_kernelILi1ELb0E",
