@@ -107,6 +107,7 @@ SIGNATURES = {
     "abn_dp_optimizer_step": (_I, [_P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _P, _P]),
     "abn_dp_grad_reset": (_I, [_P, _L, _P, _P]),
     "abn_dp_push_step": (_I, [_P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _P, _P]),
+    "abn_dp_set_trace": (_I, [_P]),
 }
 
 _lib = None

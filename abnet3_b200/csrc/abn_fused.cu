@@ -778,6 +778,16 @@ enum { DPF_PUSHED = 0, DPF_UPDATED = DP_MAX_WORLD, DPF_STEP = 2 * DP_MAX_WORLD,
        DPF_TICKET_A = 2 * DP_MAX_WORLD + 1, DPF_TICKET_B = 2 * DP_MAX_WORLD + 2,
        DPF_TICKET_C = 2 * DP_MAX_WORLD + 3 };
 
+// debug timeline (tools/dp_trace.py): globaltimer stamps of block 0, [step % 64][8]
+__device__ long long *g_dp_trace = nullptr;
+__device__ __forceinline__ void dp_stamp(unsigned long long step, int slot) {
+    if (g_dp_trace && blockIdx.x == 0 && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_dp_trace[(step & 63ull) * 8 + slot] = t;
+    }
+}
+
 struct DpPush {
     float *param[DP_MAX_WORLD];
     float *recv[DP_MAX_WORLD];
@@ -796,9 +806,12 @@ __device__ __forceinline__ void dp_st4(float *p, float4 v) {
 __device__ __forceinline__ void dp_grid_raise(const DpPush &pp, int ticket, int slot,
                                               unsigned long long step) {
     __shared__ int last_s;
-    __threadfence_system();
+    // the block's (remote) writes are ordered before the barrier; ONE system-scope fence by the
+    // thread that takes the ticket publishes them (fences are cumulative) -- 512 membar.sys per
+    // block cost 5-8 us per raise (tools/dp_trace.py)
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         unsigned long long *mine = pp.flags[pp.rank];
         const unsigned long long t = atomicAdd(mine + ticket, 1ull);
         last_s = t == (unsigned long long)gridDim.x - 1;
@@ -834,6 +847,7 @@ dp_push_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restri
     const long long gstride = (long long)gridDim.x * blockDim.x;
     const int W = pp.world, R = pp.rank;
 
+    dp_stamp(step, 0);
     // phase 0: slice j of my bucket -> owner j's receive row R (one pass over the bucket: every
     // thread has stores in flight to several owners)
     for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride) {
@@ -842,10 +856,13 @@ dp_push_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restri
         dp_st4(pp.recv[j] + (long long)R * pp.cap + (i - (long long)j * pp.cap),
                *reinterpret_cast<const float4 *>(grad + i));
     }
+    dp_stamp(step, 1);
     dp_grid_raise(pp, DPF_TICKET_A, DPF_PUSHED, step);
+    dp_stamp(step, 2);
 
     // phase 1: reduce + update my slice, push the new parameters to everybody
     dp_wait_all_par(mine + DPF_PUSHED, W, step);
+    dp_stamp(step, 3);
     {
         const long long lo = R * pp.cap, hi = min(pp.n, lo + pp.cap);
         const float *rv = pp.recv[R];
@@ -867,10 +884,13 @@ dp_push_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restri
             for (int q = 0; q < W; ++q) dp_st4(pp.param[q] + i, out);
         }
     }
+    dp_stamp(step, 4);
     dp_grid_raise(pp, DPF_TICKET_B, DPF_UPDATED, step);
+    dp_stamp(step, 5);
 
     // phase 2: all slices are in: bf16 operand copies, gradient bucket cleared
     dp_wait_all_par(mine + DPF_UPDATED, W, step);
+    dp_stamp(step, 6);
     const float *pl = pp.param[R];
     for (int sidx = 0; sidx < tab.n; ++sidx) {
         const abn_param_segment sg = tab.s[sidx];
@@ -883,6 +903,7 @@ dp_push_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restri
     }
     for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride)
         *reinterpret_cast<float4 *>(grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    dp_stamp(step, 7);
     // the step counter advances once every block has read it
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -916,13 +937,17 @@ dp_push1_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restr
     const int W = pp.world, R = pp.rank;
     const long long half = (long long)(step & 1ull) * W * pp.cap;       // this step's receive rows
 
+    dp_stamp(step, 0);
     for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride) {
         const float4 v = *reinterpret_cast<const float4 *>(grad + i);
         for (int q = 0; q < W; ++q)
             if (q != R) dp_st4(pp.recv[q] + half + (long long)R * pp.cap + i, v);
     }
+    dp_stamp(step, 1);
     dp_grid_raise(pp, DPF_TICKET_A, DPF_PUSHED, step);
+    dp_stamp(step, 2);
     dp_wait_all_par(mine + DPF_PUSHED, W, step);
+    dp_stamp(step, 3);
 
     const float *rv = pp.recv[R] + half;
     float *pl = pp.param[R];
@@ -983,6 +1008,12 @@ dp_push1_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restr
 }
 
 }  // namespace abn
+
+extern "C" int abn_dp_set_trace(long long *buffer) {       // debug hook: device [64][8] int64, or NULL
+    if (int rc = require_sm100()) return rc;
+    cudaError_t e = cudaMemcpyToSymbol(abn::g_dp_trace, &buffer, sizeof(buffer));
+    return e == cudaSuccess ? ABN_OK : set_error(ABN_EIO, "abn_dp_set_trace: %s", cudaGetErrorString(e));
+}
 
 extern "C" int abn_dp_push_step(float *grad, float *state0, float *state1, int kind, float lr,
                                 float momentum, float grad_scale, int64_t step,

@@ -51,6 +51,29 @@ def all_ranks_have_batch(has_batch, device, world):
     return int(more.item()) == 1
 
 
+def agree_on_batches(n_batches, device, world):
+    """The number of training steps of this epoch on EVERY rank: the minimum over the ranks'
+    batch counts, ONE reduction per epoch (each step holds one gradient exchange, so ranks must
+    run the same number; the reference already drops the tail, abnet3/dataloader.py:708)."""
+    if world <= 1:
+        return int(n_batches)
+    t = torch.tensor([int(n_batches)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item())
+
+
+def reduce_grads(parameters, avg, world):
+    """torch.optim fallback under data parallelism: sum the gradients over the ranks (mean for
+    a loss that averages over its batch), as the fused engine does inside its step."""
+    if world <= 1:
+        return
+    for p in parameters:
+        if p.grad is not None:
+            dist.all_reduce(p.grad)
+            if avg:
+                p.grad.div_(world)
+
+
 def _loss_spec(loss):
     if isinstance(loss, coscos2):
         return ("coscos2", 0.0, bool(loss.avg))
@@ -229,26 +252,10 @@ class TrainerSiamese(TrainerBuilder):
         return _joint(x1.float(), x2.float()), x1.shape[0], labels
 
     def _reduce_grads(self):
-        """torch.optim fallback under data parallelism: sum the gradients over the ranks
-        (mean for an averaged loss), as the fused engine does inside its step."""
-        if self.world <= 1:
-            return
-        avg = bool(getattr(self.loss, 'avg', False))
-        for p in self.network.parameters():
-            if p.grad is not None:
-                dist.all_reduce(p.grad)
-                if avg:
-                    p.grad.div_(self.world)
+        reduce_grads(self.network.parameters(), bool(getattr(self.loss, 'avg', False)), self.world)
 
     def _agreed_batches(self, n_batches):
-        """Ranks must run the same number of training steps (one gradient exchange each):
-        ONE min-reduction per epoch; the reference already drops the tail
-        (abnet3/dataloader.py:708)."""
-        if self.world <= 1:
-            return n_batches
-        t = torch.tensor([n_batches], dtype=torch.int64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        return int(t.item())
+        return agree_on_batches(n_batches, 'cuda', self.world)
 
     def _sweep_table(self, train_mode, do_training):
         """Sweep over a device-resident frame-pair table (FramesDataLoader.epoch_table):

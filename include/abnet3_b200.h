@@ -510,6 +510,9 @@ ABN_API int abn_dp_push_step(float *grad, float *state0, float *state1, int kind
                              float momentum, float grad_scale, int64_t step,
                              const abn_param_segment *segments, int n_segments,
                              const abn_dp_push *peers, abn_stream_t stream);
+/* debug hook (tools/dp_trace.py): device buffer [64][8] int64 that block 0 of the push kernels
+ * stamps with %globaltimer at its phase boundaries (NULL: off) */
+ABN_API int abn_dp_set_trace(long long *buffer);
 
 #ifdef __cplusplus
 }

@@ -126,7 +126,16 @@ def _gloo_worker(rank, world, port, n_batches, out):
         dist.all_reduce(g)
         bucket_sum += float(g[0])
         steps += 1
-    out.put((rank, steps, bucket_sum))
+    # per-epoch agreement (what the FramesDataLoader sweep uses) and the torch.optim fallback's
+    # gradient reduction: mean for an averaged loss, sum otherwise
+    agreed = TR.agree_on_batches(n_batches[rank], "cpu", world)
+    w = torch.nn.Parameter(torch.zeros(4))
+    w.grad = torch.full((4,), float(rank + 1))
+    TR.reduce_grads([w], True, world)
+    mean_g = float(w.grad[0])
+    w.grad = torch.full((4,), float(rank + 1))
+    TR.reduce_grads([w], False, world)
+    out.put((rank, steps, bucket_sum, agreed, mean_g, float(w.grad[0])))
     dist.destroy_process_group()
 
 
@@ -145,6 +154,29 @@ def test_step_agreement_and_gradient_allreduce_over_gloo():
         p.join(timeout=60)
     assert [r[1] for r in res] == [3, 3]                   # shortest shard decides
     assert [r[2] for r in res] == [9.0, 9.0]               # (1 + 2) summed over 3 steps
+    assert [r[3] for r in res] == [3, 3]                   # one MIN reduction per epoch
+    assert [r[4] for r in res] == [1.5, 1.5] and [r[5] for r in res] == [3.0, 3.0]
+
+
+def test_dataloader_shards_partition_the_pair_lists(tmp_path):
+    """dataloader.shard(rank, world): every rank keeps its own part of the train and dev lists
+    (what the trainer applies under torchrun)."""
+    from abnet3_b200.dataloader import OriginalDataLoader
+    lines = ["f%d 0.10 0.30 g%d 0.20 0.50 %s" % (k, k, "same" if k % 2 else "diff") for k in range(11)]
+    for mode in ("train_pairs", "dev_pairs"):
+        os.makedirs(tmp_path / mode)
+        (tmp_path / mode / "dataset").write_text("\n".join(lines) + "\n")
+    seen = []
+    for rank in range(3):
+        dl = OriginalDataLoader(str(tmp_path), None)
+        dl.features = object()                      # (only the pair lists are loaded here)
+        dl.shard(rank, 3)
+        dl.load_data()
+        seen += [p[0] for p in dl.pairs["train"]]
+        assert len(dl.pairs["dev"]) in (3, 4)
+        with pytest.raises(RuntimeError):
+            dl.shard((rank + 1) % 3, 3)             # too late: the lists are loaded
+    assert sorted(seen) == sorted("f%d" % k for k in range(11))
 
 
 def test_embedder_surface_and_feature_archives(tmp_path):

@@ -71,4 +71,17 @@ for p2p in (("push", "push2", "0") if world > 2 else ("push", "push2", "1", "0")
 rel = float((w_p2p - w_nccl).norm() / w_nccl.norm())
 if rank == 0:
     print("weights p2p vs nccl: rel diff %.3e; loss[5] %.2f vs %.2f" % (rel, l_p2p[5], l_nccl[5]), flush=True)
+# every rank draws its OWN initialisation (different seeds): the engine broadcasts rank 0's at
+# construction, so the replicas must still be identical after training
+os.environ.pop("ABN_DP_P2P", None)
+torch.manual_seed(1000 + rank)
+net = SiameseNetwork(input_dim=280, num_hidden_layers=2, hidden_dim=500, output_dim=100, p_dropout=0.0,
+                     activation_layer="sigmoid", precision="bf16").to(dev)
+step = SiameseTrainStep(net, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
+tot = step.sweep_table(feat, (idx1, idx2, y), B, 8)
+w = step.bucket.param.clone()
+ws = [torch.empty_like(w) for _ in range(world)]
+dist.all_gather(ws, w)
+if rank == 0:
+    print("unseeded init, 8 steps: replicas identical: %s" % all(torch.equal(ws[0], x) for x in ws), flush=True)
 dist.destroy_process_group()
