@@ -1007,6 +1007,258 @@ dp_push1_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restr
     }
 }
 
+// ------------------------------------------------------------------------
+// Two-shot exchange with the FLAG INSIDE THE DATA (the "LL" protocol of collective libraries):
+// every element travels as one 8-byte store {float value, uint32 step}; the receiver spins on the
+// element itself until its step field is the current step.  A naturally aligned 8-byte store is
+// single-copy atomic, so no system fence, no grid-wide ticket and no separate flag round trip are
+// needed -- the fence + flag + poll hops of the kernels above cost ~10 us each
+// (tools/dp_trace.py), which is most of what the exchange costs at this bucket size.
+//   phase 0  every element outside my slice -> its owner's receive row (recvA[owner][me][k])
+//   phase 1  my slice: sum the W contributions in rank order (spinning on the W - 1 remote ones),
+//            optimizer update, new parameter -> my bucket and -> every peer's parameter inbox
+//            (recvB[peer][i]); bf16 operand copy; gradient cleared
+//   phase 2  the other slices: spin on my inbox, store the parameter, bf16 operand copy
+// Blocks never wait for each other.  Flow control is implicit: a rank starts step s + 1 only after
+// it has received every slice of step s, and an owner sends a slice of step s only after it has
+// consumed every contribution of step s -- so a slot is never overwritten before it was read.
+// Twice the bytes of the plain form (1.4 MB more per rank and step at 8 GPUs): bandwidth is not
+// what bounds this exchange.
+__device__ __forceinline__ unsigned long long ll_pack(float v, unsigned step) {
+    return ((unsigned long long)step << 32) | (unsigned long long)__float_as_uint(v);
+}
+// four consecutive elements: two 16-byte stores (each 8-byte half is atomic on its own)
+__device__ __forceinline__ void ll_store4(unsigned long long *p, const float (&v)[4], unsigned step) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(ll_pack(v[0], step)),
+                 "l"(ll_pack(v[1], step)) : "memory");
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p + 2), "l"(ll_pack(v[2], step)),
+                 "l"(ll_pack(v[3], step)) : "memory");
+}
+__device__ __forceinline__ void ll_load4_raw(const unsigned long long *p, unsigned long long (&w)[4]) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2) : "memory");
+}
+__device__ __forceinline__ bool ll_ready4(const unsigned long long (&w)[4], unsigned step) {
+    return (unsigned)(w[0] >> 32) == step && (unsigned)(w[1] >> 32) == step &&
+           (unsigned)(w[2] >> 32) == step && (unsigned)(w[3] >> 32) == step;
+}
+// spin until all four elements carry this step's flag (a missing peer must trap, not hang forever)
+__device__ __forceinline__ void ll_wait4(const unsigned long long *p, unsigned long long (&w)[4], unsigned step) {
+    unsigned long long spins = 0;
+    while (!ll_ready4(w, step)) {
+        if (++spins > (1ull << 28)) __trap();
+        ll_load4_raw(p, w);
+    }
+}
+// bf16 operand copies of parameters i .. i+3 (segments start and end on multiples of 4 or the
+// elements are handled one by one)
+__device__ __forceinline__ void ll_bf16_4(const SegTable &tab, long long i, const float (&w)[4]) {
+    for (int sidx = 0; sidx < tab.n; ++sidx) {
+        const abn_param_segment sg = tab.s[sidx];
+        if (i + 3 < sg.offset || i >= sg.offset + sg.count || !sg.bf16) continue;
+        __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
+        if (i >= sg.offset && i + 4 <= sg.offset + sg.count && !((sg.n_in | sg.ld | (i - sg.offset)) & 3)) {
+            const long long j = i - sg.offset, r = j / sg.n_in;
+            __nv_bfloat162 lo2 = __floats2bfloat162_rn(w[0], w[1]), hi2 = __floats2bfloat162_rn(w[2], w[3]);
+            *reinterpret_cast<uint2 *>(wb + r * sg.ld + (j - r * sg.n_in)) =
+                make_uint2(*reinterpret_cast<unsigned *>(&lo2), *reinterpret_cast<unsigned *>(&hi2));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long j = i + e - sg.offset;
+                if (j >= 0 && j < sg.count) {
+                    const long long r = j / sg.n_in;
+                    wb[r * sg.ld + (j - r * sg.n_in)] = __float2bfloat16_rn(w[e]);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512)
+dp_ll_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restrict__ s1, int kind,
+             float lr, float momentum, float gscale, float bc1, float bc2_sqrt,
+             const SegTable tab, const DpPush pp) {
+    unsigned long long *mine = pp.flags[pp.rank];
+    __shared__ unsigned long long step_s;
+    if (threadIdx.x == 0) step_s = dp_ld_acquire(mine + DPF_STEP) + 1;
+    __syncthreads();
+    const unsigned step = (unsigned)step_s;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    const int W = pp.world, R = pp.rank;
+    const long long lo = (long long)R * pp.cap, hi = min(pp.n, lo + pp.cap);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    dp_stamp(step_s, 0);
+    // phase 0: four consecutive elements per thread (n, cap and lo are multiples of 4)
+    for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride) {
+        if (i >= lo && i < hi) continue;
+        const int j = (int)(i / pp.cap);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(pp.recv[j]) +
+                                  (long long)R * pp.cap + (i - (long long)j * pp.cap);
+        const float4 g4 = *reinterpret_cast<const float4 *>(grad + i);
+        const float v[4] = {g4.x, g4.y, g4.z, g4.w};
+        ll_store4(dst, v, step);
+        *reinterpret_cast<float4 *>(grad + i) = zero4;
+    }
+    dp_stamp(step_s, 1);
+    // phase 1: every remote contribution of the four elements is requested before the first is checked
+    {
+        const unsigned long long *rv = reinterpret_cast<const unsigned long long *>(pp.recv[R]);
+        float *pl = pp.param[R];
+        for (long long i = lo + 4 * gtid; i < hi; i += 4 * gstride) {
+            unsigned long long part[DP_MAX_WORLD][4];
+#pragma unroll
+            for (int p = 0; p < DP_MAX_WORLD; ++p)
+                if (p < W && p != R) ll_load4_raw(rv + (long long)p * pp.cap + (i - lo), part[p]);
+            const float4 own = *reinterpret_cast<const float4 *>(grad + i);
+            *reinterpret_cast<float4 *>(grad + i) = zero4;
+            float gs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int p = 0; p < DP_MAX_WORLD; ++p) {          // rank order
+                if (p >= W) continue;
+                if (p == R) {
+                    gs[0] += own.x; gs[1] += own.y; gs[2] += own.z; gs[3] += own.w;
+                } else {
+                    ll_wait4(rv + (long long)p * pp.cap + (i - lo), part[p], step);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) gs[e] += __uint_as_float((unsigned)part[p][e]);
+                }
+            }
+            const float4 w4 = *reinterpret_cast<const float4 *>(pl + i);
+            float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i + e < pp.n)
+                    w[e] = dp_update(w[e], gs[e] * gscale, s0, s1, i + e, kind, lr, momentum, bc1, bc2_sqrt);
+            *reinterpret_cast<float4 *>(pl + i) = make_float4(w[0], w[1], w[2], w[3]);
+            for (int q = 0; q < W; ++q)
+                if (q != R)
+                    ll_store4(reinterpret_cast<unsigned long long *>(pp.recv[q]) + (long long)W * pp.cap + i,
+                              w, step);
+            ll_bf16_4(tab, i, w);
+        }
+    }
+    dp_stamp(step_s, 2);
+    // phase 2: the other owners' slices from my parameter inbox
+    {
+        const unsigned long long *inbox = reinterpret_cast<const unsigned long long *>(pp.recv[R]) +
+                                          (long long)W * pp.cap;
+        float *pl = pp.param[R];
+        for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride) {
+            if (i >= lo && i < hi) continue;
+            unsigned long long raw[4];
+            ll_load4_raw(inbox + i, raw);
+            ll_wait4(inbox + i, raw, step);
+            const float w[4] = {__uint_as_float((unsigned)raw[0]), __uint_as_float((unsigned)raw[1]),
+                                __uint_as_float((unsigned)raw[2]), __uint_as_float((unsigned)raw[3])};
+            *reinterpret_cast<float4 *>(pl + i) = make_float4(w[0], w[1], w[2], w[3]);
+            ll_bf16_4(tab, i, w);
+        }
+    }
+    dp_stamp(step_s, 3);
+    // the step counter advances once every block has read it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(mine + DPF_TICKET_C, 1ull);
+        if (t == (unsigned long long)gridDim.x - 1) {
+            mine[DPF_TICKET_C] = 0;
+            __threadfence();
+            mine[DPF_STEP] = step_s;
+        }
+    }
+}
+
+// Hybrid for larger worlds: the reduce-scatter hop travels flag-in-data as above (no fence, no
+// ticket, no flag round trip), the all-gather of the updated parameters as plain 16-byte stores
+// followed by ONE fence + flag exchange (half the bytes of the flag-in-data form: at 8 GPUs the
+// parameter hop of dp_ll_kernel is 4.8 MB per rank and starts to cost bandwidth).
+__global__ void __launch_bounds__(512)
+dp_hybrid_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restrict__ s1, int kind,
+                 float lr, float momentum, float gscale, float bc1, float bc2_sqrt,
+                 const SegTable tab, const DpPush pp) {
+    unsigned long long *mine = pp.flags[pp.rank];
+    __shared__ unsigned long long step_s;
+    if (threadIdx.x == 0) step_s = dp_ld_acquire(mine + DPF_STEP) + 1;
+    __syncthreads();
+    const unsigned long long step64 = step_s;
+    const unsigned step = (unsigned)step_s;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    const int W = pp.world, R = pp.rank;
+    const long long lo = (long long)R * pp.cap, hi = min(pp.n, lo + pp.cap);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    dp_stamp(step64, 0);
+    for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride) {
+        if (i >= lo && i < hi) continue;
+        const int j = (int)(i / pp.cap);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(pp.recv[j]) +
+                                  (long long)R * pp.cap + (i - (long long)j * pp.cap);
+        const float4 g4 = *reinterpret_cast<const float4 *>(grad + i);
+        const float v[4] = {g4.x, g4.y, g4.z, g4.w};
+        ll_store4(dst, v, step);
+        *reinterpret_cast<float4 *>(grad + i) = zero4;
+    }
+    dp_stamp(step64, 1);
+    {
+        const unsigned long long *rv = reinterpret_cast<const unsigned long long *>(pp.recv[R]);
+        float *pl = pp.param[R];
+        for (long long i = lo + 4 * gtid; i < hi; i += 4 * gstride) {
+            unsigned long long part[DP_MAX_WORLD][4];
+#pragma unroll
+            for (int p = 0; p < DP_MAX_WORLD; ++p)
+                if (p < W && p != R) ll_load4_raw(rv + (long long)p * pp.cap + (i - lo), part[p]);
+            const float4 own = *reinterpret_cast<const float4 *>(grad + i);
+            *reinterpret_cast<float4 *>(grad + i) = zero4;
+            float gs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int p = 0; p < DP_MAX_WORLD; ++p) {          // rank order
+                if (p >= W) continue;
+                if (p == R) {
+                    gs[0] += own.x; gs[1] += own.y; gs[2] += own.z; gs[3] += own.w;
+                } else {
+                    ll_wait4(rv + (long long)p * pp.cap + (i - lo), part[p], step);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) gs[e] += __uint_as_float((unsigned)part[p][e]);
+                }
+            }
+            const float4 w4 = *reinterpret_cast<const float4 *>(pl + i);
+            float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i + e < pp.n)
+                    w[e] = dp_update(w[e], gs[e] * gscale, s0, s1, i + e, kind, lr, momentum, bc1, bc2_sqrt);
+            const float4 out = make_float4(w[0], w[1], w[2], w[3]);
+            for (int q = 0; q < W; ++q) dp_st4(pp.param[q] + i, out);
+        }
+    }
+    dp_stamp(step64, 2);
+    dp_grid_raise(pp, DPF_TICKET_B, DPF_UPDATED, step64);
+    dp_stamp(step64, 3);
+    dp_wait_all_par(mine + DPF_UPDATED, W, step64);
+    dp_stamp(step64, 4);
+    const float *pl = pp.param[R];
+    for (int sidx = 0; sidx < tab.n; ++sidx) {
+        const abn_param_segment sg = tab.s[sidx];
+        __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
+        if (!wb) continue;
+        for (long long j = gtid; j < sg.count; j += gstride) {
+            const long long r = j / sg.n_in;
+            wb[r * sg.ld + (j - r * sg.n_in)] = __float2bfloat16_rn(__ldcv(pl + sg.offset + j));
+        }
+    }
+    dp_stamp(step64, 5);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(mine + DPF_TICKET_C, 1ull);
+        if (t == (unsigned long long)gridDim.x - 1) {
+            mine[DPF_TICKET_C] = 0;
+            __threadfence();
+            mine[DPF_STEP] = step64;
+        }
+    }
+}
+
 }  // namespace abn
 
 extern "C" int abn_dp_set_trace(long long *buffer) {       // debug hook: device [64][8] int64, or NULL
@@ -1026,7 +1278,7 @@ extern "C" int abn_dp_push_step(float *grad, float *state0, float *state1, int k
         return set_error(ABN_EINVAL, "abn_dp_push_step: bad argument");
     if (peers->world < 2 || peers->world > DP_MAX_WORLD || peers->rank < 0 ||
         peers->rank >= peers->world || peers->n <= 0 || (peers->n & 3) || (peers->slice_cap & 3) ||
-        peers->slice_cap * peers->world < peers->n || (peers->one_shot && peers->slice_cap < peers->n))
+        peers->slice_cap * peers->world < peers->n || (peers->one_shot == 1 && peers->slice_cap < peers->n))
         return set_error(ABN_EINVAL, "abn_dp_push_step: world 2..%d, n and slice_cap multiples of 4, "
                          "world * slice_cap >= n", DP_MAX_WORLD);
     DpPush pp;
@@ -1050,7 +1302,13 @@ extern "C" int abn_dp_push_step(float *grad, float *state0, float *state1, int k
     }
     const float bc1 = 1.f - powf(0.9f, (float)step);
     const float bc2s = sqrtf(1.f - powf(0.999f, (float)step));
-    if (pp.one_shot)
+    if (pp.one_shot == 2)
+        dp_ll_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
+                                                            grad_scale, bc1, bc2s, tab, pp);
+    else if (pp.one_shot == 3)
+        dp_hybrid_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
+                                                                grad_scale, bc1, bc2s, tab, pp);
+    else if (pp.one_shot)
         dp_push1_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
                                                                grad_scale, bc1, bc2s, tab, pp);
     else

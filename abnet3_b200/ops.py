@@ -606,7 +606,7 @@ def dp_grad_reset(grad, peers):
     check(_lib.lib().abn_dp_grad_reset(ptr(grad), grad.numel(), ctypes.byref(peers), stream_ptr()))
 
 
-def dp_push_setup(param, n_trained, group=None, one_shot=True):
+def dp_push_setup(param, n_trained, group=None, one_shot=True, ll=False, hybrid=False):
     """Write-only exchange over NVLink peer memory: share the parameter bucket, a receive buffer
     and a flag block with every rank of ``group`` (CUDA IPC).  Collective.  one_shot: every rank
     pushes its whole gradient bucket to every peer (one flag exchange); otherwise the two-shot
@@ -619,7 +619,15 @@ def dp_push_setup(param, n_trained, group=None, one_shot=True):
         raise RuntimeError("peer-memory data parallelism serves one box (world <= 8)")
     if n_trained % 4:
         raise RuntimeError("the trained parameter count must be a multiple of 4")
-    if one_shot:
+    if hybrid:      # gradient slices flag-in-data (uint64 inbox [world, cap]), parameters as plain stores
+        cap = ((n_trained + world - 1) // world + 3) // 4 * 4
+        recv = torch.zeros(2 * world * cap, dtype=torch.float32, device=param.device)
+        one_shot = 3
+    elif ll:        # flag-in-data two-shot: uint64 gradient inbox [world, cap] + parameter inbox [n]
+        cap = ((n_trained + world - 1) // world + 3) // 4 * 4
+        recv = torch.zeros(2 * (world * cap + n_trained), dtype=torch.float32, device=param.device)
+        one_shot = 2
+    elif one_shot:
         cap = (n_trained + 3) // 4 * 4
         recv = torch.zeros(2 * world * cap, dtype=torch.float32, device=param.device)
     else:
@@ -635,14 +643,14 @@ def dp_push_setup(param, n_trained, group=None, one_shot=True):
         return bytes(h), int(off.value)
 
     mine = {"param": export(param), "recv": export(recv), "flags": export(flags), "n": n_trained,
-            "one_shot": bool(one_shot)}
+            "one_shot": int(one_shot)}
     everyone = [None] * world
     dist.all_gather_object(everyone, mine, group=group)
     pp = _lib.DpPush()
-    pp.rank, pp.world, pp.n, pp.slice_cap, pp.one_shot = rank, world, n_trained, cap, int(bool(one_shot))
+    pp.rank, pp.world, pp.n, pp.slice_cap, pp.one_shot = rank, world, n_trained, cap, int(one_shot)
     local = {"param": param, "recv": recv, "flags": flags}
     for r, info in enumerate(everyone):
-        if info["n"] != n_trained or info["one_shot"] != bool(one_shot):
+        if info["n"] != n_trained or info["one_shot"] != int(one_shot):
             raise RuntimeError("rank %d set the exchange up differently" % r)
         for key, arr in (("param", pp.param), ("recv", pp.recv), ("flags", pp.flags)):
             if r == rank:

@@ -28,7 +28,8 @@ def run(p2p, steps=12, graph=True, opt="adadelta", no_comm=False):
         step = SiameseTrainStep(net, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
     else:
         step = SiameseTrainStep(net, ("coscos2", 0.0, False), "sgd", lr=1e-4, momentum=0.9)
-    mode = "push" if step._dp_push is not None else ("read" if step._dp is not None else "nccl")
+    mode = {0: "push2", 1: "push", 2: "ll", 3: "hybrid"}[int(step._dp_push.one_shot)] if step._dp_push is not None else (
+        "read" if step._dp is not None else "nccl")
     if rank == 0:
         print("   exchange: %s" % mode, flush=True)
     if no_comm:
@@ -58,7 +59,7 @@ def run(p2p, steps=12, graph=True, opt="adadelta", no_comm=False):
 l0, w0, dt0 = run(False, no_comm=True)
 if rank == 0:
     print("no communication at all: us/step %.1f" % (dt0 * 1e6), flush=True)
-for p2p in (("push", "push2", "0") if world > 2 else ("push", "push2", "1", "0")):
+for p2p in (("ll", "push", "push2", "0") if world > 2 else ("ll", "push", "push2", "1", "0")):
     losses, w, dt = run(p2p, opt="sgd")
     # every rank must hold the same weights
     ws = [torch.empty_like(w) for _ in range(world)]
@@ -66,7 +67,7 @@ for p2p in (("push", "push2", "0") if world > 2 else ("push", "push2", "1", "0")
     same = all(torch.equal(ws[0], x) for x in ws)
     if rank == 0:
         print("p2p=%s  us/step %.1f  ranks identical: %s  losses %s" % (p2p, dt * 1e6, same, ["%.1f" % l for l in losses[:6]]), flush=True)
-    if p2p == "push": w_p2p, l_p2p = w, losses
+    if p2p == "ll": w_p2p, l_p2p = w, losses
     elif p2p == "0": w_nccl, l_nccl = w, losses
 rel = float((w_p2p - w_nccl).norm() / w_nccl.norm())
 if rank == 0:

@@ -33,14 +33,20 @@ eng.sweep_table(feat, table, B, 400)
 b.record(); torch.cuda.synchronize()
 us = a.elapsed_time(b) / 400 * 1e3
 t = trace.view(64, 8).cpu().double()
-mode = "one-shot" if eng._dp_push is not None and eng._dp_push.one_shot else "two-shot"
+mode = {0: "two-shot", 1: "one-shot", 2: "ll", 3: "hybrid"}[int(eng._dp_push.one_shot)] if eng._dp_push is not None else "nccl"
 d = (t[:, 1:] - t[:, :-1]) / 1e3
 names = ["push", "fence+ticket+raise", "wait pushed", "reduce+update(+push params)", "fence+ticket+raise", "wait updated", "bf16+zero"]
 if mode == "one-shot":
     names = ["push all", "fence+ticket+raise", "wait pushed"]
     d = d[:, :3]
+if mode == "hybrid":
+    names = ["push (LL)", "spin+reduce+update+push params", "fence+ticket+raise", "wait updated", "bf16"]
+    d = d[:, :5]
+if mode == "ll":
+    names = ["push (LL)", "spin+reduce+update+push params", "spin+store others' slices"]
+    d = d[:, :3]
 ok = (t[:, 0] > 0)
-print("rank %d %s: step %.1f us | exchange kernel phases (us, mean over %d steps): %s | total %.1f" % (
+print("\nrank %d %s: step %.1f us | exchange kernel phases (us, mean over %d steps): %s | total %.1f" % (
     rank, mode, us, int(ok.sum()), " | ".join("%s %.1f" % (n, float(d[ok, k].mean())) for k, n in enumerate(names)),
     float((t[ok, len(names)] - t[ok, 0]).mean() / 1e3)), flush=True)
 dist.destroy_process_group()
