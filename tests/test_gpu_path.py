@@ -163,3 +163,40 @@ def test_engine_refreshes_bf16_weights_after_load_state_dict():
     net.load_state_dict(other.state_dict())              # copies into the fp32 masters in place
     got = float(eng.sweep_table(feat, table, 1000, 2, do_training=False).item())
     assert abs(got - want) <= 1e-6 * abs(want)     # (block partial sums are added atomically)
+
+
+def test_trainer_train_loop_saves_best_checkpoints_like_the_reference(tmp_path):
+    """TrainerBuilder.train() (abnet3/trainer.py:117-173): epoch-0 evaluation pass, epochs with the
+    train + dev sweeps, best-model checkpoints under the reference's file names, early stopping on
+    the summed dev loss; the saved state_dict reloads into a fresh network (reference key names)."""
+    c = synth.make_corpus(300, cluster_size=8, tokens_per_file=50, seed=5, device=DEV)
+    same = synth.make_same_pairs(c, 200, seed=6)
+    diff = synth.make_diff_pairs(c, 200, seed=7)
+    tokens = {"train": (same, diff), "dev": (same[:50], diff[:50])}
+    dl = FramesDataLoader.from_tokens(utils.FeatureTable.from_device(c.feat, c.file_off), tokens,
+                                      batch_size=1024)
+    torch.manual_seed(0)
+    net = SiameseNetwork(input_dim=280, num_hidden_layers=1, hidden_dim=500, output_dim=100,
+                         p_dropout=0.1, activation_layer="sigmoid",
+                         output_path=str(tmp_path / "model")).to(DEV)
+    tr = TrainerSiamese(network=net, loss=coscos2(avg=False), optimizer_type="adadelta", lr=0.1,
+                        momentum=None, cuda=True, dataloader=dl, num_epochs=3, patience=1,
+                        checkpoints=True, log_dir=str(tmp_path / "runs"))
+    tr.train()
+    assert len(tr.train_losses) == len(tr.dev_losses) and 2 <= len(tr.train_losses) <= 4
+    assert tr.train_losses[-1] < tr.train_losses[0]              # epoch 0 is the untrained evaluation pass
+    assert (tmp_path / "model.pth").exists() and (tmp_path / "model0.pth").exists()
+    assert (tmp_path / "model.params").exists()
+    sd = torch.load(str(tmp_path / "model.pth"))
+    assert sorted(sd) == ["hidden_layers.0.bias", "hidden_layers.0.weight", "input_emb.0.bias",
+                          "input_emb.0.weight", "output_layer.0.bias", "output_layer.0.weight"]
+    fresh = SiameseNetwork(input_dim=280, num_hidden_layers=1, hidden_dim=500, output_dim=100,
+                           p_dropout=0.1, activation_layer="sigmoid").to(DEV)
+    fresh.load_network(str(tmp_path / "model.pth"))
+    fresh.eval()
+    x = torch.randn(64, 280, device=DEV)
+    best = SiameseNetwork(input_dim=280, num_hidden_layers=1, hidden_dim=500, output_dim=100,
+                          p_dropout=0.1, activation_layer="sigmoid").to(DEV)
+    best.load_state_dict(sd)
+    best.eval()
+    assert torch.equal(fresh.forward_once(x), best.forward_once(x))
