@@ -1169,96 +1169,6 @@ dp_ll_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restrict
     }
 }
 
-// Hybrid for larger worlds: the reduce-scatter hop travels flag-in-data as above (no fence, no
-// ticket, no flag round trip), the all-gather of the updated parameters as plain 16-byte stores
-// followed by ONE fence + flag exchange (half the bytes of the flag-in-data form: at 8 GPUs the
-// parameter hop of dp_ll_kernel is 4.8 MB per rank and starts to cost bandwidth).
-__global__ void __launch_bounds__(512)
-dp_hybrid_kernel(float *__restrict__ grad, float *__restrict__ s0, float *__restrict__ s1, int kind,
-                 float lr, float momentum, float gscale, float bc1, float bc2_sqrt,
-                 const SegTable tab, const DpPush pp) {
-    unsigned long long *mine = pp.flags[pp.rank];
-    __shared__ unsigned long long step_s;
-    if (threadIdx.x == 0) step_s = dp_ld_acquire(mine + DPF_STEP) + 1;
-    __syncthreads();
-    const unsigned long long step64 = step_s;
-    const unsigned step = (unsigned)step_s;
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long gstride = (long long)gridDim.x * blockDim.x;
-    const int W = pp.world, R = pp.rank;
-    const long long lo = (long long)R * pp.cap, hi = min(pp.n, lo + pp.cap);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    dp_stamp(step64, 0);
-    for (long long i = 4 * gtid; i < pp.n; i += 4 * gstride) {
-        if (i >= lo && i < hi) continue;
-        const int j = (int)(i / pp.cap);
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(pp.recv[j]) +
-                                  (long long)R * pp.cap + (i - (long long)j * pp.cap);
-        const float4 g4 = *reinterpret_cast<const float4 *>(grad + i);
-        const float v[4] = {g4.x, g4.y, g4.z, g4.w};
-        ll_store4(dst, v, step);
-        *reinterpret_cast<float4 *>(grad + i) = zero4;
-    }
-    dp_stamp(step64, 1);
-    {
-        const unsigned long long *rv = reinterpret_cast<const unsigned long long *>(pp.recv[R]);
-        float *pl = pp.param[R];
-        for (long long i = lo + 4 * gtid; i < hi; i += 4 * gstride) {
-            unsigned long long part[DP_MAX_WORLD][4];
-#pragma unroll
-            for (int p = 0; p < DP_MAX_WORLD; ++p)
-                if (p < W && p != R) ll_load4_raw(rv + (long long)p * pp.cap + (i - lo), part[p]);
-            const float4 own = *reinterpret_cast<const float4 *>(grad + i);
-            *reinterpret_cast<float4 *>(grad + i) = zero4;
-            float gs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int p = 0; p < DP_MAX_WORLD; ++p) {          // rank order
-                if (p >= W) continue;
-                if (p == R) {
-                    gs[0] += own.x; gs[1] += own.y; gs[2] += own.z; gs[3] += own.w;
-                } else {
-                    ll_wait4(rv + (long long)p * pp.cap + (i - lo), part[p], step);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) gs[e] += __uint_as_float((unsigned)part[p][e]);
-                }
-            }
-            const float4 w4 = *reinterpret_cast<const float4 *>(pl + i);
-            float w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (i + e < pp.n)
-                    w[e] = dp_update(w[e], gs[e] * gscale, s0, s1, i + e, kind, lr, momentum, bc1, bc2_sqrt);
-            const float4 out = make_float4(w[0], w[1], w[2], w[3]);
-            for (int q = 0; q < W; ++q) dp_st4(pp.param[q] + i, out);
-        }
-    }
-    dp_stamp(step64, 2);
-    dp_grid_raise(pp, DPF_TICKET_B, DPF_UPDATED, step64);
-    dp_stamp(step64, 3);
-    dp_wait_all_par(mine + DPF_UPDATED, W, step64);
-    dp_stamp(step64, 4);
-    const float *pl = pp.param[R];
-    for (int sidx = 0; sidx < tab.n; ++sidx) {
-        const abn_param_segment sg = tab.s[sidx];
-        __nv_bfloat16 *wb = static_cast<__nv_bfloat16 *>(sg.bf16);
-        if (!wb) continue;
-        for (long long j = gtid; j < sg.count; j += gstride) {
-            const long long r = j / sg.n_in;
-            wb[r * sg.ld + (j - r * sg.n_in)] = __float2bfloat16_rn(__ldcv(pl + sg.offset + j));
-        }
-    }
-    dp_stamp(step64, 5);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long t = atomicAdd(mine + DPF_TICKET_C, 1ull);
-        if (t == (unsigned long long)gridDim.x - 1) {
-            mine[DPF_TICKET_C] = 0;
-            __threadfence();
-            mine[DPF_STEP] = step64;
-        }
-    }
-}
-
 }  // namespace abn
 
 extern "C" int abn_dp_set_trace(long long *buffer) {       // debug hook: device [64][8] int64, or NULL
@@ -1305,9 +1215,6 @@ extern "C" int abn_dp_push_step(float *grad, float *state0, float *state1, int k
     if (pp.one_shot == 2)
         dp_ll_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
                                                             grad_scale, bc1, bc2s, tab, pp);
-    else if (pp.one_shot == 3)
-        dp_hybrid_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
-                                                                grad_scale, bc1, bc2s, tab, pp);
     else if (pp.one_shot)
         dp_push1_kernel<<<sms, 512, 0, (cudaStream_t)stream>>>(grad, state0, state1, kind, lr, momentum,
                                                                grad_scale, bc1, bc2s, tab, pp);

@@ -159,19 +159,20 @@ class SiameseTrainStep(object):
             # bucket size (2.8 MB); measured us/step (tools/dp_trace.py, 133 us without exchange):
             #   2 GPUs: flag-in-data two-shot ("ll") 154 | two-shot push 163 | one-shot push 168 | NCCL 173
             #   4 GPUs: ll 165 | two-shot push ~165
-            #   8 GPUs: ll 177 | two-shot push 166 | hybrid (ll slices + plain parameters) 179 |
-            #           one-shot push 197 | NCCL 206
+            #   8 GPUs: ll 177 | two-shot push 166 | one-shot push 197 | NCCL 206
+            #           (mixed forms, tried and removed: ll slices + plain parameters 179, plain
+            #           slices + ll parameters 171 -- at 8 GPUs the flag-in-data stores to 7 peers
+            #           cost more than the fence + flag hop they replace)
             # auto: ll at world == 2 (no fences, no flag round trips; twice the bytes), two-shot push
-            # beyond.  ABN_DP_P2P = ll | push | push2 | hybrid | 1 (reads) | 0 (NCCL all-reduce in the
-            # graph).
+            # beyond.  ABN_DP_P2P = ll | push | push2 | 1 (reads) | 0 (NCCL all-reduce in the graph).
             p2p = os.environ.get("ABN_DP_P2P", "auto")
-            if self.world > 1 and p2p in ("push", "push2", "ll", "hybrid", "auto") and \
+            if self.world > 1 and p2p in ("push", "push2", "ll", "auto") and \
                     self.bucket.n_trained % 4 == 0:
                 try:        # write-only exchange fused with the optimizer
                     one_shot = p2p == "push"
                     use_ll = p2p == "ll" or (p2p == "auto" and self.world <= 2)
                     self._dp_push = ops.dp_push_setup(self.bucket.param, self.bucket.n_trained, self.group,
-                                                      one_shot=one_shot, ll=use_ll, hybrid=p2p == "hybrid")
+                                                      one_shot=one_shot, ll=use_ll)
                 except Exception as exc:
                     import warnings
                     warnings.warn("peer-memory data parallelism unavailable (%s); using NCCL" % exc)

@@ -606,7 +606,7 @@ def dp_grad_reset(grad, peers):
     check(_lib.lib().abn_dp_grad_reset(ptr(grad), grad.numel(), ctypes.byref(peers), stream_ptr()))
 
 
-def dp_push_setup(param, n_trained, group=None, one_shot=True, ll=False, hybrid=False):
+def dp_push_setup(param, n_trained, group=None, one_shot=True, ll=False):
     """Write-only exchange over NVLink peer memory: share the parameter bucket, a receive buffer
     and a flag block with every rank of ``group`` (CUDA IPC).  Collective.  one_shot: every rank
     pushes its whole gradient bucket to every peer (one flag exchange); otherwise the two-shot
@@ -619,11 +619,7 @@ def dp_push_setup(param, n_trained, group=None, one_shot=True, ll=False, hybrid=
         raise RuntimeError("peer-memory data parallelism serves one box (world <= 8)")
     if n_trained % 4:
         raise RuntimeError("the trained parameter count must be a multiple of 4")
-    if hybrid:      # gradient slices flag-in-data (uint64 inbox [world, cap]), parameters as plain stores
-        cap = ((n_trained + world - 1) // world + 3) // 4 * 4
-        recv = torch.zeros(2 * world * cap, dtype=torch.float32, device=param.device)
-        one_shot = 3
-    elif ll:        # flag-in-data two-shot: uint64 gradient inbox [world, cap] + parameter inbox [n]
+    if ll:          # flag-in-data two-shot: uint64 gradient inbox [world, cap] + parameter inbox [n]
         cap = ((n_trained + world - 1) // world + 3) // 4 * 4
         recv = torch.zeros(2 * (world * cap + n_trained), dtype=torch.float32, device=param.device)
         one_shot = 2

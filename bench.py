@@ -647,7 +647,7 @@ def dp_check(args, corpus, table_src, world, rank, dev, multitask, steps=12):
             # plain SGD: the comparison is about the summed gradient (Adadelta's ratio of running
             # averages amplifies the last-bit differences of the two summation orders)
             eng = SiameseTrainStep(net, _loss_spec(loss), "sgd", lr=1e-3, momentum=0.0)
-            mode = {0: "push2", 1: "push1", 2: "ll", 3: "hybrid"}[int(eng._dp_push.one_shot)] if eng._dp_push is not None else (
+            mode = {0: "push2", 1: "push1", 2: "ll"}[int(eng._dp_push.one_shot)] if eng._dp_push is not None else (
                 "reads" if eng._dp is not None else "nccl")
             eng.sweep_table(feat, table, B, steps, start=0, do_training=True)
             torch.cuda.synchronize()

@@ -507,9 +507,7 @@ typedef struct {
     int one_shot;
     /* one_shot == 2: two-shot exchange with the flag inside the data (8-byte {value, step} stores,
      * receivers spin on the elements themselves: no fences, no tickets, no flag round trips).
-     * recv = uint64 [world * slice_cap] gradient inbox followed by uint64 [n] parameter inbox.
-     * one_shot == 3: hybrid -- the gradient slices travel flag-in-data (recv = uint64
-     * [world * slice_cap]), the updated parameters as plain stores + one flag exchange. */
+     * recv = uint64 [world * slice_cap] gradient inbox followed by uint64 [n] parameter inbox. */
 } abn_dp_push;
 ABN_API int abn_dp_push_step(float *grad, float *state0, float *state1, int kind, float lr,
                              float momentum, float grad_scale, int64_t step,

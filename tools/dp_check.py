@@ -28,7 +28,7 @@ def run(p2p, steps=12, graph=True, opt="adadelta", no_comm=False):
         step = SiameseTrainStep(net, ("coscos2", 0.0, False), "adadelta", lr=0.1, momentum=None)
     else:
         step = SiameseTrainStep(net, ("coscos2", 0.0, False), "sgd", lr=1e-4, momentum=0.9)
-    mode = {0: "push2", 1: "push", 2: "ll", 3: "hybrid"}[int(step._dp_push.one_shot)] if step._dp_push is not None else (
+    mode = {0: "push2", 1: "push", 2: "ll"}[int(step._dp_push.one_shot)] if step._dp_push is not None else (
         "read" if step._dp is not None else "nccl")
     if rank == 0:
         print("   exchange: %s" % mode, flush=True)

@@ -33,15 +33,12 @@ eng.sweep_table(feat, table, B, 400)
 b.record(); torch.cuda.synchronize()
 us = a.elapsed_time(b) / 400 * 1e3
 t = trace.view(64, 8).cpu().double()
-mode = {0: "two-shot", 1: "one-shot", 2: "ll", 3: "hybrid"}[int(eng._dp_push.one_shot)] if eng._dp_push is not None else "nccl"
+mode = {0: "two-shot", 1: "one-shot", 2: "ll"}[int(eng._dp_push.one_shot)] if eng._dp_push is not None else "nccl"
 d = (t[:, 1:] - t[:, :-1]) / 1e3
 names = ["push", "fence+ticket+raise", "wait pushed", "reduce+update(+push params)", "fence+ticket+raise", "wait updated", "bf16+zero"]
 if mode == "one-shot":
     names = ["push all", "fence+ticket+raise", "wait pushed"]
     d = d[:, :3]
-if mode == "hybrid":
-    names = ["push (LL)", "spin+reduce+update+push params", "fence+ticket+raise", "wait updated", "bf16"]
-    d = d[:, :5]
 if mode == "ll":
     names = ["push (LL)", "spin+reduce+update+push params", "spin+store others' slices"]
     d = d[:, :3]
