@@ -1,6 +1,8 @@
-// abn_align.cu -- kernels (1) cosine frame distance and (2) DTW wavefront +
-// traceback, fused: one CTA aligns one token pair at a time; the distance
-// matrix, the accumulated costs and the traceback directions never leave the SM.
+// abn_align.cu -- kernels (1) cosine frame distance and (2) DTW wavefront + traceback, as TWO
+// stages per pair: a distance kernel leaves the pair's float32 distance matrix in a "skew"
+// (anti-diagonal-major) layout in a device workspace slot, a DTW kernel (one warp per pair) reads
+// it back with coalesced loads.  (Round 1 began with one fused kernel per pair; three of its four
+// warps idled while warp 0 swept the wavefront: 22.8 M -> 27.8 M pairs/s for the split.)
 //
 // Reference behaviour reproduced (paths relative to /root/reference):
 //   cosine_distance     abnet3/utils.py:40-60   (float32 arithmetic, zero-norm
@@ -12,20 +14,22 @@
 //
 // Design
 // ------
-// Token pairs are ragged (20-80 frames in the canonical corpus), and the
-// distance stage is a small dense contraction per pair, so pairs are first
-// bucketed on the device into SIZE CLASSES (ceil(n1/16), ceil(n2/16)); every
-// class has its own kernel instantiation with a right-sized register tile and
-// shared-memory footprint (more resident CTAs for short tokens, no wasted
-// FMAs on padding beyond 16 frames, a few KB of code per kernel).  Inside a
-// class kernel (128 threads, persistent over the class's pair list):
-//   HBM --cp.async 16 B--> smem K-chunks of both tokens (double buffered)
-//       --LDS.128--> register-tiled fp32 FMA, accumulated per 40-wide chunk
-//       in a fixed order (run-to-run and GPU-count invariant) --> norms,
-//       divide, acosf --> D in smem (aliases the staging buffers)
-//       --> warp 0: branch-free anti-diagonal wavefront in fp64 with warp
-//       shuffles, 1 byte direction per cell in smem --> lane 0 traceback
-//       --> all threads write global frame-index pairs.
+// Token pairs are ragged (20-80 frames in the canonical corpus), and the distance stage is a
+// small dense contraction per pair, so pairs are first bucketed on the device into SIZE CLASSES
+// (ceil(n1/16), ceil(n2/16)); every class has its own kernel instantiation with a right-sized
+// register tile and shared-memory footprint (more resident CTAs for short tokens, no wasted FMAs
+// on padding beyond 16 frames).
+//   generic class kernel (128 threads, persistent over the class's pair list):
+//     HBM --cp.async 16 B--> smem K-chunks of both tokens (double buffered) --LDS.128-->
+//     register-tiled fp32 FMA, accumulated per 40-wide chunk in a fixed order --> reciprocal
+//     norms, acosf --> D in smem in skew layout --> 16-byte copies to the hand-over slot
+//   stacked class kernel (7 x 40 frame stacks): one 160-byte 1-D TMA copy per extended frame,
+//     40-deep Gram tile, 7-tap diagonal sums in the generic kernel's order (same bits)
+//   DTW kernel (dtw_skew_kernel<G>): lane l owns rows G l .. G l + G - 1, float64 recurrence
+//     with the oracle's tie order, 2-bit directions in smem, lane 0 walks them back, all lanes
+//     write the global frame-index pairs
+//   long tokens: long_tile_kernel (one CTA per tile of a pair's matrix) + dtw_band_kernel
+//     (128-row bands, directions in global memory)
 #include "abn_common.cuh"
 
 namespace abn {

@@ -261,7 +261,8 @@ ABN_API int abn_dropout_mask(const abn_dropout *drop, int64_t rows, int cols, ui
  *   act: 0 none, 1 sigmoid, 2 tanh, 3 relu
  *   W [n_out, n_in] row-major float32 (nn.Linear layout), b [n_out].
  *   precision: 0 = fp32 SIMT (the 1e-4 parity path).  The bf16 tcgen05 path needs
- *              bf16 operand buffers and is exposed as abn_gemm_bf16_tn below.
+ *              bf16 operand buffers and is exposed as abn_gemm_bf16_group /
+ *              abn_mlp_forward_fused / abn_mlp_dgrad_fused below.
  * Forward:   y[m, n_out] = act(x[m, n_in] @ W^T + b)
  * Backward:  dz = dy * act'(y);  dx = dz @ W (NULL to skip);
  *            dW += dz^T @ x;  db += colsum(dz)
