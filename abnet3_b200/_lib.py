@@ -44,6 +44,12 @@ class MlpLayer(_c.Structure):
                 ("out", _P), ("ldo", _L), ("out_f32", _I), ("ones_col", _I), ("drop", Dropout)]
 
 
+class MlpLoss(_c.Structure):
+    """abn_mlp_loss (include/abnet3_b200.h): the pair loss fused into the forward chain."""
+    _fields_ = [("y", _P), ("loss", _P), ("dz", _P), ("ld_dz", _L), ("kind", _I), ("margin", _F),
+                ("scale", _F), ("write_embeddings", _I)]
+
+
 class MlpDLayer(_c.Structure):
     """abn_mlp_dlayer (include/abnet3_b200.h)."""
     _fields_ = [("W", _P), ("ldw", _L), ("n_in", _I), ("n_out", _I), ("act_below", _I),
@@ -94,11 +100,12 @@ SIGNATURES = {
     "abn_linear_backward_drop": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _L, _P]),
     "abn_gemm_bf16_group": (_I, [_P, _I, _P]),
     "abn_mlp_forward_fused": (_I, [_P, _L, _L, _P, _I, _P]),
+    "abn_mlp_forward_loss_fused": (_I, [_P, _L, _L, _P, _I, _P, _P]),
     "abn_mlp_dgrad_fused": (_I, [_P, _L, _L, _P, _I, _P]),
     "abn_cast_bf16": (_I, [_P, _L, _I, _L, _P, _L, _P, _L, _P]),
     "abn_optimizer_step": (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _F, _L, _P]),
     "abn_gather_batch_bf16": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _I, _P]),
-    "abn_gather_step_bf16": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P, _P, _I, _P, _P]),
+    "abn_gather_step_bf16": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P, _P, _I, _P, _I, _P]),
     "abn_pair_loss_dz": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _I, _P, _P, _P, _L, _P]),
     "abn_pair_loss_dz_drop": (_I, [_P, _P, _P, _L, _I, _L, _I, _F, _F, _I, _P, _P, _P, _L, _P, _L, _I, _P]),
     "abn_optimizer_step_fused": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _I, _I, _P]),

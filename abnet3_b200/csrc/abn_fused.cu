@@ -37,7 +37,7 @@ __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
                                    __nv_bfloat16 *__restrict__ xb, int64_t ldx,
                                    float *__restrict__ y_out, float *__restrict__ y2_out,
                                    unsigned *__restrict__ zero_me, int zero_words,
-                                   double *__restrict__ loss_acc) {
+                                   double *__restrict__ loss_acc, int interleave) {
     pdl_wait();
     if (zero_me && blockIdx.x == 0) {
         if (loss_acc && threadIdx.x == 0) loss_acc[0] += (double)__uint_as_float(zero_me[0]);
@@ -56,7 +56,7 @@ __global__ void gather_bf16_kernel(const float *__restrict__ feat, int dim,
         const int64_t pos = sel ? sel[k] : base + k;
         const int32_t row = side ? idx2[pos] : idx1[pos];
         const float4 *src = reinterpret_cast<const float4 *>(feat + (size_t)row * dim);
-        uint2 *dst = reinterpret_cast<uint2 *>(xb + (size_t)(side ? n + k : k) * ldx);
+        uint2 *dst = reinterpret_cast<uint2 *>(xb + (size_t)(interleave ? w : (side ? n + k : k)) * ldx);
         const int nv = dim >> 2;
         if (nv <= 96) {            // (280-wide rows: 70 float4) every load in flight before the first store
             float4 v[3];
@@ -390,7 +390,8 @@ extern "C" int abn_gather_step_bf16(const float *feat, int dim, const int32_t *i
                                     const int64_t *sel, int64_t *cursor, int64_t table_rows,
                                     int64_t n, void *xb,
                                     int64_t ldx, float *y_out, float *y2_out, void *zero_me,
-                                    int zero_words, double *loss_acc, abn_stream_t stream) {
+                                    int zero_words, double *loss_acc, int interleave,
+                                    abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (n == 0) return ABN_OK;
     if (!feat || !idx1 || !idx2 || !xb || n < 0 || dim <= 0 || (dim & 3) || ldx < dim || (ldx & 3) ||
@@ -400,7 +401,7 @@ extern "C" int abn_gather_step_bf16(const float *feat, int dim, const int32_t *i
     const int64_t warps = 2 * n;
     launch_pdl(gather_bf16_kernel, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), (cudaStream_t)stream,
         feat, dim, idx1, idx2, y_in, y2_in, sel, cursor, table_rows, n, static_cast<__nv_bfloat16 *>(xb), ldx, y_out,
-        y2_out, static_cast<unsigned *>(zero_me), zero_me ? zero_words : 0, loss_acc);
+        y2_out, static_cast<unsigned *>(zero_me), zero_me ? zero_words : 0, loss_acc, interleave);
     return check_launch("abn_gather_step_bf16");
 }
 
@@ -409,7 +410,7 @@ extern "C" int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *
                                      int64_t n, void *xb, int64_t ldx, float *y_out,
                                      void *zero_me, int zero_words, abn_stream_t stream) {
     return abn_gather_step_bf16(feat, dim, idx1, idx2, y_in, nullptr, sel, nullptr, 0, n, xb, ldx, y_out,
-                                nullptr, zero_me, zero_words, nullptr, stream);
+                                nullptr, zero_me, zero_words, nullptr, 0, stream);
 }
 
 extern "C" int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,

@@ -243,7 +243,7 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
         gen + STAGES * STAGE + OUT_BYTES + 16 * STAGES + 32);
     float *bias_s = reinterpret_cast<float *>(gen + STAGES * STAGE + OUT_BYTES + 256);      // [2][BN]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (provably warp-uniform)
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { g_mbar_init(full0 + 8 * s, 1); g_mbar_init(empty0 + 8 * s, 1); }
         for (int w = 0; w < G_EPI_WARPS; ++w) g_mbar_init(ybar0 + 8 * w, 1);
@@ -275,108 +275,120 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            unsigned n = 0;                                  // k-blocks issued so far (ring position)
+        // (a convergent warp on warp-uniform values, the issuing lane elected per instruction,
+        // like the MMA issuer below: four TMA requests per k-block of a wgrad tile cost ~600
+        // clocks of issue from a single-lane branch, more than the 512 clocks its MMAs take)
+        {
+            const int rank_u = NCTA == 2 ? (int)(blockIdx.x & 1) : 0;   // == %cluster_ctarank (clusters of 2 along x)
+            unsigned s = 0, ephase = 1;                      // ring slot and the parity its `empty` wait uses
             for (unsigned pit = 0;; ++pit) {
                 const int tile = g_tile_of(g, tile0, tile_step, pit);
                 if (tile >= g.total_tiles) break;
-                const GTile t = g_decode(g, tile, BN, NCTA, rank);
+                const GTile t = g_decode(g, tile, BN, NCTA, rank_u);
                 const GProblem &P = g.p[t.pi];
-                g_trace(g, pit, 0);
+                if (lane == 0) g_trace(g, pit, 0);
                 // in-launch dependency: the rows of A are the output of an earlier problem of
                 // this group (possibly computed by other CTAs).  Row problems (forward, dgrad)
                 // need their own 256-row block; a reduction over the rows (wgrad) needs the blocks
                 // its K range crosses and asks for each one when its first k-block comes up.
                 const bool wait_rows = P.wait && P.epi != GE_ATOMIC;
                 const bool wait_k = P.wait && P.epi == GE_ATOMIC;
-                if (wait_rows) g_wait_block(P.wait + t.mt, P.wait_count);
+                if (wait_rows) { g_wait_block(P.wait + t.mt, P.wait_count); __syncwarp(); }
                 // this CTA's share of the B tile: n_eff / NCTA columns from nb0 on
-                const int nb_cols = t.n_eff / NCTA, nb0 = t.n0 + rank * nb_cols;
+                const int nb_cols = t.n_eff / NCTA, nb0 = t.n0 + rank_u * nb_cols;
                 const int nbox_b = (nb_cols + 63) >> 6;
-                const unsigned bytes = A_BYTES + (P.b_mn ? (unsigned)nbox_b * 8192u : B_BYTES);
-                for (int i = 0; i < t.nkb; ++i, ++n) {
-                    const int s = n % STAGES;
-                    g_mbar_wait(empty0 + 8 * s, ((n / STAGES) & 1) ^ 1);
+                const int a_mn = P.a_mn, b_mn = P.b_mn, nkb = t.nkb;
+                const unsigned bytes = A_BYTES + (b_mn ? (unsigned)nbox_b * 8192u : B_BYTES);
+                for (int i = 0; i < nkb; ++i) {
+                    g_mbar_wait_warp(empty0 + 8 * s, ephase);
                     const unsigned sa = base + s * STAGE, sb = sa + A_BYTES;
                     const int k0 = (t.kb0 + i) * G_BK;
-                    if (wait_k && (i == 0 || k0 % (G_BM * NCTA) == 0))
+                    if (wait_k && (i == 0 || k0 % (G_BM * NCTA) == 0)) {
                         g_wait_block(P.wait + k0 / (G_BM * NCTA), P.wait_count);
+                        __syncwarp();
+                    }
                     if (NCTA == 2) {
                         // both CTAs' copies complete on the LEADER's barrier, which expects them all
                         const unsigned fb = (full0 + 8 * s) & G_PEER_MASK;
-                        if (rank == 0) g_mbar_expect_tx(full0 + 8 * s, 2u * bytes);
-                        if (P.a_mn) {
-                            g_tma_2d_pair(sa, &P.map_a, fb, t.m0, k0);
-                            g_tma_2d_pair(sa + 8192, &P.map_a, fb, t.m0 + 64, k0);
+                        if (rank_u == 0) g_mbar_expect_tx_warp(full0 + 8 * s, 2u * bytes);
+                        if (a_mn) {
+                            g_tma_2d_pair_warp(sa, &P.map_a, fb, t.m0, k0);
+                            g_tma_2d_pair_warp(sa + 8192, &P.map_a, fb, t.m0 + 64, k0);
                         } else {
-                            g_tma_2d_pair(sa, &P.map_a, fb, k0, t.m0);
+                            g_tma_2d_pair_warp(sa, &P.map_a, fb, k0, t.m0);
                         }
-                        if (P.b_mn) {
+                        if (b_mn) {
                             for (int j = 0; j < nbox_b; ++j)
-                                g_tma_2d_pair(sb + j * 8192, &P.map_b, fb, nb0 + 64 * j, k0);
+                                g_tma_2d_pair_warp(sb + j * 8192, &P.map_b, fb, nb0 + 64 * j, k0);
                         } else {
-                            g_tma_2d_pair(sb, &P.map_b, fb, k0, nb0);
+                            g_tma_2d_pair_warp(sb, &P.map_b, fb, k0, nb0);
                         }
                     } else {
-                        g_mbar_expect_tx(full0 + 8 * s, bytes);
-                        if (P.a_mn) {
-                            g_tma_2d(sa, &P.map_a, full0 + 8 * s, t.m0, k0);
-                            g_tma_2d(sa + 8192, &P.map_a, full0 + 8 * s, t.m0 + 64, k0);
+                        g_mbar_expect_tx_warp(full0 + 8 * s, bytes);
+                        if (a_mn) {
+                            g_tma_2d_warp(sa, &P.map_a, full0 + 8 * s, t.m0, k0);
+                            g_tma_2d_warp(sa + 8192, &P.map_a, full0 + 8 * s, t.m0 + 64, k0);
                         } else {
-                            g_tma_2d(sa, &P.map_a, full0 + 8 * s, k0, t.m0);
+                            g_tma_2d_warp(sa, &P.map_a, full0 + 8 * s, k0, t.m0);
                         }
-                        if (P.b_mn) {
+                        if (b_mn) {
                             for (int j = 0; j < nbox_b; ++j)
-                                g_tma_2d(sb + j * 8192, &P.map_b, full0 + 8 * s, nb0 + 64 * j, k0);
+                                g_tma_2d_warp(sb + j * 8192, &P.map_b, full0 + 8 * s, nb0 + 64 * j, k0);
                         } else {
-                            g_tma_2d(sb, &P.map_b, full0 + 8 * s, k0, nb0);
+                            g_tma_2d_warp(sb, &P.map_b, full0 + 8 * s, k0, nb0);
                         }
                     }
+                    if (++s == STAGES) { s = 0; ephase ^= 1u; }
                 }
-                g_trace(g, pit, 1);
+                if (lane == 0) g_trace(g, pit, 1);
             }
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer
-        if (lane == 0 && rank == 0) {       // of a pair, only the leader CTA issues
-            unsigned n = 0;
+        // the WHOLE warp runs the loop on warp-uniform values; the issuing lane is elected
+        // inside g_mma*_warp / g_commit*_warp (abn_tc_ptx.cuh: why).  Of a pair, only the leader
+        // CTA issues.
+        if (NCTA == 1 || (blockIdx.x & 1) == 0) {
+            const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            unsigned s = 0, fphase = 0;                     // ring slot and its phase
             for (unsigned it = 0;; ++it) {
                 const int tile = g_tile_of(g, tile0, tile_step, it);
                 if (tile >= g.total_tiles) break;
-                const GTile t = g_decode(g, tile, BN, NCTA, rank);
+                const GTile t = g_decode(g, tile, BN, NCTA, 0);
                 const GProblem &P = g.p[t.pi];
                 const unsigned ab = it & 1;
-                g_trace(g, it, 2);
-                g_mbar_wait(tempty0 + 8 * ab, ((it >> 1) & 1) ^ 1);      // epilogue(s) drained this accumulator
+                if (lane == 0) g_trace(g, it, 2);
+                g_mbar_wait_warp(tempty0 + 8 * ab, ((it >> 1) & 1) ^ 1);      // epilogue(s) drained this accumulator
                 g_fence_after();
-                g_trace(g, it, 3);
+                if (lane == 0) g_trace(g, it, 3);
                 const unsigned idesc = g_idesc(G_BM * NCTA, t.n_eff, P.a_mn, P.b_mn);
-                const unsigned d_tmem = tmem + ab * BN;
+                const unsigned d_tmem = tmem_u + ab * BN;
                 const unsigned a_step = P.a_mn ? (2048 >> 4) : (32 >> 4);
                 const unsigned b_step = P.b_mn ? (2048 >> 4) : (32 >> 4);
-                for (int i = 0; i < t.nkb; ++i, ++n) {
-                    const int s = n % STAGES;
-                    g_mbar_wait(full0 + 8 * s, (n / STAGES) & 1);
+                const int a_mn = P.a_mn, b_mn = P.b_mn, nkb = t.nkb;
+                for (int i = 0; i < nkb; ++i) {
+                    g_mbar_wait_warp(full0 + 8 * s, fphase);
                     g_fence_after();
                     const unsigned sa = base + s * STAGE;
-                    const unsigned long long da = g_desc(sa, P.a_mn);
-                    const unsigned long long db = g_desc(sa + A_BYTES, P.b_mn);
+                    const unsigned long long da = g_desc(sa, a_mn);
+                    const unsigned long long db = g_desc(sa + A_BYTES, b_mn);
 #pragma unroll
                     for (int k = 0; k < G_BK / G_UK; ++k) {
                         if (G_DBG(g, 8)) continue;
                         if (NCTA == 2)
-                            g_mma_pair(d_tmem, da + (unsigned long long)(a_step * k),
-                                       db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
+                            g_mma_pair_warp(d_tmem, da + (unsigned long long)(a_step * k),
+                                            db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
                         else
-                            g_mma(d_tmem, da + (unsigned long long)(a_step * k),
-                                  db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
+                            g_mma_warp(d_tmem, da + (unsigned long long)(a_step * k),
+                                       db + (unsigned long long)(b_step * k), idesc, (i | k) != 0);
                     }
                     // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-                    if (NCTA == 2) g_commit_pair(empty0 + 8 * s); else g_commit(empty0 + 8 * s);
+                    if (NCTA == 2) g_commit_pair_warp(empty0 + 8 * s); else g_commit_warp(empty0 + 8 * s);
+                    if (++s == STAGES) { s = 0; fphase ^= 1u; }
                 }
                 // accumulator complete (each CTA's epilogue watches its own barrier)
-                if (NCTA == 2) g_commit_pair(tfull0 + 8 * ab); else g_commit(tfull0 + 8 * ab);
-                g_trace(g, it, 4);
+                if (NCTA == 2) g_commit_pair_warp(tfull0 + 8 * ab); else g_commit_warp(tfull0 + 8 * ab);
+                if (lane == 0) g_trace(g, it, 4);
             }
         }
     } else {

@@ -45,11 +45,23 @@ struct FLayer {
     int nkb, tiles_n, n_cap;        // GEMM view: K = 64 nkb, N = n_cap (forward: n_out + ones_col; dgrad: n_in)
     DropArgs drop;                  // forward: this layer's dropout; dgrad: the dropout of the layer below
 };
+// MODE 0 with the pair loss fused into the last layer's epilogue (abnet3/loss.py:46-67, :85-105 +
+// the output layer's act'): rows are INTERLEAVED (row 2k = x1[k], row 2k + 1 = x2[k]) so both
+// embeddings of a pair sit in neighbouring lanes of one epilogue warp.
+struct FLoss {
+    int on, kind, write_emb;
+    float margin, scale;
+    const float *y;                 // [rows / 2] labels
+    float *loss;                    // += sum of the loss terms * scale
+    __nv_bfloat16 *dz; long long ld_dz;     // dz of the output layer, bf16 [rows, ld_dz]
+};
 struct FChain {
+    FLoss loss;
     CUtensorMap map_x;              // x [rows, n_in0] bf16, box {64, 128}
     FLayer L[F_MAXL];
     int n_layers, rows, tiles_m;
     long long *trace;               // debug: role timestamps per CTA and layer (NULL in production)
+    int debug;                      // debug (tools/trace_fused.py): 1 skip the B-ring waits, 2 skip the slab waits
 };
 
 // debug timeline (tools/trace_fused.py): [cta][layer][slot]
@@ -180,10 +192,117 @@ __device__ __forceinline__ void f_epi_block_d(unsigned taddr, const uint4 (&yc)[
                      : "memory");
 }
 
+// The last forward layer with the loss fused in: this warp holds rows row0 .. row0 + 31 (one per
+// lane) of the 64-column block cb of the embeddings (n_out <= 128: blocks 0 and 1, taken by two
+// warps of a lane quarter, which meet at named barrier 2 + wq).
+//   pass 1  e = act(z + b); dot / |a|^2 partials with the partner row (lane ^ 1) by shuffle
+//   ------  the two column blocks exchange their partials through shared memory
+//   pass 2  dz = dL/dc * (partner * inv - k * e) * act'(e) -> bf16 rows; embeddings -> fp32 rows
+// Same arithmetic per element as pair_loss_dz_vec_kernel (abn_fused.cu).  The loops stay ROLLED
+// (16 columns per trip): this code runs once per row block, so a fully unrolled body is paid for
+// in instruction-cache misses (27 KB of straight-line code: 10 us per launch, tools/
+// trace_fused_loss.py), not in issue slots.
+template <int ACT>
+__device__ __noinline__ void f_epi_loss(const FLoss &F, int rows, int n_out, float *out32, long long ld32,
+                                        unsigned taddr, const float *bs, float *exch, int wq, int cb,
+                                        int nblk, int row0, int lane) {
+    const int row = row0 + lane;
+    const int col0 = 64 * cb;
+    const int ncol = n_out - col0 < 64 ? n_out - col0 : 64;
+    float dot = 0.f, na = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < ncol; c += 16) {
+        float v[16];
+        g_ld16(taddr + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float e = g_act<ACT>(v[j] + bs[c + j]);
+            const float pr = __shfl_xor_sync(0xffffffffu, e, 1);
+            if (c + j < ncol) {
+                dot = fmaf(e, pr, dot);
+                na = fmaf(e, e, na);
+            }
+        }
+    }
+    if (nblk > 1) {                                       // the other block's partials of the same rows
+        float *mine = exch + ((wq * 2 + cb) * 32 + lane) * 2;
+        mine[0] = dot; mine[1] = na;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + wq) : "memory");
+        const float *other = exch + ((wq * 2 + (cb ^ 1)) * 32 + lane) * 2;
+        // (block 0's sum first in both warps: the two halves of a row agree bit for bit)
+        dot = cb == 0 ? dot + other[0] : other[0] + dot;
+        na = cb == 0 ? na + other[1] : other[1] + na;
+    }
+    const float nb = __shfl_xor_sync(0xffffffffu, na, 1);
+    constexpr float EPS = 1e-6f;                          // nn.CosineSimilarity(eps=1e-6), loss.py:44
+    const float ra = sqrtf(na), rb = sqrtf(nb);
+    const float an = fmaxf(ra, EPS), bn = fmaxf(rb, EPS);
+    const float inv = 1.f / (an * bn);
+    const float c = dot * inv;
+    const bool live = row < rows;
+    const float lab = live ? __ldg(F.y + (row >> 1)) : 0.f;
+    float term, dldc;
+    if (F.kind == 0) {            // coscos2, loss.py:59-62
+        if (lab == 1.f)       { term = 0.5f * (1.f - c); dldc = -0.5f; }
+        else if (lab == -1.f) { term = c * c;            dldc = 2.f * c; }
+        else                  { term = c;                dldc = 1.f; }
+    } else {                      // cosmargin, loss.py:98-101
+        if (lab == 1.f)       { term = 1.f - c;          dldc = -1.f; }
+        else if (lab == -1.f) { const float h = c - F.margin;
+                                term = fmaxf(h, 0.f);    dldc = h > 0.f ? 1.f : 0.f; }
+        else                  { term = c;                dldc = 1.f; }
+    }
+    if (cb == 0) {                // one term per pair: the even row of the pair, first column block
+        float t = (live && !(lane & 1)) ? term : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && t != 0.f) atomicAdd(F.loss, t * F.scale);
+    }
+    const float g = dldc * F.scale;
+    const float ka = ra > EPS ? c / (an * an) : 0.f;
+    __nv_bfloat16 *zp = F.dz + (long long)row * F.ld_dz + col0;
+    float *op = out32 + (long long)row * ld32 + col0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < ncol; c0 += 16) {
+        float v[16];
+        g_ld16(taddr + c0, v);
+        unsigned pk[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const float e0 = g_act<ACT>(v[j] + bs[c0 + j]), e1 = g_act<ACT>(v[j + 1] + bs[c0 + j + 1]);
+            const float p0 = __shfl_xor_sync(0xffffffffu, e0, 1), p1 = __shfl_xor_sync(0xffffffffu, e1, 1);
+            v[j] = e0; v[j + 1] = e1;
+            pk[j >> 1] = g_pack_bf16(g_dact<ACT>(g * (p0 * inv - ka * e0), e0),
+                                     g_dact<ACT>(g * (p1 * inv - ka * e1), e1));
+        }
+        if (!live) continue;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (c0 + 8 * q + 8 <= ncol) {
+                *reinterpret_cast<uint4 *>(zp + c0 + 8 * q) =
+                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int e2 = 0; e2 < 8; ++e2)
+                    if (c0 + 8 * q + e2 < ncol) {
+                        const unsigned w = pk[4 * q + (e2 >> 1)];
+                        reinterpret_cast<unsigned short *>(zp)[c0 + 8 * q + e2] =
+                            (unsigned short)((e2 & 1) ? (w >> 16) : (w & 0xffffu));
+                    }
+            }
+        }
+        if (F.write_emb) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c0 + j < ncol) op[c0 + j] = v[j];
+        }
+    }
+}
+
 // MODE 0: forward (B = W K-major, bias + activation, last layer fp32)
 // MODE 1: dgrad   (B = W MN-major, x act'(y_below) with y_below fetched per warp by TMA)
 constexpr int F_EW_FWD = 16, F_EW_DGRAD = 8;        // epilogue warps: NQ = EW / 4 share a TMEM lane quarter
-template <int MODE, bool DROP>
+template <int MODE, bool DROP, bool LOSS>
 __global__ void __launch_bounds__(64 + 32 * (MODE == 0 ? F_EW_FWD : F_EW_DGRAD), 1)
 mlp_chain_kernel(const __grid_constant__ FChain ch) {
     constexpr int EW = MODE == 0 ? F_EW_FWD : F_EW_DGRAD, NQ = EW / 4;
@@ -212,7 +331,9 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
 
     const int rank = (int)g_cluster_rank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (the shuffle makes the warp index provably warp-uniform: role branches and everything
+    // derived from it stay on the uniform datapath)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < F_STAGES; ++s) { g_mbar_init(bfull0 + 8 * s, 1); g_mbar_init(bempty0 + 8 * s, 1); }
         for (int k = 0; k < F_KB; ++k) {
@@ -237,43 +358,49 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
     g_cluster_sync();
     g_fence_after();
     const unsigned tmem = *tptr_gen;
+    if (threadIdx.x == 0) f_trace(ch, 7, 13);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) f_trace(ch, 7, 14);
 
     if (warp == 0) {
         // -------------------------------------------------- TMA producer: x, then the weights
-        if (lane == 0) {
-            unsigned n = 0, iter = 0;
-            for (int rb = pair; rb < ch.tiles_m; rb += npairs, ++iter) {
-                const int m0 = (rb * 2 + rank) * G_BM;
+        // (a convergent warp on warp-uniform values, the issuing lane elected per instruction,
+        // like the MMA issuer below)
+        {
+            const int rank_u = blockIdx.x & 1;          // == %cluster_ctarank (clusters of 2 along x)
+            unsigned s = 0, ephase = 1, iter = 0;       // B ring slot and the parity its `empty` wait uses
+            for (int rb = blockIdx.x >> 1; rb < ch.tiles_m; rb += gridDim.x >> 1, ++iter) {
+                const int m0 = (rb * 2 + rank_u) * G_BM;
                 if (iter > 0) {          // the slab is reused: MMAs and output stores of the last block are done
-                    g_mbar_wait(slab_free, (iter - 1) & 1);
-                    g_mbar_wait(drained, (iter - 1) & 1);
+                    g_mbar_wait_warp(slab_free, (iter - 1) & 1);
+                    g_mbar_wait_warp(drained, (iter - 1) & 1);
                 }
-                const FLayer &L0 = ch.L[0];
-                for (int kb = 0; kb < L0.nkb; ++kb) {
-                    if (rank == 0) g_mbar_expect_tx(xfull0 + 8 * kb, 2u * F_SLAB_KB_BYTES);
-                    g_tma_2d_pair(slab + kb * F_SLAB_KB_BYTES, &ch.map_x, (xfull0 + 8 * kb) & G_PEER_MASK,
-                                  kb * G_BK, m0);
+                const int nkb0 = ch.L[0].nkb;
+                for (int kb = 0; kb < nkb0; ++kb) {
+                    if (rank_u == 0) g_mbar_expect_tx_warp(xfull0 + 8 * kb, 2u * F_SLAB_KB_BYTES);
+                    g_tma_2d_pair_warp(slab + kb * F_SLAB_KB_BYTES, &ch.map_x, (xfull0 + 8 * kb) & G_PEER_MASK,
+                                       kb * G_BK, m0);
                 }
                 for (int l = 0; l < ch.n_layers; ++l) {
                     const FLayer &L = ch.L[l];
+                    const int nkb = L.nkb;
                     for (int nt = 0; nt < L.tiles_n; ++nt) {
-                        const int nb_cols = f_n_eff(L, nt) >> 1, nb0 = nt * 256 + rank * nb_cols;
+                        const int nb_cols = f_n_eff(L, nt) >> 1, nb0 = nt * 256 + rank_u * nb_cols;
                         const int nbox = (nb_cols + 63) >> 6;
-                        for (int kb = 0; kb < L.nkb; ++kb, ++n) {
-                            const int s = n % F_STAGES;
-                            g_mbar_wait(bempty0 + 8 * s, ((n / F_STAGES) & 1) ^ 1);
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            g_mbar_wait_warp(bempty0 + 8 * s, ephase);
                             const unsigned fb = (bfull0 + 8 * s) & G_PEER_MASK;
                             if (MODE == 0) {
-                                if (rank == 0) g_mbar_expect_tx(bfull0 + 8 * s, 2u * F_B_BYTES);
-                                g_tma_2d_pair(ring + s * F_B_BYTES, &L.map_w, fb, kb * G_BK, nb0);
+                                if (rank_u == 0) g_mbar_expect_tx_warp(bfull0 + 8 * s, 2u * F_B_BYTES);
+                                g_tma_2d_pair_warp(ring + s * F_B_BYTES, &L.map_w, fb, kb * G_BK, nb0);
                             } else {
-                                if (rank == 0) g_mbar_expect_tx(bfull0 + 8 * s, 2u * (unsigned)nbox * 8192u);
+                                if (rank_u == 0) g_mbar_expect_tx_warp(bfull0 + 8 * s, 2u * (unsigned)nbox * 8192u);
                                 for (int j = 0; j < nbox; ++j)
-                                    g_tma_2d_pair(ring + s * F_B_BYTES + j * 8192, &L.map_w, fb,
-                                                  nb0 + 64 * j, kb * G_BK);
+                                    g_tma_2d_pair_warp(ring + s * F_B_BYTES + j * 8192, &L.map_w, fb,
+                                                       nb0 + 64 * j, kb * G_BK);
                             }
+                            if (++s == F_STAGES) { s = 0; ephase ^= 1u; }
                         }
                     }
                 }
@@ -281,45 +408,51 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA)
-        if (lane == 0 && rank == 0) {
-            unsigned n = 0, iter = 0, sphase = 0, aphase = 0;     // phase bits per barrier
-            for (int rb = pair; rb < ch.tiles_m; rb += npairs, ++iter) {
+        // The WHOLE warp runs this loop on warp-uniform values (g_mma_pair_warp elects the
+        // issuing lane inside the asm block): see abn_tc_ptx.cuh.
+        if ((blockIdx.x & 1) == 0) {
+            const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            unsigned aphase = 0, sphase = 0, iter = 0;      // phase bits per barrier
+            unsigned s = 0, bphase = 0;                     // B ring slot and its phase
+            for (int rb = blockIdx.x >> 1; rb < ch.tiles_m; rb += gridDim.x >> 1, ++iter) {
                 for (int l = 0; l < ch.n_layers; ++l) {
                     const FLayer &L = ch.L[l];
+                    const int nkb = L.nkb;
                     for (int nt = 0; nt < L.tiles_n; ++nt) {
-                        f_trace(ch, l, 0 + 4 * nt);
-                        g_mbar_wait(aempty0 + 8 * nt, ((aphase >> nt) & 1) ^ 1);     // epilogues drained it
+                        if (lane == 0) f_trace(ch, l, 0 + 4 * nt);
+                        g_mbar_wait_warp(aempty0 + 8 * nt, ((aphase >> nt) & 1) ^ 1);   // epilogues drained it
                         aphase ^= 1u << nt;
-                        f_trace(ch, l, 1 + 4 * nt);
+                        if (lane == 0) f_trace(ch, l, 1 + 4 * nt);
                         g_fence_after();
                         const unsigned idesc = g_idesc(2 * G_BM, f_n_eff(L, nt), 0, MODE);
-                        const unsigned d_tmem = tmem + nt * 256;
-                        for (int kb = 0; kb < L.nkb; ++kb, ++n) {
-                            if (nt == 0) {          // this k-block of the layer's input is in both slabs
+                        const unsigned d_tmem = tmem_u + nt * 256;
+                        unsigned long long da = g_desc(slab, 0);
+                        for (int kb = 0; kb < nkb; ++kb, da += (F_SLAB_KB_BYTES >> 4)) {
+                            if (nt == 0 && !(ch.debug & 2)) {   // this k-block of the layer's input is in both slabs
                                 if (l == 0) {
-                                    g_mbar_wait(xfull0 + 8 * kb, iter & 1);
+                                    g_mbar_wait_warp(xfull0 + 8 * kb, iter & 1);
                                 } else {
-                                    f_mbar_wait_cluster(sfull0 + 8 * kb, (sphase >> kb) & 1);
+                                    g_mbar_wait_cluster_warp(sfull0 + 8 * kb, (sphase >> kb) & 1);
                                     sphase ^= 1u << kb;
                                 }
+                                g_fence_after();
                             }
-                            const int s = n % F_STAGES;
-                            g_mbar_wait(bfull0 + 8 * s, (n / F_STAGES) & 1);
+                            if (!(ch.debug & 1)) g_mbar_wait_warp(bfull0 + 8 * s, bphase);
                             g_fence_after();
-                            const unsigned long long da = g_desc(slab + kb * F_SLAB_KB_BYTES, 0);
                             const unsigned long long db = g_desc(ring + s * F_B_BYTES, MODE);
                             constexpr unsigned b_step = MODE ? (2048 >> 4) : (32 >> 4);
 #pragma unroll
                             for (int k = 0; k < G_BK / G_UK; ++k)
-                                g_mma_pair(d_tmem, da + (unsigned long long)(2 * k),
-                                           db + (unsigned long long)(b_step * k), idesc, (kb | k) != 0);
-                            g_commit_pair(bempty0 + 8 * s);
+                                g_mma_pair_warp(d_tmem, da + (unsigned long long)(2 * k),
+                                                db + (unsigned long long)(b_step * k), idesc, (kb | k) != 0);
+                            g_commit_pair_warp(bempty0 + 8 * s);
+                            if (++s == F_STAGES) { s = 0; bphase ^= 1u; }
                         }
-                        g_commit_pair(afull0 + 8 * nt);
-                        f_trace(ch, l, 2 + 4 * nt);
+                        g_commit_pair_warp(afull0 + 8 * nt);
+                        if (lane == 0) f_trace(ch, l, 2 + 4 * nt);
                     }
                 }
-                g_commit_pair(slab_free);
+                g_commit_pair_warp(slab_free);
             }
         }
     } else {
@@ -398,7 +531,13 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                                  : "=r"(yc[q].x), "=r"(yc[q].y), "=r"(yc[q].z), "=r"(yc[q].w)
                                                  : "r"(ybuf + lane * 128 + (((unsigned)q ^ (unsigned)(lane & 7)) << 4))
                                                  : "memory");
-                                __syncwarp();               // every lane holds its y_below row: fetch the next box
+                                // every lane holds its y_below row: fetch the next box into the same
+                                // buffer.  The TMA write is an async-proxy access: program order does
+                                // not order it after these generic-proxy reads (with the tensor pipe
+                                // saturating shared memory the loads can still be in flight when the
+                                // box lands) -- the proxy fence does, lane by lane, before the warp meets
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                __syncwarp();
                                 if (lane == 0 && cb + NQ < nblk) {
                                     g_mbar_expect_tx(ybar, 4096u);
                                     g_tma_2d(ybuf, &L.map_y, ybar, (cb + NQ) * 64, row0);
@@ -418,6 +557,15 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                 if (l + 1 < ch.n_layers && cb < ch.L[l + 1].nkb)
                                     f_arrive_leader_release(sfull0 + 8 * cb);
                                 g_tma_store_2d(&L.map_out, dst, cb * 64, row0);
+                            }
+                        } else if (MODE == 0 && LOSS) {
+                            // the embeddings never leave the SM: loss + dz of the output layer here
+                            float *exch = bias_s + 1024 + 32;
+                            switch (L.act) {
+                                case 1: f_epi_loss<1>(ch.loss, ch.rows, L.n_out, L.out32, L.ld32, taddr, bs + cb * 64, exch, wq, cb, nblk, row0, lane); break;
+                                case 2: f_epi_loss<2>(ch.loss, ch.rows, L.n_out, L.out32, L.ld32, taddr, bs + cb * 64, exch, wq, cb, nblk, row0, lane); break;
+                                case 3: f_epi_loss<3>(ch.loss, ch.rows, L.n_out, L.out32, L.ld32, taddr, bs + cb * 64, exch, wq, cb, nblk, row0, lane); break;
+                                default: f_epi_loss<0>(ch.loss, ch.rows, L.n_out, L.out32, L.ld32, taddr, bs + cb * 64, exch, wq, cb, nblk, row0, lane); break;
                             }
                         } else {
                             // the embeddings: fp32 rows, 16-byte stores
@@ -473,6 +621,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
     if (warp >= 2 && lane == 0) g_store_wait_all();
     g_fence_before();
     g_cluster_sync();
+    if (threadIdx.x == 0) f_trace(ch, 7, 15);
     if (warp == 2) {
         g_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512)
@@ -485,6 +634,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
 using namespace abn;
 
 extern "C" void *abn_gemm_trace_buffer;      // debug hook (abn_tc2.cu)
+extern "C" { __attribute__((visibility("default"))) int abn_chain_debug = 0; }      // debug hook: FChain::debug of the next launches
 
 namespace {
 
@@ -498,15 +648,15 @@ int f_sm_count() {
     return sm_count;
 }
 
-template <int MODE, bool DROP>
+template <int MODE, bool DROP, bool LOSS = false>
 int f_launch(const FChain &ch, cudaStream_t st, const char *what) {
     // slab + weight ring + barriers + (forward: staged biases | dgrad: y_below boxes) + alignment slack
     constexpr int F_STAGES = MODE == 0 ? F_STAGES_FWD : F_STAGES_DGRAD;
     constexpr unsigned smem = F_KB * F_SLAB_KB_BYTES + F_STAGES * F_B_BYTES + 1024 +
-                              (MODE == 0 ? 512 + 2 * 512 * 4 + 128 : 1024 + F_EW_DGRAD * 4096);
+                              (MODE == 0 ? 512 + 2 * 512 * 4 + 128 + (LOSS ? 2048 : 0) : 1024 + F_EW_DGRAD * 4096);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(mlp_chain_kernel<MODE, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(mlp_chain_kernel<MODE, DROP, LOSS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return set_error(ABN_EIO, "%s: cannot reserve %u bytes of shared memory", what, smem);
         configured = true;
@@ -528,21 +678,54 @@ int f_launch(const FChain &ch, cudaStream_t st, const char *what) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl() ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, mlp_chain_kernel<MODE, DROP>, ch);
+    cudaLaunchKernelEx(&cfg, mlp_chain_kernel<MODE, DROP, LOSS>, ch);
     return check_launch(what);
 }
 
 }  // namespace
 
+static int f_forward(const void *x, int64_t ldx, int64_t rows, const abn_mlp_layer *layers, int n_layers,
+                     const abn_mlp_loss *loss, abn_stream_t stream);
+
 extern "C" int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
                                      const abn_mlp_layer *layers, int n_layers,
                                      abn_stream_t stream) {
+    return f_forward(x, ldx, rows, layers, n_layers, nullptr, stream);
+}
+
+extern "C" int abn_mlp_forward_loss_fused(const void *x, int64_t ldx, int64_t rows,
+                                          const abn_mlp_layer *layers, int n_layers,
+                                          const abn_mlp_loss *loss, abn_stream_t stream) {
+    if (!loss || !loss->y || !loss->loss || !loss->dz || (loss->kind != 0 && loss->kind != 1) ||
+        (rows & 1) || loss->ld_dz < 8 || (loss->ld_dz & 7) || (reinterpret_cast<uintptr_t>(loss->dz) & 15))
+        return set_error(ABN_EINVAL, "abn_mlp_forward_loss_fused: bad loss description (even, interleaved "
+                         "rows; dz rows 16-byte aligned)");
+    return f_forward(x, ldx, rows, layers, n_layers, loss, stream);
+}
+
+static int f_forward(const void *x, int64_t ldx, int64_t rows, const abn_mlp_layer *layers, int n_layers,
+                     const abn_mlp_loss *loss, abn_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     if (rows == 0) return ABN_OK;
     if (!x || !layers || rows < 0 || n_layers < 1 || n_layers > F_MAXL)
         return set_error(ABN_EINVAL, "abn_mlp_forward_fused: 1..%d layers", F_MAXL);
     FChain ch;
     memset(&ch, 0, sizeof(ch));
+    if (loss) {
+        const abn_mlp_layer &last = layers[n_layers - 1];
+        if (!last.out_f32 || last.n_out > 128 || loss->ld_dz < last.n_out || last.drop.p > 0.f)
+            return set_error(ABN_EINVAL, "abn_mlp_forward_loss_fused: the last layer must write fp32 "
+                             "embeddings of at most 128 columns, without dropout");
+        ch.loss.on = 1;
+        ch.loss.kind = loss->kind;
+        ch.loss.write_emb = loss->write_embeddings ? 1 : 0;
+        ch.loss.margin = loss->margin;
+        ch.loss.scale = loss->scale;
+        ch.loss.y = loss->y;
+        ch.loss.loss = loss->loss;
+        ch.loss.dz = static_cast<__nv_bfloat16 *>(loss->dz);
+        ch.loss.ld_dz = loss->ld_dz;
+    }
     ch.n_layers = n_layers;
     ch.rows = (int)rows;
     ch.tiles_m = (int)((rows + 2 * G_BM - 1) / (2 * G_BM));
@@ -580,8 +763,13 @@ extern "C" int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
         }
     }
     ch.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
+    ch.debug = abn_chain_debug;
     bool any_drop = false;
     for (int l = 0; l < n_layers; ++l) any_drop |= ch.L[l].drop.state != nullptr;
+    if (loss) {
+        if (any_drop) return f_launch<0, true, true>(ch, (cudaStream_t)stream, "abn_mlp_forward_loss_fused");
+        return f_launch<0, false, true>(ch, (cudaStream_t)stream, "abn_mlp_forward_loss_fused");
+    }
     return any_drop ? f_launch<0, true>(ch, (cudaStream_t)stream, "abn_mlp_forward_fused")
                     : f_launch<0, false>(ch, (cudaStream_t)stream, "abn_mlp_forward_fused");
 }
@@ -625,6 +813,7 @@ extern "C" int abn_mlp_dgrad_fused(const void *dz_top, int64_t ld_top, int64_t r
         if (rc) return rc;
     }
     ch.trace = reinterpret_cast<long long *>(abn_gemm_trace_buffer);
+    ch.debug = abn_chain_debug;
     bool any_drop = false;
     for (int l = 0; l < n_layers; ++l) any_drop |= ch.L[l].drop.state != nullptr;
     return any_drop ? f_launch<1, true>(ch, (cudaStream_t)stream, "abn_mlp_dgrad_fused")

@@ -89,6 +89,20 @@ __device__ __forceinline__ void g_ld32(unsigned taddr, float (&v)[32]) {
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+__device__ __forceinline__ void g_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
 // 64 consecutive accumulator columns of this warp's 32 TMEM lanes in one request
 __device__ __forceinline__ void g_ld64(unsigned taddr, float (&v)[64]) {
     unsigned r[64];
@@ -219,6 +233,100 @@ __device__ __forceinline__ void g_mma_pair(unsigned d_tmem, unsigned long long a
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// ---- the MMA issuer as a CONVERGENT warp --------------------------------------------------
+// tcgen05.mma / tcgen05.commit take their descriptors from uniform registers.  Issued from a
+// single-lane branch (`if (lane == 0)`) the operands live in per-thread registers and every
+// instruction is wrapped in an ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY loop: ~150 clocks of issue
+// per 128-clock MMA (tools/mma_rate.cu), i.e. the tensor pipe idles half of the time.  Run by
+// the whole warp on warp-uniform values, with elect.sync inside the asm block, the operands stay
+// in uniform registers and one MMA costs a handful of issue slots.
+__device__ __forceinline__ void g_mma_pair_warp(unsigned d_tmem, unsigned long long a_desc,
+                                                unsigned long long b_desc, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void g_tma_2d_pair_warp(unsigned dst, const CUtensorMap *map, unsigned bar_cta0,
+                                                   int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar_cta0), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void g_tma_2d_warp(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void g_mbar_expect_tx_warp(unsigned bar, unsigned bytes) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mma_warp(unsigned d_tmem, unsigned long long a_desc,
+                                           unsigned long long b_desc, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void g_commit_warp(unsigned bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void g_commit_pair_warp(unsigned bar) {      // arrives on `bar` in BOTH CTAs
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;\n\t}" ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+// all 32 lanes poll; the loop lives inside the asm block, so the compiler sees no divergence
+// (bounded like g_mbar_wait: a protocol bug traps)
+__device__ __forceinline__ void g_mbar_wait_warp(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, 0x8000000;\n\t"
+        "@p bra WAIT_LOOP;\n\t"
+        "trap;\n"
+        "WAIT_DONE:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait_cluster_warp(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, 0x8000000;\n\t"
+        "@p bra WAIT_LOOP;\n\t"
+        "trap;\n"
+        "WAIT_DONE:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void g_commit_pair(unsigned bar) {      // arrives on `bar` in BOTH CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "

@@ -689,6 +689,26 @@ class SiameseTrainStep(object):
         network may have been built or put in eval() before the engine was)."""
         self.network._check_supported(training=True)
 
+    def _fuse_loss(self):
+        """The table-driven step computes the loss inside the forward chain kernel (interleaved
+        pair rows, ops.mlp_forward_loss_fused) when the network is a single-head chain of at most
+        128 outputs and dropout is off; the embeddings then never reach HBM."""
+        return (self._fwd_fused is not None and not self.heads and self.chain[-1].n_out <= 128
+                and not self._drop_on() and os.environ.get("ABN_FUSE_LOSS", "1") != "0")
+
+    def _fwd_loss(self, n):
+        """forward + loss + dz of the output layer on the gathered operand set."""
+        self._loss_cleared = True
+        if self._fuse_loss():
+            kind, margin, avg = self.loss_spec
+            ops.mlp_forward_loss_fused(self.xb, self._fwd_rows, self._fwd_fused, self._gy[0],
+                                       self.dzb[-1], kind, margin, 1.0 / n if avg else 1.0,
+                                       loss_out=self.loss_buf)
+            self._loss_cleared = False
+            return
+        out = self._forward_bf16(None)
+        self._loss_and_seed(out, n, self._gy)
+
     def _table_fwd_loss(self, feat, table, n, sel, train):
         """gather -> forward -> loss [-> backward] of one batch of the table."""
         self._reserve(2 * n)
@@ -700,10 +720,8 @@ class SiameseTrainStep(object):
                               zero=self._zbuf, y2=ys[1] if two else None,
                               y2_out=self._gy[1] if two else None,
                               cursor=None if sel is not None else self._cursor,
-                              loss_acc=self._loss_acc)
-        self._loss_cleared = True
-        out = self._forward_bf16(None)
-        self._loss_and_seed(out, n, self._gy)
+                              loss_acc=self._loss_acc, interleave=self._fuse_loss())
+        self._fwd_loss(n)
         if train:
             self.backward(None)
         else:
@@ -825,7 +843,8 @@ class SiameseTrainStep(object):
         ops.gather_batch_bf16(feat, table[0], table[1], ys[0], None, n, q["xb"], y_out=q["_gy"][0],
                               zero=q["_zbuf"], y2=ys[1] if two else None,
                               y2_out=q["_gy"][1] if two else None, cursor=self._cursor,
-                              loss_acc=self._loss_acc, table_rows=table[0].numel())
+                              loss_acc=self._loss_acc, table_rows=table[0].numel(),
+                              interleave=self._fuse_loss())
 
     def _pipe_step(self, feat, table, n, p, train, scale, step):
         """Step on operand set p; the gather of the NEXT batch into set 1 - p runs on the side
@@ -839,9 +858,7 @@ class SiameseTrainStep(object):
         with torch.cuda.stream(side):
             self._pipe_gather(feat, table, n, 1 - p)
         self._use_parity(p)
-        self._loss_cleared = True
-        out = self._forward_bf16(None)
-        self._loss_and_seed(out, n, self._gy)
+        self._fwd_loss(n)
         if train:
             self.backward(None)
             if self.world > 1:

@@ -4,6 +4,7 @@ torch is used here for device memory, streams and prefix sums only; all the
 arithmetic of the hot path happens inside libabnet3_b200.so.  Every function
 requires CUDA tensors and raises if the library or an sm_100 device is missing.
 """
+import ctypes as _c
 import os
 from collections import namedtuple
 
@@ -459,6 +460,25 @@ def mlp_forward_fused(x, rows, layers):
                                            stream_ptr()))
 
 
+def mlp_forward_loss_fused(x, rows, layers, y, dz, kind="coscos2", margin=0.5, scale=1.0,
+                           loss_out=None, write_embeddings=False):
+    """mlp_forward_fused on INTERLEAVED pair rows (x[2k], x[2k + 1] = the two frames of pair k) with
+    the pair loss (abnet3/loss.py:46-67, :85-105) computed in the last layer's epilogue: the loss
+    is accumulated into ``loss_out`` and dz of the output layer written to ``dz`` (bf16
+    [rows, ld]); the fp32 embeddings go to the last layer's ``out`` only on request."""
+    _req(y, torch.float32, "y")
+    if y.numel() * 2 < rows:
+        raise ValueError("one label per pair of rows expected")
+    if not (dz.is_cuda and dz.dtype == torch.bfloat16 and dz.stride(-1) == 1 and dz.shape[0] >= rows):
+        raise TypeError("dz must be a CUDA bf16 [>= rows, ld] tensor")
+    loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=x.device)
+    spec = _lib.MlpLoss(ptr(y), ptr(loss), ptr(dz), dz.stride(0), LOSS_KIND[kind], float(margin),
+                        float(scale), int(bool(write_embeddings)))
+    check(_lib.lib().abn_mlp_forward_loss_fused(ptr(x), x.stride(0), int(rows), layers, len(layers),
+                                                _c.byref(spec), stream_ptr()))
+    return loss
+
+
 def mlp_dlayers(specs):
     """specs, top layer first: [(W bf16 [n_out, ld], n_in, act_below, y_below, dz_below)] ->
     ctypes array of abn_mlp_dlayer."""
@@ -486,8 +506,9 @@ def mlp_dgrad_fused(dz_top, rows, layers):
 
 # ------------------------------- fused companions of the tensor-core step ---
 def gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=None, zero=None, y2=None, y2_out=None,
-                      cursor=None, loss_acc=None, table_rows=0):
-    """xb[:n] = bf16(feat[idx1[pos]]), xb[n:2n] = bf16(feat[idx2[pos]]), y_out = float(y[pos]) (and
+                      cursor=None, loss_acc=None, table_rows=0, interleave=False):
+    """xb[:n] = bf16(feat[idx1[pos]]), xb[n:2n] = bf16(feat[idx2[pos]]) -- or, ``interleave``,
+    xb[2k] and xb[2k + 1], the layout of mlp_forward_loss_fused --, y_out = float(y[pos]) (and
     y2_out = float(y2[pos])) with pos = sel[k], or cursor[0] + k when ``sel`` is None and a
     ``cursor`` (device int64 [2]) is given -- the kernel then advances cursor[0] by n.  ``zero``
     (contiguous 4-byte-element tensor) is cleared by the same kernel, after its word 0 (the
@@ -512,7 +533,7 @@ def gather_batch_bf16(feat, idx1, idx2, y, sel, n, xb, y_out=None, zero=None, y2
                                           xb.stride(0), ptr(y_out),
                                           ptr(y2_out), ptr(zero),
                                           zero.numel() if zero is not None else 0, ptr(loss_acc),
-                                          stream_ptr()))
+                                          int(bool(interleave)), stream_ptr()))
 
 
 def pair_loss_dz(e1, e2, y, dz1, dz2, kind="coscos2", margin=0.5, scale=1.0, act=None,

@@ -361,6 +361,24 @@ typedef struct {
 } abn_mlp_layer;
 ABN_API int abn_mlp_forward_fused(const void *x, int64_t ldx, int64_t rows,
                                   const abn_mlp_layer *layers, int n_layers, abn_stream_t stream);
+/* The same launch with the pair loss FUSED into the last layer's epilogue (abnet3/trainer.py:231-236:
+ * forward, then loss): the rows of x are INTERLEAVED -- row 2k = X1[k], row 2k + 1 = X2[k], what
+ * abn_gather_step_bf16(interleave = 1) writes -- so both embeddings of a pair meet in one warp;
+ * coscos2 (kind 0) / cosmargin (kind 1) value (added to *loss, times scale) and
+ * dz = dL/de * act'(e) of the output layer as bf16 rows [rows, ld_dz] (what abn_pair_loss_dz
+ * produces) come straight from the accumulators.  Last layer: fp32 output of at most 128 columns,
+ * no dropout; the fp32 embeddings are written only if write_embeddings. */
+typedef struct {
+    const float *y;             /* [rows / 2] labels (+1 / -1 / other, loss.py:59-62) */
+    float *loss;                /* accumulated into */
+    void *dz; int64_t ld_dz;    /* bf16 [rows, ld_dz] */
+    int kind;                   /* 0 coscos2, 1 cosmargin */
+    float margin, scale;
+    int write_embeddings;
+} abn_mlp_loss;
+ABN_API int abn_mlp_forward_loss_fused(const void *x, int64_t ldx, int64_t rows,
+                                       const abn_mlp_layer *layers, int n_layers,
+                                       const abn_mlp_loss *loss, abn_stream_t stream);
 /* The input-gradient chain of the backward pass the same way (the autograd of those blocks,
  * abnet3/trainer.py:238): layers listed from the top down, layer l computes
  *   dz_below = (dz . W) * act'(y_below)      W [n_out, n_in] as stored, dz [rows, n_out]
@@ -430,13 +448,16 @@ ABN_API int abn_gather_batch_bf16(const float *feat, int dim, const int32_t *idx
  *     a batch that would run past row table_rows is not gathered (prefetch of the batch after
  *     the sweep's last one);
  *   - loss_acc (nullable, device double[1]): before zero_me is cleared its word 0 (the previous
- *     step's float loss) is added to loss_acc -- `train_loss += loss.data[0]`, trainer.py:242. */
+ *     step's float loss) is added to loss_acc -- `train_loss += loss.data[0]`, trainer.py:242;
+ *   - interleave != 0: X1[k] -> row 2k, X2[k] -> row 2k + 1 of xb (instead of rows k and n + k):
+ *     the layout abn_mlp_forward_loss_fused needs. */
 ABN_API int abn_gather_step_bf16(const float *feat, int dim, const int32_t *idx1,
                                  const int32_t *idx2, const int8_t *y_in, const int8_t *y2_in,
                                  const int64_t *sel, int64_t *cursor, int64_t table_rows,
                                  int64_t n, void *xb,
                                  int64_t ldx, float *y_out, float *y2_out, void *zero_me,
-                                 int zero_words, double *loss_acc, abn_stream_t stream);
+                                 int zero_words, double *loss_acc, int interleave,
+                                 abn_stream_t stream);
 ABN_API int abn_pair_loss_dz(const float *e1, const float *e2, const float *y, int64_t n, int dim,
                              int64_t ld, int kind, float margin, float scale, int act, float *loss,
                              void *dz1, void *dz2, int64_t ld_dz, abn_stream_t stream);

@@ -126,3 +126,77 @@ def test_fused_dgrad_chain_is_bit_identical_to_the_layer_by_layer_gemms(rows, di
     torch.cuda.synchronize()
     for l in range(1, n_layers):
         assert torch.equal(got[l][:, :dims[l]], ref[l][:, :dims[l]]), "dz of layer %d" % l
+
+
+# ---- the pair loss inside the forward chain's last epilogue (abn_mlp_forward_loss_fused) ----------
+@pytest.mark.parametrize("n_pairs,dims,act,kind", [
+    (8192, [280, 500, 500, 500, 100], "sigmoid", "coscos2"),     # the canonical training batch
+    (8192, [280, 500, 500, 500, 100], "sigmoid", "cosmargin"),
+    (501, [280, 500, 100], "tanh", "coscos2"),                   # ragged last row block
+    (333, [40, 64, 36], "relu", "cosmargin"),                    # one 64-column block
+    (70, [280, 128], "none", "coscos2"),                         # single layer, both blocks full
+    (40000, [280, 500, 64], "sigmoid", "coscos2"),               # more row blocks than CTA pairs
+])
+def test_loss_fused_into_the_forward_chain_matches_forward_then_loss_kernel(n_pairs, dims, act, kind):
+    """Interleaved rows (2k, 2k + 1 = the two frames of pair k) through the fused launch against
+    the stacked rows (k, n + k) through abn_mlp_forward_fused + abn_pair_loss_dz: the embeddings
+    are bit-identical (same MMAs per row), so dz is, and the loss agrees to fp32 summation order."""
+    rows = 2 * n_pairs
+    n_layers = len(dims) - 1
+    x = _bf(rows, dims[0], 3)                              # stacked: x1 rows, then x2 rows
+    xi = torch.empty_like(x)
+    xi[0::2], xi[1::2] = x[:n_pairs], x[n_pairs:]
+    Ws = [_bf(dims[l + 1], dims[l], 30 + l, dims[l] ** -0.5) for l in range(n_layers)]
+    bs = [(torch.randn(dims[l + 1], generator=torch.Generator().manual_seed(40 + l)) * 0.2).to(DEV)
+          for l in range(n_layers)]
+    acts = [act] * n_layers
+    g = torch.Generator().manual_seed(5)
+    y = torch.randint(0, 3, (n_pairs,), generator=g).float().sub(1).to(DEV)     # -1 / 0 / +1
+    ld_dz = ops.pad_row(dims[-1])
+
+    def run(xin, fused):
+        hid = [torch.zeros((rows, ops.pad_row(dims[l + 1] + 1)), dtype=torch.bfloat16, device=DEV)
+               for l in range(n_layers - 1)]
+        emb = torch.full((rows, dims[-1]), float("nan"), device=DEV)
+        dz = torch.zeros((rows, ld_dz), dtype=torch.bfloat16, device=DEV)
+        loss = torch.zeros(1, device=DEV)
+        layers = ops.mlp_layers([(Ws[l], dims[l], bs[l], acts[l], (hid + [emb])[l], l < n_layers - 1)
+                                 for l in range(n_layers)])
+        if fused:
+            ops.mlp_forward_loss_fused(xin, rows, layers, y, dz, kind, 0.4, 1.0 / n_pairs, loss_out=loss,
+                                       write_embeddings=True)
+        else:
+            ops.mlp_forward_fused(xin, rows, layers)
+            ops.pair_loss_dz(emb[:n_pairs], emb[n_pairs:], y, dz[:n_pairs], dz[n_pairs:], kind, 0.4,
+                             1.0 / n_pairs, act, loss_out=loss)
+        torch.cuda.synchronize()
+        return emb, dz, loss
+
+    emb_r, dz_r, loss_r = run(x, False)
+    emb_f, dz_f, loss_f = run(xi, True)
+    d = dims[-1]
+    assert torch.equal(emb_f[0::2], emb_r[:n_pairs]) and torch.equal(emb_f[1::2], emb_r[n_pairs:])
+    # dot / norms are summed in another order (per 64-column block instead of 8 lanes x 4): the
+    # cosine differs in its last bits, dz (bf16) in at most one unit of ITS last place
+    a = torch.cat([dz_f[0::2, :d], dz_f[1::2, :d]]).float()
+    b = dz_r[:, :d].float()
+    assert float((a - b).abs().max()) <= 2 ** -7 * float(b.abs().max()) + 1e-12
+    assert float((a != b).float().mean()) < 0.05
+    np.testing.assert_allclose(loss_f.item(), loss_r.item(), rtol=2e-5, atol=1e-7)
+
+
+def test_loss_fused_without_the_embeddings_leaves_their_buffer_alone():
+    rows, dims = 512, [280, 500, 100]
+    x = _bf(rows, dims[0], 3)
+    Ws = [_bf(dims[l + 1], dims[l], 30 + l, dims[l] ** -0.5) for l in range(2)]
+    bs = [torch.zeros(dims[l + 1], device=DEV) for l in range(2)]
+    hid = torch.zeros((rows, ops.pad_row(501)), dtype=torch.bfloat16, device=DEV)
+    emb = torch.full((rows, 100), 3.0, device=DEV)
+    dz = torch.zeros((rows, ops.pad_row(100)), dtype=torch.bfloat16, device=DEV)
+    y = torch.ones(rows // 2, device=DEV)
+    layers = ops.mlp_layers([(Ws[0], 280, bs[0], "sigmoid", hid, True), (Ws[1], 500, bs[1], "sigmoid", emb, False)])
+    loss = ops.mlp_forward_loss_fused(x, rows, layers, y, dz, "coscos2", 0.5, 1.0)
+    torch.cuda.synchronize()
+    assert bool((emb == 3.0).all()) and float(loss) > 0 and bool((dz[:, :100] != 0).any())
+    with pytest.raises(Exception):
+        ops.mlp_forward_loss_fused(x, rows - 1, layers, y, dz, "coscos2", 0.5, 1.0)     # odd row count

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from abnet3_b200 import ops, _lib
 DEV = "cuda"
-rows = 16384
+rows = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 def bf(r, c):
     return (torch.randn(r, ops.pad_row(c + 1), device=DEV) * 0.05).bfloat16()
 dims = [280, 500, 500, 500, 100]
@@ -20,17 +20,20 @@ if which == "fwd":
 else:
     dl = ops.mlp_dlayers([(Ws[l], dims[l], "sigmoid", acts[l], dzs[l]) for l in range(3, 0, -1)])
     run = lambda: ops.mlp_dgrad_fused(dzs[4], rows, dl)
+dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 for _ in range(3): run()
 torch.cuda.synchronize()
 tr = torch.zeros(148 * 8 * 16, dtype=torch.int64, device=DEV)
 ctypes.c_void_p.in_dll(_lib.lib(), "abn_gemm_trace_buffer").value = tr.data_ptr()
+ctypes.c_int.in_dll(_lib.lib(), "abn_chain_debug").value = dbg
 run()
 torch.cuda.synchronize()
+ctypes.c_int.in_dll(_lib.lib(), "abn_chain_debug").value = 0
 ctypes.c_void_p.in_dll(_lib.lib(), "abn_gemm_trace_buffer").value = None
 t = tr.cpu().view(148, 8, 16)
 t0 = int(t[t > 0].min())
 names = ["m0wait", "m0go", "m0done", "-", "m1wait", "m1go", "m1done", "-", "e_top", "e_afull", "e_acc0", "e_acc1"]
-for cta in (0, 1, 64, 127):
+for cta in (0, 64):
     for l in range(8):
         if int(t[cta, l].max()) == 0: continue
         print("cta %3d layer %d: " % (cta, l) + "  ".join("%s %6.2f" % (n, (int(v) - t0) / 1e3) if v > 0 else "%s    -  " % n
