@@ -73,6 +73,16 @@ __device__ __forceinline__ void f_trace(const FChain &ch, int layer, int slot) {
     }
 }
 
+// second debug region: when each B stage was (a) requested by the producer, (b) seen full by the
+// MMA issuer -- [which][cta][layer][tile][k-block] behind the 148 x 8 x 16 role stamps
+__device__ __forceinline__ void f_trace_kb(const FChain &ch, int which, int layer, int nt, int kb) {
+    if (ch.trace) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        ch.trace[148 * 8 * 16 + ((((size_t)which * 148 + blockIdx.x) * 8 + layer) * 2 + nt) * 8 + kb] = t;
+    }
+}
+
 __device__ __forceinline__ void f_mbar_wait_cluster(unsigned bar, unsigned parity) {
     unsigned done = 0;
     for (unsigned spin = 0; spin < (1u << 27); ++spin) {
@@ -117,7 +127,8 @@ __device__ __forceinline__ void f_drop32(float (&v)[32], const DropArgs &dr, uns
 template <int ACT, bool DROP>
 __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, unsigned dst, int lane,
                                             int ones_at, const DropArgs &dr, unsigned long long dkey,
-                                            long long row, int col0, unsigned gate, unsigned gate_parity) {
+                                            long long row, int col0, unsigned gate, unsigned gate_parity,
+                                            long long *tr = nullptr) {
     const unsigned swz = (unsigned)(lane & 7);
     float v64[64];
     g_ld64(taddr, v64);
@@ -150,10 +161,12 @@ __device__ __forceinline__ void f_epi_block(unsigned taddr, const float *bs, uns
             }
         }
     }
+    if (tr) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[0] = t; }
     if (gate) {
         g_mbar_wait(gate, gate_parity);
         g_fence_after();
     }
+    if (tr) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[1] = t; }
 #pragma unroll
     for (int q = 0; q < 8; ++q)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
@@ -321,7 +334,8 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
     const unsigned slab_free = aempty0 + 16, drained = slab_free + 8;
     const unsigned tptr = drained + 8;
     const unsigned ybar0 = tptr + 8;                                    // [F_EW_DGRAD] dgrad: y_below boxes
-    constexpr unsigned BAR_BYTES = 16 * F_STAGES + 16 * F_KB + 32 + 16 + 16 + 8 * F_EW_DGRAD;
+    const unsigned kfree0 = ybar0 + 8 * F_EW_DGRAD;                     // [F_KB] slab k-block no longer read by this layer
+    constexpr unsigned BAR_BYTES = 16 * F_STAGES + 16 * F_KB + 32 + 16 + 16 + 8 * F_EW_DGRAD + 8 * F_KB;
     volatile unsigned *tptr_gen = reinterpret_cast<volatile unsigned *>(
         gen + F_KB * F_SLAB_KB_BYTES + F_STAGES * F_B_BYTES + (tptr - bars));
     float *bias_s = reinterpret_cast<float *>(
@@ -339,6 +353,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
         for (int k = 0; k < F_KB; ++k) {
             g_mbar_init(xfull0 + 8 * k, 1);
             g_mbar_init(sfull0 + 8 * k, 8);          // 4 row-quarter warps x 2 CTAs
+            g_mbar_init(kfree0 + 8 * k, 1);
         }
         for (int a = 0; a < 2; ++a) {
             g_mbar_init(afull0 + 8 * a, 1);
@@ -390,6 +405,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                         const int nbox = (nb_cols + 63) >> 6;
                         for (int kb = 0; kb < nkb; ++kb) {
                             g_mbar_wait_warp(bempty0 + 8 * s, ephase);
+                            if (lane == 0) f_trace_kb(ch, 0, l, nt, kb);
                             const unsigned fb = (bfull0 + 8 * s) & G_PEER_MASK;
                             if (MODE == 0) {
                                 if (rank_u == 0) g_mbar_expect_tx_warp(bfull0 + 8 * s, 2u * F_B_BYTES);
@@ -438,6 +454,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                 g_fence_after();
                             }
                             if (!(ch.debug & 1)) g_mbar_wait_warp(bfull0 + 8 * s, bphase);
+                            if (lane == 0) f_trace_kb(ch, 1, l, nt, kb);
                             g_fence_after();
                             const unsigned long long db = g_desc(ring + s * F_B_BYTES, MODE);
                             constexpr unsigned b_step = MODE ? (2048 >> 4) : (32 >> 4);
@@ -446,6 +463,9 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                 g_mma_pair_warp(d_tmem, da + (unsigned long long)(2 * k),
                                                 db + (unsigned long long)(b_step * k), idesc, (kb | k) != 0);
                             g_commit_pair_warp(bempty0 + 8 * s);
+                            // the layer's LAST tile: once its MMAs on k-block kb retire, nothing reads
+                            // slab block kb any more -- the epilogue may overwrite it (kfree)
+                            if (nt + 1 == L.tiles_n && nt > 0) g_commit_pair_warp(kfree0 + 8 * kb);
                             if (++s == F_STAGES) { s = 0; bphase ^= 1u; }
                         }
                         g_commit_pair_warp(afull0 + 8 * nt);
@@ -461,7 +481,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
         const int wq = warp & 3;                        // TMEM lane quarter of this warp
         const int half = ew >> 2;                       // takes the 64-column blocks cb = half, half + NQ, ..
         const int et = ew * 32 + lane;
-        unsigned afphase = 0, lcount = 0, ycount = 0;
+        unsigned afphase = 0, kphase = 0, lcount = 0, ycount = 0;
         for (int rb = pair; rb < ch.tiles_m; rb += npairs) {
             const int m0 = (rb * 2 + rank) * G_BM;
             const int row0 = m0 + wq * 32;
@@ -488,38 +508,35 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                 if (MODE == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
                 else __syncwarp();
                 if (et == 0) f_trace(ch, l, 8);
-                // accumulator a is read as soon as ITS MMAs are complete; the slab (which the
-                // layer's remaining MMAs still read) is written only after the last accumulator's
-                // commit (tcgen05.commit covers every MMA issued before it) -- the `gate` of the
-                // first blocks
-                unsigned waited = 0;
+                // accumulator a is read as soon as ITS MMAs are complete; slab block cb (which the
+                // layer's last tile still reads) is written once that tile's MMAs on k-block cb have
+                // retired -- the `gate` of the earlier accumulators' blocks
                 const int a_last = L.tiles_n - 1;
                 for (int a = 0; a < L.tiles_n; ++a) {
-                    if (!((waited >> a) & 1u)) {
-                        g_mbar_wait(afull0 + 8 * a, (afphase >> a) & 1);
-                        afphase ^= 1u << a;
-                        waited |= 1u << a;
-                    }
+                    g_mbar_wait(afull0 + 8 * a, (afphase >> a) & 1);
+                    afphase ^= 1u << a;
                     g_fence_after();
                     if (et == 0) f_trace(ch, l, 9);
                     for (int cb = 4 * a + half; cb < 4 * a + 4 && cb < nblk; cb += NQ) {
+                        // blocks of the earlier accumulators are written while the last tile's MMAs
+                        // still read the slab: block cb waits for THEIR k-block cb only (kfree)
                         unsigned gate = 0, gate_parity = 0;
-                        if ((MODE == 1 || !L.out_f32) && !((waited >> a_last) & 1u)) {
-                            gate = afull0 + 8 * a_last;
-                            gate_parity = (afphase >> a_last) & 1;
-                            afphase ^= 1u << a_last;            // (waited on inside the block function)
-                            waited |= 1u << a_last;
+                        if ((MODE == 1 || !L.out_f32) && a < a_last && cb < L.nkb) {
+                            gate = kfree0 + 8 * cb;
+                            gate_parity = (kphase >> cb) & 1;
                         }
                         const unsigned taddr = tmem + ((unsigned)(wq * 32) << 16) + cb * 64;
+                        long long *dbg_tr = (ch.trace && et == 0 && a == 0)
+                            ? ch.trace + ((size_t)blockIdx.x * 8 + l) * 16 + 12 : nullptr;
                         if (MODE == 1 || !L.out_f32) {
                             const unsigned dst = slab + cb * F_SLAB_KB_BYTES + wq * 4096u;
                             if (MODE == 0) {
                                 const int ones_at = L.ones_col ? L.n_out - cb * 64 : -1;
                                 switch (L.act) {
-                                    case 1: f_epi_block<1, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
-                                    case 2: f_epi_block<2, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
-                                    case 3: f_epi_block<3, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
-                                    default: f_epi_block<0, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity); break;
+                                    case 1: f_epi_block<1, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity, dbg_tr); break;
+                                    case 2: f_epi_block<2, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity, dbg_tr); break;
+                                    case 3: f_epi_block<3, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity, dbg_tr); break;
+                                    default: f_epi_block<0, DROP>(taddr, bs + cb * 64, dst, lane, ones_at, L.drop, dkey, drow, cb * 64, gate, gate_parity, dbg_tr); break;
                                 }
                             } else {
                                 g_mbar_wait(ybar, ycount & 1u);
@@ -558,6 +575,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                     f_arrive_leader_release(sfull0 + 8 * cb);
                                 g_tma_store_2d(&L.map_out, dst, cb * 64, row0);
                             }
+                            if (dbg_tr) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg_tr[2] = t; }
                         } else if (MODE == 0 && LOSS) {
                             // the embeddings never leave the SM: loss + dz of the output layer here
                             float *exch = bias_s + 1024 + 32;
@@ -610,6 +628,8 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                     if (lane == 0) g_mbar_arrive_cta0(aempty0 + 8 * a);
                     if (et == 0) f_trace(ch, l, 10 + a);
                 }
+                // (every kfree barrier of this layer's k-blocks completed one phase, waited for or not)
+                if (L.tiles_n > 1) kphase ^= (1u << L.nkb) - 1u;
             }
             // the block's output boxes have been read out of the slab (the next block's x may land)
             if (lane == 0) {

@@ -247,6 +247,11 @@ class ClockSampler:
             return
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
+        # nvidia-smi takes up to a second to come up, and its start-up (NVML initialisation)
+        # stalls kernel submission: the timed region must not begin before the first sample
+        t_end = time.perf_counter() + 8.0
+        while not self.rows and time.perf_counter() < t_end and self.proc.poll() is None:
+            time.sleep(0.02)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -597,13 +602,18 @@ def kernel_times(engine, feat, table, B, iters=30):
     out["gather"] = t(lambda: ops.gather_batch_bf16(
         feat, table[0], table[1], ys[0], sel, B, engine.xb, y_out=engine._gy[0], zero=engine._zbuf,
         y2=ys[1] if len(ys) > 1 else None, y2_out=engine._gy[1] if len(ys) > 1 else None))
-    if engine._fwd_fused is not None:
-        out["forward"] = t(lambda: ops.mlp_forward_fused(engine.xb, engine._fwd_rows, engine._fwd_fused))
+    if engine._fwd_fused is not None and engine._fuse_loss():
+        # the step's own launch: forward chain with the pair loss in its last epilogue
+        out["forward"] = t(lambda: engine._fwd_loss(B))
+        out["loss"] = 0.0
     else:
-        out["forward"] = t(lambda: engine._forward_bf16(None))
-    o = engine.out_last
-    outs = [o[:, :engine.head_dim], o[:, engine.head_dim:]] if engine.heads else o
-    out["loss"] = t(lambda: engine._loss_and_seed_bf16(outs, B, engine._gy))
+        if engine._fwd_fused is not None:
+            out["forward"] = t(lambda: ops.mlp_forward_fused(engine.xb, engine._fwd_rows, engine._fwd_fused))
+        else:
+            out["forward"] = t(lambda: engine._forward_bf16(None))
+        o = engine.out_last
+        outs = [o[:, :engine.head_dim], o[:, engine.head_dim:]] if engine.heads else o
+        out["loss"] = t(lambda: engine._loss_and_seed_bf16(outs, B, engine._gy))
     if engine._dgrad_fused is not None:
         out["dgrad"] = t(lambda: ops.mlp_dgrad_fused(engine.dzb[-1], engine._fwd_rows, engine._dgrad_fused))
 
@@ -826,7 +836,8 @@ def run_path(args, rank, world, local_rank, dev):
             "frac": ach / pk["bf16_tflops"], "peak_source": pk["source"] + " bf16_tflops (burst: the "
             "kernel is timed alone)",
             "kernel": "mlp_chain_kernel<0> (forward chain: every layer in one launch, tcgen05 "
-                      "cta_group::2, activations resident in shared memory)",
+                      "cta_group::2, activations resident in shared memory%s)"
+                      % (", pair loss + output-layer dz in the last epilogue" if engine._fuse_loss() else ""),
             "kernel_us": fwd_us, "algorithmic_flops_per_launch": bs * MLP_FLOP_FWD[cfg],
             "algorithmic_flops_def": "2 rows x 2 x sum(n_in*n_out) per frame pair, unpadded shapes "
                                      "(SURVEY 8d)",
@@ -935,6 +946,8 @@ def run_path(args, rank, world, local_rank, dev):
         kernels_per_step = 6 if engine._dgrad_fused is not None else 5
         if multitask:
             kernels_per_step += 1
+        elif engine._fuse_loss():
+            kernels_per_step -= 1          # the loss is computed inside the forward chain launch
         launches = args.steps * ((align or {}).get("launches_per_pass", 0) + 4 +
                                  n_train_b * kernels_per_step + n_dev_b * 3)
         line = {

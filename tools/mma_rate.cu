@@ -31,17 +31,28 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 // (the descriptors advance like in the chain kernels), commit_every: MMAs per tcgen05.commit.
 template <int CG>
 __global__ void __launch_bounds__(576, 1) rate_kernel(int n, int a_mn, int b_mn, int iters, int commit_every,
-                                                      int two_acc, int commit_mode, int spin_mode, long long *out) {
+                                                      int two_acc, int commit_mode, int spin_mode, long long *out, int fill, const unsigned char *src) {
     extern __shared__ unsigned char smem_raw[];
     const unsigned raw = smem_u32(smem_raw), base = (raw + 1023u) & ~1023u;
-    __shared__ unsigned long long bar[8];
+    __shared__ unsigned long long bar[16];
     __shared__ unsigned tptr;
     unsigned rank = 0;
     if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    for (unsigned i = threadIdx.x; i < 192 * 1024 / 16; i += blockDim.x)
-        reinterpret_cast<uint4 *>(smem_raw + (base - raw))[i] = make_uint4(0, 0, 0, 0);
+    // fill 0: zero operands; 1: random bf16 in [-1, 1) (the tensor pipe's rate is data dependent)
+    for (unsigned i = threadIdx.x; i < 192 * 1024 / 16; i += blockDim.x) {
+        unsigned w[4] = {0, 0, 0, 0};
+        if (fill) {
+            unsigned h = i * 2654435761u + blockIdx.x * 40503u + 12345u;
+            for (int j = 0; j < 4; ++j) {
+                h ^= h << 13; h ^= h >> 17; h ^= h << 5;
+                const unsigned lo = 0x3f00u | (h & 0x80ffu), hi = 0x3f00u | ((h >> 16) & 0x80ffu);
+                w[j] = lo | (hi << 16);
+            }
+        }
+        reinterpret_cast<uint4 *>(smem_raw + (base - raw))[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
     if (threadIdx.x == 0) {
-        for (int b = 0; b < 8; ++b)
+        for (int b = 0; b < 16; ++b)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[b])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -119,9 +130,39 @@ __global__ void __launch_bounds__(576, 1) rate_kernel(int n, int a_mn, int b_mn,
     }
     // spin_mode 1: every other thread of the leader CTA polls the final barrier like the epilogue
     // warps of the chain kernels do (all lanes, mbarrier.try_wait in a loop); 2: one lane per warp
-    if (threadIdx.x >= 64 && rank == 0 && spin_mode) {
+    if (threadIdx.x >= 64 && rank == 0 && (spin_mode == 1 || spin_mode == 2)) {
         if (spin_mode == 1 || (threadIdx.x & 31) == 0) mbar_wait(smem_u32(&bar[0]), 0);
         __syncwarp();
+    }
+    // spin_mode 3: one thread of EACH CTA streams 16 KB bulk copies global -> the B ring (what the TMA
+    // producer of the chain kernels does: 16 KB per 4 MMAs), `depth` copies in flight; 4: the same
+    // bytes written by st.shared.v4 from one warp; 5: both CTAs' warps 2-3 only READ shared memory
+    if (spin_mode == 3 && threadIdx.x == 64) {
+        unsigned ph = 0;
+        for (int it2 = 0; it2 < iters / 4; ++it2) {
+            const int slot = it2 & 3;
+            const unsigned tb = smem_u32(&bar[8 + slot]);
+            if (it2 >= 4) { mbar_wait(tb, ph); if (slot == 3) ph ^= 1; }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tb), "r"(16384u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(base + 131072u + slot * 16384u), "l"(src + (size_t)(it2 & 63) * 16384), "r"(16384u), "r"(tb) : "memory");
+        }
+        for (int slot = 0; slot < 4; ++slot) mbar_wait(smem_u32(&bar[8 + slot]), ph);
+    }
+    if (spin_mode == 4 && threadIdx.x >= 64 && threadIdx.x < 96) {
+        const unsigned dst = base + 131072u + (threadIdx.x - 64) * 16;
+        for (int it2 = 0; it2 < iters * 8; ++it2)       // 512 B per instruction, 32 instructions = 16 KB per 4 MMAs
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst + (it2 & 31) * 512), "r"(it2) : "memory");
+    }
+    if (spin_mode == 5 && threadIdx.x >= 64 && threadIdx.x < 96) {
+        const unsigned srcs = base + 131072u + (threadIdx.x - 64) * 16;
+        unsigned acc = 0;
+        for (int it2 = 0; it2 < iters * 8; ++it2) {
+            unsigned a, b, c, d;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(srcs + (it2 & 31) * 512) : "memory");
+            acc += a ^ b ^ c ^ d;
+        }
+        if (acc == 0x12345u) out[4095] = acc;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -137,7 +178,9 @@ __global__ void __launch_bounds__(576, 1) rate_kernel(int n, int a_mn, int b_mn,
 }
 
 template <int CG>
-static void run(int grid, int n, int a_mn, int b_mn, int iters, int commit_every, int two_acc, int commit_mode, const char *what, int spin_mode = 0, int threads = 128) {
+static void run(int grid, int n, int a_mn, int b_mn, int iters, int commit_every, int two_acc, int commit_mode, const char *what, int spin_mode = 0, int threads = 128, int fill = 0) {
+    static unsigned char *src = nullptr;
+    if (!src) { cudaMalloc(&src, 64 * 16384); cudaMemset(src, 0x3c, 64 * 16384); }
     long long *out;
     cudaMalloc(&out, 4096 * 8);
     cudaMemset(out, 0, 4096 * 8);
@@ -154,7 +197,7 @@ static void run(int grid, int n, int a_mn, int b_mn, int iters, int commit_every
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    for (int rep = 0; rep < 3; ++rep) cudaLaunchKernelEx(&cfg, rate_kernel<CG>, n, a_mn, b_mn, iters, commit_every, two_acc, commit_mode, spin_mode, out);
+    for (int rep = 0; rep < 3; ++rep) cudaLaunchKernelEx(&cfg, rate_kernel<CG>, n, a_mn, b_mn, iters, commit_every, two_acc, commit_mode, spin_mode, out, fill, (const unsigned char *)src);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", what, cudaGetErrorString(e)); exit(1); }
     long long h[4096];
@@ -169,13 +212,13 @@ static void run(int grid, int n, int a_mn, int b_mn, int iters, int commit_every
 }
 
 int main() {
-    const int it = 2048;
-    for (int grid : {2, 148}) {
-        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4, 128 threads, nobody polls");
-        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4, 576 threads, nobody polls", 0, 576);
-        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4, 16 warps poll (all lanes)", 1, 576);
-        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4, 16 warps poll (one lane each)", 2, 576);
-        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4, 2 warps poll (all lanes)", 1, 128);
+    const int it = 4096;
+    for (int grid : {2, 128}) {
+        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4, no other traffic", 0, 128, 1);
+        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4 + bulk copies 16 KB / 4 MMAs", 3, 128, 1);
+        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4 + st.shared 16 KB / 4 MMAs", 4, 128, 1);
+        run<2>(grid, 256, 0, 0, it, 4, 1, 0, "cg2 N256 commit/4 + ld.shared 16 KB / 4 MMAs", 5, 128, 1);
+        run<2>(grid, 128, 0, 0, it, 4, 1, 0, "cg2 N128 commit/4 + bulk copies", 3, 128, 1);
     }
     return 0;
 }

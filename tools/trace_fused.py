@@ -23,19 +23,29 @@ else:
 dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 for _ in range(3): run()
 torch.cuda.synchronize()
-tr = torch.zeros(148 * 8 * 16, dtype=torch.int64, device=DEV)
+tr = torch.zeros(148 * 8 * 16 + 2 * 148 * 8 * 2 * 8, dtype=torch.int64, device=DEV)
 ctypes.c_void_p.in_dll(_lib.lib(), "abn_gemm_trace_buffer").value = tr.data_ptr()
 ctypes.c_int.in_dll(_lib.lib(), "abn_chain_debug").value = dbg
 run()
 torch.cuda.synchronize()
 ctypes.c_int.in_dll(_lib.lib(), "abn_chain_debug").value = 0
 ctypes.c_void_p.in_dll(_lib.lib(), "abn_gemm_trace_buffer").value = None
-t = tr.cpu().view(148, 8, 16)
+t = tr[:148 * 8 * 16].cpu().view(148, 8, 16)
+kbt = tr[148 * 8 * 16:].cpu().view(2, 148, 8, 2, 8)
 t0 = int(t[t > 0].min())
-names = ["m0wait", "m0go", "m0done", "-", "m1wait", "m1go", "m1done", "-", "e_top", "e_afull", "e_acc0", "e_acc1"]
+names = ["m0wait", "m0go", "m0done", "-", "m1wait", "m1go", "m1done", "-", "e_top", "e_afull", "e_acc0", "e_acc1", "b_math", "b_gate", "b_stored"]
 for cta in (0, 64):
     for l in range(8):
         if int(t[cta, l].max()) == 0: continue
         print("cta %3d layer %d: " % (cta, l) + "  ".join("%s %6.2f" % (n, (int(v) - t0) / 1e3) if v > 0 else "%s    -  " % n
                                                             for n, v in zip(names, t[cta, l]) if n != "-"))
 print("last event us", (int(t.max()) - t0) / 1e3)
+
+for cta in (0, 64):
+    for l in range(4):
+        for nt in range(2):
+            if int(kbt[1, cta, l, nt].max()) == 0: continue
+            req = ["%6.2f" % ((int(v) - t0) / 1e3) if v > 0 else "   -  " for v in kbt[0, cta, l, nt]]
+            ful = ["%6.2f" % ((int(v) - t0) / 1e3) if v > 0 else "   -  " for v in kbt[1, cta, l, nt]]
+            print("cta %3d layer %d tile %d: B requested %s" % (cta, l, nt, " ".join(req)))
+            print("                        seen full   %s" % " ".join(ful))
