@@ -17,9 +17,10 @@ WANT = {
     "long_tile_kernel_stacked_4": r"long_tile_kernelILb1ELi4E",
     "long_tile_kernel_generic_4": r"long_tile_kernelILb0ELi4E",
     "dtw_band_kernel": r"dtw_band_kernel",
-    "mlp_chain_kernel_0_forward": r"mlp_chain_kernelILi0ELb0E",
-    "mlp_chain_kernel_1_dgrad": r"mlp_chain_kernelILi1ELb0E",
-    "mlp_chain_kernel_0_forward_dropout": r"mlp_chain_kernelILi0ELb1E",
+    "mlp_chain_kernel_0_forward": r"mlp_chain_kernelILi0ELb0ELb0E",
+    "mlp_chain_kernel_0_forward_loss": r"mlp_chain_kernelILi0ELb0ELb1E",
+    "mlp_chain_kernel_1_dgrad": r"mlp_chain_kernelILi1ELb0ELb0E",
+    "mlp_chain_kernel_0_forward_dropout": r"mlp_chain_kernelILi0ELb1ELb0E",
     "tc_group_kernel_256_2": r"tc_group_kernelILi256ELi2E",
     "gather_bf16_kernel": r"gather_bf16_kernel",
     "pair_loss_dz_vec_kernel": r"pair_loss_dz_vec_kernelILb0E",
