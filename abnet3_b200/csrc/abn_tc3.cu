@@ -321,6 +321,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
     constexpr int EW = MODE == 0 ? F_EW_FWD : F_EW_DGRAD, NQ = EW / 4;
     constexpr int F_STAGES = MODE == 0 ? F_STAGES_FWD : F_STAGES_DGRAD;
     extern __shared__ unsigned char smem_raw[];
+    if (threadIdx.x == 0) f_trace(ch, 7, 12);                           // (debug) kernel entry
     const unsigned raw = g_smem_u32(smem_raw);
     const unsigned base = (raw + 1023u) & ~1023u;
     unsigned char *gen = smem_raw + (base - raw);

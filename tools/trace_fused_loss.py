@@ -55,9 +55,9 @@ def timeline(first, label):
     us = lambda v: (v[v > 0].double() - t0) / 1e3
     print("== %s -> dgrad" % label)
     for nm, t in (("first", a), ("dgrad", b)):
-        pro, go, end = us(t[:, 7, 13]), us(t[:, 7, 14]), us(t[:, 7, 15])
-        print("  %s: prologue done %.1f..%.1f | past griddepcontrol.wait %.1f..%.1f | exit %.1f..%.1f"
-              % (nm, pro.min(), pro.max(), go.min(), go.max(), end.min(), end.max()))
+        ent, pro, go, end = us(t[:, 7, 12]), us(t[:, 7, 13]), us(t[:, 7, 14]), us(t[:, 7, 15])
+        print("  %s: entry %.1f..%.1f (median %.1f) | prologue done %.1f..%.1f (median %.1f) | past griddepcontrol.wait %.1f..%.1f | exit %.1f..%.1f"
+              % (nm, ent.min(), ent.max(), ent.median(), pro.min(), pro.max(), pro.median(), go.min(), go.max(), end.min(), end.max()))
         for l in range(4):
             if int(t[:, l].max()) == 0:
                 continue
