@@ -219,15 +219,23 @@ __device__ __forceinline__ void g_epi_bf16_tile(const GEpi &e, unsigned &nbox, u
 }
 
 // ---------------------------------------------------------------- kernel ---
-template <int BN, int NCTA>
+// WG: every problem of the group is a reduction (wgrad: fp32 reds straight from the registers) --
+// the 64 KB of output staging become two more operand stages.  A wgrad tile is a long K loop
+// over operands that both stream from L2 (32 KB per k-block and CTA): with 4 stages in flight the
+// ring is latency bound (112 ns per MMA, tools/trace_tc2.py), with 6 it is not.
+template <int BN, int NCTA, bool WG>
+constexpr int g_stages() {
+    return (G_BM * G_BK * 2 + (BN / NCTA) * G_BK * 2) > 32768 ? (WG ? 4 : 3) : (WG ? 6 : 4);
+}
+template <int BN, int NCTA, bool WG>
 __global__ void __launch_bounds__(G_THREADS, 1)
 tc_group_kernel(const __grid_constant__ GGroup g) {
     constexpr unsigned A_BYTES = G_BM * G_BK * 2;           // 16 KB: this CTA's 128 rows
     constexpr unsigned B_BYTES = (BN / NCTA) * G_BK * 2;    // this CTA's share of the B tile
     constexpr unsigned STAGE = A_BYTES + B_BYTES;
-    constexpr int STAGES = STAGE > 32768 ? 3 : 4;
+    constexpr int STAGES = g_stages<BN, NCTA, WG>();
     // per epilogue warp: two 32 x 64 bf16 boxes staged for TMA stores (y_below boxes land in them too)
-    constexpr unsigned OUT_BYTES = G_EPI_WARPS * 2u * 4096u;
+    constexpr unsigned OUT_BYTES = WG ? 0u : G_EPI_WARPS * 2u * 4096u;
     const int rank = NCTA == 2 ? (int)g_cluster_rank() : 0;
     const int tile0 = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
     extern __shared__ unsigned char smem_raw[];
@@ -549,14 +557,14 @@ tc_group_kernel(const __grid_constant__ GGroup g) {
 }
 
 // ------------------------------------------------------------------ host ---
-template <int BN, int NCTA>
+template <int BN, int NCTA, bool WG>
 static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
     constexpr unsigned stage = G_BM * G_BK * 2 + (BN / NCTA) * G_BK * 2;
-    constexpr int STAGES = stage > 32768 ? 3 : 4;
-    constexpr unsigned smem = STAGES * stage + G_EPI_WARPS * 8192 + 256 + 2 * BN * 4 + 1024;
+    constexpr int STAGES = g_stages<BN, NCTA, WG>();
+    constexpr unsigned smem = STAGES * stage + (WG ? 0 : G_EPI_WARPS * 8192) + 256 + 2 * BN * 4 + 1024;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(tc_group_kernel<BN, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(tc_group_kernel<BN, NCTA, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return set_error(ABN_EIO, "abn_gemm_bf16_group: cannot reserve %u bytes of shared memory",
                              smem);
@@ -582,7 +590,7 @@ static int g_launch(const GGroup &g, int sm_count, cudaStream_t st) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl() ? 2 : 1;
-    if (cudaLaunchKernelEx(&cfg, tc_group_kernel<BN, NCTA>, g) != cudaSuccess)
+    if (cudaLaunchKernelEx(&cfg, tc_group_kernel<BN, NCTA, WG>, g) != cudaSuccess)
         return check_launch("abn_gemm_bf16_group");
     return check_launch("abn_gemm_bf16_group");
 }
@@ -693,7 +701,15 @@ extern "C" int abn_gemm_bf16_group(const abn_gemm_problem *problems, int n_probl
     { const char *e = getenv("ABN_GEMM_DBG"); g.dbg = e ? atoi(e) : 0; }
 #endif
     cudaStream_t st = (cudaStream_t)stream;
+    bool all_red = true;
+    for (int i = 0; i < n_problems; ++i) all_red = all_red && problems[i].epilogue == GE_ATOMIC;
+    { const char *e = getenv("ABN_GEMM_WG_STAGES"); if (e && e[0] == '0') all_red = false; }
+    if (all_red) {
+        if (ncta == 2)
+            return bn == 128 ? g_launch<128, 2, true>(g, sm_count, st) : g_launch<256, 2, true>(g, sm_count, st);
+        return bn == 128 ? g_launch<128, 1, true>(g, sm_count, st) : g_launch<256, 1, true>(g, sm_count, st);
+    }
     if (ncta == 2)
-        return bn == 128 ? g_launch<128, 2>(g, sm_count, st) : g_launch<256, 2>(g, sm_count, st);
-    return bn == 128 ? g_launch<128, 1>(g, sm_count, st) : g_launch<256, 1>(g, sm_count, st);
+        return bn == 128 ? g_launch<128, 2, false>(g, sm_count, st) : g_launch<256, 2, false>(g, sm_count, st);
+    return bn == 128 ? g_launch<128, 1, false>(g, sm_count, st) : g_launch<256, 1, false>(g, sm_count, st);
 }
