@@ -95,9 +95,13 @@ __device__ __forceinline__ void f_mbar_wait_cluster(unsigned bar, unsigned parit
     }
     __trap();
 }
-// arrive on the LEADER CTA's copy of `bar` (own copy when this CTA is the leader)
+// arrive on the LEADER CTA's copy of `bar` (own copy when this CTA is the leader).  What is published
+// are this CTA's OWN shared-memory rows (st.shared + fence.proxy.async before the warp meets), which
+// the pair's tensor core reads in place: CTA-scope release, the form CUTLASS's ClusterBarrier::arrive
+// uses on remote barriers.  `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of every
+// arrive -- ~1 us per 64-column block with the TMA stores of the same warp in flight.
 __device__ __forceinline__ void f_arrive_leader_release(unsigned bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+    asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];"
                  ::"r"(bar & G_PEER_MASK) : "memory");
 }
 
@@ -449,7 +453,7 @@ mlp_chain_kernel(const __grid_constant__ FChain ch) {
                                 if (l == 0) {
                                     g_mbar_wait_warp(xfull0 + 8 * kb, iter & 1);
                                 } else {
-                                    g_mbar_wait_cluster_warp(sfull0 + 8 * kb, (sphase >> kb) & 1);
+                                    g_mbar_wait_warp(sfull0 + 8 * kb, (sphase >> kb) & 1);
                                     sphase ^= 1u << kb;
                                 }
                                 g_fence_after();
