@@ -27,13 +27,19 @@ sel = eng.gather_buffers(B)
 sel.copy_(torch.arange(B, device=dev))
 
 def stages():
+    fused = eng._fuse_loss()
     def gather():
-        ops.gather_batch_bf16(feat, idx1, idx2, y, sel, B, eng.xb, y_out=eng._gy[0], zero=eng._zbuf)
+        ops.gather_batch_bf16(feat, idx1, idx2, y, sel, B, eng.xb, y_out=eng._gy[0], zero=eng._zbuf,
+                              interleave=fused)
     def fwd():
-        ops.mlp_forward_fused(eng.xb, eng._fwd_rows, eng._fwd_fused)
+        if fused:
+            eng._fwd_loss(B)            # forward chain with the loss in its last epilogue
+        else:
+            ops.mlp_forward_fused(eng.xb, eng._fwd_rows, eng._fwd_fused)
     def loss():
-        eng._loss_cleared = True
-        eng._loss_and_seed(eng.out_last, B, eng._gy)
+        if not fused:
+            eng._loss_cleared = True
+            eng._loss_and_seed(eng.out_last, B, eng._gy)
     def dgrad():
         ops.mlp_dgrad_fused(eng.dzb[-1], eng._fwd_rows, eng._dgrad_fused)
     def wgrad():
