@@ -63,6 +63,8 @@ def timeline(first, label):
                 continue
             e0, e1 = us(t[:, l, 8]), us(t[:, l, 10])
             m0 = us(t[:, l, 1])
+            if min(e0.numel(), e1.numel(), m0.numel()) == 0:
+                continue
             print("    layer %d: first MMA %.1f..%.1f | epilogue top %.1f..%.1f | acc0 read %.1f..%.1f"
                   % (l, m0.min(), m0.max(), e0.min(), e0.max(), e1.min(), e1.max()))
 
