@@ -1,5 +1,5 @@
-// abn_tc3.cu -- kernel (3b): the embedder's FORWARD pass with the activations resident on
-// chip.  One launch runs every layer of  y = act(x W^T + b)  (abnet3/model.py:133-170,
+// abn_tc3.cu -- kernel (3b): the embedder's FORWARD pass (MODE 0) and its dz chain (MODE 1) with the
+// activations resident on chip.  One launch runs every layer of  y = act(x W^T + b)  (abnet3/model.py:133-170,
 // :179-186) for a 256-row block per CTA pair:
 //
 //   * the block's activations live in shared memory as the A operand of the next layer
@@ -18,6 +18,18 @@
 // dependencies, by the latency of store -> signal -> load between layers (44 us against 31 us
 // without dependencies).  Keeping A on chip removes half of the operand traffic and all of
 // that latency.
+//
+// Round 2, second half (all measured with the kernel's own %globaltimer stamps, tools/trace_fused.py):
+//   * the TMA producer and the MMA issuer are CONVERGENT warps on warp-uniform values (the issuing
+//     lane is elected inside the asm block, abn_tc_ptx.cuh): from a single-lane branch every
+//     tcgen05.mma cost ~150 clocks of issue (ELECT / R2UR loops) for 128 clocks of tensor work;
+//   * the epilogue publishes a slab block with a CTA-scope release (`.release.cluster` is a
+//     MEMBAR.ALL.GPU per block) and writes block cb once the layer's last tile has retired ITS
+//     k-block cb (kfree barriers), not the whole tile;
+//   * MODE 0 can compute the pair loss and the output layer's dz in the last layer's epilogue
+//     (interleaved pair rows, f_epi_loss): the embeddings never reach HBM;
+//   * MODE 1: a proxy fence orders the TMA refill of a warp's y_below box after the loads of the
+//     previous one.
 //
 // Serves networks whose layer widths fit the slab: n_in <= 512, n_out (+ the ones column)
 // <= 512; anything else takes the chained launch of abn_tc2.cu.
