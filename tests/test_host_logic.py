@@ -248,3 +248,27 @@ def test_direction_stream_decoder_restores_index_pairs():
     for p in range(P):
         np.testing.assert_array_equal(i1[off[p]:off[p + 1]], paths[p][0])
         np.testing.assert_array_equal(i2[off[p]:off[p + 1]], paths[p][1])
+
+
+def test_the_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of the package (nor the C sources) may import,
+    include or execute anything under it -- only tests/, __graft_entry__.smoke() and bench.py's CPU
+    legs may."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "abnet3_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                continue
+            text = open(os.path.join(dirpath, f), errors="ignore").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or \
+                    re.search(r"#include\s+[\"<][^\">]*oracle", text) or "import_module(\"oracle" in text:
+                offenders.append(os.path.relpath(os.path.join(dirpath, f), root))
+    assert offenders == []
+    # bench.py: only inside the CPU-baseline / reference-arm functions
+    bench = open(os.path.join(root, "bench.py")).read()
+    for m in re.finditer(r"^(\s*)import oracle\b|^(\s*)from oracle\b", bench, flags=re.M):
+        assert len((m.group(1) or m.group(2))) > 0, "bench.py imports the oracle at module level"
